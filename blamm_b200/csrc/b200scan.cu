@@ -1,0 +1,654 @@
+// libb200scan.so -- context management, motif packing, kernel launches and the C ABI of include/b200scan.h.
+// Everything device-side is sm_100a CUDA in the .cuh files next to this one; there is no CPU scoring path.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "filter_tc.cuh"
+#include "gather.cuh"
+#include "pack.cuh"
+#include "rescore.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr uint32_t kPadBytes = 16384;             // slack behind every device sequence buffer (window / span over-reads)
+constexpr size_t   kGatherSmemW = 64 * 1024;      // FP32 weights per gather column tile
+
+struct Slot {
+    // host staging (pinned)
+    uint8_t*  h_ascii = nullptr;
+    uint32_t* h_frag = nullptr;  size_t frag_cap = 0;
+    b200scan_hit* h_hits = nullptr;
+    unsigned long long* h_counters = nullptr;     // [0] n_cand, [1] n_hits, [2] has_zero|error (as 2 x u32)
+    // device
+    uint8_t*  d_ascii = nullptr;
+    uint32_t* d_codes = nullptr;
+    uint32_t* d_zmask = nullptr;
+    uint32_t* d_frag = nullptr;
+    b200scan_hit* d_hits = nullptr;  unsigned long long hit_cap = 0;
+    unsigned long long* d_counters = nullptr;     // [0] n_cand, [1] n_hits, [2] {has_zero, error_flag}, [3] {work_counter, -}
+    // state
+    bool in_flight = false, resident = false;
+    uint64_t n_total = 0, n_payload = 0, n_frag = 0;
+    bool packed_zero_known = false;               // submit_packed: has_zero decided on the host
+    cudaEvent_t ev[8] = {};                       // 0 start, 1 after h2d, 2 after pack, 3 after score, 4 after rescore, 5 after counters d2h, 6/7 hit d2h
+    b200scan_timing timing = {};
+};
+
+} // namespace
+
+struct b200scan_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t max_block = 0;
+    int engine = B200SCAN_ENGINE_AUTO;
+    std::string err;
+    Slot slot[B200SCAN_NUM_SLOTS];
+    // candidates are shared by the slots (stream order serialises filter -> rescore per block)
+    Cand* d_cand = nullptr;  unsigned long long cand_cap = 0;
+    // motifs
+    bool have_motifs = false;
+    uint32_t n_cols = 0, max_len = 0;  uint64_t sum_len = 0;
+    float4* d_w = nullptr;  uint32_t *d_woff = nullptr, *d_len = nullptr, *d_orig = nullptr;  float* d_thr = nullptr;
+    GatherTile* d_gtiles = nullptr;  std::vector<GatherTile> gtiles;  size_t gather_smem = 0;
+    TcTile* d_ttiles = nullptr;  std::vector<TcTile> ttiles;  uint8_t* d_bimg = nullptr;
+    bool tc_usable = false;
+};
+
+namespace {
+
+int fail(b200scan_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do { cudaError_t e_ = (call);                                                                        \
+         if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? B200SCAN_ENOMEM : B200SCAN_ECUDA, \
+                                            "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <class T> void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+template <class T> void hfree(T*& p) { if (p) cudaFreeHost(p); p = nullptr; }
+
+// smallest FP16 value >= x (x finite), as raw bits
+uint16_t half_round_up(double x)
+{
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    __half h = __float2half_rn(f);
+    uint16_t bits; std::memcpy(&bits, &h, 2);
+    if (__half2float(h) < f) {
+        if (bits == 0x8000u) bits = 0x0001u;            // -0 -> smallest positive
+        else if (bits & 0x8000u) bits -= 1;             // negative: towards zero
+        else bits += 1;                                 // positive: away from zero
+    }
+    return bits;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core tiling: sorted columns are cut into tiles of <= 256 columns (N padded to 32) minimising
+//   sum over tiles of  max(MMA cycles, epilogue cycles)  per 128-window tile.  This replaces the reference's
+// greedy zero-area tiling of P (MotifContainer::generateMatrixTiles, motif.cpp:482-540) -- like there, the
+// split is a pure performance device and cannot change results.
+// ---------------------------------------------------------------------------------------------------------
+void plan_tc_tiles(const std::vector<uint32_t>& len_sorted, std::vector<std::pair<uint32_t, uint32_t>>& out)
+{
+    const uint32_t n = (uint32_t)len_sorted.size();
+    const double kEpiPerCol = 2.0, kFixed = 96.0;       // cycles; refined from ncu
+    std::vector<double> best(n + 1, 1e300);
+    std::vector<uint32_t> from(n + 1, 0);
+    best[0] = 0;
+    for (uint32_t j = 1; j <= n; j++) {
+        const uint32_t nk = (len_sorted[j - 1] + 3) / 4;
+        for (uint32_t i = (j > kTcMaxN ? j - kTcMaxN : 0); i < j; i++) {
+            const uint32_t npad = ((j - i) + 31) / 32 * 32;
+            const double c = best[i] + std::max(nk * npad * 0.5, kEpiPerCol * npad) + kFixed;
+            if (c < best[j]) { best[j] = c; from[j] = i; }
+        }
+    }
+    out.clear();
+    for (uint32_t j = n; j > 0; j = from[j]) out.push_back({from[j], j});
+    std::reverse(out.begin(), out.end());
+}
+
+int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols, const int32_t* col_len, const float* thr)
+{
+    // stable sort by length
+    std::vector<uint32_t> order(n_cols);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return col_len[a] < col_len[b]; });
+
+    std::vector<uint32_t> len(n_cols), woff(n_cols), orig(n_cols);
+    std::vector<float> thr_s(n_cols);
+    uint64_t sum_len = 0; uint32_t max_len = 0;
+    for (int32_t s = 0; s < n_cols; s++) {
+        const uint32_t c = order[s];
+        len[s] = (uint32_t)col_len[c]; woff[s] = (uint32_t)sum_len; orig[s] = c; thr_s[s] = thr[c];
+        sum_len += len[s]; max_len = std::max(max_len, len[s]);
+    }
+    std::vector<float4> w(sum_len);
+    for (int32_t s = 0; s < n_cols; s++) {
+        const float* col = P + (size_t)orig[s] * ldp;
+        for (uint32_t j = 0; j < len[s]; j++)
+            w[woff[s] + j] = make_float4(col[4 * j], col[4 * j + 1], col[4 * j + 2], col[4 * j + 3]);
+    }
+
+    // ---- gather tiles: as many columns as fit the shared-memory weight budget ----
+    std::vector<GatherTile> gt;
+    size_t max_meta = 0;
+    for (uint32_t s = 0; s < (uint32_t)n_cols;) {
+        GatherTile t{s, 0, woff[s], 0};
+        while (s < (uint32_t)n_cols && (size_t)(t.n_w + len[s]) * 16 <= kGatherSmemW && t.n_cols < 1024) {
+            t.n_w += len[s]; t.n_cols++; s++;
+        }
+        gt.push_back(t);
+        max_meta = std::max(max_meta, (size_t)t.n_cols * 12);
+    }
+    ctx->gather_smem = kGatherSmemW + max_meta;
+
+    // ---- tensor-core tiles and the FP16 B image ----
+    std::vector<std::pair<uint32_t, uint32_t>> cuts;
+    plan_tc_tiles(len, cuts);
+    std::vector<TcTile> tt;
+    std::vector<uint8_t> bimg;
+    bool tc_ok = true;
+    for (auto& cut : cuts) {
+        TcTile t{};
+        t.col0 = cut.first; t.n_cols = cut.second - cut.first;
+        t.n_pad = (t.n_cols + 31) / 32 * 32;
+        t.n_k = (len[cut.second - 1] + 3) / 4;
+        const uint32_t nChunks = 2 * t.n_k;
+        t.b_off = (uint32_t)bimg.size();
+        t.b_bytes = t.n_pad * nChunks * 16;
+        bimg.resize(bimg.size() + t.b_bytes, 0);
+        uint16_t* img = reinterpret_cast<uint16_t*>(bimg.data() + t.b_off);
+        auto at = [&](uint32_t n, uint32_t j, uint32_t o) -> uint16_t& {        // column n (tile-local), position j, letter o
+            const uint32_t kk = j >> 1;
+            return img[(((n >> 3) * nChunks + kk) * 8 + (n & 7)) * 8 + (j & 1) * 4 + o];
+        };
+        for (uint32_t n = 0; n < t.n_pad; n++) {
+            if (n >= t.n_cols) {                         // padding column: can never reach acc >= 0
+                for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0xFBFFu;   // -65504
+                continue;
+            }
+            const uint32_t s = t.col0 + n, L = len[s];
+            // Conservative folding.  With x_j the FP32 weights picked by a window:
+            //   exact in-order FP32 score  s  = sum x_j + e1,   |e1| <= (L-1) * 2^-24 * A
+            //   tensor accumulator        acc = sum y_j + e2,   y_j = fp16_up(x_j - thr'/L) >= x_j - thr'/L,
+            //                                                   |e2| <= L * 2^-18 * A'   (generous for any FP32-ish accumulate)
+            // so  s >= thr  =>  acc >= thr - thr' - |e1| - |e2|;  choose thr' = thr - margin with margin >= |e1|+|e2|.
+            double A = 0, Ap = 0;
+            bool finite = std::isfinite(thr_s[s]);
+            for (uint32_t j = 0; j < L; j++) {
+                const float4 v = w[woff[s] + j];
+                const float a4[4] = {v.x, v.y, v.z, v.w};
+                double m = 0;
+                for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); }
+                A += m;
+            }
+            bool always = !finite;
+            if (!always) {
+                const double share0 = (double)thr_s[s] / L;
+                for (uint32_t j = 0; j < L; j++) {
+                    const float4 v = w[woff[s] + j];
+                    Ap += std::max(std::max(std::fabs(v.x - share0), std::fabs(v.y - share0)),
+                                   std::max(std::fabs(v.z - share0), std::fabs(v.w - share0)));
+                }
+                const double margin = 1e-3 + (L - 1) * std::ldexp(A, -24) + L * std::ldexp(Ap + 1.0, -18);
+                const double share = ((double)thr_s[s] - margin) / L;
+                for (uint32_t j = 0; j < L && !always; j++) {
+                    const float4 v = w[woff[s] + j];
+                    const float a4[4] = {v.x, v.y, v.z, v.w};
+                    for (uint32_t o = 0; o < 4; o++) {
+                        const double y = (double)a4[o] - share;
+                        if (std::fabs(y) > 30000.0) { always = true; break; }
+                        at(n, j, o) = half_round_up(y);
+                    }
+                }
+            }
+            if (always) {                                // degenerate column: let every window through to the exact rescorer
+                for (uint32_t j = 0; j < 2 * nChunks; j++) for (uint32_t o = 0; o < 4; o++) at(n, j, o) = 0;
+                for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0x3C00u;      // acc = +1
+            }
+        }
+        tt.push_back(t);
+    }
+    if (max_len > (uint32_t)kMaxLen) tc_ok = false;
+
+    // ---- upload ----
+    dfree(ctx->d_w); dfree(ctx->d_woff); dfree(ctx->d_len); dfree(ctx->d_orig); dfree(ctx->d_thr);
+    dfree(ctx->d_gtiles); dfree(ctx->d_ttiles); dfree(ctx->d_bimg);
+    CU(cudaMalloc(&ctx->d_w, sizeof(float4) * (sum_len + 80)));       // slack: the rescorer never reads past len, but keep loads in bounds
+    CU(cudaMemset(ctx->d_w, 0, sizeof(float4) * (sum_len + 80)));
+    CU(cudaMalloc(&ctx->d_woff, 4 * n_cols)); CU(cudaMalloc(&ctx->d_len, 4 * n_cols));
+    CU(cudaMalloc(&ctx->d_orig, 4 * n_cols)); CU(cudaMalloc(&ctx->d_thr, 4 * n_cols));
+    CU(cudaMalloc(&ctx->d_gtiles, sizeof(GatherTile) * gt.size()));
+    CU(cudaMalloc(&ctx->d_ttiles, sizeof(TcTile) * tt.size()));
+    CU(cudaMalloc(&ctx->d_bimg, bimg.size() + 128));
+    CU(cudaMemcpy(ctx->d_w, w.data(), sizeof(float4) * sum_len, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_woff, woff.data(), 4 * n_cols, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_len, len.data(), 4 * n_cols, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_orig, orig.data(), 4 * n_cols, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_thr, thr_s.data(), 4 * n_cols, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_gtiles, gt.data(), sizeof(GatherTile) * gt.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_ttiles, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_bimg, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
+    ctx->gtiles = gt; ctx->ttiles = tt;
+    ctx->n_cols = (uint32_t)n_cols; ctx->max_len = max_len; ctx->sum_len = sum_len;
+    ctx->tc_usable = tc_ok;
+    ctx->have_motifs = true;
+    for (auto& s : ctx->slot) s.resident = false;
+    return B200SCAN_OK;
+}
+
+MotifDev motif_dev(const b200scan_ctx* c) { return MotifDev{c->d_w, c->d_woff, c->d_len, c->d_thr, c->d_orig, c->n_cols}; }
+
+BlockDev block_dev(const Slot& s)
+{
+    BlockDev b;
+    b.codes = s.d_codes; b.zmask = s.d_zmask; b.frag = s.d_frag;
+    b.has_zero = reinterpret_cast<const uint32_t*>(s.d_counters + 2);
+    b.n_total = (uint32_t)s.n_total; b.n_payload = (uint32_t)s.n_payload; b.n_frag = (uint32_t)s.n_frag;
+    return b;
+}
+
+// Launch the scoring kernels for the block resident in `s` (counters must already be reset).
+// Returns the number of kernels launched; records ev[3] after the dominant kernel(s) and ev[4] after the rescorer.
+int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaEvent_t ev_after_rescore, int* launches)
+{
+    const MotifDev md = motif_dev(ctx);
+    const BlockDev blk = block_dev(s);
+    HitSink sink{s.d_hits, s.d_counters + 1, s.hit_cap};
+    unsigned int* err = reinterpret_cast<unsigned int*>(s.d_counters + 2) + 1;
+    unsigned int* work = reinterpret_cast<unsigned int*>(s.d_counters + 3);
+    int n = 0;
+    if (s.n_payload == 0) {                          // nothing to score (empty block): keep the event protocol intact
+        if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
+        if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
+        return B200SCAN_OK;
+    }
+    const bool want_tc = (ctx->engine != B200SCAN_ENGINE_GATHER) && ctx->tc_usable;
+    const dim3 ggrid((unsigned)((s.n_payload + kGatherSpan - 1) / kGatherSpan), (unsigned)ctx->gtiles.size());
+    if (want_tc) {
+        TcParams tp;
+        tp.bimg = ctx->d_bimg; tp.tiles = ctx->d_ttiles; tp.n_tiles = (uint32_t)ctx->ttiles.size();
+        tp.n_spans = (uint32_t)((s.n_payload + kTcSpan - 1) / kTcSpan);
+        tp.work_counter = work; tp.cand = ctx->d_cand; tp.n_cand = s.d_counters; tp.cand_cap = ctx->cand_cap;
+        tp.error_flag = err;
+        filter_tc_kernel<<<ctx->sm_count, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+        n++;
+        if (ctx->engine == B200SCAN_ENGINE_AUTO) {     // blocks with a zero mask: exact gather-add (kernel exits at once otherwise)
+            gather_scan_kernel<true><<<ggrid, kGatherThreads, ctx->gather_smem, ctx->stream>>>(md, blk, ctx->d_gtiles, sink, 1);
+            n++;
+        }
+        if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
+        rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(md, blk, ctx->d_cand, s.d_counters, ctx->cand_cap, sink);
+        n++;
+        if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
+    } else {
+        gather_scan_kernel<false><<<ggrid, kGatherThreads, ctx->gather_smem, ctx->stream>>>(md, blk, ctx->d_gtiles, sink, 0);
+        gather_scan_kernel<true><<<ggrid, kGatherThreads, ctx->gather_smem, ctx->stream>>>(md, blk, ctx->d_gtiles, sink, 1);
+        n += 2;
+        if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
+        if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
+    }
+    CU(cudaGetLastError());
+    if (launches) *launches += n;
+    return B200SCAN_OK;
+}
+
+int reset_counters(b200scan_ctx* ctx, Slot& s, bool keep_has_zero)
+{
+    // [0] n_cand [1] n_hits: zero.  [2] = {has_zero, error}: keep has_zero on re-runs.  [3] work counter: zero.
+    CU(cudaMemsetAsync(s.d_counters, 0, 16, ctx->stream));
+    if (keep_has_zero) CU(cudaMemsetAsync(reinterpret_cast<uint32_t*>(s.d_counters + 2) + 1, 0, 4, ctx->stream));
+    else CU(cudaMemsetAsync(s.d_counters + 2, 0, 8, ctx->stream));
+    CU(cudaMemsetAsync(s.d_counters + 3, 0, 8, ctx->stream));
+    return B200SCAN_OK;
+}
+
+int check_common(b200scan_ctx* ctx, int slot, uint64_t n_total, uint64_t n_payload, const uint64_t* frag, uint64_t n_frag)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (slot < 0 || slot >= B200SCAN_NUM_SLOTS) return fail(ctx, B200SCAN_EINVAL, "slot %d out of range", slot);
+    if (!ctx->have_motifs) return fail(ctx, B200SCAN_ESTATE, "b200scan_set_motifs has not been called");
+    if (ctx->slot[slot].in_flight) return fail(ctx, B200SCAN_ESTATE, "slot %d has an uncollected block", slot);
+    if (n_payload > n_total) return fail(ctx, B200SCAN_EINVAL, "n_payload > n_total");
+    if (n_total > ctx->max_block) return fail(ctx, B200SCAN_ELIMIT, "block of %llu characters exceeds max_block_nt %llu",
+                                             (unsigned long long)n_total, (unsigned long long)ctx->max_block);
+    if (n_frag && !frag) return fail(ctx, B200SCAN_EINVAL, "frag_starts is NULL");
+    for (uint64_t i = 0; i < n_frag; i++)
+        if (frag[i] == 0 || frag[i] >= n_total || (i && frag[i] <= frag[i - 1]))
+            return fail(ctx, B200SCAN_EINVAL, "frag_starts must be strictly ascending inside (0, n_total)");
+    return B200SCAN_OK;
+}
+
+int stage_frags(b200scan_ctx* ctx, Slot& s, const uint64_t* frag, uint64_t n_frag)
+{
+    if (n_frag > s.frag_cap) {
+        size_t cap = std::max<size_t>(n_frag * 2, 1 << 16);
+        hfree(s.h_frag); dfree(s.d_frag);
+        CU(cudaMallocHost(&s.h_frag, cap * 4)); CU(cudaMalloc(&s.d_frag, cap * 4));
+        s.frag_cap = cap;
+    }
+    for (uint64_t i = 0; i < n_frag; i++) s.h_frag[i] = (uint32_t)frag[i];
+    if (n_frag) CU(cudaMemcpyAsync(s.d_frag, s.h_frag, n_frag * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return B200SCAN_OK;
+}
+
+int finish_submit(b200scan_ctx* ctx, Slot& s)
+{
+    s.timing.kernel_launches = 0;
+    int launches = 0;
+    int rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
+    if (rc) return rc;
+    s.timing.kernel_launches += launches;
+    CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(s.ev[5], ctx->stream));
+    s.in_flight = true; s.resident = true;
+    return B200SCAN_OK;
+}
+
+} // namespace
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int b200scan_abi_version(void) { return B200SCAN_ABI_VERSION; }
+
+const char* b200scan_last_error(const b200scan_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint64_t max_hits)
+{
+    b200scan_ctx* ctx = nullptr;      // CU() reports into g_create_error while ctx == nullptr
+    if (!out) return B200SCAN_EINVAL;
+    *out = nullptr;
+    if (max_block_nt == 0 || max_block_nt > 0xF0000000ull) return fail(nullptr, B200SCAN_EINVAL, "max_block_nt must be in (0, 2^32)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, B200SCAN_ENODEVICE, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, B200SCAN_ENODEVICE, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(nullptr, B200SCAN_ENODEVICE, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+
+    b200scan_ctx* c = new b200scan_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount; c->max_block = max_block_nt;
+    ctx = c;
+    auto bail = [&](int rc) { std::string e = c->err; b200scan_destroy(c); g_create_error = e; return rc; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B200SCAN_ECUDA, "%s -> %s", #call, cudaGetErrorString(e_)); \
+                       return bail(e_ == cudaErrorMemoryAllocation ? B200SCAN_ENOMEM : B200SCAN_ECUDA); } } while (0)
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
+    CUB(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
+    if (max_hits == 0) max_hits = 1 << 20;
+    const size_t nb = (size_t)max_block_nt;
+    for (auto& s : c->slot) {
+        CUB(cudaMallocHost(&s.h_ascii, nb + 64));
+        CUB(cudaMallocHost(&s.h_hits, sizeof(b200scan_hit) * max_hits));
+        CUB(cudaMallocHost(&s.h_counters, 32));
+        CUB(cudaMalloc(&s.d_ascii, nb + kPadBytes));
+        CUB(cudaMalloc(&s.d_codes, nb / 4 + kPadBytes));
+        CUB(cudaMalloc(&s.d_zmask, nb / 8 + kPadBytes));
+        CUB(cudaMemset(s.d_codes, 0, nb / 4 + kPadBytes));
+        CUB(cudaMemset(s.d_zmask, 0, nb / 8 + kPadBytes));
+        CUB(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * max_hits));
+        s.hit_cap = max_hits;
+        CUB(cudaMalloc(&s.d_counters, 32));
+        CUB(cudaMemset(s.d_counters, 0, 32));
+        for (auto& e : s.ev) CUB(cudaEventCreate(&e));
+    }
+    c->cand_cap = std::max<unsigned long long>(2 * max_hits, 1 << 20);
+    CUB(cudaMalloc(&c->d_cand, sizeof(Cand) * c->cand_cap));
+#undef CUB
+    *out = c;
+    return B200SCAN_OK;
+}
+
+void b200scan_destroy(b200scan_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& s : c->slot) {
+        hfree(s.h_ascii); hfree(s.h_frag); hfree(s.h_hits); hfree(s.h_counters);
+        dfree(s.d_ascii); dfree(s.d_codes); dfree(s.d_zmask); dfree(s.d_frag); dfree(s.d_hits); dfree(s.d_counters);
+        for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+    }
+    dfree(c->d_cand);
+    dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
+    dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int b200scan_set_engine(b200scan_ctx* ctx, int engine)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (engine < B200SCAN_ENGINE_AUTO || engine > B200SCAN_ENGINE_TENSOR) return fail(ctx, B200SCAN_EINVAL, "unknown engine %d", engine);
+    ctx->engine = engine;
+    return B200SCAN_OK;
+}
+
+int b200scan_set_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols, const int32_t* col_len, const float* thr)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (!P || !col_len || !thr || n_cols <= 0) return fail(ctx, B200SCAN_EINVAL, "set_motifs: NULL or empty input");
+    for (auto& s : ctx->slot) if (s.in_flight) return fail(ctx, B200SCAN_ESTATE, "set_motifs while a block is in flight");
+    for (int32_t c = 0; c < n_cols; c++) {
+        if (col_len[c] < 1) return fail(ctx, B200SCAN_EINVAL, "column %d has length %d", c, col_len[c]);
+        if (col_len[c] > B200SCAN_MAX_MOTIF_LEN) return fail(ctx, B200SCAN_ELIMIT, "column %d has length %d > %d", c, col_len[c], B200SCAN_MAX_MOTIF_LEN);
+        if (4 * col_len[c] > ldp) return fail(ctx, B200SCAN_EINVAL, "ldp %d < 4*len of column %d", ldp, c);
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return build_motifs(ctx, P, ldp, n_cols, col_len, thr);
+}
+
+int b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64_t n_total, uint64_t n_payload,
+                          const uint64_t* frag_starts, uint64_t n_frag, int lowercase_mode)
+{
+    int rc = check_common(ctx, slot, n_total, n_payload, frag_starts, n_frag);
+    if (rc) return rc;
+    if (!block && n_total) return fail(ctx, B200SCAN_EINVAL, "block is NULL");
+    if (lowercase_mode != B200SCAN_LOWER_ZERO && lowercase_mode != B200SCAN_LOWER_FOLD) return fail(ctx, B200SCAN_EINVAL, "bad lowercase_mode");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[slot];
+    s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag;
+    s.timing = b200scan_timing{};
+    CU(cudaEventRecord(s.ev[0], ctx->stream));
+    // pinned caller memory goes straight to the device; pageable memory is staged through the slot's pinned buffer
+    const void* src = block;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, block) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        std::memcpy(s.h_ascii, block, n_total);
+        src = s.h_ascii;
+    }
+    if (n_total) CU(cudaMemcpyAsync(s.d_ascii, src, n_total, cudaMemcpyHostToDevice, ctx->stream));
+    rc = stage_frags(ctx, s, frag_starts, n_frag);
+    if (rc) return rc;
+    rc = reset_counters(ctx, s, false);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.ev[1], ctx->stream));
+    if (n_total) {
+        const unsigned threads = (unsigned)((n_total + 31) / 32);
+        pack_ascii_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(s.d_ascii, (uint32_t)n_total, lowercase_mode == B200SCAN_LOWER_FOLD,
+                                                                          s.d_codes, s.d_zmask, reinterpret_cast<uint32_t*>(s.d_counters + 2));
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(s.ev[2], ctx->stream));
+    rc = finish_submit(ctx, s);
+    if (rc == B200SCAN_OK && n_total) s.timing.kernel_launches += 1;
+    return rc;
+}
+
+int b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2, const uint32_t* zero_mask, uint64_t n_total,
+                           uint64_t n_payload, const uint64_t* frag_starts, uint64_t n_frag)
+{
+    int rc = check_common(ctx, slot, n_total, n_payload, frag_starts, n_frag);
+    if (rc) return rc;
+    if (!codes2 && n_total) return fail(ctx, B200SCAN_EINVAL, "codes2 is NULL");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[slot];
+    s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag;
+    s.timing = b200scan_timing{};
+    CU(cudaEventRecord(s.ev[0], ctx->stream));
+    const size_t cw = (n_total + 15) / 16, zw = (n_total + 31) / 32;
+    // pageable sources: cudaMemcpyAsync stages them itself and returns once the source may be reused
+    if (cw) CU(cudaMemcpyAsync(s.d_codes, codes2, cw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t hz = 0;
+    if (zero_mask) {
+        for (size_t i = 0; i < zw && !hz; i++) {
+            uint32_t live = (i + 1 == zw && (n_total & 31)) ? ((1u << (n_total & 31)) - 1u) : 0xffffffffu;
+            if (zero_mask[i] & live) hz = 1;
+        }
+        if (hz) CU(cudaMemcpyAsync(s.d_zmask, zero_mask, zw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = stage_frags(ctx, s, frag_starts, n_frag);
+    if (rc) return rc;
+    rc = reset_counters(ctx, s, false);
+    if (rc) return rc;
+    if (hz) CU(cudaMemsetAsync(s.d_counters + 2, 1, 1, ctx->stream));      // has_zero = 1 (little endian)
+    CU(cudaEventRecord(s.ev[1], ctx->stream));
+    CU(cudaEventRecord(s.ev[2], ctx->stream));
+    return finish_submit(ctx, s);
+}
+
+int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits, b200scan_timing* timing)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (slot < 0 || slot >= B200SCAN_NUM_SLOTS) return fail(ctx, B200SCAN_EINVAL, "slot %d out of range", slot);
+    Slot& s = ctx->slot[slot];
+    if (!s.in_flight) return fail(ctx, B200SCAN_ESTATE, "slot %d has nothing to collect", slot);
+    CU(cudaSetDevice(ctx->device));
+    s.in_flight = false;
+    for (int attempt = 0;; attempt++) {
+        cudaError_t e = cudaEventSynchronize(s.ev[5]);
+        if (e != cudaSuccess) { s.resident = false; return fail(ctx, B200SCAN_ECUDA, "scan failed: %s", cudaGetErrorString(e)); }
+        const unsigned long long n_cand = s.h_counters[0], nh = s.h_counters[1];
+        const uint32_t has_zero = (uint32_t)(s.h_counters[2] & 0xffffffffu), errflag = (uint32_t)(s.h_counters[2] >> 32);
+        if (errflag) return fail(ctx, B200SCAN_ECUDA, "kernel reported error flag 0x%08x", errflag);
+        if (ctx->engine == B200SCAN_ENGINE_TENSOR && has_zero)
+            return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR cannot score a block with zero-contribution characters (use AUTO)");
+        if (ctx->engine == B200SCAN_ENGINE_TENSOR && !ctx->tc_usable)
+            return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR unavailable for this motif set");
+        const bool cand_over = n_cand > ctx->cand_cap, hit_over = nh > s.hit_cap;
+        if (!cand_over && !hit_over) {
+            s.timing.n_candidates = n_cand; s.timing.n_hits = nh;
+            s.timing.engine_used = (has_zero || ctx->engine == B200SCAN_ENGINE_GATHER || !ctx->tc_usable) ? B200SCAN_ENGINE_GATHER : B200SCAN_ENGINE_TENSOR;
+            break;
+        }
+        if (attempt >= 2) return fail(ctx, B200SCAN_ECUDA, "hit buffers still too small after regrowing");
+        // the counters kept counting, so they say exactly how much room a re-run needs
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (cand_over) {
+            dfree(ctx->d_cand);
+            ctx->cand_cap = n_cand + n_cand / 8 + 1024;
+            CU(cudaMalloc(&ctx->d_cand, sizeof(Cand) * ctx->cand_cap));
+        }
+        if (hit_over || cand_over) {
+            unsigned long long want = std::max<unsigned long long>(nh + nh / 8 + 1024, s.hit_cap);
+            if (cand_over) want = std::max(want, ctx->cand_cap);        // every candidate could be a hit
+            if (want > s.hit_cap) {
+                dfree(s.d_hits); hfree(s.h_hits);
+                CU(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * want));
+                CU(cudaMallocHost(&s.h_hits, sizeof(b200scan_hit) * want));
+                s.hit_cap = want;
+            }
+        }
+        int rc = reset_counters(ctx, s, true);
+        if (rc) return rc;
+        int launches = 0;
+        rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
+        if (rc) return rc;
+        s.timing.kernel_launches += launches;
+        CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(s.ev[5], ctx->stream));
+    }
+    const unsigned long long nh = s.h_counters[1];
+    CU(cudaEventRecord(s.ev[6], ctx->stream));
+    if (nh) CU(cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(b200scan_hit) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(s.ev[7], ctx->stream));
+    CU(cudaEventSynchronize(s.ev[7]));
+    cudaEventElapsedTime(&s.timing.h2d_ms, s.ev[0], s.ev[1]);
+    cudaEventElapsedTime(&s.timing.pack_ms, s.ev[1], s.ev[2]);
+    cudaEventElapsedTime(&s.timing.score_ms, s.ev[2], s.ev[3]);
+    cudaEventElapsedTime(&s.timing.rescore_ms, s.ev[3], s.ev[4]);
+    cudaEventElapsedTime(&s.timing.d2h_ms, s.ev[6], s.ev[7]);
+    if (hits) *hits = s.h_hits;
+    if (n_hits) *n_hits = nh;
+    if (timing) *timing = s.timing;
+    return B200SCAN_OK;
+}
+
+int b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total_ms, float* score_kernel_ms, uint64_t* n_hits_last)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (slot < 0 || slot >= B200SCAN_NUM_SLOTS || iters < 1 || iters > 4096) return fail(ctx, B200SCAN_EINVAL, "bad slot / iters");
+    Slot& s = ctx->slot[slot];
+    if (s.in_flight || !s.resident) return fail(ctx, B200SCAN_ESTATE, "slot %d holds no collected resident block", slot);
+    CU(cudaSetDevice(ctx->device));
+    std::vector<cudaEvent_t> ev(3 * (size_t)iters);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    int rc = B200SCAN_OK;
+    for (int i = 0; i < iters && rc == B200SCAN_OK; i++) {
+        rc = reset_counters(ctx, s, true);
+        if (rc) break;
+        CU(cudaEventRecord(ev[3 * i], ctx->stream));
+        rc = launch_scoring(ctx, s, ev[3 * i + 1], ev[3 * i + 2], nullptr);
+    }
+    if (rc == B200SCAN_OK) {
+        CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, B200SCAN_ECUDA, "rerun failed: %s", cudaGetErrorString(e));
+    }
+    float tot = 0, sc = 0;
+    if (rc == B200SCAN_OK) {
+        for (int i = 0; i < iters; i++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ev[3 * i], ev[3 * i + 2]);
+            cudaEventElapsedTime(&b, ev[3 * i], ev[3 * i + 1]);
+            tot += a; sc += b;
+        }
+        if ((uint32_t)(s.h_counters[2] >> 32)) rc = fail(ctx, B200SCAN_ECUDA, "kernel reported error flag 0x%08x", (uint32_t)(s.h_counters[2] >> 32));
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (total_ms) *total_ms = tot;
+    if (score_kernel_ms) *score_kernel_ms = sc;
+    if (n_hits_last) *n_hits_last = s.h_counters[1];
+    return rc;
+}
+
+int b200scan_describe(const b200scan_ctx* ctx, int32_t* n_cols, int32_t* max_len, int32_t* n_tiles, int32_t* sm_count, uint64_t* sum_len)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (n_cols) *n_cols = (int32_t)ctx->n_cols;
+    if (max_len) *max_len = (int32_t)ctx->max_len;
+    if (n_tiles) *n_tiles = (int32_t)ctx->ttiles.size();
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (sum_len) *sum_len = ctx->sum_len;
+    return B200SCAN_OK;
+}
+
+} // extern "C"

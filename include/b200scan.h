@@ -1,0 +1,142 @@
+/*
+ * b200scan.h -- C ABI of the B200-native `blamm scan` hot path (libb200scan.so).
+ *
+ * This is the drop-in boundary for the part of biointec/blamm that scores every window of a block of
+ * filtered sequence against every motif column and extracts the occurrences.  Each entry point names the
+ * reference interface it replaces (paths are relative to the reference's src/):
+ *
+ *   b200scan_create / _destroy     cudaSetDevice + cublasCreate + the cudaMalloc/cudaFree blocks of
+ *                                  PWMScan::scanThreadCUBLAS                       pwmscan.cpp:309-357, 428-436
+ *   b200scan_set_motifs            upload of matrix P and the per-column thresholds  pwmscan.cpp:316-342
+ *                                  (P as produced by MotifContainer::generateMatrix  motif.cpp:542-564,
+ *                                   thresholds as set in the species loop            pwmscan.cpp:599-616)
+ *   b200scan_submit_ascii          SeqMatrix::getNextSeqMatrix one-hot fill + cublasSetVector(S)
+ *                                                                            sequence.cpp:299-340, pwmscan.cpp:383
+ *                                  + the w-iteration loop { Matrix::sgemm_batch_cuda; kernel_wrapper }
+ *                                                                  pwmscan.cpp:385-391, matrix.h:314-323, kernel.cu:21-45
+ *   b200scan_submit_packed         same, for callers that already hold the 2-bit packed stream
+ *   b200scan_collect               cublasGetVector(d_nOcc / occIdx / occScore) + the boundary filter of
+ *                                  PWMScan::extractOccurrences2                      pwmscan.cpp:393-406, 135-163
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * B200SCAN_E* code (no exception crosses the ABI); b200scan_last_error() gives the text.  The context owns
+ * all device and pinned memory; inputs are copied before the call returns unless stated; outputs are
+ * borrowed until the next submit on the same slot.  A context is bound to one CUDA device and must be
+ * driven by one host thread at a time (the reference uses one host thread per device, pwmscan.cpp:444-447).
+ * There is NO CPU fallback: without a usable sm_100 device b200scan_create fails.
+ *
+ * A "block" is what the reference calls SeqBlock (sequence.h:95-184): the concatenation of valid
+ * (ACGTacgt) fragments of one species group, `n_total` = payload + halo characters, where only windows
+ * starting in the first `n_payload` characters are reported (the halo of maxLen-1 characters belongs to the
+ * next block, sequence.cpp:274-293).  `frag_starts` are the block positions at which a new fragment begins
+ * (the keys of SeqBlock::block2seq, position 0 is implied); a window is an occurrence only if it lies wholly
+ * inside one fragment (pwmscan.cpp:122-126).  Unlike the reference's h*w = 250,000 character blocks, a block
+ * here may hold up to `max_block_nt` characters (hundreds of Mnt).
+ */
+#ifndef B200SCAN_H
+#define B200SCAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SCAN_ABI_VERSION 1
+
+/* error codes */
+#define B200SCAN_OK            0
+#define B200SCAN_EINVAL       -1   /* bad argument */
+#define B200SCAN_ECUDA        -2   /* CUDA runtime error (text in last_error) */
+#define B200SCAN_ENODEVICE    -3   /* no sm_100 device / device index out of range */
+#define B200SCAN_ENOMEM       -4   /* host or device allocation failed */
+#define B200SCAN_ESTATE       -5   /* call order violated (e.g. collect without submit) */
+#define B200SCAN_ELIMIT       -6   /* motif longer than B200SCAN_MAX_MOTIF_LEN, block larger than max_block_nt */
+
+#define B200SCAN_MAX_MOTIF_LEN 64
+#define B200SCAN_NUM_SLOTS      2  /* submit/collect double buffering */
+
+/* scoring engines (b200scan_set_engine) */
+#define B200SCAN_ENGINE_AUTO    0  /* tensor-core filter + exact rescore; gather-add for blocks with a zero-mask */
+#define B200SCAN_ENGINE_GATHER  1  /* shared-memory gather-add, every score in exact reference order */
+#define B200SCAN_ENGINE_TENSOR  2  /* tcgen05 filter + exact rescore (fails with ESTATE on a zero-mask block) */
+
+/* how lower-case acgt is scored (b200scan_submit_ascii) */
+#define B200SCAN_LOWER_ZERO     0  /* BLAS-path semantics: valid character, contributes 0 (sequence.cpp:312-319) */
+#define B200SCAN_LOWER_FOLD     1  /* naive-path semantics: scored like upper case (motif.cpp:138-149)           */
+
+typedef struct b200scan_ctx b200scan_ctx;
+
+/* One occurrence.  `pos` is the block position of the window start (0-based, < n_payload), `col` the motif
+ * column as passed to b200scan_set_motifs, `score` the FP32 log-odds score summed in position order
+ * (bit-identical to the in-order FMA chain of the reference's sgemm on a one-hot operand). */
+typedef struct b200scan_hit {
+    uint64_t pos;
+    uint32_t col;
+    float    score;
+} b200scan_hit;
+
+/* timings of the last launch on a slot, CUDA events on the context's stream (milliseconds) */
+typedef struct b200scan_timing {
+    float h2d_ms;        /* host->device copy of the block (+ fragment table)          */
+    float pack_ms;       /* ASCII -> 2-bit pack kernel                                 */
+    float score_ms;      /* dominant kernel: tensor filter or gather-add               */
+    float rescore_ms;    /* exact rescore + boundary filter + compaction (tensor path) */
+    float d2h_ms;        /* hit download                                               */
+    uint64_t n_candidates;   /* tensor path: candidates the filter passed to the rescorer */
+    uint64_t n_hits;
+    int32_t  engine_used;    /* B200SCAN_ENGINE_GATHER or _TENSOR */
+    int32_t  kernel_launches;/* kernels launched for this block */
+} b200scan_timing;
+
+int  b200scan_abi_version(void);
+
+/* Create a context on CUDA device `device`.  max_block_nt: largest n_total a submit may carry.
+ * max_hits: capacity of the per-slot device hit buffer (a block producing more is rescanned in halves). */
+int  b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint64_t max_hits);
+void b200scan_destroy(b200scan_ctx* ctx);
+const char* b200scan_last_error(const b200scan_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
+
+int  b200scan_set_engine(b200scan_ctx* ctx, int engine);
+
+/* Motif matrix of the current species: P is column-major with leading dimension ldp >= 4*max(col_len),
+ * P[col*ldp + 4*j + o] = PWM_col[j][o], o in ACGT order (motif.cpp:556-563); col_len[col] in
+ * [1, B200SCAN_MAX_MOTIF_LEN]; thr[col] the score cut-off (hit <=> score >= thr, pwmscan.cpp:115-117). */
+int  b200scan_set_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
+                         const int32_t* col_len, const float* thr);
+
+/* Asynchronous scan of one block held in host memory.  `block` = n_total characters from "ACGTacgt"
+ * (anything else is scored as a zero contribution).  frag_starts: n_frag ascending block positions in
+ * (0, n_total) where a new fragment starts; may be NULL when n_frag == 0.  The buffers may be reused as soon
+ * as the call returns (they are copied to pinned staging).  slot in [0, B200SCAN_NUM_SLOTS). */
+int  b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64_t n_total,
+                           uint64_t n_payload, const uint64_t* frag_starts, uint64_t n_frag,
+                           int lowercase_mode);
+
+/* Same for a pre-packed block: codes2 holds 2 bits per character (A=0,C=1,G=2,T=3; character i in bits
+ * 2*(i%16) of 32-bit word i/16); zero_mask (may be NULL) holds 1 bit per character (bit i%32 of word i/32),
+ * set = the character contributes 0. */
+int  b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2, const uint32_t* zero_mask,
+                            uint64_t n_total, uint64_t n_payload, const uint64_t* frag_starts,
+                            uint64_t n_frag);
+
+/* Wait for the slot's scan and return its occurrences (unordered; owned by ctx until the next submit on
+ * the slot).  timing may be NULL. */
+int  b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits,
+                      b200scan_timing* timing);
+
+/* Measurement hook (bench.py `value`): re-run the scoring kernels `iters` times on the block that is
+ * already resident in the slot's device buffers (after a submit+collect), timed with CUDA events on the
+ * context's stream.  Returns total milliseconds for all iterations and for the dominant kernel alone. */
+int  b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total_ms, float* score_kernel_ms,
+                             uint64_t* n_hits_last);
+
+/* Introspection: number of window x column scores one pass over the slot's block computes. */
+int  b200scan_describe(const b200scan_ctx* ctx, int32_t* n_cols, int32_t* max_len, int32_t* n_tiles,
+                       int32_t* sm_count, uint64_t* sum_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SCAN_H */

@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY -- builds the UNMODIFIED reference (biointec/blamm) from the sources where
+# they lie under /root/reference into the git-ignored oracle/_ref/.  Nothing here is product code and no
+# reference source is copied into the repository.  Recipe: SURVEY.md section 8c.
+#   * cmake/FortranScheme.cmake would emit  F77_FUNC(name,NAME) name##_  for gfortran -> hand-written config.h
+#   * species.h uses std::array without <array>  ->  -include array
+#   * BLAS = OpenBLAS 0.3.15 that ships inside the opencv wheel of this image (exports plain sgemm_)
+# Outputs:  oracle/_ref/blamm          the reference CLI (CPU BLAS path + naive path)
+#           oracle/_ref/refdump        float-level harness linking the reference's own classes (refdump.cpp)
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${BLAMM_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+OB="${OPENBLAS_DIR:-/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs}"
+OBLIB="$(ls "$OB" | grep -m1 '^libopenblas' || true)"
+if [ ! -d "$REF/src" ]; then echo "build_ref: $REF/src absent (GPU box?) - keeping prebuilt files"; exit 0; fi
+if [ -z "$OBLIB" ]; then echo "build_ref: no OpenBLAS under $OB"; exit 1; fi
+mkdir -p "$OUT/cfg"
+cat > "$OUT/cfg/config.h" <<'EOC'
+#define F77_FUNC(name,NAME) name ## _
+EOC
+CXXFLAGS="-O3 -std=c++11 -DNDEBUG -DHAVE_CONFIG_H -DBLAMM_MAJOR_VERSION=1 -DBLAMM_MINOR_VERSION=0 -DBLAMM_PATCH_LEVEL=0 -I$OUT/cfg -include array -w"
+LDFLAGS="-L$OB -l:$OBLIB -Wl,--disable-new-dtags -Wl,-rpath,$OB -lpthread"
+g++ $CXXFLAGS "$REF"/src/*.cpp -o "$OUT/blamm" $LDFLAGS
+g++ $CXXFLAGS -I"$REF/src" "$HERE/refdump.cpp" "$REF"/src/{motif,sequence,species,settings,matrix}.cpp -o "$OUT/refdump" $LDFLAGS
+echo "$OB" > "$OUT/openblas_dir.txt"
+echo "build_ref: built $OUT/blamm and $OUT/refdump"
