@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- the `blamm scan` hot path on N B200s (one process per GPU, launched by torchrun for N > 1).
+
+Workload (BASELINE.json configs[1]): JASPAR-LIKE set of 900 PWMs (real JASPAR CORE is not available offline;
+seeded Dirichlet-multinomial count matrices with CORE-like lengths, see blamm_b200/synth.py) x both strands =
+1800 columns, against 100 Mbp of synthetic upper-case ACGT PER GPU (weak scaling: rank r scans its own
+100 Mbp chunk shard, no collective on the data path), thresholds from `-pt 1e-4` theoretical histograms.
+
+A step = one pass of the hot path over the rank's 100 Mbp block.
+  value : device-resident input (2-bit codes already in HBM), CUDA events around the scoring kernels
+          (tensor-core filter + exact rescore), L2 flushed between steps, max over ranks.
+  e2e   : the same block from PINNED HOST memory through the C ABI (b200scan_submit_ascii + b200scan_collect):
+          H2D of the ASCII block, pack, score, rescore, D2H of the hit list -- host clock, max over ranks.
+--impl reference times the reference's own CPU implementation (oracle/_ref/blamm, built from the unmodified
+sources by oracle/build_ref.sh; falls back to the C oracle port if that binary is absent) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "window x motif x strand scores per second"
+UNIT = "scores/s"
+N_MOTIFS, MOTIF_SEED, SEQ_SEED = 900, 2024, 4242
+SPECIES = "syn"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.f, self.p = gpu_index, None, None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        busy = [s for s, r in zip(sm, rows) if float(r[3]) > 200.0] or sm
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[5 + k].strip() == "Active" for r in rows)]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(rows[0][2]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def build_inputs(workdir: str, n_nt: int, rank: int):
+    """Motif file + histograms + thresholds (host C++ model through its C ABI) and the rank's sequence shard."""
+    from blamm_b200 import capi, synth
+    mfile = os.path.join(workdir, "motifs.jaspar")
+    synth.make_jaspar_like(mfile, N_MOTIFS, MOTIF_SEED)
+    seq = synth.random_acgt(n_nt, SEQ_SEED + rank)
+    bg = synth.counts_of(seq[: min(n_nt, 4_000_000)])
+    scale = n_nt / min(n_nt, 4_000_000)
+    bg = [int(round(c * scale)) for c in bg]                        # uniform synthetic sequence: counts scale linearly
+    ms = capi.MotifSet(mfile, revcompl=True)
+    ms.write_histograms(bg, SPECIES, workdir)
+    P, col_len, is_rc = ms.generate_matrix(bg)
+    thr = ms.thresholds("pt", 1e-4, SPECIES, workdir)
+    return ms, P, col_len, thr, seq, bg
+
+
+def _ref_scan_once(ref_bin, work, env, cores):
+    subprocess.run([ref_bin, "scan", "-rc", "-pt", "0.0001", "-t", str(cores), "motifs.jaspar", "sequences.mf"], cwd=work, env=env,
+                   check=True, stdout=subprocess.DEVNULL)
+
+
+def _ref_prepare(ref_bin, work, env, seq, n_nt):
+    """FASTA + manifest + dict + histograms for the first n_nt characters, made by the reference's own modules."""
+    from blamm_b200 import synth
+    q = n_nt // 4
+    synth.write_fasta(os.path.join(work, "sample.fa"), [("chr%d" % (i + 1), seq[i * q:(i + 1) * q]) for i in range(4)])
+    open(os.path.join(work, "sequences.mf"), "w").write("%s\tsample.fa\n" % SPECIES)
+    subprocess.run([ref_bin, "dict", "sequences.mf"], cwd=work, env=env, check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([ref_bin, "hist", "motifs.jaspar", "sequences.mf"], cwd=work, env=env, check=True, stdout=subprocess.DEVNULL)
+    return 4 * q
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """The reference arm: the reference's own CPU implementation (all host threads) on a bounded sample per step,
+    sized from a short calibration pass so that warmup + steps finish in about two minutes."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    work = tempfile.mkdtemp(prefix="bench_ref_")
+    try:
+        max_nt = 16_000_000
+        ms, P, col_len, thr, seq, bg = build_inputs(work, max_nt, 0)
+        n_cols = len(col_len)
+        ref_bin = os.path.join(ROOT, "oracle", "_ref", "blamm")
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+        usable = os.path.exists(ref_bin)
+        n_steps = args.warmup + args.steps
+        if usable:
+            try:
+                n_cal = _ref_prepare(ref_bin, work, env, seq, 1_000_000)
+                t0 = time.perf_counter(); _ref_scan_once(ref_bin, work, env, cores); cal = time.perf_counter() - t0
+                per_step = max(2.0, 120.0 / n_steps)
+                n_nt = int(min(max_nt, max(500_000, n_cal * per_step / max(cal, 1e-3))))
+                n_nt = _ref_prepare(ref_bin, work, env, seq, n_nt)
+            except Exception:
+                usable = False
+        if not usable:
+            from oracle import oracle as O
+            n_nt = 200_000
+        times = []
+        for step in range(n_steps):
+            t0 = time.perf_counter()
+            if usable:
+                _ref_scan_once(ref_bin, work, env, cores)
+            else:
+                O.scan_stream(bytes(seq[:n_nt]), np.zeros(1, np.uint64), P, col_len, thr)
+            if step >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        value = n_nt * n_cols * len(times) / sum(times)
+        kind = "reference" if usable else "port"
+        sample = ("%.2f Mbp x %d columns per step, `blamm scan -rc -pt 1e-4 -t %d`, OPENBLAS_NUM_THREADS=1, wall clock of the whole process"
+                  % (n_nt / 1e6, n_cols, cores)) if usable else "%.2f Mbp x %d columns per step, single-thread C oracle port" % (n_nt / 1e6, n_cols)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1] sample: JASPAR-like %d PWMs x2 strands (%d columns) x synthetic uniform ACGT, -rc -pt 1e-4"
+                                       % (N_MOTIFS, n_cols)},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores if usable else 1, "kind": kind, "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def cpu_baseline(work: str, seq: np.ndarray, n_cols: int, sample_nt: int) -> dict:
+    """Reference binary on a bounded sample of the same workload (rank 0, N = 1 only)."""
+    from blamm_b200 import synth
+    cores = os.cpu_count() or 1
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "blamm")
+    sub = os.path.join(work, "cpu")
+    os.makedirs(sub, exist_ok=True)
+    try:
+        if not os.path.exists(ref_bin):
+            raise RuntimeError("oracle/_ref/blamm absent")
+        shutil.copy(os.path.join(work, "motifs.jaspar"), sub)
+        part = seq[:sample_nt]
+        synth.write_fasta(os.path.join(sub, "sample.fa"), [("chr%d" % (i + 1), part[i * (sample_nt // 4):(i + 1) * (sample_nt // 4)]) for i in range(4)])
+        open(os.path.join(sub, "sequences.mf"), "w").write("%s\tsample.fa\n" % SPECIES)
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+        subprocess.run([ref_bin, "dict", "sequences.mf"], cwd=sub, env=env, check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([ref_bin, "hist", "motifs.jaspar", "sequences.mf"], cwd=sub, env=env, check=True, stdout=subprocess.DEVNULL)
+        t0 = time.perf_counter()
+        subprocess.run([ref_bin, "scan", "-rc", "-pt", "0.0001", "-t", str(cores), "motifs.jaspar", "sequences.mf"], cwd=sub, env=env,
+                       check=True, stdout=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+        return {"value": (sample_nt // 4) * 4 * n_cols / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": "first %.1f Mbp of the workload x %d columns, `blamm scan -rc -pt 1e-4 -t %d` (OpenBLAS threads=1), %.1f s wall" % (
+                    sample_nt / 1e6, n_cols, cores, dt)}
+    except Exception as e:                                        # reference binary unusable: time the C oracle port instead
+        from blamm_b200 import capi
+        from oracle import oracle as O
+        ms = capi.MotifSet(os.path.join(work, "motifs.jaspar"), revcompl=True)
+        bg = synth.counts_of(seq[:1_000_000])
+        P, col_len, _ = ms.generate_matrix(bg)
+        thr = ms.thresholds("pt", 1e-4, SPECIES, work)
+        n = min(sample_nt // 16, 500_000)
+        t0 = time.perf_counter()
+        O.scan_stream(bytes(seq[:n]), np.zeros(1, np.uint64), P, col_len, thr)
+        dt = time.perf_counter() - t0
+        return {"value": n * n_cols / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "first %.2f Mbp x %d columns, single-thread C oracle (%s)" % (n / 1e6, n_cols, e)}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mbp", type=float, default=100.0, help="Mbp per GPU")
+    ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "gather"])
+    ap.add_argument("--cpu-sample-nt", type=int, default=4_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from blamm_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the scan path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_nt = int(args.mbp * 1e6)
+    work = tempfile.mkdtemp(prefix="bench_b200_")
+    try:
+        ms, P, col_len, thr, seq, bg = build_inputs(work, n_nt, rank)
+        n_cols, sum_len = len(col_len), int(col_len.sum())
+        L = capi.scan_lib()
+        host_ptr = L.b200scan_host_alloc(n_nt + 64)                 # pinned host block (the e2e input)
+        if not host_ptr:
+            raise SystemExit("pinned allocation failed")
+        import ctypes
+        ctypes.memmove(host_ptr, seq.ctypes.data, n_nt)
+        sc = capi.Scanner(local_rank, max_block_nt=n_nt + 64, max_hits=max(1 << 20, int(2.2e-4 * n_nt * n_cols)))
+        sc.set_engine({"auto": capi.ENGINE_AUTO, "tensor": capi.ENGINE_TENSOR, "gather": capi.ENGINE_GATHER}[args.engine])
+        sc.set_motifs(P, col_len, thr)
+        scores_per_step = n_nt * n_cols
+
+        # ---- warm-up: also makes the block resident ----
+        for _ in range(args.warmup):
+            sc.submit_ascii(0, host_ptr, n_total=n_nt, n_payload=n_nt)
+            hits, t_e2e = sc.collect(0, copy=False)
+        n_hits = len(hits)
+
+        sampler = ClockSampler(local_rank)
+        # ---- timed: device-resident steps (CUDA events on the scan stream), L2 flushed between steps ----
+        barrier()
+        sampler.start()
+        tot_ms = k_ms = 0.0
+        for _ in range(args.steps):
+            sc.flush_l2()
+            a, b, nh = sc.rerun_resident(0, 1)
+            tot_ms += a; k_ms += b
+            assert nh == n_hits, "resident re-run changed the hit count"
+        barrier()
+        # ---- timed: end to end from pinned host memory through the C ABI ----
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            sc.submit_ascii(0, host_ptr, n_total=n_nt, n_payload=n_nt)
+            hits, t_e2e = sc.collect(0, copy=False)
+            d2h += len(hits) * 16 + 24
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        clocks = sampler.stop()
+
+        stats = torch.tensor([tot_ms, k_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        tot_ms, k_ms, e2e_ms = stats.tolist()
+        launches_per_pass = t_e2e["kernel_launches"] - 1           # the e2e pass also launches the pack kernel
+        engine_used = "tensor+rescore" if t_e2e["engine_used"] == capi.ENGINE_TENSOR else "gather"
+
+        if rank == 0:
+            burst, sustained, how = peaks()
+            flops_per_launch = 8.0 * sum_len * n_nt                 # 2 flop x 4 one-hot rows x L per score, un-padded
+            achieved = flops_per_launch / (k_ms / args.steps * 1e-3) / 1e12
+            line = {
+                "metric": METRIC, "value": world * scores_per_step * args.steps / (tot_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]: JASPAR-like %d PWMs x2 strands (%d columns, sum L = %d) x %.0f Mbp synthetic uniform ACGT per GPU, "
+                                       "-rc -pt 1e-4 (real JASPAR CORE unavailable offline)" % (N_MOTIFS, n_cols, sum_len, args.mbp),
+                           "engine": engine_used, "parallelism": "chunk-sharded x%d, no collective" % world,
+                           "l2": "flushed between steps (256 MiB memset outside the event pairs)", "hits_per_step": int(n_hits),
+                           "candidates_per_step": int(t_e2e["n_candidates"])},
+                "gpu_launches": int(launches_per_pass * args.steps * 2 + args.steps),
+                "clocks": clocks,
+                "e2e": {"value": world * scores_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_nt),
+                        "d2h_bytes_per_step": int(d2h // args.steps), "ms_per_step": e2e_ms / args.steps,
+                        "stages_ms": {k: t_e2e[k] for k in ("h2d_ms", "pack_ms", "score_ms", "rescore_ms", "d2h_ms")}},
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                             "traffic": None, "peak_source": how + ", bf16 cuBLAS burst; sustained %.0f" % sustained,
+                             "kernel": "filter_tc_kernel" if engine_used != "gather" else "gather_scan_kernel",
+                             "kernel_ms": k_ms / args.steps, "algorithmic_flops_per_launch": flops_per_launch},
+            }
+            if world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(work, seq, n_cols, min(args.cpu_sample_nt, n_nt))
+            print(json.dumps(line), flush=True)
+        sc.close()
+        L.b200scan_host_free(host_ptr)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

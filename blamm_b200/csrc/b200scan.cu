@@ -67,6 +67,7 @@ struct b200scan_ctx {
     GatherTile* d_gtiles = nullptr;  std::vector<GatherTile> gtiles;  size_t gather_smem = 0;
     TcTile* d_ttiles = nullptr;  std::vector<TcTile> ttiles;  uint8_t* d_bimg = nullptr;
     bool tc_usable = false;
+    uint8_t* d_flush = nullptr;
 };
 
 namespace {
@@ -375,6 +376,25 @@ extern "C" {
 
 int b200scan_abi_version(void) { return B200SCAN_ABI_VERSION; }
 
+int b200scan_device_count(void)
+{
+    int n = 0, ok = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (int d = 0; d < n; d++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+void* b200scan_host_alloc(uint64_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void b200scan_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 const char* b200scan_last_error(const b200scan_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint64_t max_hits)
@@ -435,7 +455,7 @@ void b200scan_destroy(b200scan_ctx* c)
         dfree(s.d_ascii); dfree(s.d_codes); dfree(s.d_zmask); dfree(s.d_frag); dfree(s.d_hits); dfree(s.d_counters);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     }
-    dfree(c->d_cand);
+    dfree(c->d_cand); dfree(c->d_flush);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -638,6 +658,16 @@ int b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total
     if (score_kernel_ms) *score_kernel_ms = sc;
     if (n_hits_last) *n_hits_last = s.h_counters[1];
     return rc;
+}
+
+int b200scan_flush_l2(b200scan_ctx* ctx)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = 256u << 20;
+    if (!ctx->d_flush) CU(cudaMalloc(&ctx->d_flush, bytes));
+    CU(cudaMemsetAsync(ctx->d_flush, 0x5a, bytes, ctx->stream));
+    return B200SCAN_OK;
 }
 
 int b200scan_describe(const b200scan_ctx* ctx, int32_t* n_cols, int32_t* max_len, int32_t* n_tiles, int32_t* sm_count, uint64_t* sum_len)

@@ -1,0 +1,420 @@
+// blamm-b200: command line front end (dict / hist / scan) with the reference's flags, inputs and outputs.
+// The scan module drives libb200scan.so through its C ABI (include/b200scan.h); there is no CPU scoring path.
+#include "host.h"
+#include "../../include/b200scan.h"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <iostream>
+#include <mutex>
+#include <sstream>
+#include <thread>
+
+using namespace std;
+
+namespace blamm {
+
+int formatScore(char* dst, float v) { return snprintf(dst, 32, "%g", (double)v); }
+
+// =========================================================================================================
+// dict  (reference dict.cpp:53-115)
+// =========================================================================================================
+static void dictUsage()
+{
+    cout << "Usage: blamm dict [options] sequences.input\n"
+            "Goal: compute nucleotide frequencies for the input sequences and generate a sequence dictionary file\n\n"
+            " [options]\n  -h\t--help\t\tdisplay help message\n\n"
+            " File \"sequences.input\" contains a list of input fasta files in the following format:\n"
+            "   speciesID_1\tspecies1_sequences.fasta\n   speciesID_2\tspecies2_sequences.fasta\n"
+            "   speciesID_3\tspecies2_sequences.fasta\n   ...\n"
+            " where speciesID_x is a user-defined identifier per species\n\n"
+            " Example:\n  blamm dict sequences.input\n\n";
+}
+
+int runDict(int argc, char** argv)
+{
+    if (argc < 3) { dictUsage(); return EXIT_FAILURE; }
+    for (int i = 2; i < argc - 1; i++) {
+        string arg(argv[i]);
+        dictUsage();
+        return (arg == "-h" || arg == "--help") ? EXIT_SUCCESS : EXIT_FAILURE;
+    }
+    cout << "Welcome to blamm -- dictionary model" << endl;
+    const string manifest(argv[argc - 1]);
+    ifstream in(manifest);
+    if (!in) throw runtime_error("Could not open file: " + manifest);
+    SpeciesSet set;
+    string line;
+    while (getline(in, line)) {
+        if (line.empty()) continue;
+        string group, fasta;
+        istringstream ls(line);
+        ls >> group >> fasta;
+        if (group.empty() || fasta.empty())
+            throw runtime_error("File " + manifest + " has incorrect format.\nRefer to the documention for more information.");
+        if (!ifstream(fasta)) throw runtime_error("Could not open fasta file: " + fasta);
+        set.addFile(group, fasta);
+    }
+    for (auto& s : set.species) {
+        cout << "Computing nucleotide composition for " << s.name << " ...";
+        cout.flush();
+        FastaStream fs(s.files);
+        FastaStream::Chunk c;
+        while (fs.next(1 << 24, 0, c)) {}
+        s.nuclCounts = fs.counts();
+        s.totSeqLen = s.nuclCounts[0] + s.nuclCounts[1] + s.nuclCounts[2] + s.nuclCounts[3];
+        s.seqNames = fs.seqNames();
+        cout << "\n";
+    }
+    set.writeDict(manifest + ".dict");
+    cout << "Done!  Dictionary written to " << manifest + ".dict" << endl;
+    return EXIT_SUCCESS;
+}
+
+// =========================================================================================================
+// hist  (reference hist.cpp:177-266; theoretical spectra only -- the empirical `-e` mode is the GPU histogram
+//        epilogue listed as "next" in DESIGN.md and is refused rather than silently computed on the CPU)
+// =========================================================================================================
+static void histUsage()
+{
+    cout << "Usage: blamm hist [options] motifs.input sequences.input\n"
+            "Goal: compute PWM score histograms\n\n"
+            " [options]\n  -h\t--help\t\tdisplay help message\n\n"
+            " [options arg]\n"
+            "  -l\t--length\tmaximum sequence length to analyze (default = 10000000)\n"
+            "  -b\t--numbins\tnumber of bins per histogram (default = 250)\n"
+            "  -t\t--numthreads\tset the number of parallel threads [default = #cores]\n\n"
+            " [file_options]\n  -H\t--histdir\toutput directory for the histogram file(s) [default = .]\n\n"
+            " Example:\n  blamm hist motifs.input sequences.input\n\n";
+}
+
+int runHist(int argc, char** argv)
+{
+    if (argc < 4) { histUsage(); return EXIT_FAILURE; }
+    uint64_t maxLength = 10000000; size_t numBins = 250; bool empirical = false; string histdir;
+    for (int i = 2; i < argc - 2; i++) {
+        string arg(argv[i]);
+        const bool hasVal = i + 1 < argc - 2;
+        if (arg == "-h" || arg == "--help") { histUsage(); return EXIT_SUCCESS; }
+        else if ((arg == "-l" || arg == "--length") && hasVal) maxLength = atoll(argv[++i]);
+        else if ((arg == "-b" || arg == "--numbins") && hasVal) { numBins = atoll(argv[++i]); if (numBins < 2) numBins = 2; }
+        else if (arg == "-e" || arg == "--empirical") empirical = true;
+        else if ((arg == "-t" || arg == "--numthreads") && hasVal) ++i;
+        else if ((arg == "-H" || arg == "--histdir") && hasVal) { histdir = argv[++i]; if (histdir.back() != '/') histdir.push_back('/'); }
+        else { histUsage(); return EXIT_FAILURE; }
+    }
+    cout << "Welcome to blamm -- histogram module" << endl;
+    if (empirical) throw runtime_error("Empirical histograms (-e) are not available in this build; omit -e for theoretical spectra.");
+    Settings settings;
+    SpeciesSet sc;
+    sc.loadDict(string(argv[argc - 1]) + ".dict");
+    MotifSet mc;
+    mc.load(argv[argc - 2], false);
+    cout << "Loaded " << mc.motifs.size() << " motifs from disk";
+    cout << "\nMaximum motif size: " << mc.maxLen() << endl;
+    for (const auto& sp : sc.species) {
+        cout << "Generating histograms for species: " << sp.name;
+        sp.printNuclProb(settings.pseudocount);
+        mc.generateMatrix(sp.nuclCounts, settings.pseudocount);
+        const auto bg = sp.nuclProb(settings.pseudocount);
+        for (const auto& m : mc.motifs) {
+            ScoreHistogram h(m.minScore(), m.maxScore(), numBins);
+            MotifSet::theoreticalHistogram(m, bg, numBins, maxLength, h);
+            h.writeGNUPlot(histdir, "hist_" + sp.name + "_" + m.name, m.name + " (" + sp.name + ")");
+        }
+    }
+    return EXIT_SUCCESS;
+}
+
+// =========================================================================================================
+// scan
+// =========================================================================================================
+static void scanUsage()
+{
+    cout << "Usage: blamm scan [options] motifs.input sequences.input\n"
+            "Goal: find PWM matches in sequences\n\n"
+            " [options]\n"
+            "  -h\t--help\t\tdisplay help message\n"
+            "  -s\t--simple\tscore lower-case nucleotides like upper case (the reference's simple-scan semantics)\n"
+            "  -c\t--cuda\t\taccepted for compatibility (this build always scans on the GPU)\n"
+            "  -rc\t--revcompl\talso search the reverse strand for occurrences\n\n"
+            " [options arg]\n"
+            "  -at\t--absthreshold\tset the minimal absolute score for a motif occurrence\n"
+            "  -rt\t--relthreshold\tset the minimal relative score [0..1] for a motif occurrence (default = 0.95)\n"
+            "  -pt\t--pthreshold\tcompute the motif score threshold from p-value [0..1] (default = 1E-4)\n"
+            "  -t\t--numthreads\tset the number of host formatting threads [default = #cores]\n"
+            "  -g\t--gpus\t\tnumber of GPUs to use [default = all]\n"
+            "  -e\t--engine\tauto | tensor | gather [default = auto]\n\n"
+            " [file_options]\n"
+            "  -H\t--histdir\tdirectory where the histogram file(s) are stored [default = .]\n"
+            "  -o\t--output\tfilename for the motif occurrences [default = occurences.txt]\n\n"
+            " File \"motifs.input\" should contain the motifs in Jaspar format\n"
+            " File \"sequences.input\" should contain a list of input fasta files (see blamm dict)\n\n"
+            " Example:\n  blamm scan -o occurences.txt motifs.input sequences.input\n\n";
+}
+
+namespace {
+
+struct Job {
+    vector<char> chars;
+    vector<uint64_t> fragStarts;
+    vector<Fragment> frags;
+    uint64_t nTotal = 0, nPayload = 0;
+};
+
+struct ScanShared {
+    const MotifSet* motifs = nullptr;
+    const Species* species = nullptr;
+    ofstream* os = nullptr;
+    mutex outMutex;
+    uint64_t totMatches = 0;
+    // job queue (producer = FASTA reader, consumers = one thread per GPU)
+    mutex qMutex; condition_variable qCv;
+    deque<unique_ptr<Job>> queue; bool done = false; size_t maxQueue = 2;
+    string error; atomic<bool> failed{false};
+};
+
+// hits of one block -> text lines (reference format: pwmscan.cpp:88-95), in (position, column) order
+void writeHits(ScanShared& sh, const Job& job, const b200scan_hit* hits, uint64_t n)
+{
+    vector<b200scan_hit> sorted(hits, hits + n);
+    sort(sorted.begin(), sorted.end(), [](const b200scan_hit& a, const b200scan_hit& b) {
+        return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; });
+    string text;
+    text.reserve(n * 56);
+    char num[64];
+    size_t f = 0;
+    for (const auto& h : sorted) {
+        while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= h.pos) f++;
+        const Fragment& fr = job.frags[f];
+        const uint64_t seqPos = fr.seqPos + (h.pos - fr.streamPos);
+        const Motif& m = sh.motifs->motifs[h.col];
+        text += sh.species->seqNames.at(fr.seqIdx);
+        text += "\tblamm\t";
+        text += m.name;
+        text += '\t';
+        text.append(num, snprintf(num, sizeof num, "%llu\t%llu\t", (unsigned long long)seqPos, (unsigned long long)(seqPos + m.size())));
+        text.append(num, formatScore(num, h.score));
+        text += '\t';
+        text += m.revComp ? '-' : '+';
+        text += "\t.\t.\n";
+    }
+    lock_guard<mutex> lock(sh.outMutex);
+    sh.totMatches += n;
+    sh.os->write(text.data(), (streamsize)text.size());
+}
+
+void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, int engine, bool foldLower)
+{
+    b200scan_ctx* ctx = nullptr;
+    auto die = [&](const string& what) {
+        lock_guard<mutex> l(sh.qMutex);
+        if (!sh.failed.exchange(true)) sh.error = what;
+        sh.qCv.notify_all();
+    };
+    if (b200scan_create(&ctx, dev, maxBlock, 0) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(nullptr)); return; }
+    const auto len = sh.motifs->colLen();
+    const auto thr = sh.motifs->colThr();
+    if (b200scan_set_engine(ctx, engine) != B200SCAN_OK ||
+        b200scan_set_motifs(ctx, sh.motifs->P().data(), sh.motifs->ldp(), (int32_t)len.size(), len.data(), thr.data()) != B200SCAN_OK) {
+        die(string("CUDA error: ") + b200scan_last_error(ctx)); b200scan_destroy(ctx); return;
+    }
+    unique_ptr<Job> inFlight[B200SCAN_NUM_SLOTS];
+    int slot = 0;
+    auto collect = [&](int s) -> bool {
+        const b200scan_hit* hits = nullptr; uint64_t n = 0;
+        if (b200scan_collect(ctx, s, &hits, &n, nullptr) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
+        writeHits(sh, *inFlight[s], hits, n);
+        inFlight[s].reset();
+        return true;
+    };
+    while (!sh.failed) {
+        unique_ptr<Job> job;
+        {
+            unique_lock<mutex> l(sh.qMutex);
+            sh.qCv.wait(l, [&] { return !sh.queue.empty() || sh.done || sh.failed; });
+            if (sh.failed) break;
+            if (sh.queue.empty()) break;                 // done
+            job = std::move(sh.queue.front()); sh.queue.pop_front();
+            sh.qCv.notify_all();
+        }
+        if (inFlight[slot] && !collect(slot)) break;
+        if (b200scan_submit_ascii(ctx, slot, job->chars.data(), job->nTotal, job->nPayload, job->fragStarts.data(),
+                                  job->fragStarts.size(), foldLower ? B200SCAN_LOWER_FOLD : B200SCAN_LOWER_ZERO) != B200SCAN_OK) {
+            die(string("CUDA error: ") + b200scan_last_error(ctx)); break;
+        }
+        inFlight[slot] = std::move(job);
+        slot ^= 1;
+        if (inFlight[slot] && !collect(slot)) break;     // overlap: format block k-1 while the GPU scores block k
+    }
+    for (int s = 0; s < B200SCAN_NUM_SLOTS && !sh.failed; s++) { if (inFlight[slot]) collect(slot); slot ^= 1; }
+    b200scan_destroy(ctx);
+}
+
+} // namespace
+
+int runScan(int argc, char** argv)
+{
+    bool foldLower = false, revCompl = false;
+    bool absSpec = false, relSpec = false, pSpec = false;
+    float absThr = 0.0f, relThr = 0.95f, pvalue = 0.0001f;
+    size_t numThreads = thread::hardware_concurrency();
+    int gpusWanted = 0, engine = B200SCAN_ENGINE_AUTO;
+    string histdir, outputFilename = "occurrences.txt";
+    if (argc < 4) { scanUsage(); return EXIT_FAILURE; }
+    for (int i = 2; i < argc - 2; i++) {
+        string arg(argv[i]);
+        const bool hasVal = i + 1 < argc - 2;
+        if (arg == "-h" || arg == "--help") { scanUsage(); return EXIT_SUCCESS; }
+        else if (arg == "-rc" || arg == "--revcompl") revCompl = true;
+        else if (arg == "-s" || arg == "--simple") foldLower = true;
+        else if (arg == "-c" || arg == "--cuda") {}
+        else if ((arg == "-at" || arg == "--absthreshold") && hasVal) { absSpec = true; absThr = atof(argv[++i]); }
+        else if ((arg == "-rt" || arg == "--relthreshold") && hasVal) {
+            relSpec = true; relThr = atof(argv[++i]);
+            if (relThr < 0.0 || relThr > 1.0) throw runtime_error("The relative threshold should be in range [0..1].");
+        } else if ((arg == "-pt" || arg == "--pthreshold") && hasVal) {
+            pSpec = true; pvalue = atof(argv[++i]);
+            if (pvalue < 0.0 || pvalue > 1.0) throw runtime_error("The p-value should be in range [0..1].");
+        } else if ((arg == "-t" || arg == "--numthreads") && hasVal) {
+            const int t = atoi(argv[++i]);
+            if (t < 1) throw runtime_error("Number of threads must be a non-zero positive number");
+            numThreads = t;
+        } else if ((arg == "-g" || arg == "--gpus") && hasVal) gpusWanted = atoi(argv[++i]);
+        else if ((arg == "-e" || arg == "--engine") && hasVal) {
+            string e(argv[++i]);
+            if (e == "auto") engine = B200SCAN_ENGINE_AUTO; else if (e == "tensor") engine = B200SCAN_ENGINE_TENSOR;
+            else if (e == "gather") engine = B200SCAN_ENGINE_GATHER; else throw runtime_error("Unknown engine: " + e);
+        } else if ((arg == "-H" || arg == "--histdir") && hasVal) { histdir = argv[++i]; if (histdir.back() != '/') histdir.push_back('/'); }
+        else if ((arg == "-o" || arg == "--output") && hasVal) outputFilename = argv[++i];
+        else { scanUsage(); return EXIT_FAILURE; }
+    }
+    (void)numThreads;
+    if (!(absSpec || relSpec || pSpec)) relSpec = true;
+    if (absSpec && relSpec) throw runtime_error("Specify either the absolute or relative threshold, not both.");
+    if (absSpec && pSpec) throw runtime_error("Specify either the absolute or p-value threshold, not both.");
+    if (relSpec && pSpec) throw runtime_error("Specify either the relative or p-value threshold, not both.");
+
+    cout << "Welcome to blamm -- PWM scan module" << endl;
+    Settings settings;
+    settings.print();
+
+    SpeciesSet sc;
+    sc.loadDict(string(argv[argc - 1]) + ".dict");
+    MotifSet mc;
+    mc.load(argv[argc - 2], true);
+    cout << "Loaded " << mc.motifs.size() << " motifs from disk\n";
+    cout << "Maximum motif size: " << mc.maxLen() << endl;
+    if (mc.motifs.empty()) throw runtime_error("No motifs found in " + string(argv[argc - 2]));
+    if (mc.maxLen() > B200SCAN_MAX_MOTIF_LEN)
+        throw runtime_error("Motifs longer than " + to_string(B200SCAN_MAX_MOTIF_LEN) + " positions are not supported by this build");
+    if (revCompl) { mc.addReverseComplements(); cout << "Scanning both forward and reverse strand of the input sequence(s)" << endl; }
+    else cout << "Scanning only the forward strand of the input sequence(s)" << endl;
+    cout << "Matrix P has dimensions: " << 4 * mc.maxLen() << " x " << mc.motifs.size() << endl;
+    if (absSpec) cout << "Absolute motif score threshold set to: " << absThr << endl;
+    else if (relSpec) cout << "Relative motif score threshold set to: " << relThr << endl;
+    else cout << "P-value motif score threshold set to: " << pvalue << endl;
+
+    int nDev = b200scan_device_count();
+    if (nDev == 0) throw runtime_error("CUDA error: no sm_100 devices found. Aborting...");
+    if (gpusWanted > 0) nDev = min(nDev, gpusWanted);
+    cout << "Using " << nDev << " GPU devices" << endl;
+
+    ofstream ofsCutoff("PWMthresholds.txt");
+    ofstream os(outputFilename);
+    if (!os) throw runtime_error("Cannot write to file: " + outputFilename);
+
+    uint64_t chunk = 32ull << 20;
+    if (const char* e = getenv("BLAMM_B200_CHUNK")) chunk = max<uint64_t>(strtoull(e, nullptr, 10), 1024);
+    const uint64_t halo = mc.maxLen() - 1;
+    uint64_t totMatches = 0;
+
+    for (const auto& sp : sc.species) {
+        cout << "Scanning species: " << sp.name;
+        sp.printNuclProb(settings.pseudocount);
+        mc.generateMatrix(sp.nuclCounts, settings.pseudocount);
+        for (auto& m : mc.motifs) {
+            if (absSpec) m.threshold = absThr;
+            else if (relSpec) { const float mx = m.maxScore(), mn = m.minScore(); m.threshold = relThr * (mx - mn) + mn; }
+            else { ScoreHistogram h; h.load(histdir, "hist_" + sp.name + "_" + m.baseName()); m.threshold = h.scoreCutoff(pvalue); }
+        }
+        for (const auto& m : mc.motifs) {
+            if (m.size() > 15) continue;                 // the reference lists only short motifs (pwmscan.cpp:620)
+            ofsCutoff << sp.name << "\t" << m.name << "\t" << m.minScore() << "\t" << m.threshold << "\t" << m.maxScore() << endl;
+        }
+
+        ScanShared sh;
+        sh.motifs = &mc; sh.species = &sp; sh.os = &os;
+        const uint64_t maxBlock = min<uint64_t>(chunk, max<uint64_t>(sp.totSeqLen, 1024)) + halo + 64;
+        vector<thread> workers;
+        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), d, maxBlock, engine, foldLower);
+        try {
+            FastaStream fs(sp.files, sp.totSeqLen);
+            FastaStream::Chunk c;
+            while (!sh.failed && fs.next(maxBlock - halo - 64, halo, c)) {
+                unique_ptr<Job> job(new Job);
+                job->chars.assign(c.chars, c.chars + c.nTotal);
+                job->fragStarts = c.fragStarts; job->frags = c.frags;
+                job->nTotal = c.nTotal; job->nPayload = c.nPayload;
+                unique_lock<mutex> l(sh.qMutex);
+                sh.qCv.wait(l, [&] { return sh.queue.size() < sh.maxQueue || sh.failed; });
+                sh.queue.push_back(std::move(job));
+                sh.qCv.notify_all();
+                if (sp.totSeqLen) { cout << "Progress... " << (100 * min(fs.filteredLength(), sp.totSeqLen)) / sp.totSeqLen << "%\r"; cout.flush(); }
+            }
+        } catch (...) {
+            { lock_guard<mutex> l(sh.qMutex); sh.done = true; sh.failed = true; }
+            sh.qCv.notify_all();
+            for (auto& w : workers) w.join();
+            throw;
+        }
+        { lock_guard<mutex> l(sh.qMutex); sh.done = true; }
+        sh.qCv.notify_all();
+        for (auto& w : workers) w.join();
+        if (sh.failed) throw runtime_error(sh.error.empty() ? "scan failed" : sh.error);
+        cout << "Progress... 100%  " << endl;
+        totMatches += sh.totMatches;
+    }
+    os.close();
+    ofsCutoff.close();
+    cout << "\nWrote " << totMatches << " matches to " << outputFilename << ".\n";
+    return EXIT_SUCCESS;
+}
+
+} // namespace blamm
+
+// =========================================================================================================
+// main  (reference blstools.cpp:113-166)
+// =========================================================================================================
+static void usage()
+{
+    cout << "Usage: blamm command [options]\n\n command\n"
+            "  dict\t\t\tmake a dictionary for the input sequences\n"
+            "  hist\t\t\tgenerate PWM score histograms\n"
+            "  scan\t\t\tscan for pwm occurrences\n\n"
+            " [options]\n  -h\t--help\t\tdisplay help page\n  -v\t--version\tdisplay version\n\n";
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 2) { usage(); return EXIT_FAILURE; }
+    const string cmd(argv[1]);
+    try {
+        if (cmd == "dict") { int rc = blamm::runDict(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
+        if (cmd == "hist") { int rc = blamm::runHist(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
+        if (cmd == "scan") { int rc = blamm::runScan(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
+    } catch (const exception& e) {
+        cerr << e.what() << endl;
+        return EXIT_FAILURE;
+    }
+    if (cmd == "-h" || cmd == "--help") { usage(); return EXIT_SUCCESS; }
+    if (cmd == "-v" || cmd == "--version") { cout << "blamm-b200 1.0.0 (B200-native scan path; drop-in for blamm 1.0.0)\n"; return EXIT_SUCCESS; }
+    usage();
+    return EXIT_FAILURE;
+}

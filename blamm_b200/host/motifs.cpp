@@ -1,0 +1,338 @@
+// Settings, motifs, PWMs, thresholds and score histograms (host side of the scan path).
+#include "host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+namespace blamm {
+
+// ---------------------------------------------------------------------------------------------------------
+// Settings  (keys and defaults: reference settings.cpp:34-74)
+// ---------------------------------------------------------------------------------------------------------
+Settings::Settings() { load("settings.cnf"); }
+Settings::Settings(const std::string& path) { load(path); }
+
+void Settings::load(const std::string& path)
+{
+    std::ifstream in(path);
+    if (!in) return;
+    defaultVal = false;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        std::istringstream ls(line);
+        std::string key;
+        ls >> key;
+        if (key == "MATRIX_S_W") ls >> matrix_S_w;
+        else if (key == "MATRIX_S_H") ls >> matrix_S_h;
+        else if (key == "MATRIX_P_TILE_MIN_ZERO_AREA") ls >> matrix_P_tile_min_zero_area;
+        else if (key == "PSEUDOCOUNT") ls >> pseudocount;
+        else if (key == "FLUSHOUTPUT") ls >> flushOutput;
+        else std::cerr << "WARNING: settings.cnf contains unknown key: " << key << std::endl;
+    }
+}
+
+void Settings::print() const
+{
+    if (defaultVal) std::cout << "File settings.cnf not found, using default values" << std::endl;
+    else std::cout << "Loaded configuration from file settings.cnf" << std::endl;
+    std::cout << "  MATRIX_S_W = " << matrix_S_w << "; MATRIX_S_H = " << matrix_S_h
+              << "; MATRIX_P_TILE_MIN_ZERO_AREA = " << matrix_P_tile_min_zero_area
+              << "; PSEUDOCOUNT = " << pseudocount << "; FLUSHOUTPUT = " << flushOutput << "\n";
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Motif
+// ---------------------------------------------------------------------------------------------------------
+static bool splitPermutationSuffix(const std::string& name, size_t& cut)
+{
+    // "<base>__<digits>" with a non-empty base (reference motif.h:256-281)
+    ssize_t i = (ssize_t)name.size() - 1;
+    while (i >= 0 && isdigit((unsigned char)name[i])) i--;
+    if (i < 1) return false;
+    if (name[i] != '_' || name[i - 1] != '_') return false;
+    cut = (size_t)(i - 1);
+    return true;
+}
+
+std::string Motif::baseName() const
+{
+    size_t cut;
+    return splitPermutationSuffix(name, cut) ? name.substr(0, cut) : name;
+}
+
+bool Motif::isPermutation() const
+{
+    size_t cut;
+    return splitPermutationSuffix(name, cut);
+}
+
+void Motif::computePWM(const std::array<uint64_t, 4>& bg, float pseudo)
+{
+    // background probabilities with pseudocount, complemented for a reverse-complement column
+    float bgTot = (float)(bg[0] + bg[1] + bg[2] + bg[3]);
+    bgTot += 4.0f * pseudo;
+    std::array<float, 4> q;
+    for (int b = 0; b < 4; b++) q[b] = ((float)bg[b] + pseudo) / bgTot;
+    if (revComp) { std::swap(q[0], q[3]); std::swap(q[1], q[2]); }
+
+    pwm.resize(pfm.size());
+    for (size_t j = 0; j < pfm.size(); j++) {
+        float tot = (float)(pfm[j][0] + pfm[j][1] + pfm[j][2] + pfm[j][3]);
+        tot += 4.0f * pseudo;
+        for (int b = 0; b < 4; b++) {
+            const float p = ((float)pfm[j][b] + pseudo) / tot;
+            pwm[j][b] = log2f(p / q[b]);
+        }
+    }
+}
+
+void Motif::reverseComplement()
+{
+    std::reverse(pfm.begin(), pfm.end());
+    for (auto& r : pfm) { std::swap(r[0], r[3]); std::swap(r[1], r[2]); }
+    std::reverse(pwm.begin(), pwm.end());
+    for (auto& r : pwm) { std::swap(r[0], r[3]); std::swap(r[1], r[2]); }
+    revComp = !revComp;
+}
+
+float Motif::maxScore() const
+{
+    float s = 0.0f;
+    for (const auto& r : pwm) s += std::max(std::max(r[0], r[1]), std::max(r[2], r[3]));
+    return s;
+}
+
+float Motif::minScore() const
+{
+    float s = 0.0f;
+    for (const auto& r : pwm) s += std::min(std::min(r[0], r[1]), std::min(r[2], r[3]));
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ScoreHistogram
+// ---------------------------------------------------------------------------------------------------------
+ScoreHistogram::ScoreHistogram(float mn, float mx, size_t bins) : counts(bins, 0), minScore(mn), maxScore(mx)
+{
+    width = (maxScore - minScore) / (float)bins;
+}
+
+static int binOf(float score, float mn, float width, size_t bins)
+{
+    int b = int((score - mn) / width);
+    b = std::max(0, b);
+    return std::min<int>((int)bins - 1, b);
+}
+
+void ScoreHistogram::setNumObservations(float score, uint64_t count) { counts[binOf(score, minScore, width, counts.size())] = count; }
+void ScoreHistogram::addObservation(float score) { counts[binOf(score, minScore, width, counts.size())]++; }
+
+float ScoreHistogram::scoreCutoff(float pvalue) const
+{
+    // walk down from the best bin until the requested fraction of observations is covered, then interpolate
+    double total = 0.0;
+    for (uint64_t c : counts) total += (double)c;
+    double left = pvalue * total;
+    for (ssize_t i = (ssize_t)counts.size() - 1; i >= 0; i--) {
+        const double c = (double)counts[i];
+        if (c < left) { left -= c; continue; }
+        const double frac = left / c;
+        const float edge = frac * i + (1.0 - frac) * (i + 1);
+        return edge * width + minScore;
+    }
+    return maxScore;
+}
+
+void ScoreHistogram::load(const std::string& dir, const std::string& base)
+{
+    const std::string filename = dir + base + ".dat";
+    std::ifstream in(filename);
+    if (!in) throw std::runtime_error("Error: cannot read file " + filename + ". Did you run the hist module?");
+    size_t bins = 0;
+    in >> bins >> minScore >> maxScore;
+    width = (maxScore - minScore) / (float)bins;
+    counts.assign(bins, 0);
+    for (size_t i = 0; i < bins; i++) {
+        float centre; uint64_t v;
+        in >> centre >> v;
+        counts[i] = v;
+    }
+    if (!in) throw std::runtime_error("Unexpected end-of-file reached");
+}
+
+void ScoreHistogram::writeGNUPlot(const std::string& dir, const std::string& base, const std::string& label) const
+{
+    std::string filename = dir + base + ".dat";
+    std::ofstream out(filename);
+    if (!out) throw std::runtime_error("Error: cannot write to file " + filename);
+    out << counts.size() << "\t" << minScore << "\t" << maxScore << "\n";
+    for (size_t i = 0; i < counts.size(); i++) out << (0.5 + i) * width + minScore << "\t" << counts[i] << "\n";
+    out.close();
+
+    size_t maxy = 0;
+    for (uint64_t c : counts) maxy = std::max<size_t>(maxy, c);
+    maxy *= 1.1;
+    filename = dir + base + ".gnu";
+    out.open(filename);
+    if (!out) throw std::runtime_error("Error: cannot write to file " + filename);
+    out << "set output \"" << base << ".ps\"\n"
+        << "set key autotitle columnhead\n"
+        << "set terminal postscript landscape\n"
+        << "set terminal postscript noenhanced\n"
+        << "set xrange [" << minScore << ":" << maxScore << "]\n"
+        << "set yrange [" << 0 << ":" << maxy << "]\n"
+        << "set xlabel 'PWM score'" << std::endl
+        << "set ylabel 'count'" << std::endl
+        << "plot \"" << base << ".dat\" using 1:2 title '" << label << "' with boxes\n";
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MotifSet
+// ---------------------------------------------------------------------------------------------------------
+static void parseJaspar(const std::string& filename, std::vector<Motif>& out)
+{
+    // ">NAME anything" then four rows "X [ c c c ... ]"; the first two tokens of a row are skipped and
+    // unsigned integers are read until the first token that is not one (reference motif.cpp:377-407).
+    std::ifstream in(filename);
+    if (!in) throw std::runtime_error("Could not open file: " + filename);
+    while (in.good()) {
+        std::string name, rest;
+        in >> name;
+        if (!name.empty()) name = name.substr(1);
+        std::getline(in, rest);
+        if (!in) break;
+        std::vector<uint64_t> row[4];
+        for (int r = 0; r < 4; r++) {
+            std::string line, skip;
+            std::getline(in, line);
+            std::istringstream ls(line);
+            ls >> skip >> skip;
+            size_t v;
+            while (ls >> v) row[r].push_back(v);
+        }
+        Motif m;
+        m.name = name;
+        for (size_t j = 0; j < row[0].size(); j++)
+            m.pfm.push_back({row[0][j], j < row[1].size() ? row[1][j] : 0, j < row[2].size() ? row[2][j] : 0,
+                             j < row[3].size() ? row[3][j] : 0});
+        out.push_back(std::move(m));
+    }
+}
+
+static void parseClusterBuster(const std::string& filename, std::vector<Motif>& out)
+{
+    // ">NAME" then one "A C G T" count row per position (reference motif.cpp:340-368)
+    std::ifstream in(filename);
+    if (!in) throw std::runtime_error("Could not open file: " + filename);
+    std::string line;
+    while (in.good()) {
+        std::getline(in, line);
+        if (line.empty()) continue;
+        if (line.front() == '>') { Motif m; m.name = line.substr(1); out.push_back(m); continue; }
+        if (out.empty()) throw std::runtime_error("Incorrect motif file format: " + filename);
+        std::istringstream ls(line);
+        size_t a = 0, c = 0, g = 0, t = 0;
+        ls >> a >> c >> g >> t;
+        out.back().pfm.push_back({a, c, g, t});
+    }
+}
+
+void MotifSet::load(const std::string& filename, bool loadPermutations)
+{
+    std::vector<Motif> all;
+    const bool jaspar = filename.size() > 7 && filename.compare(filename.size() - 7, 7, ".jaspar") == 0;
+    if (jaspar) parseJaspar(filename, all); else parseClusterBuster(filename, all);
+    // ascending length; same comparator and the same std::sort as the reference (motif.cpp:436, motif.h:318),
+    // so ties land in the same (implementation-defined) order and column indices agree with the reference's
+    std::sort(all.begin(), all.end(), [](const Motif& a, const Motif& b) { return a.size() < b.size(); });
+    for (auto& m : all)
+        if (loadPermutations || !m.isPermutation()) motifs.push_back(std::move(m));
+}
+
+void MotifSet::addReverseComplements()
+{
+    std::vector<Motif> both;
+    both.reserve(2 * motifs.size());
+    for (auto& m : motifs) {
+        both.push_back(m);
+        Motif r = m;
+        r.reverseComplement();
+        both.push_back(std::move(r));
+    }
+    motifs.swap(both);
+}
+
+size_t MotifSet::maxLen() const
+{
+    size_t n = 0;
+    for (const auto& m : motifs) n = std::max(n, m.size());
+    return n;
+}
+
+void MotifSet::generateMatrix(const std::array<uint64_t, 4>& bgCounts, float pseudo)
+{
+    for (auto& m : motifs) m.computePWM(bgCounts, pseudo);
+    const size_t ld = 4 * maxLen();
+    P_.assign(ld * motifs.size(), 0.0f);
+    for (size_t c = 0; c < motifs.size(); c++)
+        for (size_t j = 0; j < motifs[c].size(); j++)
+            for (int b = 0; b < 4; b++) P_[c * ld + 4 * j + b] = motifs[c].pwm[j][b];
+}
+
+std::vector<int32_t> MotifSet::colLen() const
+{
+    std::vector<int32_t> v;
+    for (const auto& m : motifs) v.push_back((int32_t)m.size());
+    return v;
+}
+
+std::vector<float> MotifSet::colThr() const
+{
+    std::vector<float> v;
+    for (const auto& m : motifs) v.push_back(m.threshold);
+    return v;
+}
+
+void MotifSet::theoreticalHistogram(const Motif& m, const std::array<float, 4>& bg, size_t numBins, uint64_t maxLength,
+                                    ScoreHistogram& hist)
+{
+    // Discretise the PWM to integers so that the score range maps onto numBins steps, convolve the
+    // per-position score distributions under the background, and store maxLength * pdf per bin
+    // (reference motif.cpp:151-192 + hist.cpp:162-175; maps walked in ascending key order there, dense
+    // arrays walked in ascending index order here -- same float additions in the same order).
+    const size_t L = m.size();
+    const float minS = m.minScore(), maxS = m.maxScore();
+    const float a = (float)numBins / (maxS - minS);
+    const float b = -a * minS / (float)L;
+    std::vector<std::array<int, 4>> w(L);
+    long lo = 0, hi = 0, runLo = 0, runHi = 0;
+    for (size_t p = 0; p < L; p++) {
+        for (int k = 0; k < 4; k++) w[p][k] = (int)std::round(a * m.pwm[p][k] + b);
+        runLo += *std::min_element(w[p].begin(), w[p].end());
+        runHi += *std::max_element(w[p].begin(), w[p].end());
+        lo = std::min(lo, runLo); hi = std::max(hi, runHi);
+    }
+    const long span = hi - lo + 1;
+    std::vector<float> cur(span, 0.0f), nxt(span, 0.0f);
+    std::vector<char> curSet(span, 0), nxtSet(span, 0);
+    for (int k = 0; k < 4; k++) { cur[w[0][k] - lo] += bg[k]; curSet[w[0][k] - lo] = 1; }
+    for (size_t p = 1; p < L; p++) {
+        std::fill(nxt.begin(), nxt.end(), 0.0f); std::fill(nxtSet.begin(), nxtSet.end(), 0);
+        for (long s = 0; s < span; s++) {
+            if (!curSet[s]) continue;
+            for (int k = 0; k < 4; k++) { nxt[s + w[p][k]] += cur[s] * bg[k]; nxtSet[s + w[p][k]] = 1; }
+        }
+        cur.swap(nxt); curSet.swap(nxtSet);
+    }
+    for (long s = 0; s < span; s++) {
+        if (!curSet[s]) continue;
+        const float score = ((float)(s + lo) - L * b) / a;
+        hist.setNumObservations(score, (uint64_t)(maxLength * cur[s]));
+    }
+}
+
+} // namespace blamm

@@ -92,6 +92,9 @@ typedef struct b200scan_timing {
 
 int  b200scan_abi_version(void);
 
+/* Number of usable (sm_100) CUDA devices, 0 if none.  Replaces cudaGetDeviceCount in PWMScan's ctor (pwmscan.cpp:563). */
+int  b200scan_device_count(void);
+
 /* Create a context on CUDA device `device`.  max_block_nt: largest n_total a submit may carry.
  * max_hits: capacity of the per-slot device hit buffer (a block producing more is rescanned in halves). */
 int  b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint64_t max_hits);
@@ -106,10 +109,16 @@ int  b200scan_set_engine(b200scan_ctx* ctx, int engine);
 int  b200scan_set_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                          const int32_t* col_len, const float* thr);
 
+/* Page-locked host memory for blocks (cudaMallocHost / cudaFreeHost).  A block submitted from such memory is
+ * read by the copy engine directly and must stay unchanged until b200scan_collect; a block in ordinary
+ * pageable memory is copied to the slot's staging buffer before b200scan_submit_ascii returns. */
+void* b200scan_host_alloc(uint64_t bytes);
+void  b200scan_host_free(void* p);
+
 /* Asynchronous scan of one block held in host memory.  `block` = n_total characters from "ACGTacgt"
  * (anything else is scored as a zero contribution).  frag_starts: n_frag ascending block positions in
- * (0, n_total) where a new fragment starts; may be NULL when n_frag == 0.  The buffers may be reused as soon
- * as the call returns (they are copied to pinned staging).  slot in [0, B200SCAN_NUM_SLOTS). */
+ * (0, n_total) where a new fragment starts; may be NULL when n_frag == 0 (copied before the call returns).
+ * slot in [0, B200SCAN_NUM_SLOTS). */
 int  b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64_t n_total,
                            uint64_t n_payload, const uint64_t* frag_starts, uint64_t n_frag,
                            int lowercase_mode);
@@ -131,6 +140,9 @@ int  b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, ui
  * context's stream.  Returns total milliseconds for all iterations and for the dominant kernel alone. */
 int  b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total_ms, float* score_kernel_ms,
                              uint64_t* n_hits_last);
+
+/* Measurement hygiene: overwrite a 256 MiB scratch buffer on the context's stream (evicts the 126 MB L2). */
+int  b200scan_flush_l2(b200scan_ctx* ctx);
 
 /* Introspection: number of window x column scores one pass over the slot's block computes. */
 int  b200scan_describe(const b200scan_ctx* ctx, int32_t* n_cols, int32_t* max_len, int32_t* n_tiles,

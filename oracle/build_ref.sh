@@ -21,7 +21,7 @@ cat > "$OUT/cfg/config.h" <<'EOC'
 EOC
 CXXFLAGS="-O3 -std=c++11 -DNDEBUG -DHAVE_CONFIG_H -DBLAMM_MAJOR_VERSION=1 -DBLAMM_MINOR_VERSION=0 -DBLAMM_PATCH_LEVEL=0 -I$OUT/cfg -include array -w"
 LDFLAGS="-L$OB -l:$OBLIB -Wl,--disable-new-dtags -Wl,-rpath,$OB -lpthread"
-g++ $CXXFLAGS "$REF"/src/*.cpp -o "$OUT/blamm" $LDFLAGS
-g++ $CXXFLAGS -I"$REF/src" "$HERE/refdump.cpp" "$REF"/src/{motif,sequence,species,settings,matrix}.cpp -o "$OUT/refdump" $LDFLAGS
+/usr/bin/g++ $CXXFLAGS "$REF"/src/*.cpp -o "$OUT/blamm" $LDFLAGS
+/usr/bin/g++ $CXXFLAGS -I"$REF/src" "$HERE/refdump.cpp" "$REF"/src/{motif,sequence,species,settings,matrix}.cpp -o "$OUT/refdump" $LDFLAGS
 echo "$OB" > "$OUT/openblas_dir.txt"
 echo "build_ref: built $OUT/blamm and $OUT/refdump"

@@ -14,7 +14,9 @@
 // out.bin (little endian):
 //   "RDMP" u32 nSpecies
 //   per species: u32 nameLen, name | u32 nCols | u32 ldp | per col {u32 len, u32 isRC, f32 thr, u32 nameLen, name}
-//                | f32 P[ldp*nCols] (column major) | u64 nHits | per hit {u32 seqIdx, u64 seqPos, u32 col, f32 score}
+//                | f32 P[ldp*nCols] (column major) | u64 nHits | per hit {u32 seqIdx, u64 seqPos, u32 col, f32 score, f32 naive}
+//   score = the BLAS path's R(i,j) (pwmscan.cpp:113); naive = the reference's own Motif::getScore on the same window
+//   (motif.cpp:225-239, the `-s` path: plain in-order float adds, case-insensitive).
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
@@ -37,7 +39,7 @@ static void wu64(FILE* f, uint64_t v) { wr(f, &v, 8); }
 static void wf32(FILE* f, float v) { wr(f, &v, 4); }
 static void wstr(FILE* f, const string& s) { wu32(f, (uint32_t)s.size()); wr(f, s.data(), s.size()); }
 
-struct Hit { uint32_t seqIdx; uint64_t seqPos; uint32_t col; float score; };
+struct Hit { uint32_t seqIdx; uint64_t seqPos; uint32_t col; float score; float naive; };
 
 int main(int argc, char** argv)
 {
@@ -123,13 +125,14 @@ int main(int argc, char** argv)
                                                 if (s < thr) continue;
                                                 SeqPos sp = sm.getSeqPos(i, offset);
                                                 if (m.size() > sm.getRemainingSeqLen(i, offset)) continue;
-                                                hits.push_back(Hit{(uint32_t)sp.getSeqIndex(), (uint64_t)sp.getSeqPos(), (uint32_t)j, s});
+                                                float naive = m.getScore(sm.block.substr(w * i + offset, m.size()));
+                                                hits.push_back(Hit{(uint32_t)sp.getSeqIndex(), (uint64_t)sp.getSeqPos(), (uint32_t)j, s, naive});
                                         }
                                 }
                         }
                 }
                 wu64(out, hits.size());
-                for (const Hit& hh : hits) { wu32(out, hh.seqIdx); wu64(out, hh.seqPos); wu32(out, hh.col); wf32(out, hh.score); }
+                for (const Hit& hh : hits) { wu32(out, hh.seqIdx); wu64(out, hh.seqPos); wu32(out, hh.col); wf32(out, hh.score); wf32(out, hh.naive); }
                 cerr << "refdump: species " << species.getName() << ": " << P.nRows() << " x " << P.nCols()
                      << ", " << hits.size() << " hits\n";
         }

@@ -1,0 +1,267 @@
+"""Parity of the CUDA path (through the C ABI, libb200scan.so) with the oracle and with the golden fixtures
+produced by the compiled reference.  Bar: identical occurrence set; scores bit-identical to the oracle's
+in-order FP32 sum (== the reference's naive path) and within 1e-5 of the reference's BLAS path."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from blamm_b200 import capi, lib_dir, shard, synth
+from oracle import oracle as O
+from oracle.refdump_io import read_refdump
+from tests import util
+
+pytestmark = pytest.mark.gpu
+ENGINES = [capi.ENGINE_GATHER, capi.ENGINE_TENSOR, capi.ENGINE_AUTO]
+
+
+@pytest.fixture(scope="module")
+def scanner():
+    s = capi.Scanner(0, max_block_nt=1 << 25, max_hits=1 << 20)
+    yield s
+    s.close()
+
+
+def _sorted(h):
+    return h[np.lexsort((h["col"], h["pos"]))]
+
+
+def _oracle_hits(case, n_payload=None, lower_fold=False):
+    pos, col, sc = O.scan_stream(bytes(case["chars"]), case["frag_start"], case["P"], case["col_len"], case["thr"],
+                                 n_payload=n_payload, lower_fold=lower_fold)
+    return pos, col, sc
+
+
+def _assert_same(hits, pos, col, sc):
+    h = _sorted(hits)
+    assert len(h) == len(pos), "hit count %d vs oracle %d" % (len(h), len(pos))
+    assert np.array_equal(h["pos"], pos) and np.array_equal(h["col"], col)
+    assert np.array_equal(h["score"].view(np.uint32), sc.view(np.uint32))       # bit-exact (integer compare of the FP32 bits)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case_name,mode_key", [("example", "pt_rc"), ("example", "pt_fwd"), ("example", "rt_rc"), ("example", "at_rc"),
+                                                 ("edge", "pt_rc"), ("edge", "rt_rc"), ("edge", "at_low")])
+def test_golden_cases(scanner, golden, engine, case_name, mode_key):
+    """Full `blamm scan` semantics on the fixtures: host model (C++) -> C ABI -> hits -> occurrence lines."""
+    d = os.path.join(golden, case_name)
+    mode, value, rc = util.MODES[mode_key]
+    ms = capi.MotifSet(os.path.join(d, "motifs.jaspar"), rc)
+    dump = read_refdump(os.path.join(d, "refdump_%s.bin" % mode_key))
+    has_lower = case_name == "edge"
+    lines = []
+    scanner.set_engine(engine)
+    for sp, r in zip(O.load_dict(os.path.join(d, "sequences.mf.dict")), dump):
+        P, col_len, is_rc = ms.generate_matrix(sp.counts)
+        thr = ms.thresholds(mode, value, sp.name, d)
+        scanner.set_motifs(P, col_len, thr)
+        fs = capi.FastaStream([os.path.join(d, f) for f in sp.files], sp.tot_len)
+        halo = int(col_len.max()) - 1
+        got = []
+        while True:
+            c = fs.next(20000, halo)            # several chunks per group: exercises the halo hand-over
+            if c is None:
+                break
+            if engine == capi.ENGINE_TENSOR and any(ch in c["chars"] for ch in b"acgt"):
+                with pytest.raises(capi.ScanError):
+                    scanner.scan(c["chars"], c["frag_start"][1:], c["n_payload"])
+                return
+            hits, t = scanner.scan(c["chars"], c["frag_start"][1:], c["n_payload"])
+            f = np.searchsorted(c["frag_start"], hits["pos"], side="right") - 1
+            for h, fi in zip(hits, f):
+                got.append((int(c["frag_seq"][fi]), int(c["frag_pos"][fi] + h["pos"] - c["frag_start"][fi]), int(h["col"]),
+                            int(np.float32(h["score"]).view(np.uint32))))
+        ref = r["hits"]
+        assert sorted(g[:3] for g in got) == sorted(zip(ref["seq"].tolist(), ref["pos"].tolist(), ref["col"].tolist()))
+        got.sort()
+        refs = ref[np.lexsort((ref["col"], ref["pos"], ref["seq"]))]
+        mine = np.array([g[3] for g in got], dtype=np.uint32).view(np.float32)
+        assert np.max(np.abs(mine - refs["score"]), initial=0.0) <= 1e-5          # vs the reference's BLAS path
+        for g in got:
+            nm, L = ms.names[g[2]], int(col_len[g[2]])
+            lines.append("%s\tblamm\t%s\t%d\t%d\t%s\t%s\t.\t.\n" % (sp.seq_names[g[0]], nm, g[1], g[1] + L,
+                                                                 O.fmt_g(np.uint32(g[3]).view(np.float32)), "-" if is_rc[g[2]] else "+"))
+    if case_name == "example":      # byte-identical to the reference's occurrences.txt (sorted)
+        assert sorted(lines) == open(os.path.join(d, "occ_%s.txt" % mode_key)).read().splitlines(True)
+
+
+@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_cases_bit_exact(scanner, engine, seed):
+    case = util.random_case(seed, n_motifs=30, n_nt=300_000)
+    scanner.set_engine(engine)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    hits, t = scanner.scan(case["chars"], case["frag_start"][1:])
+    _assert_same(hits, *_oracle_hits(case))
+    assert t["engine_used"] == engine and t["kernel_launches"] >= 2
+
+
+@pytest.mark.parametrize("lower", [capi.LOWER_ZERO, capi.LOWER_FOLD])
+def test_lower_case_semantics(scanner, lower):
+    case = util.random_case(11, n_motifs=16, n_nt=120_000, lower=True)
+    scanner.set_engine(capi.ENGINE_AUTO)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    hits, t = scanner.scan(case["chars"], case["frag_start"][1:], lower=lower)
+    _assert_same(hits, *_oracle_hits(case, lower_fold=(lower == capi.LOWER_FOLD)))
+    assert t["engine_used"] == (capi.ENGINE_GATHER if lower == capi.LOWER_ZERO else capi.ENGINE_TENSOR)
+
+
+@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+def test_edge_blocks(scanner, engine):
+    case = util.random_case(21, n_motifs=12, n_nt=5000, len_range=(6, 40))
+    scanner.set_engine(engine)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    maxlen = int(case["col_len"].max())
+    # empty block, block shorter than every motif, block of exactly one window, ragged payload/halo splits
+    hits, _ = scanner.scan(b"", None)
+    assert len(hits) == 0
+    for n in (1, 3, maxlen - 1, maxlen, maxlen + 1, 127, 128, 129, 4097):
+        sub = dict(case, chars=case["chars"][:n], frag_start=case["frag_start"][case["frag_start"] < n])
+        hits, _ = scanner.scan(sub["chars"], sub["frag_start"][1:])
+        _assert_same(hits, *_oracle_hits(sub))
+    for n_payload in (0, 1, 100, 4999 - maxlen, 5000):
+        hits, _ = scanner.scan(case["chars"], case["frag_start"][1:], n_payload)
+        _assert_same(hits, *_oracle_hits(case, n_payload=n_payload))
+
+
+@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+def test_max_length_and_many_columns(scanner, engine):
+    """Motifs up to the ABI limit of 64 positions and >256 columns (several tensor tiles, several gather tiles)."""
+    case = util.random_case(31, n_motifs=150, n_nt=60_000, len_range=(4, 64))
+    assert case["col_len"].max() == 64 and len(case["col_len"]) == 300
+    scanner.set_engine(engine)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    hits, _ = scanner.scan(case["chars"], case["frag_start"][1:])
+    _assert_same(hits, *_oracle_hits(case))
+
+
+def test_packed_submit_and_zero_mask(scanner):
+    case = util.random_case(41, n_motifs=10, n_nt=50_000)
+    chars = case["chars"]
+    code = np.zeros(256, dtype=np.uint32); code[ord("C")] = 1; code[ord("G")] = 2; code[ord("T")] = 3
+    c = code[chars]
+    n = len(c)
+    padded = np.zeros((n + 15) // 16 * 16, dtype=np.uint32); padded[:n] = c
+    words = (padded.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    scanner.set_engine(capi.ENGINE_AUTO)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    scanner.submit_packed(0, words, None, n, n, case["frag_start"][1:])
+    hits, t = scanner.collect(0)
+    _assert_same(hits, *_oracle_hits(case))
+    # zero mask: positions 1000..1999 contribute nothing == the oracle's lower-case (BLAS path) semantics
+    zm = np.zeros((n + 31) // 32, dtype=np.uint32)
+    for p in range(1000, 2000):
+        zm[p // 32] |= np.uint32(1 << (p % 32))
+    scanner.submit_packed(1, words, zm, n, n, case["frag_start"][1:])
+    hits, t = scanner.collect(1)
+    low = chars.copy(); low[1000:2000] = np.frombuffer(bytes(low[1000:2000]).lower(), dtype=np.uint8)
+    _assert_same(hits, *_oracle_hits(dict(case, chars=low)))
+    assert t["engine_used"] == capi.ENGINE_GATHER
+
+
+@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+def test_hit_buffer_overflow_regrows(engine):
+    """Thresholds so low that almost every window is an occurrence: far more hits than max_hits."""
+    s = capi.Scanner(0, max_block_nt=1 << 20, max_hits=1024)
+    try:
+        case = util.random_case(51, n_motifs=4, n_nt=40_000, len_range=(5, 9))
+        thr = np.full(len(case["thr"]), -1000.0, dtype=np.float32)
+        s.set_engine(engine)
+        s.set_motifs(case["P"], case["col_len"], thr)
+        hits, _ = s.scan(case["chars"], case["frag_start"][1:])
+        _assert_same(hits, *_oracle_hits(dict(case, thr=thr)))
+        assert len(hits) > 100_000
+    finally:
+        s.close()
+
+
+def test_double_buffered_slots_and_state_errors(scanner):
+    a, b = util.random_case(61, n_motifs=8, n_nt=80_000), util.random_case(62, n_motifs=8, n_nt=70_000)
+    scanner.set_engine(capi.ENGINE_AUTO)
+    scanner.set_motifs(a["P"], a["col_len"], a["thr"])
+    scanner.submit_ascii(0, a["chars"], frag_starts=a["frag_start"][1:])
+    scanner.submit_ascii(1, b["chars"], frag_starts=b["frag_start"][1:])
+    with pytest.raises(capi.ScanError):
+        scanner.submit_ascii(0, a["chars"])                  # slot busy
+    h1, _ = scanner.collect(1)
+    h0, _ = scanner.collect(0)
+    _assert_same(h0, *_oracle_hits(a))
+    _assert_same(h1, *_oracle_hits(dict(b, P=a["P"], col_len=a["col_len"], thr=a["thr"])))
+    with pytest.raises(capi.ScanError):
+        scanner.collect(0)                                   # nothing in flight
+    with pytest.raises(capi.ScanError):
+        scanner.submit_ascii(0, a["chars"], frag_starts=np.array([5, 5], dtype=np.uint64))   # not ascending
+
+
+def test_engines_agree_at_scale_and_properties(scanner):
+    """32 Mnt x 400 columns (1.3e10 scores): too big for the oracle's full scan, so check size-independent
+    properties: both engines return the identical hit list; every reported score re-verifies against the
+    oracle at that (position, column); every hit clears its threshold and lies inside one fragment; shifting
+    the block start by k moves every hit by k (translation invariance)."""
+    case = util.random_case(71, n_motifs=200, n_nt=1 << 25, len_range=(5, 30))
+    for c in range(len(case["thr"])):
+        case["thr"][c] = max(case["thr"][c], 11.0)
+    res = {}
+    for engine in (capi.ENGINE_GATHER, capi.ENGINE_TENSOR):
+        scanner.set_engine(engine)
+        scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+        res[engine], t = scanner.scan(case["chars"], case["frag_start"][1:])
+        res[engine] = _sorted(res[engine])
+    g, tcs = res[capi.ENGINE_GATHER], res[capi.ENGINE_TENSOR]
+    assert len(g) > 1000 and np.array_equal(g, tcs)
+    want = O.score_at(bytes(case["chars"]), case["P"], case["col_len"], g["pos"], g["col"])
+    assert np.array_equal(want.view(np.uint32), g["score"].view(np.uint32))
+    assert np.all(g["score"] >= case["thr"][g["col"]])
+    fi = np.searchsorted(case["frag_start"], g["pos"], side="right")
+    end = np.append(case["frag_start"], len(case["chars"]))[fi]
+    assert np.all(g["pos"] + case["col_len"][g["col"]].astype(np.uint64) <= end)
+    k = 4099
+    scanner.set_engine(capi.ENGINE_TENSOR)
+    shifted, _ = scanner.scan(case["chars"][k:], (case["frag_start"][case["frag_start"] > k] - np.uint64(k)))
+    shifted = _sorted(shifted)
+    # hits whose window lies in a fragment that started before k may appear (their fragment is cut open); others must map 1:1
+    first_frag_after = case["frag_start"][case["frag_start"] > k].min()
+    keep = g[g["pos"] >= first_frag_after].copy(); keep["pos"] -= np.uint64(k)
+    assert np.array_equal(keep, shifted[shifted["pos"] >= first_frag_after - k])
+
+
+def test_sharded_scan_matches_single_pass(scanner):
+    """The multi-GPU decomposition (chunks + halo, round-robin over ranks, host merge) on one device."""
+    case = util.random_case(81, n_motifs=20, n_nt=500_000)
+    halo = int(case["col_len"].max()) - 1
+    scanner.set_engine(capi.ENGINE_AUTO)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    shards = shard.plan_shards(len(case["chars"]), world=4, halo=halo, chunk=70_001)
+    parts = []
+    for s in shards:
+        block = case["chars"][s.start:s.start + s.n_total]
+        h, _ = scanner.scan(block, shard.local_frag_starts(case["frag_start"], s), s.n_payload)
+        parts.append(h)
+    merged = shard.merge_hits(parts, shards)
+    pos, col, sc = _oracle_hits(case)
+    assert np.array_equal(merged["pos"], pos) and np.array_equal(merged["col"], col)
+    assert np.array_equal(merged["score"].view(np.uint32), sc.view(np.uint32))
+
+
+def test_cli_end_to_end_example(golden, tmp_path):
+    """blamm-b200 dict / hist / scan on the reference's example: occurrences.txt == the reference's, sorted."""
+    cli = os.path.join(lib_dir(), "blamm-b200")
+    work = tmp_path / "ex"
+    shutil.copytree(os.path.join(golden, "example"), work)
+    for f in os.listdir(work):
+        if f.startswith(("hist_", "occ_", "refdump_", "PWM")) or f.endswith(".dict"):
+            os.remove(work / f)
+    env = dict(os.environ, BLAMM_B200_CHUNK="30000")
+    for args in (["dict", "sequences.mf"], ["hist", "motifs.jaspar", "sequences.mf"]):
+        subprocess.run([cli] + args, cwd=work, check=True, stdout=subprocess.DEVNULL)
+    for mode_key, flags in (("pt_rc", ["-rc", "-pt", "0.0001"]), ("pt_fwd", ["-pt", "0.0001"]), ("rt_rc", ["-rc"]),
+                            ("at_rc", ["-rc", "-at", "9.5"])):
+        r = subprocess.run([cli, "scan"] + flags + ["motifs.jaspar", "sequences.mf"], cwd=work, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = sorted(open(work / "occurrences.txt").read().splitlines(True))
+        assert got == open(os.path.join(golden, "example", "occ_%s.txt" % mode_key)).read().splitlines(True)
+        assert ("Wrote %d matches" % len(got)) in r.stdout
+        if mode_key == "pt_rc":
+            assert open(work / "PWMthresholds.txt").read() == open(os.path.join(golden, "example", "PWMthresholds_pt_rc.txt")).read()
