@@ -22,16 +22,19 @@
 // Roofline: tensor pipe.  One tcgen05.mma (M=128, N, K=16) covers 4 motif positions of N columns for 128
 // windows and takes N/2 cycles; the epilogue must drain 128 x N FP32 accumulators per tile from TMEM.
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent with an atomic work counter):
+// Warp roles (320 threads, 1 CTA/SM, persistent with an atomic work counter):
 //   warp 0      producer: codes -> E ring (8 stages of 128 entries + mirrored halo)
 //   warp 1      TMEM allocation, B/codes bulk loads are issued by thread 0; lane 0 issues tcgen05.mma
-//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32, sign test, candidate staging + flush
+//   warps 2..9  epilogue, two warps per TMEM lane quarter (they alternate 32-column chunks so that each SM
+//               sub-partition always has an independent instruction stream to issue from): tcgen05.ld
+//               32x32b.x32 (two in flight), tree-shaped AND of the sign bits, candidate staging + flush
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int      kTcThreads  = 192;
+constexpr int      kTcThreads  = 320;
+constexpr uint32_t kTcEpiWarps = 8;
 constexpr uint32_t kTcSpan     = 32768;      // windows per work item
 constexpr uint32_t kTcStages   = 8;          // E ring stages (128 entries = 2 KB each)
 constexpr uint32_t kTcMirror   = 64;         // entries mirrored past the ring end (>= 2*(2*nK_max-1))
@@ -63,7 +66,7 @@ struct TcParams {
 constexpr uint32_t kSmE      = (kTcStages * 128 + kTcMirror) * 16;            // 17408
 constexpr uint32_t kSmCodes  = kTcSpan / 4 + 128;                              //  8320
 constexpr uint32_t kSmB      = kTcMaxN * (2 * (kMaxLen / 4)) * 16;             // 131072
-constexpr uint32_t kSmStage  = 4 * kTcStageCap * 8;                            //  2048
+constexpr uint32_t kSmStage  = kTcEpiWarps * kTcStageCap * 8;                  //  4096
 constexpr uint32_t kSmBars   = 32 * 8;
 constexpr uint32_t kTcSmemBytes = kSmE + kSmCodes + kSmB + kSmStage + kSmBars + 128;
 
@@ -146,6 +149,60 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
+
+// AND of 32 accumulators as a depth-4 tree of 3-input LOP3s: sign bit set <=> all 32 are negative.
+__device__ __forceinline__ uint32_t and_tree32(const uint32_t (&v)[32]) {
+    const uint32_t t0 = v[0] & v[1] & v[2],    t1 = v[3] & v[4] & v[5],    t2 = v[6] & v[7] & v[8],    t3 = v[9] & v[10] & v[11];
+    const uint32_t t4 = v[12] & v[13] & v[14], t5 = v[15] & v[16] & v[17], t6 = v[18] & v[19] & v[20], t7 = v[21] & v[22] & v[23];
+    const uint32_t t8 = v[24] & v[25] & v[26], t9 = v[27] & v[28] & v[29], t10 = v[30] & v[31];
+    const uint32_t u0 = t0 & t1 & t2, u1 = t3 & t4 & t5, u2 = t6 & t7 & t8, u3 = t9 & t10;
+    return (u0 & u1) & (u2 & u3);
+}
+// bit (31 - j) = sign bit of v[j]; four independent funnel-shift chains of 8
+__device__ __forceinline__ uint32_t sign_mask32(const uint32_t (&v)[32]) {
+    uint32_t m[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) m[c] = __funnelshift_l(v[8 * c + j], m[c], 1);
+    }
+    return (m[0] << 24) | (m[1] << 16) | (m[2] << 8) | m[3];
+}
+
+struct CandStage {          // per-warp candidate staging (warp-uniform count in a register)
+    Cand* buf; uint32_t n;
+};
+__device__ __forceinline__ void stage_flush(CandStage& st, const TcParams& P, uint32_t lane) {
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.n_cand, (unsigned long long)st.n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t s = lane; s < st.n; s += 32)
+        if (base + s < P.cand_cap) P.cand[base + s] = st.buf[s];
+    __syncwarp();
+    st.n = 0;
+}
+// One 32-column chunk of this thread's window: fast sign test, rare slow path that lists the candidates.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], bool winOk, uint32_t win, uint32_t col_base,
+                                               CandStage& st, const TcParams& P, uint32_t lane) {
+    const uint32_t a = and_tree32(v);
+    if (!__any_sync(0xffffffffu, winOk && (int32_t)a >= 0)) return;
+    uint32_t c = winOk ? ~sign_mask32(v) : 0u;          // bit (31-j) set <=> accumulator j >= 0 <=> candidate
+    while (true) {                                      // rounds: every lane with candidates left pushes one (ascending column)
+        const bool has = c != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (!bal) break;
+        if (has) {
+            const int b = 31 - __clz(c);
+            c &= ~(1u << b);
+            Cand cd; cd.pos = win; cd.col = col_base + (31 - b);
+            st.buf[st.n + __popc(bal & ((1u << lane) - 1u))] = cd;
+        }
+        st.n += __popc(bal);
+        if (st.n > kTcStageCap - 32) stage_flush(st, P, lane);      // one global atomic per >= 32 candidates
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -171,7 +228,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, 1); mbar_init(eEmpty + 8 * i, 1); }
-        for (uint32_t i = 0; i < 2; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, 4); }
+        for (uint32_t i = 0; i < 2; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, kTcEpiWarps); }
         mbar_init(cBar, 1); mbar_init(bBar, 1);
         fence_mbar_init();
     }
@@ -185,8 +242,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     uint32_t kT = 0;            // window tiles so far
     uint32_t nItem = 0, nBload = 0;
     int32_t  curTile = -1;
-    uint32_t nStaged = 0;       // epilogue: staged candidates of this warp (warp-uniform)
-    Cand* myStage = sStage + ((warp >= 2) ? (warp - 2) : 0) * kTcStageCap;
+    CandStage stage;            // epilogue: staged candidates of this warp (count is warp-uniform)
+    stage.buf = sStage + ((warp >= 2) ? (warp - 2) : 0) * kTcStageCap; stage.n = 0;
     const uint32_t nItems = P.n_tiles * P.n_spans;
 
     while (true) {
@@ -248,7 +305,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 const uint32_t k = kE + i, slot = k % kTcStages, ph = (k / kTcStages) & 1;
                 const uint32_t k1 = k + 1, slot1 = k1 % kTcStages, ph1 = (k1 / kTcStages) & 1;
                 const uint32_t kt = kT + i, buf = kt & 1, tph = (kt >> 1) & 1;
-                mbar_wait(eFull + 8 * slot, ph, P.error_flag);
+                if (i == 0) mbar_wait(eFull + 8 * slot, ph, P.error_flag);     // later tiles waited for it as their halo stage
                 mbar_wait(eFull + 8 * slot1, ph1, P.error_flag);
                 mbar_wait(tEmpty + 8 * buf, tph ^ 1, P.error_flag);
                 tc_fence_after();
@@ -271,6 +328,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
             const uint32_t q = warp & 3;                              // TMEM lane quarter this warp may read
+            const uint32_t half = (warp - 2) >> 2;                    // which of the quarter's two warps
             for (uint32_t i = 0; i < nT; i++) {
                 const uint32_t kt = kT + i, buf = kt & 1, tph = (kt >> 1) & 1;
                 mbar_wait(tFull + 8 * buf, tph, P.error_flag);
@@ -278,38 +336,20 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 const uint32_t win = w0 + 128 * i + 32 * q + lane;
                 const bool winOk = win < blk.n_payload;
                 const uint32_t taddr = tmem_base + ((32 * q) << 16) + buf * kTcMaxN;
-                for (uint32_t cc = 0; cc < tile.n_pad; cc += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + cc, v);
+                uint32_t cc = 32 * half;                              // this warp takes chunks half, half+2, half+4, ...
+                for (; cc + 64 < tile.n_pad; cc += 128) {             // two chunks per trip, both loads in flight
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr + cc, v0);
+                    tmem_ld32(taddr + cc + 64, v1);
                     tmem_ld_wait();
-                    uint32_t a = v[0];
-#pragma unroll
-                    for (int j = 1; j < 32; j += 2) a &= v[j] & ((j + 1 < 32) ? v[j + 1] : 0xffffffffu);
-                    // sign bit of the AND is set  <=>  every accumulator is negative  <=>  no candidate
-                    if (__any_sync(0xffffffffu, winOk && (int32_t)a >= 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const bool p = winOk && (int32_t)v[j] >= 0;
-                            const unsigned m = __ballot_sync(0xffffffffu, p);
-                            if (m) {
-                                if (p) {
-                                    Cand c; c.pos = win; c.col = tile.col0 + cc + j;
-                                    myStage[nStaged + __popc(m & ((1u << lane) - 1u))] = c;
-                                }
-                                nStaged += __popc(m);
-                                if (nStaged > kTcStageCap - 32) {        // flush: one global atomic per >=32 candidates
-                                    __syncwarp();
-                                    unsigned long long base = 0;
-                                    if (lane == 0) base = atomicAdd(P.n_cand, (unsigned long long)nStaged);
-                                    base = __shfl_sync(0xffffffffu, base, 0);
-                                    for (uint32_t s = lane; s < nStaged; s += 32)
-                                        if (base + s < P.cand_cap) P.cand[base + s] = myStage[s];
-                                    __syncwarp();
-                                    nStaged = 0;
-                                }
-                            }
-                        }
-                    }
+                    epilogue_chunk(v0, winOk, win, tile.col0 + cc, stage, P, lane);
+                    epilogue_chunk(v1, winOk, win, tile.col0 + cc + 64, stage, P, lane);
+                }
+                if (cc < tile.n_pad) {
+                    uint32_t v0[32];
+                    tmem_ld32(taddr + cc, v0);
+                    tmem_ld_wait();
+                    epilogue_chunk(v0, winOk, win, tile.col0 + cc, stage, P, lane);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -323,13 +363,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         __syncthreads();          // item boundary: every role is done with sCodes / sB / the pipelines are drained
     }
 
-    if (warp >= 2 && nStaged) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(P.n_cand, (unsigned long long)nStaged);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (uint32_t s = lane; s < nStaged; s += 32)
-            if (base + s < P.cand_cap) P.cand[base + s] = myStage[s];
-    }
+    if (warp >= 2 && stage.n) stage_flush(stage, P, lane);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
