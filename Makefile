@@ -16,6 +16,11 @@ $(LIBDIR)/libb200scan.so: $(CSRC)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared blamm_b200/csrc/b200scan.cu -o $@
 
+# diagnostic build with clock64 probes in the filter kernel (tools/tc_trace.py); never used by the product
+$(LIBDIR)/libb200scan_trace.so: $(CSRC)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -DB200_TRACE -shared blamm_b200/csrc/b200scan.cu -o $@
+
 $(LIBDIR)/libblammhost.so: $(HSRC) blamm_b200/host/host_abi.cpp $(HHDR)
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(CXXFLAGS) -shared $(HSRC) blamm_b200/host/host_abi.cpp -o $@

@@ -37,7 +37,7 @@ _u64p = ctypes.POINTER(ctypes.c_uint64)
 def scan_lib() -> ctypes.CDLL:
     global _scan
     if _scan is None:
-        path = os.path.join(lib_dir(), "libb200scan.so")
+        path = os.environ.get("B200SCAN_LIB") or os.path.join(lib_dir(), "libb200scan.so")     # override: diagnostic builds only
         if not os.path.exists(path):
             raise RuntimeError("libb200scan.so is missing (run `make` / __graft_entry__.build()); there is no fallback path")
         L = ctypes.CDLL(path)
@@ -48,6 +48,8 @@ def scan_lib() -> ctypes.CDLL:
         L.b200scan_destroy.argtypes = [vp]; L.b200scan_destroy.restype = None
         L.b200scan_last_error.argtypes = [vp]; L.b200scan_last_error.restype = ctypes.c_char_p
         L.b200scan_set_engine.argtypes = [vp, ctypes.c_int]
+        L.b200scan_set_tensor_accumulator.argtypes = [vp, ctypes.c_int]
+        L.b200scan_tensor_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_double)]
         L.b200scan_set_motifs.argtypes = [vp, vp, i32, i32, vp, vp]
         L.b200scan_host_alloc.argtypes = [u64]; L.b200scan_host_alloc.restype = vp
         L.b200scan_host_free.argtypes = [vp]; L.b200scan_host_free.restype = None
@@ -124,6 +126,14 @@ class Scanner:
 
     def set_engine(self, engine: int) -> None:
         self._chk(self._L.b200scan_set_engine(self._ctx, engine))
+
+    def set_tensor_accumulator(self, bits: int) -> None:
+        self._chk(self._L.b200scan_set_tensor_accumulator(self._ctx, bits))
+
+    def tensor_info(self) -> dict:
+        b, m = ctypes.c_int32(), ctypes.c_double()
+        self._chk(self._L.b200scan_tensor_info(self._ctx, ctypes.byref(b), ctypes.byref(m)))
+        return dict(accumulator_bits=b.value, mean_margin=m.value)
 
     def set_motifs(self, P: np.ndarray, col_len: np.ndarray, thr: np.ndarray) -> None:
         """P: (n_cols, ldp) C-contiguous float32 == column-major ldp x n_cols."""

@@ -23,6 +23,7 @@ using namespace b200;
 namespace {
 
 thread_local std::string g_create_error;
+double g_margin16_scale = 1.0;        // debug knob (env B200SCAN_MARGIN16_SCALE): scales the FP16-accumulation error bound
 
 constexpr uint32_t kPadBytes = 16384;             // slack behind every device sequence buffer (window / span over-reads)
 constexpr size_t   kGatherSmemW = 64 * 1024;      // FP32 weights per gather column tile
@@ -60,6 +61,8 @@ struct b200scan_ctx {
     Slot slot[B200SCAN_NUM_SLOTS];
     // candidates are shared by the slots (stream order serialises filter -> rescore per block)
     Cand* d_cand = nullptr;  unsigned long long cand_cap = 0;
+    // raw entries of the tensor filter (blocks of kRawBlock entries of kRawWords words), also shared by the slots
+    uint32_t* d_raw = nullptr;  uint32_t* d_blk_count = nullptr;  uint32_t blk_cap = 0;
     // motifs
     bool have_motifs = false;
     uint32_t n_cols = 0, max_len = 0;  uint64_t sum_len = 0;
@@ -67,7 +70,11 @@ struct b200scan_ctx {
     GatherTile* d_gtiles = nullptr;  std::vector<GatherTile> gtiles;  size_t gather_smem = 0;
     TcTile* d_ttiles = nullptr;  std::vector<TcTile> ttiles;  uint8_t* d_bimg = nullptr;
     bool tc_usable = false;
+    bool tc_acc16 = false;        // FP16 accumulators in TMEM (else FP32)
+    int  acc_pref = 0;            // 0 auto, 16, 32 (b200scan_set_tensor_accumulator)
+    double cand_inflation = 0;    // mean margin over columns (diagnostic)
     uint8_t* d_flush = nullptr;
+    unsigned long long* d_trace = nullptr;   // B200_TRACE builds only
 };
 
 namespace {
@@ -109,17 +116,18 @@ uint16_t half_round_up(double x)
 // greedy zero-area tiling of P (MotifContainer::generateMatrixTiles, motif.cpp:482-540) -- like there, the
 // split is a pure performance device and cannot change results.
 // ---------------------------------------------------------------------------------------------------------
-void plan_tc_tiles(const std::vector<uint32_t>& len_sorted, std::vector<std::pair<uint32_t, uint32_t>>& out)
+void plan_tc_tiles(const std::vector<uint32_t>& len_sorted, bool acc16, std::vector<std::pair<uint32_t, uint32_t>>& out)
 {
     const uint32_t n = (uint32_t)len_sorted.size();
-    const double kEpiPerCol = 2.0, kFixed = 96.0;       // cycles; refined from ncu
+    // epilogue cycles per column per 128-window tile (ALU-pipe bound, from ncu: profiles/), MMA = n_k * N / 2
+    const double kEpiPerCol = acc16 ? 1.1 : 2.9, kFixed = 96.0;
     std::vector<double> best(n + 1, 1e300);
     std::vector<uint32_t> from(n + 1, 0);
     best[0] = 0;
     for (uint32_t j = 1; j <= n; j++) {
         const uint32_t nk = (len_sorted[j - 1] + 3) / 4;
         for (uint32_t i = (j > kTcMaxN ? j - kTcMaxN : 0); i < j; i++) {
-            const uint32_t npad = ((j - i) + 31) / 32 * 32;
+            const uint32_t npad = ((j - i) + 63) / 64 * 64;
             const double c = best[i] + std::max(nk * npad * 0.5, kEpiPerCol * npad) + kFixed;
             if (c < best[j]) { best[j] = c; from[j] = i; }
         }
@@ -165,15 +173,95 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     ctx->gather_smem = kGatherSmemW + max_meta;
 
     // ---- tensor-core tiles and the FP16 B image ----
+    // Conservative folding.  With x_j the FP32 weights picked by a window (exact in-order FP32 score s = sum x_j + e1,
+    // |e1| <= (L-1) 2^-24 A, A = sum_j max|x_j|), the tensor accumulator is  acc = sum y_j + e2  with
+    //     y_j = fp16_up(x_j - thr'/L) >= x_j - thr'/L,      thr' = thr - margin,
+    // so  s >= thr  =>  acc >= margin - |e1| - |e2|, and the filter is exact-recall when margin >= |e1| + |e2|.
+    //   FP32 accumulators: |e2| <= L 2^-18 (A'+1)  (generous for any FP32-ish accumulate, A' = sum_j max|y_j|).
+    //   FP16 accumulators: D is rounded to FP16 after every MMA (4 positions).  For a window that is a true hit
+    //     (final sum >= 0) the partial sum after step k lies in [-R_k, M_k] (R_k = largest possible remaining sum,
+    //     M_k = largest possible prefix), so |D_k| <= B_k = max(M_k, R_k, 0).  Allowing a rounding of one FP16 ulp
+    //     (2^-10 relative: covers round-to-nearest and truncation) on EVERY internal add of the 4 products and the
+    //     old accumulator:  |e2| <= 2^-10 * 4 * sum_k (B_{k-1} + A_k),  A_k = sum of max|y_j| over the step.
+    struct Folded { std::vector<uint16_t> y; double margin; bool always; };
+    auto fold = [&](uint32_t sc, bool acc16) {
+        const uint32_t L = len[sc];
+        Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false;
+        double A = 0;
+        bool finite = std::isfinite(thr_s[sc]);
+        for (uint32_t j = 0; j < L; j++) {
+            const float4 v = w[woff[sc] + j];
+            const float a4[4] = {v.x, v.y, v.z, v.w};
+            double m = 0;
+            for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); }
+            A += m;
+        }
+        if (!finite) { f.always = true; return f; }
+        const double e1 = (L - 1) * std::ldexp(A, -24);
+        double margin = 1e-3 + e1 + L * std::ldexp(A + std::fabs((double)thr_s[sc]) + 1.0, -18);
+        for (int iter = 0; iter < 6; iter++) {
+            const double share = ((double)thr_s[sc] - margin) / L;
+            std::vector<double> ymax(L), yabs(L);
+            for (uint32_t j = 0; j < L; j++) {
+                const float4 v = w[woff[sc] + j];
+                const float a4[4] = {v.x, v.y, v.z, v.w};
+                double mx = -1e300, ma = 0;
+                for (uint32_t o = 0; o < 4; o++) {
+                    const double y = (double)a4[o] - share;
+                    if (std::fabs(y) > 30000.0) { f.always = true; return f; }
+                    const uint16_t h = half_round_up(y);
+                    f.y[4 * j + o] = h;
+                    __half hh; std::memcpy(&hh, &h, 2);
+                    const double yr = (double)__half2float(hh);
+                    mx = std::max(mx, yr); ma = std::max(ma, std::fabs(yr));
+                }
+                ymax[j] = mx; yabs[j] = ma;
+            }
+            if (!acc16) { f.margin = margin; return f; }
+            // FP16 accumulation bound
+            const uint32_t nk = (L + 3) / 4;
+            std::vector<double> pre(nk + 1, 0.0), suf(nk + 1, 0.0);
+            for (uint32_t k = 1; k <= nk; k++) { pre[k] = pre[k - 1]; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) pre[k] += ymax[j]; }
+            for (uint32_t k = nk; k-- > 0;) { suf[k] = suf[k + 1]; for (uint32_t j = 4 * k; j < std::min(L, 4 * (k + 1)); j++) suf[k] += ymax[j]; }
+            double sum = 0, tot_abs = 0;
+            for (uint32_t k = 1; k <= nk; k++) {
+                double Ak = 0; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) Ak += yabs[j];
+                const double Bprev = (k == 1) ? 0.0 : std::max(std::max(pre[k - 1], suf[k - 1]), 0.0);
+                sum += Bprev + Ak; tot_abs += Ak;
+            }
+            if (tot_abs > 30000.0) { f.always = true; return f; }
+            const double need = 1e-3 + e1 + g_margin16_scale * std::ldexp(4.0 * sum, -10);
+            if (need <= margin) { f.margin = margin; return f; }
+            margin = need * 1.02;
+        }
+        f.margin = 1e9;           // did not converge: the caller falls back to FP32 accumulators
+        return f;
+    };
+
+    bool acc16 = ctx->acc_pref != 32 && max_len <= (uint32_t)kMaxLen;
+    double margin_sum = 0;
+    std::vector<Folded> folded(n_cols);
+    for (int pass = 0; pass < 2; pass++) {
+        bool ok = true; margin_sum = 0;
+        for (int32_t sc = 0; sc < n_cols; sc++) {
+            folded[sc] = fold((uint32_t)sc, acc16);
+            if (!folded[sc].always) { margin_sum += folded[sc].margin; if (acc16 && folded[sc].margin > 2.0) ok = false; }
+        }
+        if (ok || !acc16) break;
+        if (ctx->acc_pref == 16) break;      // forced: keep FP16 accumulators, the margins stay rigorous (just looser)
+        acc16 = false;
+    }
+    if (acc16) for (auto& f : folded) if (!f.always && f.margin > 1e8) { f.always = true; }
+
     std::vector<std::pair<uint32_t, uint32_t>> cuts;
-    plan_tc_tiles(len, cuts);
+    plan_tc_tiles(len, acc16, cuts);
     std::vector<TcTile> tt;
     std::vector<uint8_t> bimg;
     bool tc_ok = true;
     for (auto& cut : cuts) {
         TcTile t{};
         t.col0 = cut.first; t.n_cols = cut.second - cut.first;
-        t.n_pad = (t.n_cols + 31) / 32 * 32;
+        t.n_pad = (t.n_cols + 63) / 64 * 64;
         t.n_k = (len[cut.second - 1] + 3) / 4;
         const uint32_t nChunks = 2 * t.n_k;
         t.b_off = (uint32_t)bimg.size();
@@ -189,49 +277,19 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                 for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0xFBFFu;   // -65504
                 continue;
             }
-            const uint32_t s = t.col0 + n, L = len[s];
-            // Conservative folding.  With x_j the FP32 weights picked by a window:
-            //   exact in-order FP32 score  s  = sum x_j + e1,   |e1| <= (L-1) * 2^-24 * A
-            //   tensor accumulator        acc = sum y_j + e2,   y_j = fp16_up(x_j - thr'/L) >= x_j - thr'/L,
-            //                                                   |e2| <= L * 2^-18 * A'   (generous for any FP32-ish accumulate)
-            // so  s >= thr  =>  acc >= thr - thr' - |e1| - |e2|;  choose thr' = thr - margin with margin >= |e1|+|e2|.
-            double A = 0, Ap = 0;
-            bool finite = std::isfinite(thr_s[s]);
-            for (uint32_t j = 0; j < L; j++) {
-                const float4 v = w[woff[s] + j];
-                const float a4[4] = {v.x, v.y, v.z, v.w};
-                double m = 0;
-                for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); }
-                A += m;
-            }
-            bool always = !finite;
-            if (!always) {
-                const double share0 = (double)thr_s[s] / L;
-                for (uint32_t j = 0; j < L; j++) {
-                    const float4 v = w[woff[s] + j];
-                    Ap += std::max(std::max(std::fabs(v.x - share0), std::fabs(v.y - share0)),
-                                   std::max(std::fabs(v.z - share0), std::fabs(v.w - share0)));
-                }
-                const double margin = 1e-3 + (L - 1) * std::ldexp(A, -24) + L * std::ldexp(Ap + 1.0, -18);
-                const double share = ((double)thr_s[s] - margin) / L;
-                for (uint32_t j = 0; j < L && !always; j++) {
-                    const float4 v = w[woff[s] + j];
-                    const float a4[4] = {v.x, v.y, v.z, v.w};
-                    for (uint32_t o = 0; o < 4; o++) {
-                        const double y = (double)a4[o] - share;
-                        if (std::fabs(y) > 30000.0) { always = true; break; }
-                        at(n, j, o) = half_round_up(y);
-                    }
-                }
-            }
-            if (always) {                                // degenerate column: let every window through to the exact rescorer
-                for (uint32_t j = 0; j < 2 * nChunks; j++) for (uint32_t o = 0; o < 4; o++) at(n, j, o) = 0;
+            const Folded& f = folded[t.col0 + n];
+            if (f.always) {                              // degenerate column: every window goes to the exact rescorer
                 for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0x3C00u;      // acc = +1
+                continue;
             }
+            for (uint32_t j = 0; j < len[t.col0 + n]; j++)
+                for (uint32_t o = 0; o < 4; o++) at(n, j, o) = f.y[4 * j + o];
         }
         tt.push_back(t);
     }
     if (max_len > (uint32_t)kMaxLen) tc_ok = false;
+    ctx->tc_acc16 = acc16;
+    ctx->cand_inflation = n_cols ? margin_sum / n_cols : 0;
 
     // ---- upload ----
     dfree(ctx->d_w); dfree(ctx->d_woff); dfree(ctx->d_len); dfree(ctx->d_orig); dfree(ctx->d_thr);
@@ -291,15 +349,20 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
         TcParams tp;
         tp.bimg = ctx->d_bimg; tp.tiles = ctx->d_ttiles; tp.n_tiles = (uint32_t)ctx->ttiles.size();
         tp.n_spans = (uint32_t)((s.n_payload + kTcSpan - 1) / kTcSpan);
-        tp.work_counter = work; tp.cand = ctx->d_cand; tp.n_cand = s.d_counters; tp.cand_cap = ctx->cand_cap;
+        tp.work_counter = work; tp.raw = ctx->d_raw; tp.blk_count = ctx->d_blk_count; tp.n_blocks = work + 1; tp.blk_cap = ctx->blk_cap;
         tp.error_flag = err;
-        filter_tc_kernel<<<ctx->sm_count, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+        tp.trace = ctx->d_trace;
+        if (ctx->tc_acc16) filter_tc_kernel<true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+        else filter_tc_kernel<false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
         n++;
         if (ctx->engine == B200SCAN_ENGINE_AUTO) {     // blocks with a zero mask: exact gather-add (kernel exits at once otherwise)
             gather_scan_kernel<true><<<ggrid, kGatherThreads, ctx->gather_smem, ctx->stream>>>(md, blk, ctx->d_gtiles, sink, 1);
             n++;
         }
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
+        if (ctx->tc_acc16) expand_kernel<true><<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
+        else expand_kernel<false><<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
+        n++;
         rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(md, blk, ctx->d_cand, s.d_counters, ctx->cand_cap, sink);
         n++;
         if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
@@ -361,7 +424,7 @@ int finish_submit(b200scan_ctx* ctx, Slot& s)
     int rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
     if (rc) return rc;
     s.timing.kernel_launches += launches;
-    CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(s.ev[5], ctx->stream));
     s.in_flight = true; s.resident = true;
     return B200SCAN_OK;
@@ -418,7 +481,9 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B200SCAN_ECUDA, "%s -> %s", #call, cudaGetErrorString(e_)); \
                        return bail(e_ == cudaErrorMemoryAllocation ? B200SCAN_ENOMEM : B200SCAN_ECUDA); } } while (0)
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUB(cudaFuncSetAttribute(filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) g_margin16_scale = atof(e);
     CUB(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     if (max_hits == 0) max_hits = 1 << 20;
@@ -438,8 +503,15 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
         CUB(cudaMemset(s.d_counters, 0, 32));
         for (auto& e : s.ev) CUB(cudaEventCreate(&e));
     }
+#ifdef B200_TRACE
+    CUB(cudaMalloc(&c->d_trace, 4 * kTraceTiles * 4 * 8));
+    CUB(cudaMemset(c->d_trace, 0, 4 * kTraceTiles * 4 * 8));
+#endif
     c->cand_cap = std::max<unsigned long long>(2 * max_hits, 1 << 20);
     CUB(cudaMalloc(&c->d_cand, sizeof(Cand) * c->cand_cap));
+    c->blk_cap = (uint32_t)std::max<unsigned long long>(c->cand_cap / kRawBlock + 4096, 8192);
+    CUB(cudaMalloc(&c->d_raw, ((size_t)c->blk_cap + 1) * kRawBlock * kRawWords * 4));     // + the sacrificial overflow block
+    CUB(cudaMalloc(&c->d_blk_count, (size_t)c->blk_cap * 4));
 #undef CUB
     *out = c;
     return B200SCAN_OK;
@@ -455,7 +527,7 @@ void b200scan_destroy(b200scan_ctx* c)
         dfree(s.d_ascii); dfree(s.d_codes); dfree(s.d_zmask); dfree(s.d_frag); dfree(s.d_hits); dfree(s.d_counters);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     }
-    dfree(c->d_cand); dfree(c->d_flush);
+    dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_flush);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -467,6 +539,14 @@ int b200scan_set_engine(b200scan_ctx* ctx, int engine)
     if (!ctx) return B200SCAN_EINVAL;
     if (engine < B200SCAN_ENGINE_AUTO || engine > B200SCAN_ENGINE_TENSOR) return fail(ctx, B200SCAN_EINVAL, "unknown engine %d", engine);
     ctx->engine = engine;
+    return B200SCAN_OK;
+}
+
+int b200scan_set_tensor_accumulator(b200scan_ctx* ctx, int bits)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (bits != 0 && bits != 16 && bits != 32) return fail(ctx, B200SCAN_EINVAL, "accumulator must be 0 (auto), 16 or 32");
+    ctx->acc_pref = bits;
     return B200SCAN_OK;
 }
 
@@ -573,23 +653,32 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
             return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR cannot score a block with zero-contribution characters (use AUTO)");
         if (ctx->engine == B200SCAN_ENGINE_TENSOR && !ctx->tc_usable)
             return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR unavailable for this motif set");
-        const bool cand_over = n_cand > ctx->cand_cap, hit_over = nh > s.hit_cap;
+        const uint32_t n_blocks = (uint32_t)(s.h_counters[3] >> 32);
+        const bool raw_over = n_blocks > ctx->blk_cap;
+        const bool cand_over = raw_over || n_cand > ctx->cand_cap, hit_over = nh > s.hit_cap;
         if (!cand_over && !hit_over) {
             s.timing.n_candidates = n_cand; s.timing.n_hits = nh;
             s.timing.engine_used = (has_zero || ctx->engine == B200SCAN_ENGINE_GATHER || !ctx->tc_usable) ? B200SCAN_ENGINE_GATHER : B200SCAN_ENGINE_TENSOR;
             break;
         }
-        if (attempt >= 2) return fail(ctx, B200SCAN_ECUDA, "hit buffers still too small after regrowing");
+        if (attempt >= 4) return fail(ctx, B200SCAN_ECUDA, "hit buffers still too small after regrowing");
         // the counters kept counting, so they say exactly how much room a re-run needs
         CU(cudaStreamSynchronize(ctx->stream));
-        if (cand_over) {
+        if (raw_over) {
+            dfree(ctx->d_raw); dfree(ctx->d_blk_count);
+            ctx->blk_cap = n_blocks + n_blocks / 8 + 1024;
+            CU(cudaMalloc(&ctx->d_raw, ((size_t)ctx->blk_cap + 1) * kRawBlock * kRawWords * 4));
+            CU(cudaMalloc(&ctx->d_blk_count, (size_t)ctx->blk_cap * 4));
+            // every raw entry holds at least one candidate and at most 64; size the candidate list for the typical ~1.5
+            const unsigned long long want = (unsigned long long)ctx->blk_cap * kRawBlock * 2;
+            if (want > ctx->cand_cap) { dfree(ctx->d_cand); ctx->cand_cap = want; CU(cudaMalloc(&ctx->d_cand, sizeof(Cand) * ctx->cand_cap)); }
+        } else if (n_cand > ctx->cand_cap) {
             dfree(ctx->d_cand);
             ctx->cand_cap = n_cand + n_cand / 8 + 1024;
             CU(cudaMalloc(&ctx->d_cand, sizeof(Cand) * ctx->cand_cap));
         }
         if (hit_over || cand_over) {
             unsigned long long want = std::max<unsigned long long>(nh + nh / 8 + 1024, s.hit_cap);
-            if (cand_over) want = std::max(want, ctx->cand_cap);        // every candidate could be a hit
             if (want > s.hit_cap) {
                 dfree(s.d_hits); hfree(s.h_hits);
                 CU(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * want));
@@ -603,7 +692,7 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
         rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
         if (rc) return rc;
         s.timing.kernel_launches += launches;
-        CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(s.ev[5], ctx->stream));
     }
     const unsigned long long nh = s.h_counters[1];
@@ -639,7 +728,7 @@ int b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total
         rc = launch_scoring(ctx, s, ev[3 * i + 1], ev[3 * i + 2], nullptr);
     }
     if (rc == B200SCAN_OK) {
-        CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, B200SCAN_ECUDA, "rerun failed: %s", cudaGetErrorString(e));
     }
@@ -660,6 +749,17 @@ int b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total
     return rc;
 }
 
+#ifdef B200_TRACE
+int b200scan_debug_trace(b200scan_ctx* ctx, unsigned long long* out, int n)
+{
+    if (!ctx || !out) return B200SCAN_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, ctx->d_trace, std::min<size_t>((size_t)n, 4 * kTraceTiles * 4) * 8, cudaMemcpyDeviceToHost));
+    return B200SCAN_OK;
+}
+#endif
+
 int b200scan_flush_l2(b200scan_ctx* ctx)
 {
     if (!ctx) return B200SCAN_EINVAL;
@@ -667,6 +767,14 @@ int b200scan_flush_l2(b200scan_ctx* ctx)
     const size_t bytes = 256u << 20;
     if (!ctx->d_flush) CU(cudaMalloc(&ctx->d_flush, bytes));
     CU(cudaMemsetAsync(ctx->d_flush, 0x5a, bytes, ctx->stream));
+    return B200SCAN_OK;
+}
+
+int b200scan_tensor_info(const b200scan_ctx* ctx, int32_t* accumulator_bits, double* mean_margin)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (accumulator_bits) *accumulator_bits = ctx->tc_acc16 ? 16 : 32;
+    if (mean_margin) *mean_margin = ctx->cand_inflation;
     return B200SCAN_OK;
 }
 

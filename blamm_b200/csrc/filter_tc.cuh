@@ -12,8 +12,10 @@
 //    overlapping windows straight out of E.  128 windows x (4 positions per MMA) cost 2 KB of smem, not
 //    128 x K x 2 B.
 //  * All columns of a length-bucket tile (<= 256 columns, FP16 weights, threshold folded in) stay resident
-//    in shared memory; a CTA sweeps windows, D[128 windows x N columns] accumulates in TMEM (FP32), double
-//    buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//    in shared memory; a CTA sweeps windows, D[128 windows x N columns] accumulates in TMEM, double buffered
+//    so the epilogue of tile i overlaps the MMAs of tile i+1.  Accumulators are FP16 when the host's
+//    per-column error bound allows it (tcgen05.ld .pack::16b then delivers two of them per register, halving
+//    the epilogue's ALU work), else FP32.
 //  * The tensor pass is a CONSERVATIVE FILTER: weights are  fp16_round_up(W[j][b] - thr'/L)  with
 //    thr' = thr - margin, so  acc >= 0  whenever the exact FP32 score >= thr (b200scan.cu: build_tc_tiles).
 //    The epilogue only tests sign bits (AND-reduction, half a LOP3 per score) and appends (pos, col)
@@ -22,29 +24,58 @@
 // Roofline: tensor pipe.  One tcgen05.mma (M=128, N, K=16) covers 4 motif positions of N columns for 128
 // windows and takes N/2 cycles; the epilogue must drain 128 x N FP32 accumulators per tile from TMEM.
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent with an atomic work counter):
-//   warp 0      producer: codes -> E ring (8 stages of 128 entries + mirrored halo)
-//   warp 1      TMEM allocation, B/codes bulk loads are issued by thread 0; lane 0 issues tcgen05.mma
-//   warps 2..9  epilogue, two warps per TMEM lane quarter (they alternate 32-column chunks so that each SM
-//               sub-partition always has an independent instruction stream to issue from): tcgen05.ld
-//               32x32b.x32 (two in flight), tree-shaped AND of the sign bits, candidate staging + flush
+// Warp roles (416 threads, 1 CTA/SM, persistent with an atomic work counter):
+//   warps 0..3   producers: codes -> E ring (8 stages of 128 entries + mirrored halo) through a 16-entry one-hot LUT,
+//                32 entries of every stage each (a single producer warp needed ~650 cycles per stage and set the pace)
+//   warp 4       TMEM allocation; one elected lane issues tcgen05.mma / tcgen05.commit (B/codes bulk loads: thread 0)
+//   warps 5..12  epilogue, two warps per TMEM lane quarter; warp k of a quarter owns the 32-word chunks k, k+2, ... of
+//                every tile: tcgen05.ld 32x32b.x32 into registers, RELEASE the TMEM buffer at once, tree-shaped AND of
+//                the sign bits.  A lane that saw a non-negative accumulator stores its 32 words + {window, column} as
+//                one raw entry in global memory (blocks of 32 entries reserved per warp: fire-and-forget stores, one
+//                atomic per block) -- the epilogue's per-tile time must not depend on how many candidates it meets,
+//                because every warp has to release a buffer before the next MMAs may start.
+//   expand_kernel (rescore.cuh) later turns raw entries into (position, column) candidates for the exact rescorer.
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int      kTcThreads  = 320;
-constexpr uint32_t kTcEpiWarps = 8;
+#ifndef TC_EPI_WARPS
+#define TC_EPI_WARPS 8
+#endif
+#ifndef TC_KNOCKOUT
+#define TC_KNOCKOUT 0      // diagnostic only: 1 skip epilogue ld+reduce, 2 skip MMA issue, 4 skip producer fill, 8 skip FIFO push
+#endif
+#ifndef TC_PRODUCERS
+#define TC_PRODUCERS 4
+#endif
+#ifndef TC_BUFS
+#define TC_BUFS 2
+#endif
+#ifndef TC_MAXN
+#define TC_MAXN 256
+#endif
+#ifndef TC_CTAS_PER_SM
+#define TC_CTAS_PER_SM 1
+#endif
+constexpr uint32_t kTcEpiWarps = TC_EPI_WARPS;                 // per TMEM lane quarter: kTcEpiWarps / 4
+constexpr uint32_t kTcCtasPerSm = TC_CTAS_PER_SM;             // co-resident CTAs share the SM's 512 TMEM columns
+constexpr uint32_t kTcProducers = TC_PRODUCERS;                         // warps filling the E ring, 32 entries of every stage each
+constexpr uint32_t kTcEpiWarp0 = kTcProducers + 1;            // first epilogue warp (warp kTcProducers issues the MMAs)
+constexpr int      kTcThreads  = 32 * (kTcProducers + 1 + kTcEpiWarps);
 constexpr uint32_t kTcSpan     = 32768;      // windows per work item
 constexpr uint32_t kTcStages   = 8;          // E ring stages (128 entries = 2 KB each)
 constexpr uint32_t kTcMirror   = 64;         // entries mirrored past the ring end (>= 2*(2*nK_max-1))
-constexpr uint32_t kTcMaxN     = 256;
-constexpr uint32_t kTcStageCap = 64;         // staged candidates per epilogue warp
+constexpr uint32_t kTcMaxN     = TC_MAXN;     // columns per tile; 2 accumulator buffers of kTcMaxN TMEM columns per CTA
+static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N columns x CTAs per SM must fit 512 columns");
+static_assert(128 % TC_PRODUCERS == 0 && TC_EPI_WARPS % 4 == 0, "warp role split");
+constexpr uint32_t kRawBlock   = 32;         // raw entries per block (an epilogue warp reserves a block at a time)
+constexpr uint32_t kRawWords   = 40;         // 32 TMEM words + {window, first column} + padding = 160 B per entry (32 B aligned)
 
 struct TcTile {
     uint32_t col0;      // first sorted column
     uint32_t n_cols;    // real columns
-    uint32_t n_pad;     // N of the MMA, multiple of 32, <= 256 (padding columns can never pass the filter)
+    uint32_t n_pad;     // N of the MMA, multiple of 64, <= 256 (padding columns can never pass the filter)
     uint32_t n_k;       // MMAs per 128-window tile = ceil(Lmax / 4)
     uint32_t b_off;     // byte offset of the tile's B image in TcParams::bimg
     uint32_t b_bytes;   // n_pad * (2*n_k) * 16
@@ -56,19 +87,29 @@ struct TcParams {
     uint32_t       n_tiles;
     uint32_t       n_spans;
     unsigned int*  work_counter;
-    Cand*          cand;
-    unsigned long long* n_cand;
-    unsigned long long  cand_cap;
+    uint32_t*      raw;            // raw entries: block b, entry e at raw[(b * kRawBlock + e) * kRawWords]
+    uint32_t*      blk_count;      // entries used in block b
+    unsigned int*  n_blocks;       // blocks reserved so far (keeps counting past blk_cap so the host can size a retry)
+    uint32_t       blk_cap;
     unsigned int*  error_flag;
+    unsigned long long* trace;      // B200_TRACE builds only: [role 0..3][tile 0..kTraceTiles)[event 0..3] clock64 stamps of CTA 0, item 0
 };
+
+constexpr uint32_t kTraceTiles = 256;
+#ifdef B200_TRACE
+#define TC_TRACE(role, tile_i, ev) do { if (blockIdx.x == 0 && nItem == 0 && lane == 0 && (tile_i) < kTraceTiles) \
+        P.trace[((role) * kTraceTiles + (tile_i)) * 4 + (ev)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TC_TRACE(role, tile_i, ev) do {} while (0)
+#endif
 
 // shared memory carve-up (bytes)
 constexpr uint32_t kSmE      = (kTcStages * 128 + kTcMirror) * 16;            // 17408
 constexpr uint32_t kSmCodes  = kTcSpan / 4 + 128;                              //  8320
 constexpr uint32_t kSmB      = kTcMaxN * (2 * (kMaxLen / 4)) * 16;             // 131072
-constexpr uint32_t kSmStage  = kTcEpiWarps * kTcStageCap * 8;                  //  4096
 constexpr uint32_t kSmBars   = 32 * 8;
-constexpr uint32_t kTcSmemBytes = kSmE + kSmCodes + kSmB + kSmStage + kSmBars + 128;
+constexpr uint32_t kSmLut    = 16 * 16;                                        //   256: E entry for every (code, next code)
+constexpr uint32_t kTcSmemBytes = kSmE + kSmCodes + kSmB + kSmBars + kSmLut + 128;
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -126,6 +167,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One elected lane of a fully converged warp (elect.sync).  Keeping the issuing warp converged and predicating only the
+// tcgen05 instruction lets ptxas keep descriptors in uniform registers; an `if (lane == 0)` block instead costs an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY loop (~100 cycles) per instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+// Same, with the descriptors as (lo, hi) words: stepping along K is then a single 32-bit add on the address field.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}"
+                 ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -139,6 +195,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
 }
+// Same shape with .pack::16b: register k = the low 16 bits of TMEM columns 2k (low half) and 2k+1 (high half), i.e.
+// 64 FP16 accumulators (stored one per 32-bit column) arrive as 32 registers.
+__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+template <bool ACC16> __device__ __forceinline__ void tmem_ld_words(uint32_t taddr_buf, uint32_t word, uint32_t (&v)[32]) {
+    if (ACC16) tmem_ld32_pack16(taddr_buf + 2 * word, v); else tmem_ld32(taddr_buf + word, v);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle ("interleave") shared memory descriptor: rows 16 B apart inside an 8-row core matrix,
@@ -150,65 +221,80 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 
-// AND of 32 accumulators as a depth-4 tree of 3-input LOP3s: sign bit set <=> all 32 are negative.
-__device__ __forceinline__ uint32_t and_tree32(const uint32_t (&v)[32]) {
-    const uint32_t t0 = v[0] & v[1] & v[2],    t1 = v[3] & v[4] & v[5],    t2 = v[6] & v[7] & v[8],    t3 = v[9] & v[10] & v[11];
-    const uint32_t t4 = v[12] & v[13] & v[14], t5 = v[15] & v[16] & v[17], t6 = v[18] & v[19] & v[20], t7 = v[21] & v[22] & v[23];
-    const uint32_t t8 = v[24] & v[25] & v[26], t9 = v[27] & v[28] & v[29], t10 = v[30] & v[31];
-    const uint32_t u0 = t0 & t1 & t2, u1 = t3 & t4 & t5, u2 = t6 & t7 & t8, u3 = t9 & t10;
-    return (u0 & u1) & (u2 & u3);
+// a & b & c as ONE opaque lop3: keeps the reduction a tree (nvcc otherwise re-associates the ANDs into a
+// 16-deep dependent chain, which a warp can only issue every ~4.5 cycles).
+__device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
-// bit (31 - j) = sign bit of v[j]; four independent funnel-shift chains of 8
-__device__ __forceinline__ uint32_t sign_mask32(const uint32_t (&v)[32]) {
-    uint32_t m[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) m[c] = __funnelshift_l(v[8 * c + j], m[c], 1);
-    }
-    return (m[0] << 24) | (m[1] << 16) | (m[2] << 8) | m[3];
+// AND of 32 TMEM words as a depth-4 tree of 3-input LOP3s.  A sign bit of the result (bit 31; with FP16
+// accumulators also bit 15) is set <=> every accumulator in that position is negative.
+__device__ __forceinline__ uint32_t and_tree32(const uint32_t (&v)[32]) {
+    const uint32_t t0 = and3(v[0], v[1], v[2]),    t1 = and3(v[3], v[4], v[5]),    t2 = and3(v[6], v[7], v[8]);
+    const uint32_t t3 = and3(v[9], v[10], v[11]),  t4 = and3(v[12], v[13], v[14]), t5 = and3(v[15], v[16], v[17]);
+    const uint32_t t6 = and3(v[18], v[19], v[20]), t7 = and3(v[21], v[22], v[23]), t8 = and3(v[24], v[25], v[26]);
+    const uint32_t t9 = and3(v[27], v[28], v[29]), t10 = and3(v[30], v[31], 0xffffffffu);
+    const uint32_t u0 = and3(t0, t1, t2), u1 = and3(t3, t4, t5), u2 = and3(t6, t7, t8), u3 = and3(t9, t10, 0xffffffffu);
+    return and3(and3(u0, u1, u2), u3, 0xffffffffu);
+}
+template <bool ACC16> __device__ __forceinline__ bool any_nonneg(uint32_t a) {
+    return ACC16 ? ((a & 0x80008000u) != 0x80008000u) : ((int32_t)a >= 0);
 }
 
-struct CandStage {          // per-warp candidate staging (warp-uniform count in a register)
-    Cand* buf; uint32_t n;
-};
-__device__ __forceinline__ void stage_flush(CandStage& st, const TcParams& P, uint32_t lane) {
-    __syncwarp();
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(P.n_cand, (unsigned long long)st.n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t s = lane; s < st.n; s += 32)
-        if (base + s < P.cand_cap) P.cand[base + s] = st.buf[s];
-    __syncwarp();
-    st.n = 0;
-}
-// One 32-column chunk of this thread's window: fast sign test, rare slow path that lists the candidates.
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], bool winOk, uint32_t win, uint32_t col_base,
-                                               CandStage& st, const TcParams& P, uint32_t lane) {
-    const uint32_t a = and_tree32(v);
-    if (!__any_sync(0xffffffffu, winOk && (int32_t)a >= 0)) return;
-    uint32_t c = winOk ? ~sign_mask32(v) : 0u;          // bit (31-j) set <=> accumulator j >= 0 <=> candidate
-    while (true) {                                      // rounds: every lane with candidates left pushes one (ascending column)
-        const bool has = c != 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, has);
-        if (!bal) break;
-        if (has) {
-            const int b = 31 - __clz(c);
-            c &= ~(1u << b);
-            Cand cd; cd.pos = win; cd.col = col_base + (31 - b);
-            st.buf[st.n + __popc(bal & ((1u << lane) - 1u))] = cd;
-        }
-        st.n += __popc(bal);
-        if (st.n > kTcStageCap - 32) stage_flush(st, P, lane);      // one global atomic per >= 32 candidates
+// Per-epilogue-warp cursor into the raw-entry blocks.  next/left/blk are warp-uniform; `spare` (meaningful in lane 0) is
+// the index of a block reserved AHEAD of time: the global atomic that reserves it is issued when the previous block is
+// opened and its result is only consumed ~32 entries later, so its ~1 us latency never stalls the epilogue (a stalled
+// epilogue warp stalls the whole MMA pipeline one tile later).
+struct RawCursor { uint32_t* next; uint32_t left; uint32_t blk; uint32_t spare; };
+// Open the pre-reserved block and reserve the one after it.  When the buffer is full the cursor points at the
+// sacrificial block behind blk_cap, whose contents are never read: the host sees n_blocks > blk_cap and re-runs.
+__device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, uint32_t lane) {      // (inlined: a call would spill the cursor to local memory)
+    const uint32_t nb = __shfl_sync(0xffffffffu, rc.spare, 0);
+    if (lane == 0) {
+        if (rc.blk < P.blk_cap) P.blk_count[rc.blk] = kRawBlock - rc.left;          // close the old block
+        rc.spare = atomicAdd(P.n_blocks, 1u);
     }
+    rc.blk = nb;
+    rc.next = P.raw + (size_t)min(rc.blk, P.blk_cap) * (kRawBlock * kRawWords);
+    rc.left = kRawBlock;
+}
+__device__ __forceinline__ void st_global_v8(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+// Every lane with `mine` appends its 32 words + {window, first column} to the warp's current block: four 256-bit and one
+// 128-bit fire-and-forget stores per candidate lane (~2e-4 of the accumulators are candidates).
+__device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, const uint32_t (&v)[32], bool mine, uint32_t win,
+                                         uint32_t col_base, uint32_t lane) {
+    const unsigned todo = __ballot_sync(0xffffffffu, mine);
+    if (!todo) return;
+    const uint32_t n = __popc(todo);
+    if (n > rc.left) raw_new_block(rc, P, lane);
+    if (mine) {
+        uint32_t* d = rc.next + __popc(todo & ((1u << lane) - 1u)) * kRawWords;
+        st_global_v8(d,      v[0],  v[1],  v[2],  v[3],  v[4],  v[5],  v[6],  v[7]);
+        st_global_v8(d + 8,  v[8],  v[9],  v[10], v[11], v[12], v[13], v[14], v[15]);
+        st_global_v8(d + 16, v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
+        st_global_v8(d + 24, v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
+        *reinterpret_cast<uint2*>(d + 32) = make_uint2(win, col_base);
+    }
+    rc.next += n * kRawWords;
+    rc.left -= n;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <bool ACC16>
+__global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm)
 filter_tc_kernel(TcParams P, BlockDev blk)
 {
+    constexpr uint32_t kBufs    = TC_BUFS;              // TMEM accumulator buffers
+    constexpr uint32_t kBufCols = kTcMaxN;              // TMEM columns per buffer: one accumulator per column, FP32 or FP16
+    constexpr uint32_t kColsPerWord = ACC16 ? 2 : 1;
+    constexpr uint32_t kEpiPerQ = kTcEpiWarps / 4;
+
     extern __shared__ __align__(128) uint8_t smem_raw[];
     if (__ldg(blk.has_zero) != 0) return;                       // zero-mask blocks take the gather kernel
 
@@ -216,23 +302,28 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     uint8_t*  sE     = smem;
     uint8_t*  sCodes = sE + kSmE;
     uint8_t*  sB     = sCodes + kSmCodes;
-    Cand*     sStage = reinterpret_cast<Cand*>(sB + kSmB);
-    uint64_t* sBars  = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStage) + kSmStage);
-    // barrier map: [0..7] e_full, [8..15] e_empty, [16,17] t_full, [18,19] t_empty, [20] codes, [21] B
-    volatile uint32_t* sMisc = reinterpret_cast<volatile uint32_t*>(sBars + 24);   // [0] work item, [1] tmem base
+    uint64_t* sBars  = reinterpret_cast<uint64_t*>(sB + kSmB);
+    // barrier map: [0..7] e_full, [8..15] e_empty, [16..19] t_full, [20..23] t_empty, [24] codes, [25] B
+    volatile uint32_t* sMisc = reinterpret_cast<volatile uint32_t*>(sBars + 28);   // [0] work item, [1] tmem base
+    uint4* sLut = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sBars) + kSmBars);
 
     const uint32_t bars   = smem_u32(sBars);
-    const uint32_t eFull  = bars, eEmpty = bars + 8 * 8, tFull = bars + 16 * 8, tEmpty = bars + 18 * 8;
-    const uint32_t cBar   = bars + 20 * 8, bBar = bars + 21 * 8;
+    const uint32_t eFull  = bars, eEmpty = bars + 8 * 8, tFull = bars + 16 * 8, tEmpty = bars + 20 * 8;
+    const uint32_t cBar   = bars + 24 * 8, bBar = bars + 25 * 8;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, 1); mbar_init(eEmpty + 8 * i, 1); }
-        for (uint32_t i = 0; i < 2; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, kTcEpiWarps); }
+        for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, kTcProducers); mbar_init(eEmpty + 8 * i, 1); }
+        for (uint32_t i = 0; i < kBufs; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, kTcEpiWarps); }
         mbar_init(cBar, 1); mbar_init(bBar, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(&sMisc[1])), 512);
+    if (warp == kTcProducers) tmem_alloc(smem_u32(const_cast<uint32_t*>(&sMisc[1])), kBufs * kBufCols);
+    if (threadIdx.x < 16) {                      // one-hot FP16 (1.0 = 0x3C00) of code c in halves 0..3, of the next code in 4..7
+        const uint32_t c0 = threadIdx.x & 3, c1 = threadIdx.x >> 2;
+        const uint32_t v0 = 0x3C00u << (16 * (c0 & 1)), v1 = 0x3C00u << (16 * (c1 & 1));
+        sLut[threadIdx.x] = make_uint4((c0 & 2) ? 0u : v0, (c0 & 2) ? v0 : 0u, (c1 & 2) ? 0u : v1, (c1 & 2) ? v1 : 0u);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -242,8 +333,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     uint32_t kT = 0;            // window tiles so far
     uint32_t nItem = 0, nBload = 0;
     int32_t  curTile = -1;
-    CandStage stage;            // epilogue: staged candidates of this warp (count is warp-uniform)
-    stage.buf = sStage + ((warp >= 2) ? (warp - 2) : 0) * kTcStageCap; stage.n = 0;
+    RawCursor rawc; rawc.blk = 0xffffffffu; rawc.left = 0; rawc.next = P.raw; rawc.spare = 0;
+    if (warp >= kTcEpiWarp0 && lane == 0) rawc.spare = atomicAdd(P.n_blocks, 1u);      // epilogue warps: reserve the first block early
     const uint32_t nItems = P.n_tiles * P.n_spans;
 
     while (true) {
@@ -271,89 +362,114 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             }
         }
 
-        if (warp == 0) {
-            // ===================== producer: codes -> E ring =====================
+        if (warp < kTcProducers) {
+            // ===================== producers: codes -> E ring (warp p fills entries 32p .. 32p+31 of every stage) =====================
             mbar_wait(cBar, nItem & 1, P.error_flag);
             for (uint32_t i = 0; i <= nT; i++) {
                 const uint32_t k = kE + i, slot = k % kTcStages, ph = (k / kTcStages) & 1;
                 mbar_wait(eEmpty + 8 * slot, ph ^ 1, P.error_flag);
+                if (warp == 0) TC_TRACE(0, i, 0);
+                if (!(TC_KNOCKOUT & 4)) {
 #pragma unroll
-                for (uint32_t q = 0; q < 4; q++) {
-                    const uint32_t e = 32 * q + lane;                 // entry within the stage
-                    const uint32_t byte = 32 * i + (e >> 2);
-                    const uint32_t two = (uint32_t)sCodes[byte] | ((uint32_t)sCodes[byte + 1] << 8);
-                    const uint32_t c0 = (two >> (2 * (e & 3))) & 3u, c1 = (two >> (2 * (e & 3) + 2)) & 3u;
-                    const uint32_t v0 = 0x3C00u << (16 * (c0 & 1)), v1 = 0x3C00u << (16 * (c1 & 1));
-                    uint4 val;
-                    val.x = (c0 & 2) ? 0u : v0;  val.y = (c0 & 2) ? v0 : 0u;
-                    val.z = (c1 & 2) ? 0u : v1;  val.w = (c1 & 2) ? v1 : 0u;
-                    *reinterpret_cast<uint4*>(sE + (slot * 128 + e) * 16) = val;
-                    if (slot == 0 && e < kTcMirror)
-                        *reinterpret_cast<uint4*>(sE + (kTcStages * 128 + e) * 16) = val;
+                    for (uint32_t r = 0; r < 4 / kTcProducers; r++) {
+                        const uint32_t e = 32 * (warp + r * kTcProducers) + lane;      // entry within the stage
+                        const uint32_t byte = 32 * i + (e >> 2);
+                        const uint32_t two = (uint32_t)sCodes[byte] | ((uint32_t)sCodes[byte + 1] << 8);
+                        const uint4 val = sLut[(two >> (2 * (e & 3))) & 15u];          // [onehot(code e) | onehot(code e+1)]
+                        *reinterpret_cast<uint4*>(sE + (slot * 128 + e) * 16) = val;
+                        if (slot == 0 && e < kTcMirror)
+                            *reinterpret_cast<uint4*>(sE + (kTcStages * 128 + e) * 16) = val;
+                    }
                 }
                 fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(eFull + 8 * slot);
+                if (warp == 0) TC_TRACE(0, i, 1);
             }
-        } else if (warp == 1) {
+        } else if (warp == kTcProducers) {
             // ===================== MMA issuer =====================
             if (newTile) mbar_wait(bBar, nBload & 1, P.error_flag);
-            const uint32_t idesc = (1u << 4) | ((tile.n_pad >> 3) << 17) | ((128u >> 4) << 24);   // F16 x F16 -> F32, K-major A and B
-            const uint32_t nChunks = 2 * tile.n_k;
-            const uint32_t bBase = smem_u32(sB), eBase = smem_u32(sE);
+            // instruction descriptor: F16 x F16, D = F32 (c_format 1) or F16 (c_format 0), K-major A and B, M = 128, N = n_pad
+            const uint32_t idesc = (ACC16 ? 0u : (1u << 4)) | ((tile.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t n_k = __shfl_sync(0xffffffffu, tile.n_k, 0);
+            const uint32_t nChunks = 2 * n_k;
+            const uint64_t ad0 = umma_desc(smem_u32(sE), 32, 128), bd0 = umma_desc(smem_u32(sB), 128, nChunks * 128);
+            const uint32_t aLo0 = (uint32_t)ad0, aHi = (uint32_t)(ad0 >> 32), bLo0 = (uint32_t)bd0, bHi = (uint32_t)(bd0 >> 32);
             for (uint32_t i = 0; i < nT; i++) {
                 const uint32_t k = kE + i, slot = k % kTcStages, ph = (k / kTcStages) & 1;
                 const uint32_t k1 = k + 1, slot1 = k1 % kTcStages, ph1 = (k1 / kTcStages) & 1;
-                const uint32_t kt = kT + i, buf = kt & 1, tph = (kt >> 1) & 1;
+                const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
                 if (i == 0) mbar_wait(eFull + 8 * slot, ph, P.error_flag);     // later tiles waited for it as their halo stage
                 mbar_wait(eFull + 8 * slot1, ph1, P.error_flag);
+                TC_TRACE(1, i, 0);
                 mbar_wait(tEmpty + 8 * buf, tph ^ 1, P.error_flag);
+                TC_TRACE(1, i, 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t d = tmem_base + buf * kTcMaxN;
-                    for (uint32_t m = 0; m < tile.n_k; m++) {
-                        // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[slot*128 + r + 2*kk]
-                        const uint64_t ad = umma_desc(eBase + (slot * 128 + 4 * m) * 16, 32, 128);
-                        // B: [8-column group][chunk] blocks of 128 B: chunks 128 B apart, column groups nChunks*128 B apart
-                        const uint64_t bd = umma_desc(bBase + (2 * m) * 128, 128, nChunks * 128);
-                        umma_f16(d, ad, bd, idesc, m > 0 ? 1u : 0u);
+                {
+                    const uint32_t d = tmem_base + buf * kBufCols;
+                    // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[slot*128 + r + 2*kk]; one MMA = 4 entries = 64 B
+                    // B: [8-column group][chunk] blocks of 128 B: one MMA = 2 chunks = 256 B
+                    uint32_t alo = aLo0 + slot * 128, blo = bLo0;          // address fields are in 16-byte units
+                    const bool leader = elect_one();
+                    if (leader && !(TC_KNOCKOUT & 2)) umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+                    for (uint32_t m = 1; m < ((TC_KNOCKOUT & 2) ? 0u : n_k); m++) {
+                        alo += 4; blo += 16;
+                        if (leader) umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
                     }
-                    umma_commit(eEmpty + 8 * slot);       // stage k is dead once tile i (and i-1 before it) completed
-                    umma_commit(tFull + 8 * buf);
+                    if (leader) {
+                        umma_commit(eEmpty + 8 * slot);       // stage k is dead once tile i (and i-1 before it) completed
+                        umma_commit(tFull + 8 * buf);
+                    }
                 }
+                TC_TRACE(1, i, 2);
                 __syncwarp();
             }
-            if (lane == 0) umma_commit(eEmpty + 8 * ((kE + nT) % kTcStages));   // the halo stage
+            if (elect_one()) umma_commit(eEmpty + 8 * ((kE + nT) % kTcStages));   // the halo stage
             __syncwarp();
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
             const uint32_t q = warp & 3;                              // TMEM lane quarter this warp may read
-            const uint32_t half = (warp - 2) >> 2;                    // which of the quarter's two warps
+            const uint32_t sub = (warp - kTcEpiWarp0) >> 2;           // which of the quarter's warps
+            const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
             for (uint32_t i = 0; i < nT; i++) {
-                const uint32_t kt = kT + i, buf = kt & 1, tph = (kt >> 1) & 1;
+                const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
                 mbar_wait(tFull + 8 * buf, tph, P.error_flag);
+                if (warp == kTcEpiWarp0) TC_TRACE(2, i, 0); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 0);
                 tc_fence_after();
-                const uint32_t win = w0 + 128 * i + 32 * q + lane;
-                const bool winOk = win < blk.n_payload;
-                const uint32_t taddr = tmem_base + ((32 * q) << 16) + buf * kTcMaxN;
-                uint32_t cc = 32 * half;                              // this warp takes chunks half, half+2, half+4, ...
-                for (; cc + 64 < tile.n_pad; cc += 128) {             // two chunks per trip, both loads in flight
+                const uint32_t win0 = w0 + 128 * i + 32 * q;          // window of lane 0
+                const bool winOk = win0 + lane < blk.n_payload;
+                const uint32_t taddr = tmem_base + ((32 * q) << 16) + buf * kBufCols;
+                // this warp owns the 32-word chunks sub, sub + kEpiPerQ, sub + 2 kEpiPerQ, ... of the tile, taken two at a
+                // time (both loads in flight).  As soon as its LAST loads have landed in registers the warp hands the
+                // TMEM buffer back, before looking at the data.
+                constexpr uint32_t step = 32 * kEpiPerQ;
+                bool released = false;
+                for (uint32_t wc = 32 * sub; wc < ((TC_KNOCKOUT & 1) ? 0u : nWords); wc += 2 * step) {
+                    const bool has1 = wc + step < nWords;
                     uint32_t v0[32], v1[32];
-                    tmem_ld32(taddr + cc, v0);
-                    tmem_ld32(taddr + cc + 64, v1);
+                    tmem_ld_words<ACC16>(taddr, wc, v0);
+                    if (has1) tmem_ld_words<ACC16>(taddr, wc + step, v1);
                     tmem_ld_wait();
-                    epilogue_chunk(v0, winOk, win, tile.col0 + cc, stage, P, lane);
-                    epilogue_chunk(v1, winOk, win, tile.col0 + cc + 64, stage, P, lane);
+                    if (wc + 2 * step >= nWords) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tEmpty + 8 * buf);
+                        released = true;
+                        if (warp == kTcEpiWarp0) TC_TRACE(2, i, 2); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 2);
+                    }
+                    // both reductions first (independent trees interleave in the issue slots), then ONE test and ONE vote
+                    const uint32_t a0 = and_tree32(v0), a1 = has1 ? and_tree32(v1) : 0xffffffffu;
+                    if (!(TC_KNOCKOUT & 8) && __any_sync(0xffffffffu, winOk && any_nonneg<ACC16>(a0 & a1))) {
+                        raw_push(rawc, P, v0, winOk && any_nonneg<ACC16>(a0), win0 + lane, tile.col0 + wc * kColsPerWord, lane);
+                        if (has1) raw_push(rawc, P, v1, winOk && any_nonneg<ACC16>(a1), win0 + lane, tile.col0 + (wc + step) * kColsPerWord, lane);
+                    }
                 }
-                if (cc < tile.n_pad) {
-                    uint32_t v0[32];
-                    tmem_ld32(taddr + cc, v0);
-                    tmem_ld_wait();
-                    epilogue_chunk(v0, winOk, win, tile.col0 + cc, stage, P, lane);
+                if (!released) {                                      // this warp owns no chunk of such a narrow tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tEmpty + 8 * buf);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tEmpty + 8 * buf);
+                if (warp == kTcEpiWarp0) TC_TRACE(2, i, 3); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 3);
             }
         }
         kE += nT + 1;
@@ -363,10 +479,13 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         __syncthreads();          // item boundary: every role is done with sCodes / sB / the pipelines are drained
     }
 
-    if (warp >= 2 && stage.n) stage_flush(stage, P, lane);
+    if (warp >= kTcEpiWarp0 && lane == 0) {                                          // close the open block and the unused spare
+        if (rawc.blk < P.blk_cap) P.blk_count[rawc.blk] = kRawBlock - rawc.left;
+        if (rawc.spare < P.blk_cap) P.blk_count[rawc.spare] = 0;
+    }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == kTcProducers) tmem_dealloc(tmem_base, kBufs * kBufCols);
 }
 
 } // namespace b200

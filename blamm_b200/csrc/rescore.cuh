@@ -4,8 +4,64 @@
 // the payload limit, and appended to the hit list.  Rare work (about 1e-4 of all scores), L2-resident.
 #pragma once
 #include "common.cuh"
+#include "filter_tc.cuh"
 
 namespace b200 {
+
+// Raw entries of the tensor-core filter -> (position, sorted column) candidates.  One warp per block of entries; lane k
+// tests word k of an entry (FP32 accumulators: word k = column first + k; FP16 via .pack::16b: word k = columns
+// first + 2k in the low half and first + 2k + 1 in the high half; candidate <=> sign bit clear).  Candidates are staged
+// in shared memory and appended with one global atomic per >= 64 of them.
+template <bool ACC16>
+__global__ void __launch_bounds__(256)
+expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count, const unsigned int* __restrict__ n_blocks_ptr,
+              uint32_t blk_cap, Cand* __restrict__ cand, unsigned long long* n_cand, unsigned long long cand_cap,
+              const uint32_t* __restrict__ has_zero)
+{
+    __shared__ Cand s_stage[8][128];
+    if (__ldg(has_zero) != 0) return;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t nb = min(*n_blocks_ptr, blk_cap);
+    Cand* st = s_stage[wib];
+    uint32_t n = 0;
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(n_cand, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t s = lane; s < n; s += 32)
+            if (base + s < cand_cap) cand[base + s] = st[s];
+        __syncwarp();
+        n = 0;
+    };
+    const uint32_t lt = (1u << lane) - 1u;
+    // one warp per entry slot (block, e): entries of a block beyond its count are skipped
+    const unsigned long long slots = (unsigned long long)nb * kRawBlock;
+    for (unsigned long long sl = (unsigned long long)blockIdx.x * 8 + wib; sl < slots; sl += (unsigned long long)gridDim.x * 8) {
+        const uint32_t b = (uint32_t)(sl / kRawBlock), e = (uint32_t)(sl % kRawBlock);
+        if (e >= __ldg(blk_count + b)) continue;
+        {
+            const uint32_t* ent = raw + sl * kRawWords;
+            const uint32_t w = __ldg(ent + lane);
+            Cand cd; cd.pos = __ldg(ent + 32);
+            const uint32_t first = __ldg(ent + 33);
+            if (ACC16) {
+                const bool lo = !(w & 0x8000u), hi = !(w & 0x80000000u);
+                const unsigned blo = __ballot_sync(0xffffffffu, lo), bhi = __ballot_sync(0xffffffffu, hi);
+                if (lo) { cd.col = first + 2 * lane;     st[n + __popc(blo & lt)] = cd; }
+                if (hi) { cd.col = first + 2 * lane + 1; st[n + __popc(blo) + __popc(bhi & lt)] = cd; }
+                n += __popc(blo) + __popc(bhi);
+            } else {
+                const bool c = (int32_t)w >= 0;
+                const unsigned bb = __ballot_sync(0xffffffffu, c);
+                if (c) { cd.col = first + lane; st[n + __popc(bb & lt)] = cd; }
+                n += __popc(bb);
+            }
+            if (n > 64) flush();
+        }
+    }
+    if (n) flush();
+}
 
 __global__ void __launch_bounds__(256)
 rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
@@ -20,7 +76,7 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
         bool hit = false;
         uint32_t pos = 0, col = 0;
         float s = 0.0f;
-        if (i < n_cand) {
+        if (i < n_cand && cand[i].col < md.n_cols) {      // (a candidate can never name a padding column; belt and braces)
             Cand c = cand[i];
             pos = c.pos; col = c.col;
             const uint32_t L = __ldg(md.len + col);

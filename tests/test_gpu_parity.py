@@ -87,15 +87,21 @@ def test_golden_cases(scanner, golden, engine, case_name, mode_key):
         assert sorted(lines) == open(os.path.join(d, "occ_%s.txt" % mode_key)).read().splitlines(True)
 
 
-@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+@pytest.mark.parametrize("engine,acc", [(capi.ENGINE_GATHER, 0), (capi.ENGINE_TENSOR, 16), (capi.ENGINE_TENSOR, 32)])
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_random_cases_bit_exact(scanner, engine, seed):
+def test_random_cases_bit_exact(scanner, engine, acc, seed):
     case = util.random_case(seed, n_motifs=30, n_nt=300_000)
     scanner.set_engine(engine)
+    scanner.set_tensor_accumulator(acc)
     scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    if acc:
+        assert scanner.tensor_info()["accumulator_bits"] == acc
     hits, t = scanner.scan(case["chars"], case["frag_start"][1:])
+    scanner.set_tensor_accumulator(0)
     _assert_same(hits, *_oracle_hits(case))
     assert t["engine_used"] == engine and t["kernel_launches"] >= 2
+    if acc:      # the filter is conservative (no hit may be lost) and tight (few wasted candidates)
+        assert len(hits) <= t["n_candidates"] <= 2.5 * len(hits) + 100
 
 
 @pytest.mark.parametrize("lower", [capi.LOWER_ZERO, capi.LOWER_FOLD])
@@ -131,10 +137,13 @@ def test_max_length_and_many_columns(scanner, engine):
     """Motifs up to the ABI limit of 64 positions and >256 columns (several tensor tiles, several gather tiles)."""
     case = util.random_case(31, n_motifs=150, n_nt=60_000, len_range=(4, 64))
     assert case["col_len"].max() == 64 and len(case["col_len"]) == 300
-    scanner.set_engine(engine)
-    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
-    hits, _ = scanner.scan(case["chars"], case["frag_start"][1:])
-    _assert_same(hits, *_oracle_hits(case))
+    for acc in ((16, 32) if engine == capi.ENGINE_TENSOR else (0,)):
+        scanner.set_engine(engine)
+        scanner.set_tensor_accumulator(acc)
+        scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+        hits, _ = scanner.scan(case["chars"], case["frag_start"][1:])
+        _assert_same(hits, *_oracle_hits(case))
+    scanner.set_tensor_accumulator(0)
 
 
 def test_packed_submit_and_zero_mask(scanner):
@@ -204,13 +213,15 @@ def test_engines_agree_at_scale_and_properties(scanner):
     for c in range(len(case["thr"])):
         case["thr"][c] = max(case["thr"][c], 11.0)
     res = {}
-    for engine in (capi.ENGINE_GATHER, capi.ENGINE_TENSOR):
+    for engine, acc in ((capi.ENGINE_GATHER, 0), (capi.ENGINE_TENSOR, 16), (capi.ENGINE_TENSOR, 32)):
         scanner.set_engine(engine)
+        scanner.set_tensor_accumulator(acc)
         scanner.set_motifs(case["P"], case["col_len"], case["thr"])
-        res[engine], t = scanner.scan(case["chars"], case["frag_start"][1:])
-        res[engine] = _sorted(res[engine])
-    g, tcs = res[capi.ENGINE_GATHER], res[capi.ENGINE_TENSOR]
-    assert len(g) > 1000 and np.array_equal(g, tcs)
+        res[acc], t = scanner.scan(case["chars"], case["frag_start"][1:])
+        res[acc] = _sorted(res[acc])
+    scanner.set_tensor_accumulator(0)
+    g, tcs = res[0], res[16]
+    assert len(g) > 1000 and np.array_equal(g, tcs) and np.array_equal(g, res[32])
     want = O.score_at(bytes(case["chars"]), case["P"], case["col_len"], g["pos"], g["col"])
     assert np.array_equal(want.view(np.uint32), g["score"].view(np.uint32))
     assert np.all(g["score"] >= case["thr"][g["col"]])

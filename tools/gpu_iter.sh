@@ -2,6 +2,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
+if [ "${DEBUG:-0}" = "1" ]; then timeout 600 python tools/tc_debug.py > gpurun_out/tc_debug.log 2>&1; echo "tc_debug rc=$?"; grep -E "info|hits|IDENT|MISM|missing|scaled|FAILED" gpurun_out/tc_debug.log | tail -40; fi
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps ${STEPS:-5} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.log 2>&1; echo "bench rc=$?"; tail -2 gpurun_out/bench.log
 if [ "${NCU:-1}" = "1" ]; then

@@ -13,12 +13,15 @@ from blamm_b200 import capi  # noqa: E402
 from tests import util  # noqa: E402
 
 
-def diff(case, n_nt_label):
+def diff(case, n_nt_label, acc=0):
     sc = capi.Scanner(0, max_block_nt=max(1 << 20, len(case["chars"]) + 64), max_hits=1 << 22)
     out = {}
     for name, eng in (("gather", capi.ENGINE_GATHER), ("tensor", capi.ENGINE_TENSOR)):
         sc.set_engine(eng)
+        sc.set_tensor_accumulator(acc)
         sc.set_motifs(case["P"], case["col_len"], case["thr"])
+        if name == "tensor":
+            print("  tensor info:", sc.tensor_info())
         t0 = time.time()
         try:
             hits, t = sc.scan(case["chars"], case["frag_start"][1:])
@@ -52,4 +55,11 @@ if __name__ == "__main__":
     print("case C: 300 motifs L 5..35, 8M nt")
     c = util.random_case(3, n_motifs=300, n_nt=8_000_000, len_range=(5, 35))
     c["thr"] = np.maximum(c["thr"], 10.0).astype(np.float32)
-    diff(c, "8M")
+    for acc in (32, 16):
+        diff(c, "8M acc%d" % acc, acc)
+    # how much of the FP16-accumulation error bound does the hardware actually use?  Shrink the bound and count misses.
+    for scale in ("0.25", "0.05", "0.0"):
+        os.environ["B200SCAN_MARGIN16_SCALE"] = scale
+        print("FP16 accumulators with the error bound scaled by", scale)
+        diff(c, "8M acc16 x" + scale, 16)
+    os.environ["B200SCAN_MARGIN16_SCALE"] = "1.0"
