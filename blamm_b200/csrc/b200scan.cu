@@ -55,6 +55,7 @@ struct b200scan_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // hit downloads: overlap the next block's kernels
     uint64_t max_block = 0;
     int engine = B200SCAN_ENGINE_AUTO;
     std::string err;
@@ -481,6 +482,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B200SCAN_ECUDA, "%s -> %s", #call, cudaGetErrorString(e_)); \
                        return bail(e_ == cudaErrorMemoryAllocation ? B200SCAN_ENOMEM : B200SCAN_ECUDA); } } while (0)
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) g_margin16_scale = atof(e);
@@ -530,6 +532,7 @@ void b200scan_destroy(b200scan_ctx* c)
     dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_flush);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -696,9 +699,11 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
         CU(cudaEventRecord(s.ev[5], ctx->stream));
     }
     const unsigned long long nh = s.h_counters[1];
-    CU(cudaEventRecord(s.ev[6], ctx->stream));
-    if (nh) CU(cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(b200scan_hit) * nh, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaEventRecord(s.ev[7], ctx->stream));
+    // the scan of this slot is complete (ev[5] was waited for): download its hits on the copy stream, so that the
+    // kernels of a block already submitted on the other slot keep the compute stream busy meanwhile
+    CU(cudaEventRecord(s.ev[6], ctx->copy_stream));
+    if (nh) CU(cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(b200scan_hit) * nh, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaEventRecord(s.ev[7], ctx->copy_stream));
     CU(cudaEventSynchronize(s.ev[7]));
     cudaEventElapsedTime(&s.timing.h2d_ms, s.ev[0], s.ev[1]);
     cudaEventElapsedTime(&s.timing.pack_ms, s.ev[1], s.ev[2]);

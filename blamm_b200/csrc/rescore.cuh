@@ -11,14 +11,14 @@ namespace b200 {
 // Raw entries of the tensor-core filter -> (position, sorted column) candidates.  One warp per block of entries; lane k
 // tests word k of an entry (FP32 accumulators: word k = column first + k; FP16 via .pack::16b: word k = columns
 // first + 2k in the low half and first + 2k + 1 in the high half; candidate <=> sign bit clear).  Candidates are staged
-// in shared memory and appended with one global atomic per >= 64 of them.
+// in shared memory and appended with one global atomic per ~450 of them.
 template <bool ACC16>
 __global__ void __launch_bounds__(256)
 expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count, const unsigned int* __restrict__ n_blocks_ptr,
               uint32_t blk_cap, Cand* __restrict__ cand, unsigned long long* n_cand, unsigned long long cand_cap,
               const uint32_t* __restrict__ has_zero)
 {
-    __shared__ Cand s_stage[8][128];
+    __shared__ Cand s_stage[8][512];      // per-warp staging: one global atomic per >= 448 candidates
     if (__ldg(has_zero) != 0) return;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t nb = min(*n_blocks_ptr, blk_cap);
@@ -57,7 +57,7 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
                 if (c) { cd.col = first + lane; st[n + __popc(bb & lt)] = cd; }
                 n += __popc(bb);
             }
-            if (n > 64) flush();
+            if (n > 448) flush();
         }
     }
     if (n) flush();
