@@ -11,14 +11,14 @@ namespace b200 {
 // Raw entries of the tensor-core filter -> (position, sorted column) candidates.  One warp per block of entries; lane k
 // tests word k of an entry (FP32 accumulators: word k = column first + k; FP16 via .pack::16b: word k = columns
 // first + 2k in the low half and first + 2k + 1 in the high half; candidate <=> sign bit clear).  Candidates are staged
-// in shared memory and appended with one global atomic per ~450 of them.
+// in shared memory and appended with one global atomic per >= 256 of them.
 template <bool ACC16>
 __global__ void __launch_bounds__(256)
 expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count, const unsigned int* __restrict__ n_blocks_ptr,
               uint32_t blk_cap, Cand* __restrict__ cand, unsigned long long* n_cand, unsigned long long cand_cap,
               const uint32_t* __restrict__ has_zero)
 {
-    __shared__ Cand s_stage[8][512];      // per-warp staging: one global atomic per >= 448 candidates
+    __shared__ Cand s_stage[8][512];      // per-warp staging (a trip adds <= 256): one global atomic per >= 256 candidates
     if (__ldg(has_zero) != 0) return;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t nb = min(*n_blocks_ptr, blk_cap);
@@ -35,30 +35,39 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
         n = 0;
     };
     const uint32_t lt = (1u << lane) - 1u;
-    // one warp per entry slot (block, e): entries of a block beyond its count are skipped
+    // Each warp takes 4 consecutive entry slots (block, e) per trip and issues all their loads before using any
+    // (the kernel is latency bound otherwise); slots beyond a block's count are skipped.
     const unsigned long long slots = (unsigned long long)nb * kRawBlock;
-    for (unsigned long long sl = (unsigned long long)blockIdx.x * 8 + wib; sl < slots; sl += (unsigned long long)gridDim.x * 8) {
-        const uint32_t b = (uint32_t)(sl / kRawBlock), e = (uint32_t)(sl % kRawBlock);
-        if (e >= __ldg(blk_count + b)) continue;
-        {
-            const uint32_t* ent = raw + sl * kRawWords;
-            const uint32_t w = __ldg(ent + lane);
-            Cand cd; cd.pos = __ldg(ent + 32);
-            const uint32_t first = __ldg(ent + 33);
+    for (unsigned long long s0 = ((unsigned long long)blockIdx.x * 8 + wib) * 4; s0 < slots; s0 += (unsigned long long)gridDim.x * 8 * 4) {
+        const uint32_t b = (uint32_t)(s0 / kRawBlock), e0 = (uint32_t)(s0 % kRawBlock);       // kRawBlock % 4 == 0: same block
+        const uint32_t cnt = __ldg(blk_count + b);
+        uint32_t w[4], pos[4], first[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t* ent = raw + (s0 + k) * kRawWords;
+            const bool live = e0 + k < cnt;
+            w[k] = live ? __ldg(ent + lane) : 0x80008000u;           // all-negative: no candidate
+            pos[k] = live ? __ldg(ent + 32) : 0u;
+            first[k] = live ? __ldg(ent + 33) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (e0 + k >= cnt) break;                                 // warp-uniform
+            Cand cd; cd.pos = pos[k];
             if (ACC16) {
-                const bool lo = !(w & 0x8000u), hi = !(w & 0x80000000u);
+                const bool lo = !(w[k] & 0x8000u), hi = !(w[k] & 0x80000000u);
                 const unsigned blo = __ballot_sync(0xffffffffu, lo), bhi = __ballot_sync(0xffffffffu, hi);
-                if (lo) { cd.col = first + 2 * lane;     st[n + __popc(blo & lt)] = cd; }
-                if (hi) { cd.col = first + 2 * lane + 1; st[n + __popc(blo) + __popc(bhi & lt)] = cd; }
+                if (lo) { cd.col = first[k] + 2 * lane;     st[n + __popc(blo & lt)] = cd; }
+                if (hi) { cd.col = first[k] + 2 * lane + 1; st[n + __popc(blo) + __popc(bhi & lt)] = cd; }
                 n += __popc(blo) + __popc(bhi);
             } else {
-                const bool c = (int32_t)w >= 0;
+                const bool c = (int32_t)w[k] >= 0;
                 const unsigned bb = __ballot_sync(0xffffffffu, c);
-                if (c) { cd.col = first + lane; st[n + __popc(bb & lt)] = cd; }
+                if (c) { cd.col = first[k] + lane; st[n + __popc(bb & lt)] = cd; }
                 n += __popc(bb);
             }
-            if (n > 448) flush();
         }
+        if (n > 256) flush();
     }
     if (n) flush();
 }
