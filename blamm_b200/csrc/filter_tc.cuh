@@ -63,13 +63,16 @@ constexpr uint32_t kTcCtasPerSm = TC_CTAS_PER_SM;             // co-resident CTA
 constexpr uint32_t kTcProducers = TC_PRODUCERS;                         // warps filling the E ring, 32 entries of every stage each
 constexpr uint32_t kTcEpiWarp0 = kTcProducers + 1;            // first epilogue warp (warp kTcProducers issues the MMAs)
 constexpr int      kTcThreads  = 32 * (kTcProducers + 1 + kTcEpiWarps);
-constexpr uint32_t kTcSpan     = 32768;      // windows per work item
+#ifndef TC_SPAN
+#define TC_SPAN 32768
+#endif
+constexpr uint32_t kTcSpan     = TC_SPAN;    // windows per work item
 constexpr uint32_t kTcStages   = 8;          // E ring stages (128 entries = 2 KB each)
 constexpr uint32_t kTcMirror   = 64;         // entries mirrored past the ring end (>= 2*(2*nK_max-1))
 constexpr uint32_t kTcMaxN     = TC_MAXN;     // columns per tile; 2 accumulator buffers of kTcMaxN TMEM columns per CTA
 static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N columns x CTAs per SM must fit 512 columns");
 static_assert(128 % TC_PRODUCERS == 0 && TC_EPI_WARPS % 4 == 0, "warp role split");
-constexpr uint32_t kRawBlock   = 32;         // raw entries per block (an epilogue warp reserves a block at a time)
+constexpr uint32_t kRawBlock   = 64;         // raw entries per block (an epilogue warp reserves a block at a time)
 constexpr uint32_t kRawWords   = 40;         // 32 TMEM words + {window, first column} + padding = 160 B per entry (32 B aligned)
 
 struct TcTile {
@@ -259,25 +262,31 @@ __device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, 
     rc.next = P.raw + (size_t)min(rc.blk, P.blk_cap) * (kRawBlock * kRawWords);
     rc.left = kRawBlock;
 }
-__device__ __forceinline__ void st_global_v8(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+// Predicated raw-entry store (no branch, no divergence): four 256-bit stores of the lane's 32 words + {window, column}.
+__device__ __forceinline__ void st_entry_pred(bool p, uint32_t* d, const uint32_t (&v)[32], uint32_t win, uint32_t col) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %35, 0;\n"
+                 "@q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 "@q st.global.v8.b32 [%0+32], {%9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 "@q st.global.v8.b32 [%0+64], {%17, %18, %19, %20, %21, %22, %23, %24};\n"
+                 "@q st.global.v8.b32 [%0+96], {%25, %26, %27, %28, %29, %30, %31, %32};\n"
+                 "@q st.global.v2.b32 [%0+128], {%33, %34};\n}"
+                 ::"l"(d), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]),
+                   "r"(win), "r"(col), "r"((uint32_t)p) : "memory");
 }
-// Every lane with `mine` appends its 32 words + {window, first column} to the warp's current block: four 256-bit and one
-// 128-bit fire-and-forget stores per candidate lane (~2e-4 of the accumulators are candidates).
-__device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, const uint32_t (&v)[32], bool mine, uint32_t win,
-                                         uint32_t col_base, uint32_t lane) {
-    const unsigned todo = __ballot_sync(0xffffffffu, mine);
-    if (!todo) return;
-    const uint32_t n = __popc(todo);
-    if (n > rc.left) raw_new_block(rc, P, lane);
-    if (mine) {
-        uint32_t* d = rc.next + __popc(todo & ((1u << lane) - 1u)) * kRawWords;
-        st_global_v8(d,      v[0],  v[1],  v[2],  v[3],  v[4],  v[5],  v[6],  v[7]);
-        st_global_v8(d + 8,  v[8],  v[9],  v[10], v[11], v[12], v[13], v[14], v[15]);
-        st_global_v8(d + 16, v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
-        st_global_v8(d + 24, v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
-        *reinterpret_cast<uint2*>(d + 32) = make_uint2(win, col_base);
+// Lanes with c0 / c1 append the 32 words of chunk 0 / chunk 1 (+ {window, first column}) to the warp's current block:
+// one pair of ballots, one cursor update, predicated fire-and-forget stores (~2e-4 of the accumulators are candidates).
+__device__ __forceinline__ void raw_push2(RawCursor& rc, const TcParams& P, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                          bool c0, bool c1, uint32_t win, uint32_t col0, uint32_t col1, uint32_t lane) {
+    const unsigned t0 = __ballot_sync(0xffffffffu, c0), t1 = __ballot_sync(0xffffffffu, c1);
+    const uint32_t n0 = __popc(t0), n = n0 + __popc(t1);
+    if (n > rc.left) raw_new_block(rc, P, lane);            // n <= 64 = kRawBlock
+    const uint32_t lt = (1u << lane) - 1u;
+    if (!(TC_KNOCKOUT & 16)) {
+        st_entry_pred(c0, rc.next + __popc(t0 & lt) * kRawWords, v0, win, col0);
+        st_entry_pred(c1, rc.next + (n0 + __popc(t1 & lt)) * kRawWords, v1, win, col1);
     }
     rc.next += n * kRawWords;
     rc.left -= n;
@@ -459,10 +468,9 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     }
                     // both reductions first (independent trees interleave in the issue slots), then ONE test and ONE vote
                     const uint32_t a0 = and_tree32(v0), a1 = has1 ? and_tree32(v1) : 0xffffffffu;
-                    if (!(TC_KNOCKOUT & 8) && __any_sync(0xffffffffu, winOk && any_nonneg<ACC16>(a0 & a1))) {
-                        raw_push(rawc, P, v0, winOk && any_nonneg<ACC16>(a0), win0 + lane, tile.col0 + wc * kColsPerWord, lane);
-                        if (has1) raw_push(rawc, P, v1, winOk && any_nonneg<ACC16>(a1), win0 + lane, tile.col0 + (wc + step) * kColsPerWord, lane);
-                    }
+                    if (!(TC_KNOCKOUT & 8) && __any_sync(0xffffffffu, winOk && any_nonneg<ACC16>(a0 & a1)))
+                        raw_push2(rawc, P, v0, v1, winOk && any_nonneg<ACC16>(a0), has1 && winOk && any_nonneg<ACC16>(a1), win0 + lane,
+                                  tile.col0 + wc * kColsPerWord, tile.col0 + (wc + step) * kColsPerWord, lane);
                 }
                 if (!released) {                                      // this warp owns no chunk of such a narrow tile
                     tc_fence_before();

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/.."
 V=blamm_b200/lib/variants
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared blamm_b200/csrc/b200scan.cu"
-declare -A VAR=( [base]="" [ko_fifo]="-DTC_KNOCKOUT=8" [c2]="-DTC_MAXN=128 -DTC_CTAS_PER_SM=2 -DTC_EPI_WARPS=4 -DTC_PRODUCERS=2" )
+declare -A VAR=( [base]="" [nostore]="-DTC_KNOCKOUT=16" )
 if [ "$1" = build ]; then
   mkdir -p $V
   for k in "${!VAR[@]}"; do $NV ${VAR[$k]} $EXTRA -o $V/$k.so & done; wait; ls -la $V
