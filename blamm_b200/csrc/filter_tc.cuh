@@ -24,16 +24,18 @@
 // Roofline: tensor pipe.  One tcgen05.mma (M=128, N, K=16) covers 4 motif positions of N columns for 128
 // windows and takes N/2 cycles; the epilogue must drain 128 x N FP32 accumulators per tile from TMEM.
 //
-// Warp roles (416 threads, 1 CTA/SM, persistent with an atomic work counter):
-//   warps 0..3   producers: codes -> E ring (8 stages of 128 entries + mirrored halo) through a 16-entry one-hot LUT,
-//                32 entries of every stage each (a single producer warp needed ~650 cycles per stage and set the pace)
-//   warp 4       TMEM allocation; one elected lane issues tcgen05.mma / tcgen05.commit (B/codes bulk loads: thread 0)
-//   warps 5..12  epilogue, two warps per TMEM lane quarter; warp k of a quarter owns the 32-word chunks k, k+2, ... of
-//                every tile: tcgen05.ld 32x32b.x32 into registers, RELEASE the TMEM buffer at once, tree-shaped AND of
-//                the sign bits.  A lane that saw a non-negative accumulator stores its 32 words + {window, column} as
-//                one raw entry in global memory (blocks of 32 entries reserved per warp: fire-and-forget stores, one
-//                atomic per block) -- the epilogue's per-tile time must not depend on how many candidates it meets,
-//                because every warp has to release a buffer before the next MMAs may start.
+// Warp roles (608 threads, 1 CTA/SM, persistent with an atomic work counter):
+//   warps 0..1   producers: codes -> E ring (8 stages of 128 entries + mirrored halo) through a 16-entry one-hot LUT,
+//                64 entries of every stage each (a single producer warp needed ~650 cycles per stage and set the pace)
+//   warp 2       TMEM allocation; one elected lane issues tcgen05.mma / tcgen05.commit (B/codes bulk loads: thread 0)
+//   warps 3..18  epilogue: TWO independent groups of 8 warps, group g owns TMEM buffer g (even / odd window tiles).
+//                Within a group two warps share each TMEM lane quarter and split the tile's 32-word chunks:
+//                tcgen05.ld 32x32b.x32 into registers, RELEASE the TMEM buffer at once, tree-shaped AND of the sign
+//                bits.  A lane that saw a non-negative accumulator stores its 32 words + {window, column} as one raw
+//                entry in global memory (blocks of 64 entries reserved ahead of time, predicated fire-and-forget
+//                stores).  Because a buffer is released right after the load, a group has a whole buffer round trip
+//                (~1100 cycles) for its ~650 cycles of work per tile: candidate pushes land in slack instead of
+//                delaying the next MMAs (with one group of 8 warps every tile paid for its slowest warp).
 //   expand_kernel (rescore.cuh) later turns raw entries into (position, column) candidates for the exact rescorer.
 #pragma once
 #include "common.cuh"
@@ -41,13 +43,16 @@
 namespace b200 {
 
 #ifndef TC_EPI_WARPS
-#define TC_EPI_WARPS 8
+#define TC_EPI_WARPS 16
 #endif
 #ifndef TC_KNOCKOUT
 #define TC_KNOCKOUT 0      // diagnostic only: 1 skip epilogue ld+reduce, 2 skip MMA issue, 4 skip producer fill, 8 skip FIFO push
 #endif
+#ifndef TC_EPI_GROUPS
+#define TC_EPI_GROUPS 2       // 2: two independent groups of epilogue warps, group g owns TMEM buffer g (even / odd tiles)
+#endif
 #ifndef TC_PRODUCERS
-#define TC_PRODUCERS 4
+#define TC_PRODUCERS 2
 #endif
 #ifndef TC_BUFS
 #define TC_BUFS 2
@@ -71,7 +76,8 @@ constexpr uint32_t kTcStages   = 8;          // E ring stages (128 entries = 2 K
 constexpr uint32_t kTcMirror   = 64;         // entries mirrored past the ring end (>= 2*(2*nK_max-1))
 constexpr uint32_t kTcMaxN     = TC_MAXN;     // columns per tile; 2 accumulator buffers of kTcMaxN TMEM columns per CTA
 static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N columns x CTAs per SM must fit 512 columns");
-static_assert(128 % TC_PRODUCERS == 0 && TC_EPI_WARPS % 4 == 0, "warp role split");
+static_assert(128 % TC_PRODUCERS == 0 && TC_EPI_WARPS % (4 * TC_EPI_GROUPS) == 0 && (TC_EPI_GROUPS == 1 || TC_BUFS == 2), "warp role split");
+constexpr uint32_t kTcEpiGroups = TC_EPI_GROUPS;
 constexpr uint32_t kRawBlock   = 64;         // raw entries per block (an epilogue warp reserves a block at a time)
 constexpr uint32_t kRawWords   = 40;         // 32 TMEM words + {window, first column} + padding = 160 B per entry (32 B aligned)
 
@@ -302,7 +308,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     constexpr uint32_t kBufs    = TC_BUFS;              // TMEM accumulator buffers
     constexpr uint32_t kBufCols = kTcMaxN;              // TMEM columns per buffer: one accumulator per column, FP32 or FP16
     constexpr uint32_t kColsPerWord = ACC16 ? 2 : 1;
-    constexpr uint32_t kEpiPerQ = kTcEpiWarps / 4;
+    constexpr uint32_t kEpiPerQ = kTcEpiWarps / 4 / kTcEpiGroups;      // warps sharing one TMEM lane quarter of one tile
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     if (__ldg(blk.has_zero) != 0) return;                       // zero-mask blocks take the gather kernel
@@ -323,7 +329,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, kTcProducers); mbar_init(eEmpty + 8 * i, 1); }
-        for (uint32_t i = 0; i < kBufs; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, kTcEpiWarps); }
+        for (uint32_t i = 0; i < kBufs; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, kTcEpiWarps / kTcEpiGroups); }
         mbar_init(cBar, 1); mbar_init(bBar, 1);
         fence_mbar_init();
     }
@@ -438,10 +444,12 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
             const uint32_t q = warp & 3;                              // TMEM lane quarter this warp may read
-            const uint32_t sub = (warp - kTcEpiWarp0) >> 2;           // which of the quarter's warps
+            const uint32_t ew = (warp - kTcEpiWarp0) >> 2;            // index among the warps of this TMEM lane quarter
+            const uint32_t group = ew % kTcEpiGroups, sub = ew / kTcEpiGroups;
             const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
             for (uint32_t i = 0; i < nT; i++) {
                 const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
+                if (kTcEpiGroups > 1 && buf != group) continue;       // the other group's tile
                 mbar_wait(tFull + 8 * buf, tph, P.error_flag);
                 if (warp == kTcEpiWarp0) TC_TRACE(2, i, 0); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 0);
                 tc_fence_after();

@@ -174,23 +174,24 @@ struct ScanShared {
     ofstream* os = nullptr;
     mutex outMutex;
     uint64_t totMatches = 0;
+    size_t formatThreads = 1;
     // job queue (producer = FASTA reader, consumers = one thread per GPU)
     mutex qMutex; condition_variable qCv;
     deque<unique_ptr<Job>> queue; bool done = false; size_t maxQueue = 2;
     string error; atomic<bool> failed{false};
 };
 
-// hits of one block -> text lines (reference format: pwmscan.cpp:88-95), in (position, column) order
-void writeHits(ScanShared& sh, const Job& job, const b200scan_hit* hits, uint64_t n)
+// hits of one block -> text lines (reference format: pwmscan.cpp:88-95), in (position, column) order.
+// The block is cut into position ranges; each formatting thread sorts and formats its range, the pieces are
+// written in order under the output mutex (the reference formats outside and writes inside its mutex too, :99).
+void formatRange(const ScanShared& sh, const Job& job, std::vector<b200scan_hit>& hits, std::string& text)
 {
-    vector<b200scan_hit> sorted(hits, hits + n);
-    sort(sorted.begin(), sorted.end(), [](const b200scan_hit& a, const b200scan_hit& b) {
+    sort(hits.begin(), hits.end(), [](const b200scan_hit& a, const b200scan_hit& b) {
         return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; });
-    string text;
-    text.reserve(n * 56);
+    text.reserve(hits.size() * 56);
     char num[64];
     size_t f = 0;
-    for (const auto& h : sorted) {
+    for (const auto& h : hits) {
         while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= h.pos) f++;
         const Fragment& fr = job.frags[f];
         const uint64_t seqPos = fr.seqPos + (h.pos - fr.streamPos);
@@ -205,12 +206,31 @@ void writeHits(ScanShared& sh, const Job& job, const b200scan_hit* hits, uint64_
         text += m.revComp ? '-' : '+';
         text += "\t.\t.\n";
     }
-    lock_guard<mutex> lock(sh.outMutex);
-    sh.totMatches += n;
-    sh.os->write(text.data(), (streamsize)text.size());
 }
 
-void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, int engine, bool foldLower)
+void writeHits(ScanShared& sh, const Job& job, const b200scan_hit* hits, uint64_t n)
+{
+    const size_t T = std::max<size_t>(1, std::min<size_t>(sh.formatThreads, n / 50000 + 1));
+    vector<vector<b200scan_hit>> part(T);
+    if (T == 1) part[0].assign(hits, hits + n);
+    else {
+        const uint64_t span = job.nPayload / T + 1;
+        vector<size_t> cnt(T, 0);
+        for (uint64_t i = 0; i < n; i++) cnt[hits[i].pos / span]++;
+        for (size_t t = 0; t < T; t++) part[t].reserve(cnt[t]);
+        for (uint64_t i = 0; i < n; i++) part[hits[i].pos / span].push_back(hits[i]);
+    }
+    vector<string> text(T);
+    vector<thread> pool;
+    for (size_t t = 1; t < T; t++) pool.emplace_back(formatRange, cref(sh), cref(job), ref(part[t]), ref(text[t]));
+    formatRange(sh, job, part[0], text[0]);
+    for (auto& th : pool) th.join();
+    lock_guard<mutex> lock(sh.outMutex);
+    sh.totMatches += n;
+    for (const auto& t : text) sh.os->write(t.data(), (streamsize)t.size());
+}
+
+void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, int engine, bool foldLower)
 {
     b200scan_ctx* ctx = nullptr;
     auto die = [&](const string& what) {
@@ -218,7 +238,7 @@ void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, int engine, bool f
         if (!sh.failed.exchange(true)) sh.error = what;
         sh.qCv.notify_all();
     };
-    if (b200scan_create(&ctx, dev, maxBlock, 0) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(nullptr)); return; }
+    if (b200scan_create(&ctx, dev, maxBlock, maxHits) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(nullptr)); return; }
     const auto len = sh.motifs->colLen();
     const auto thr = sh.motifs->colThr();
     if (b200scan_set_engine(ctx, engine) != B200SCAN_OK ||
@@ -295,7 +315,6 @@ int runScan(int argc, char** argv)
         else if ((arg == "-o" || arg == "--output") && hasVal) outputFilename = argv[++i];
         else { scanUsage(); return EXIT_FAILURE; }
     }
-    (void)numThreads;
     if (!(absSpec || relSpec || pSpec)) relSpec = true;
     if (absSpec && relSpec) throw runtime_error("Specify either the absolute or relative threshold, not both.");
     if (absSpec && pSpec) throw runtime_error("Specify either the absolute or p-value threshold, not both.");
@@ -351,9 +370,13 @@ int runScan(int argc, char** argv)
 
         ScanShared sh;
         sh.motifs = &mc; sh.species = &sp; sh.os = &os;
+        sh.formatThreads = std::max<size_t>(1, numThreads / (size_t)nDev);
         const uint64_t maxBlock = min<uint64_t>(chunk, max<uint64_t>(sp.totSeqLen, 1024)) + halo + 64;
         vector<thread> workers;
-        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), d, maxBlock, engine, foldLower);
+        // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block)
+        const double rate = pSpec ? std::min(1.0, 3.0 * pvalue) : 2e-4;
+        const uint64_t maxHits = std::max<uint64_t>(1 << 20, (uint64_t)(rate * (double)maxBlock * (double)mc.motifs.size()));
+        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), d, maxBlock, maxHits, engine, foldLower);
         try {
             FastaStream fs(sp.files, sp.totSeqLen);
             FastaStream::Chunk c;
