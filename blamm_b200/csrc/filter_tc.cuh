@@ -351,6 +351,13 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     RawCursor rawc; rawc.blk = 0xffffffffu; rawc.left = 0; rawc.next = P.raw; rawc.spare = 0;
     if (warp >= kTcEpiWarp0 && lane == 0) rawc.spare = atomicAdd(P.n_blocks, 1u);      // epilogue warps: reserve the first block early
     const uint32_t nItems = P.n_tiles * P.n_spans;
+    // Epilogue role constants, made opaque to the optimiser: with 64 accumulator registers live it otherwise
+    // re-derives them from threadIdx inside every tile iteration (each a ~5-cycle dependent ALU step for this warp).
+    uint32_t eQ = warp & 3;                                            // TMEM lane quarter this warp may read
+    uint32_t eGroup = ((warp - kTcEpiWarp0) >> 2) % kTcEpiGroups;      // which epilogue group (= TMEM buffer with 2 groups)
+    uint32_t eWc0 = 32 * (((warp - kTcEpiWarp0) >> 2) / kTcEpiGroups); // first 32-word chunk of a tile this warp owns
+    uint32_t eLaneAddr = tmem_base + ((32 * eQ) << 16);
+    asm volatile("" : "+r"(eQ), "+r"(eGroup), "+r"(eWc0), "+r"(eLaneAddr));
 
     while (true) {
         if (threadIdx.x == 0) sMisc[0] = atomicAdd(P.work_counter, 1u);
@@ -443,25 +450,23 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             __syncwarp();
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
-            const uint32_t q = warp & 3;                              // TMEM lane quarter this warp may read
-            const uint32_t ew = (warp - kTcEpiWarp0) >> 2;            // index among the warps of this TMEM lane quarter
-            const uint32_t group = ew % kTcEpiGroups, sub = ew / kTcEpiGroups;
             const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
-            for (uint32_t i = 0; i < nT; i++) {
-                const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
-                if (kTcEpiGroups > 1 && buf != group) continue;       // the other group's tile
+            // with two groups, group g takes the tiles whose running index is g mod 2 (= the tiles of TMEM buffer g)
+            const uint32_t i0 = (kTcEpiGroups > 1) ? ((eGroup - kT) & (kTcEpiGroups - 1)) : 0u;
+            uint32_t kt = kT + i0, win0 = w0 + 128 * i0 + 32 * eQ;    // running tile index; window of lane 0
+            for (uint32_t i = i0; i < nT; i += kTcEpiGroups, kt += kTcEpiGroups, win0 += 128 * kTcEpiGroups) {
+                const uint32_t buf = kt % kBufs, tph = (kt / kBufs) & 1;
                 mbar_wait(tFull + 8 * buf, tph, P.error_flag);
                 if (warp == kTcEpiWarp0) TC_TRACE(2, i, 0); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 0);
                 tc_fence_after();
-                const uint32_t win0 = w0 + 128 * i + 32 * q;          // window of lane 0
                 const bool winOk = win0 + lane < blk.n_payload;
-                const uint32_t taddr = tmem_base + ((32 * q) << 16) + buf * kBufCols;
+                const uint32_t taddr = eLaneAddr + buf * kBufCols;
                 // this warp owns the 32-word chunks sub, sub + kEpiPerQ, sub + 2 kEpiPerQ, ... of the tile, taken two at a
                 // time (both loads in flight).  As soon as its LAST loads have landed in registers the warp hands the
                 // TMEM buffer back, before looking at the data.
                 constexpr uint32_t step = 32 * kEpiPerQ;
                 bool released = false;
-                for (uint32_t wc = 32 * sub; wc < ((TC_KNOCKOUT & 1) ? 0u : nWords); wc += 2 * step) {
+                for (uint32_t wc = eWc0; wc < ((TC_KNOCKOUT & 1) ? 0u : nWords); wc += 2 * step) {
                     const bool has1 = wc + step < nWords;
                     uint32_t v0[32], v1[32];
                     tmem_ld_words<ACC16>(taddr, wc, v0);

@@ -24,13 +24,17 @@ assert L.b200scan_debug_trace(sc._ctx, buf, n) == 0
 T = np.frombuffer(buf, dtype=np.uint64).reshape(4, 256, 4).astype(np.int64)
 t0 = T[T > 0].min()
 T = np.where(T > 0, T - t0, -1)
-print("tile |  producer(wait,done) |  MMA(eFull, tEmpty, issued) | epi w2 (tFull, ld, released, done) | epi w9 (...)")
+print("tile |  producer(wait,done) |  MMA(eFull, tEmpty, issued) | epi first warp (tFull, -, released, done) | epi 8th warp (...)   [with 2 epilogue groups a warp only sees every other tile]")
 for i in list(range(0, 12)) + list(range(100, 112)):
     print("%4d | %6d %6d | %6d %6d %6d | %6d %6d %6d %6d | %6d %6d %6d %6d" % ((i,) + tuple(T[0, i, :2]) + tuple(T[1, i, :3]) + tuple(T[2, i]) + tuple(T[3, i])))
-sl = slice(60, 200)
-per = np.diff(T[1, sl, 2]).mean()
-print("steady state (tiles 60..200): period %.0f cyc/tile;  MMA warp: wait eFull->tEmpty %.0f, tEmpty->issued %.0f;  epilogue w2: tFull->ld %.0f, ld->release %.0f, release->done %.0f, done->next tFull %.0f" % (
-    per, (T[1, sl, 1] - T[1, sl, 0]).mean(), (T[1, sl, 2] - T[1, sl, 1]).mean(), (T[2, sl, 1] - T[2, sl, 0]).mean(), (T[2, sl, 2] - T[2, sl, 1]).mean(),
-    (T[2, sl, 3] - T[2, sl, 2]).mean(), (T[2, 61:201, 0] - T[2, 60:200, 3]).mean()))
-print("  issue(i) -> tFull seen by w2: %.0f;  release(w2, i) -> MMA tEmpty seen (i+2): %.0f;  producer stage: %.0f busy, %.0f waiting" % (
-    (T[2, sl, 0] - T[1, sl, 2]).mean(), (T[1, 62:202, 1] - T[2, 60:200, 2]).mean(), (T[0, sl, 1] - T[0, sl, 0]).mean(), (T[0, 61:201, 0] - T[0, 60:200, 1]).mean()))
+ev = np.arange(60, 200, 2)          # tiles of group 0 (even) -- valid for one or two epilogue groups
+od = ev + 1
+per = np.diff(T[1, 60:200, 2]).mean()
+def m(x): return float(np.mean(x))
+print("steady state: period %.0f cyc/tile | MMA warp: eFull->tEmpty wait %.0f, tEmpty->issued %.0f | producer: %.0f busy, %.0f waiting" % (
+    per, m(T[1, 60:200, 1] - T[1, 60:200, 0]), m(T[1, 60:200, 2] - T[1, 60:200, 1]), m(T[0, 60:200, 1] - T[0, 60:200, 0]), m(T[0, 61:201, 0] - T[0, 60:200, 1])))
+for name, r, tiles in (("first epilogue warp", 2, ev), ("8th epilogue warp", 3, od if T[3, 61, 0] > 0 else ev)):
+    print("  %s: MMA issued -> tFull seen %.0f | tFull -> released %.0f | released -> done %.0f | done -> its next tFull %.0f" % (
+        name, m(T[r, tiles, 0] - T[1, tiles, 2]), m(T[r, tiles, 2] - T[r, tiles, 0]), m(T[r, tiles, 3] - T[r, tiles, 2]),
+        m(T[r, tiles[1:], 0] - T[r, tiles[:-1], 3])))
+    print("     released(i) -> MMA sees tEmpty for tile i+2: %.0f" % m(T[1, tiles[:-1] + 2, 1] - T[r, tiles[:-1], 2]))
