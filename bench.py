@@ -38,6 +38,18 @@ N_MOTIFS, MOTIF_SEED, SEQ_SEED = 900, 2024, 4242
 SPECIES = "syn"
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_filter_traffic.json")))
+    if not files:
+        return None
+    try:
+        return json.load(open(files[-1]))["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -320,7 +332,7 @@ def main() -> None:
                         "d2h_bytes_per_step": int(d2h // args.steps), "ms_per_step": e2e_ms / args.steps,
                         "stages_ms": {k: t_e2e[k] for k in ("h2d_ms", "pack_ms", "score_ms", "rescore_ms", "d2h_ms")}},
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                             "traffic": None, "peak_source": how + ", bf16 cuBLAS burst; sustained %.0f" % sustained,
+                             "traffic": measured_traffic() if (engine_used != "gather" and abs(args.mbp - 100.0) < 1e-9) else None, "peak_source": how + ", bf16 cuBLAS burst; sustained %.0f" % sustained,
                              "kernel": "filter_tc_kernel" if engine_used != "gather" else "gather_scan_kernel",
                              "kernel_ms": k_ms / args.steps, "algorithmic_flops_per_launch": flops_per_launch},
             }
