@@ -57,6 +57,9 @@ def scan_lib() -> ctypes.CDLL:
         L.b200scan_submit_packed.argtypes = [vp, ctypes.c_int, vp, vp, u64, u64, vp, u64]
         L.b200scan_collect.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), _u64p, ctypes.POINTER(Timing)]
         L.b200scan_rerun_resident.argtypes = [vp, ctypes.c_int, ctypes.c_int, f32p, f32p, _u64p]
+        L.b200scan_hist_begin.argtypes = [vp, vp, vp, ctypes.c_uint32]
+        L.b200scan_hist_block_ascii.argtypes = [vp, vp, u64, u64, vp, u64, ctypes.c_int]
+        L.b200scan_hist_read.argtypes = [vp, vp, u64]
         L.b200scan_flush_l2.argtypes = [vp]
         L.b200scan_describe.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), _u64p]
         _scan = L
@@ -188,6 +191,23 @@ class Scanner:
         tot, sc, nh = ctypes.c_float(), ctypes.c_float(), ctypes.c_uint64()
         self._chk(self._L.b200scan_rerun_resident(self._ctx, slot, iters, ctypes.byref(tot), ctypes.byref(sc), ctypes.byref(nh)))
         return tot.value, sc.value, nh.value
+
+    def hist_begin(self, col_min: np.ndarray, col_max: np.ndarray, num_bins: int) -> None:
+        mn = np.ascontiguousarray(col_min, dtype=np.float32); mx = np.ascontiguousarray(col_max, dtype=np.float32)
+        self._hist_shape = (len(mn), num_bins)
+        self._chk(self._L.b200scan_hist_begin(self._ctx, mn.ctypes.data, mx.ctypes.data, num_bins))
+
+    def hist_block(self, block, frag_starts=None, n_payload: Optional[int] = None, lower: int = LOWER_ZERO) -> None:
+        buf = np.frombuffer(block, dtype=np.uint8) if isinstance(block, (bytes, bytearray)) else np.ascontiguousarray(block, dtype=np.uint8)
+        n_payload = len(buf) if n_payload is None else n_payload
+        fs = np.ascontiguousarray(frag_starts if frag_starts is not None else [], dtype=np.uint64)
+        self._chk(self._L.b200scan_hist_block_ascii(self._ctx, buf.ctypes.data if len(buf) else None, len(buf), n_payload,
+                                                    fs.ctypes.data if len(fs) else None, len(fs), lower))
+
+    def hist_read(self) -> np.ndarray:
+        out = np.zeros(self._hist_shape, dtype=np.uint64)
+        self._chk(self._L.b200scan_hist_read(self._ctx, out.ctypes.data, out.size))
+        return out
 
     def flush_l2(self) -> None:
         self._chk(self._L.b200scan_flush_l2(self._ctx))

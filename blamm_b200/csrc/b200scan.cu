@@ -76,6 +76,10 @@ struct b200scan_ctx {
     double cand_inflation = 0;    // mean margin over columns (diagnostic)
     uint8_t* d_flush = nullptr;
     unsigned long long* d_trace = nullptr;   // B200_TRACE builds only
+    // empirical histograms
+    uint32_t hist_bins = 0;  unsigned long long* d_hist = nullptr;  float *d_hmin = nullptr, *d_hwid = nullptr;
+    GatherTile* d_htiles = nullptr;  std::vector<GatherTile> htiles;  size_t hist_smem = 0;
+    std::vector<uint32_t> h_len_sorted, h_woff_sorted, h_orig_sorted;      // host copies of the sorted column metadata
 };
 
 namespace {
@@ -311,6 +315,8 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     CU(cudaMemcpy(ctx->d_ttiles, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_bimg, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
     ctx->gtiles = gt; ctx->ttiles = tt;
+    ctx->h_len_sorted = len; ctx->h_woff_sorted = woff; ctx->h_orig_sorted = orig;
+    ctx->hist_bins = 0;
     ctx->n_cols = (uint32_t)n_cols; ctx->max_len = max_len; ctx->sum_len = sum_len;
     ctx->tc_usable = tc_ok;
     ctx->have_motifs = true;
@@ -532,6 +538,7 @@ void b200scan_destroy(b200scan_ctx* c)
     dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_flush);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg);
+    dfree(c->d_hist); dfree(c->d_hmin); dfree(c->d_hwid); dfree(c->d_htiles);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -636,6 +643,92 @@ int b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2, 
     CU(cudaEventRecord(s.ev[1], ctx->stream));
     CU(cudaEventRecord(s.ev[2], ctx->stream));
     return finish_submit(ctx, s);
+}
+
+int b200scan_hist_begin(b200scan_ctx* ctx, const float* col_min, const float* col_max, uint32_t num_bins)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (!ctx->have_motifs) return fail(ctx, B200SCAN_ESTATE, "b200scan_set_motifs has not been called");
+    if (!col_min || !col_max || num_bins == 0) return fail(ctx, B200SCAN_EINVAL, "hist_begin: NULL or empty input");
+    for (auto& sl : ctx->slot) if (sl.in_flight) return fail(ctx, B200SCAN_ESTATE, "hist_begin while a block is in flight");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n = ctx->n_cols;
+    // column tiles: FP32 weights + metadata + u32 histograms of the tile must fit in shared memory
+    const size_t budget = 160 * 1024;
+    std::vector<GatherTile> ht;
+    size_t max_smem = 0;
+    for (uint32_t sc = 0; sc < n;) {
+        GatherTile t{sc, 0, ctx->h_woff_sorted[sc], 0};
+        auto need = [&](uint32_t nw, uint32_t nc) { return (size_t)nw * 16 + (size_t)nc * (16 + (size_t)num_bins * 4); };
+        while (sc < n && t.n_cols < 256 && need(t.n_w + ctx->h_len_sorted[sc], t.n_cols + 1) <= budget) {
+            t.n_w += ctx->h_len_sorted[sc]; t.n_cols++; sc++;
+        }
+        if (t.n_cols == 0) return fail(ctx, B200SCAN_ELIMIT, "num_bins %u too large for the shared-memory histograms", num_bins);
+        max_smem = std::max(max_smem, need(t.n_w, t.n_cols));
+        ht.push_back(t);
+    }
+    std::vector<float> mn(n), wid(n);
+    for (uint32_t sc = 0; sc < n; sc++) {
+        const uint32_t c = ctx->h_orig_sorted[sc];
+        mn[sc] = col_min[c];
+        wid[sc] = (col_max[c] - col_min[c]) / (float)num_bins;        // ScoreHistogram ctor, motif.h:66
+    }
+    dfree(ctx->d_hist); dfree(ctx->d_hmin); dfree(ctx->d_hwid); dfree(ctx->d_htiles);
+    CU(cudaMalloc(&ctx->d_hist, (size_t)n * num_bins * 8));
+    CU(cudaMemset(ctx->d_hist, 0, (size_t)n * num_bins * 8));
+    CU(cudaMalloc(&ctx->d_hmin, 4 * n)); CU(cudaMalloc(&ctx->d_hwid, 4 * n));
+    CU(cudaMalloc(&ctx->d_htiles, sizeof(GatherTile) * ht.size()));
+    CU(cudaMemcpy(ctx->d_hmin, mn.data(), 4 * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_hwid, wid.data(), 4 * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_htiles, ht.data(), sizeof(GatherTile) * ht.size(), cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(gather_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    ctx->htiles = ht; ctx->hist_smem = max_smem; ctx->hist_bins = num_bins;
+    return B200SCAN_OK;
+}
+
+int b200scan_hist_block_ascii(b200scan_ctx* ctx, const char* block, uint64_t n_total, uint64_t n_payload,
+                              const uint64_t* frag_starts, uint64_t n_frag, int lowercase_mode)
+{
+    int rc = check_common(ctx, 0, n_total, n_payload, frag_starts, n_frag);
+    if (rc) return rc;
+    if (!ctx->hist_bins) return fail(ctx, B200SCAN_ESTATE, "b200scan_hist_begin has not been called");
+    if (!block && n_total) return fail(ctx, B200SCAN_EINVAL, "block is NULL");
+    if (lowercase_mode != B200SCAN_LOWER_ZERO && lowercase_mode != B200SCAN_LOWER_FOLD) return fail(ctx, B200SCAN_EINVAL, "bad lowercase_mode");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    CU(cudaStreamSynchronize(ctx->stream));                 // the previous block still reads the staging buffers
+    s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag; s.resident = false;
+    if (n_total == 0 || n_payload == 0) return B200SCAN_OK;
+    std::memcpy(s.h_ascii, block, n_total);
+    CU(cudaMemcpyAsync(s.d_ascii, s.h_ascii, n_total, cudaMemcpyHostToDevice, ctx->stream));
+    rc = stage_frags(ctx, s, frag_starts, n_frag);
+    if (rc) return rc;
+    rc = reset_counters(ctx, s, false);
+    if (rc) return rc;
+    const unsigned threads = (unsigned)((n_total + 31) / 32);
+    pack_ascii_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(s.d_ascii, (uint32_t)n_total, lowercase_mode == B200SCAN_LOWER_FOLD,
+                                                                      s.d_codes, s.d_zmask, reinterpret_cast<uint32_t*>(s.d_counters + 2));
+    const MotifDev md = motif_dev(ctx);
+    const BlockDev blk = block_dev(s);
+    const dim3 grid((unsigned)((n_payload + kHistSpan - 1) / kHistSpan), (unsigned)ctx->htiles.size());
+    gather_hist_kernel<false><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 0);
+    gather_hist_kernel<true><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 1);
+    CU(cudaGetLastError());
+    return B200SCAN_OK;
+}
+
+int b200scan_hist_read(b200scan_ctx* ctx, uint64_t* counts, uint64_t n_counts)
+{
+    if (!ctx || !counts) return B200SCAN_EINVAL;
+    if (!ctx->hist_bins) return fail(ctx, B200SCAN_ESTATE, "b200scan_hist_begin has not been called");
+    if (n_counts != (uint64_t)ctx->n_cols * ctx->hist_bins) return fail(ctx, B200SCAN_EINVAL, "hist_read: expected %llu counts", (unsigned long long)ctx->n_cols * ctx->hist_bins);
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, B200SCAN_ECUDA, "histogram kernels failed: %s", cudaGetErrorString(e));
+    CU(cudaMemcpy(counts, ctx->d_hist, n_counts * 8, cudaMemcpyDeviceToHost));
+    return B200SCAN_OK;
 }
 
 int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits, b200scan_timing* timing)

@@ -52,6 +52,17 @@ __device__ __forceinline__ bool window_in_fragment(const BlockDev& b, uint32_t p
     return (uint64_t)pos + L <= end;
 }
 
+// Characters left in the fragment that contains pos (SeqBlock::getRemainingSeqLen, sequence.cpp:68-79).
+__device__ __forceinline__ uint32_t fragment_remaining(const BlockDev& b, uint32_t pos)
+{
+    uint32_t lo = 0, hi = b.n_frag;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(b.frag + mid) > pos) hi = mid; else lo = mid + 1;
+    }
+    return ((lo < b.n_frag) ? __ldg(b.frag + lo) : b.n_total) - pos;
+}
+
 // Warp-aggregated append: one global atomic per warp per call (every lane of the warp must call this).
 __device__ __forceinline__ void emit_hits_warp(bool pred, uint32_t pos, uint32_t col, float score,
                                                const HitSink& sink)

@@ -78,8 +78,8 @@ int runDict(int argc, char** argv)
 }
 
 // =========================================================================================================
-// hist  (reference hist.cpp:177-266; theoretical spectra only -- the empirical `-e` mode is the GPU histogram
-//        epilogue listed as "next" in DESIGN.md and is refused rather than silently computed on the CPU)
+// hist  (reference hist.cpp:177-266).  Theoretical spectra are computed on the host (cheap); the empirical mode `-e`
+//        scores the first -l characters of every group on the GPU (b200scan_hist_*), never on the CPU.
 // =========================================================================================================
 static void histUsage()
 {
@@ -110,7 +110,6 @@ int runHist(int argc, char** argv)
         else { histUsage(); return EXIT_FAILURE; }
     }
     cout << "Welcome to blamm -- histogram module" << endl;
-    if (empirical) throw runtime_error("Empirical histograms (-e) are not available in this build; omit -e for theoretical spectra.");
     Settings settings;
     SpeciesSet sc;
     sc.loadDict(string(argv[argc - 1]) + ".dict");
@@ -118,17 +117,50 @@ int runHist(int argc, char** argv)
     mc.load(argv[argc - 2], false);
     cout << "Loaded " << mc.motifs.size() << " motifs from disk";
     cout << "\nMaximum motif size: " << mc.maxLen() << endl;
+    if (mc.motifs.empty()) throw runtime_error("No motifs found in " + string(argv[argc - 2]));
+    b200scan_ctx* ctx = nullptr;
+    const uint64_t halo = mc.maxLen() - 1;
+    const uint64_t chunk = std::min<uint64_t>(maxLength, 32ull << 20);
+    if (empirical) {
+        if (mc.maxLen() > B200SCAN_MAX_MOTIF_LEN)
+            throw runtime_error("Motifs longer than " + to_string(B200SCAN_MAX_MOTIF_LEN) + " positions are not supported by this build");
+        if (b200scan_device_count() == 0) throw runtime_error("CUDA error: no sm_100 devices found. Aborting...");
+        if (b200scan_create(&ctx, 0, chunk + halo + 64, 1024) != B200SCAN_OK)
+            throw runtime_error(string("CUDA error: ") + b200scan_last_error(nullptr));
+    }
+    auto check = [&](int rc) { if (rc != B200SCAN_OK) { string e = b200scan_last_error(ctx); b200scan_destroy(ctx); throw runtime_error("CUDA error: " + e); } };
     for (const auto& sp : sc.species) {
         cout << "Generating histograms for species: " << sp.name;
         sp.printNuclProb(settings.pseudocount);
         mc.generateMatrix(sp.nuclCounts, settings.pseudocount);
         const auto bg = sp.nuclProb(settings.pseudocount);
-        for (const auto& m : mc.motifs) {
-            ScoreHistogram h(m.minScore(), m.maxScore(), numBins);
-            MotifSet::theoreticalHistogram(m, bg, numBins, maxLength, h);
-            h.writeGNUPlot(histdir, "hist_" + sp.name + "_" + m.name, m.name + " (" + sp.name + ")");
+        vector<ScoreHistogram> hists;
+        for (const auto& m : mc.motifs) hists.emplace_back(m.minScore(), m.maxScore(), numBins);
+        if (!empirical) {
+            for (size_t i = 0; i < mc.motifs.size(); i++) MotifSet::theoreticalHistogram(mc.motifs[i], bg, numBins, maxLength, hists[i]);
+        } else {
+            // reference: FastaBatch(filenames, maxLength) + histThread (hist.cpp:95-160)
+            const auto len = mc.colLen();
+            vector<float> thr(len.size(), 0.0f), mn, mx;
+            for (const auto& h : hists) { mn.push_back(h.minScore); mx.push_back(h.maxScore); }
+            check(b200scan_set_motifs(ctx, mc.P().data(), mc.ldp(), (int32_t)len.size(), len.data(), thr.data()));
+            check(b200scan_hist_begin(ctx, mn.data(), mx.data(), (uint32_t)numBins));
+            FastaStream fs(sp.files, maxLength);
+            FastaStream::Chunk c;
+            while (fs.next(chunk, halo, c)) {
+                check(b200scan_hist_block_ascii(ctx, c.chars, c.nTotal, c.nPayload, c.fragStarts.data(), c.fragStarts.size(), B200SCAN_LOWER_ZERO));
+                cout << "."; cout.flush();
+            }
+            cout << endl;
+            vector<uint64_t> counts(len.size() * numBins);
+            check(b200scan_hist_read(ctx, counts.data(), counts.size()));
+            for (size_t i = 0; i < hists.size(); i++)
+                for (size_t b = 0; b < numBins; b++) hists[i].counts[b] = counts[i * numBins + b];
         }
+        for (size_t i = 0; i < hists.size(); i++)
+            hists[i].writeGNUPlot(histdir, "hist_" + sp.name + "_" + mc.motifs[i].name, mc.motifs[i].name + " (" + sp.name + ")");
     }
+    if (ctx) b200scan_destroy(ctx);
     return EXIT_SUCCESS;
 }
 

@@ -142,6 +142,17 @@ int  b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2,
 int  b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits,
                       b200scan_timing* timing);
 
+/* Empirical score histograms (`blamm hist -e`, reference Histogram::histThread + extractObsScore, hist.cpp:70-140):
+ * same scoring as the scan, but instead of thresholding every window that lies inside one fragment adds 1 to bin
+ * clamp(int((score - col_min) / width), 0, num_bins-1) of its column, width = (col_max - col_min) / num_bins in
+ * float (ScoreHistogram, motif.h:62-66, 96-102).  Call after b200scan_set_motifs (thresholds are ignored):
+ *   hist_begin (zeroes the device histograms) -> hist_block_ascii for every block of the stream -> hist_read
+ *   (counts[col * num_bins + bin], column order as passed to set_motifs).  Blocks are accumulated in stream order. */
+int  b200scan_hist_begin(b200scan_ctx* ctx, const float* col_min, const float* col_max, uint32_t num_bins);
+int  b200scan_hist_block_ascii(b200scan_ctx* ctx, const char* block, uint64_t n_total, uint64_t n_payload,
+                               const uint64_t* frag_starts, uint64_t n_frag, int lowercase_mode);
+int  b200scan_hist_read(b200scan_ctx* ctx, uint64_t* counts, uint64_t n_counts);
+
 /* Measurement hook (bench.py `value`): re-run the scoring kernels `iters` times on the block that is
  * already resident in the slot's device buffers (after a submit+collect), timed with CUDA events on the
  * context's stream.  Returns total milliseconds for all iterations and for the dominant kernel alone. */

@@ -267,6 +267,41 @@ uint64_t oracle_scan_stream(const char* stream, uint64_t n, uint64_t n_payload, 
     return nh;
 }
 
+/* ------------------------------------------------------------------------------------------------------
+ * Empirical score histogram = Histogram::histThread + extractObsScore + ScoreHistogram::addObservation
+ * (hist.cpp:70-140, motif.h:62-66, 96-102): every window of the (already truncated) filtered stream that lies
+ * inside one fragment adds one observation to bin clamp(int((score - min) / width), 0, bins-1) of its column,
+ * width = (max - min) / (float)bins.  Scores as in oracle_scan_stream.  counts: n_cols * num_bins, zeroed by the caller.
+ * ---------------------------------------------------------------------------------------------------- */
+int oracle_empirical_hist(const char* stream, uint64_t n, const uint64_t* frag_start, uint64_t n_frag, const float* P,
+                          int ldp, int n_cols, const int32_t* col_len, const float* mins, const float* maxs,
+                          int num_bins, int lower_fold, uint64_t* counts)
+{
+    uint64_t f = 0;
+    uint8_t* code = (uint8_t*)malloc(n + 1);
+    if (!code) return -1;
+    for (uint64_t g = 0; g < n; g++) code[g] = (uint8_t)code_of(stream[g], lower_fold);
+    for (uint64_t g = 0; g < n; g++) {
+        while (f + 1 < n_frag && frag_start[f + 1] <= g) f++;
+        uint64_t frag_end = (f + 1 < n_frag) ? frag_start[f + 1] : n;
+        uint64_t remaining = frag_end - g;
+        for (int c = 0; c < n_cols; c++) {
+            int L = col_len[c];
+            if ((uint64_t)L > remaining) continue;                   /* hist.cpp:87-88 */
+            const float* w = P + (size_t)c * ldp;
+            float s = 0.0f;
+            for (int j = 0; j < L; j++) { int k = code[g + j]; if (k < 4) s += w[4 * j + k]; }
+            float width = (maxs[c] - mins[c]) / (float)num_bins;
+            int bin = (int)((s - mins[c]) / width);
+            if (bin < 0) bin = 0;
+            if (bin > num_bins - 1) bin = num_bins - 1;
+            counts[(size_t)c * num_bins + bin]++;
+        }
+    }
+    free(code);
+    return 0;
+}
+
 /* Same scoring for explicit (position, column) pairs -- used by tests to check individual scores. */
 void oracle_score_at(const char* stream, uint64_t n, const float* P, int ldp, const int32_t* col_len, int lower_fold,
                      const uint64_t* pos, const uint32_t* col, uint64_t m, float* out)

@@ -48,6 +48,11 @@ def reference_outputs(d, motifs, manifest, modes, t="1"):
         run([REF + "/refdump", dump[0], dump[1], dump[2], ".", motifs, manifest, "refdump_%s.bin" % name], d)
     os.remove(os.path.join(d, "occurrences.txt"))
     os.remove(os.path.join(d, "PWMthresholds.txt"))
+    # empirical histograms (`blamm hist -e`, first 10,000,000 characters of every group)
+    os.makedirs(os.path.join(d, "hist_e"), exist_ok=True)
+    run([REF + "/blamm", "hist", "-e", "-t", t, "-H", "hist_e", motifs, manifest], d)
+    for gnu in [f for f in os.listdir(os.path.join(d, "hist_e")) if f.endswith(".gnu")]:
+        os.remove(os.path.join(d, "hist_e", gnu))
 
 
 def make_example():

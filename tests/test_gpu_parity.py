@@ -262,7 +262,7 @@ def test_cli_end_to_end_example(golden, tmp_path):
     work = tmp_path / "ex"
     shutil.copytree(os.path.join(golden, "example"), work)
     for f in os.listdir(work):
-        if f.startswith(("hist_", "occ_", "refdump_", "PWM")) or f.endswith(".dict"):
+        if os.path.isfile(work / f) and (f.startswith(("hist_", "occ_", "refdump_", "PWM")) or f.endswith(".dict")):
             os.remove(work / f)
     env = dict(os.environ, BLAMM_B200_CHUNK="30000")
     for args in (["dict", "sequences.mf"], ["hist", "motifs.jaspar", "sequences.mf"]):
@@ -276,3 +276,40 @@ def test_cli_end_to_end_example(golden, tmp_path):
         assert ("Wrote %d matches" % len(got)) in r.stdout
         if mode_key == "pt_rc":
             assert open(work / "PWMthresholds.txt").read() == open(os.path.join(golden, "example", "PWMthresholds_pt_rc.txt")).read()
+
+
+@pytest.mark.parametrize("lower", [capi.LOWER_ZERO, capi.LOWER_FOLD])
+def test_empirical_histogram_matches_oracle(scanner, lower):
+    """b200scan_hist_* (the `blamm hist -e` epilogue on the GPU) against the oracle: every bin identical, including
+    fragment boundaries, lower-case handling, several blocks with a halo and more columns than one shared-memory tile."""
+    case = util.random_case(91, n_motifs=60, n_nt=150_000, len_range=(5, 33), lower=True)
+    P, col_len = case["P"], case["col_len"]
+    mm = [O.max_min_score(np.ascontiguousarray(P[c, :4 * int(col_len[c])])) for c in range(len(col_len))]
+    mx = np.array([a for a, b in mm], np.float32); mn = np.array([b for a, b in mm], np.float32)
+    bins = 250
+    want = O.empirical_hist(bytes(case["chars"]), case["frag_start"], P, col_len, mn, mx, bins, lower_fold=(lower == capi.LOWER_FOLD))
+    scanner.set_engine(capi.ENGINE_AUTO)
+    scanner.set_motifs(P, col_len, np.zeros(len(col_len), np.float32))
+    scanner.hist_begin(mn, mx, bins)
+    halo = int(col_len.max()) - 1
+    for s in shard.plan_shards(len(case["chars"]), world=1, halo=halo, chunk=40_003):
+        scanner.hist_block(case["chars"][s.start:s.start + s.n_total], shard.local_frag_starts(case["frag_start"], s), s.n_payload, lower=lower)
+    got = scanner.hist_read()
+    assert got.shape == want.shape and int(got.sum()) == int(want.sum()) > 0
+    assert np.array_equal(got, want)
+
+
+def test_cli_empirical_histograms_example(golden, tmp_path):
+    """`blamm-b200 hist -e` writes the same .dat files as the reference's `blamm hist -e` on the example."""
+    cli = os.path.join(lib_dir(), "blamm-b200")
+    work = tmp_path / "ex"
+    shutil.copytree(os.path.join(golden, "example"), work)
+    out = work / "he"
+    out.mkdir()
+    r = subprocess.run([cli, "hist", "-e", "-H", "he", "motifs.jaspar", "sequences.mf"], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(golden, "example", "hist_e")
+    files = sorted(f for f in os.listdir(ref) if f.endswith(".dat"))
+    assert len(files) == 4
+    for f in files:
+        assert (out / f).read_bytes() == open(os.path.join(ref, f), "rb").read(), f

@@ -86,3 +86,25 @@ def test_dict_matches_reference(golden):
             counts = synth.counts_of(np.frombuffer(st.chars, dtype=np.uint8))
             assert counts == sp.counts and len(st.chars) == sp.tot_len
             assert st.seq_names == sp.seq_names
+
+
+@pytest.mark.parametrize("case,exact", [("example", True), ("edge", False)])
+def test_empirical_histograms_match_reference(golden, case, exact):
+    """`blamm hist -e` (hist.cpp:70-160): oracle counts vs the files written by the compiled reference.  On the example
+    (short motifs, default settings) every bin is identical; on `edge` the reference's sgemm edge kernels move a few
+    scores by an ulp across a bin edge, so bins may trade single counts (total preserved)."""
+    d = os.path.join(golden, case)
+    motifs = O.load_jaspar(os.path.join(d, "motifs.jaspar"))
+    for sp in O.load_dict(os.path.join(d, "sequences.mf.dict")):
+        P, col_len = O.generate_matrix(motifs, sp.counts)
+        mm = [O.max_min_score(np.ascontiguousarray(P[c, :4 * len(m)])) for c, m in enumerate(motifs)]
+        mx = np.array([a for a, b in mm], np.float32); mn = np.array([b for a, b in mm], np.float32)
+        st = O.build_stream(sp.files, 10_000_000, d)
+        cnt = O.empirical_hist(st.chars, st.frag_start, P, col_len, mn, mx, 250)
+        for c, m in enumerate(motifs):
+            nb, hmn, hmx, ref = O.load_hist(os.path.join(d, "hist_e", "hist_%s_%s.dat" % (sp.name, m.name)))
+            assert nb == 250 and int(ref.sum()) == int(cnt[c].sum())
+            if exact:
+                assert np.array_equal(ref, cnt[c]), (sp.name, m.name)
+            else:
+                assert int(np.abs(ref.astype(np.int64) - cnt[c].astype(np.int64)).sum()) <= 1e-4 * int(ref.sum()) + 4
