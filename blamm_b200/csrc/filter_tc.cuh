@@ -54,6 +54,9 @@ namespace b200 {
 #ifndef TC_PRODUCERS
 #define TC_PRODUCERS 2
 #endif
+#ifndef TC_STAGE_TILES
+#define TC_STAGE_TILES 4      // 128-window tiles per E stage: the issuer pays one eFull wait and one eEmpty commit per stage
+#endif
 #ifndef TC_BUFS
 #define TC_BUFS 2
 #endif
@@ -72,11 +75,13 @@ constexpr int      kTcThreads  = 32 * (kTcProducers + 1 + kTcEpiWarps);
 #define TC_SPAN 32768
 #endif
 constexpr uint32_t kTcSpan     = TC_SPAN;    // windows per work item
-constexpr uint32_t kTcStages   = 8;          // E ring stages (128 entries = 2 KB each)
+constexpr uint32_t kTcStageTiles = TC_STAGE_TILES;
+constexpr uint32_t kTcStageEnt = 128 * kTcStageTiles;          // entries per E stage
+constexpr uint32_t kTcStages   = 8 / kTcStageTiles < 3 ? 3 : 8 / kTcStageTiles;     // E ring stages (<= 8: barrier map), ring of >= 8 tiles
 constexpr uint32_t kTcMirror   = 64;         // entries mirrored past the ring end (>= 2*(2*nK_max-1))
 constexpr uint32_t kTcMaxN     = TC_MAXN;     // columns per tile; 2 accumulator buffers of kTcMaxN TMEM columns per CTA
 static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N columns x CTAs per SM must fit 512 columns");
-static_assert(128 % TC_PRODUCERS == 0 && TC_EPI_WARPS % (4 * TC_EPI_GROUPS) == 0 && (TC_EPI_GROUPS == 1 || TC_BUFS == 2), "warp role split");
+static_assert((4 * TC_STAGE_TILES) % TC_PRODUCERS == 0 && TC_STAGE_TILES >= 1 && TC_STAGE_TILES <= 8 && TC_EPI_WARPS % (4 * TC_EPI_GROUPS) == 0 && (TC_EPI_GROUPS & (TC_EPI_GROUPS - 1)) == 0 && TC_BUFS % TC_EPI_GROUPS == 0, "warp role split");
 constexpr uint32_t kTcEpiGroups = TC_EPI_GROUPS;
 constexpr uint32_t kRawBlock   = 64;         // raw entries per block (an epilogue warp reserves a block at a time)
 constexpr uint32_t kRawWords   = 40;         // 32 TMEM words + {window, first column} + padding = 160 B per entry (32 B aligned)
@@ -113,7 +118,7 @@ constexpr uint32_t kTraceTiles = 256;
 #endif
 
 // shared memory carve-up (bytes)
-constexpr uint32_t kSmE      = (kTcStages * 128 + kTcMirror) * 16;            // 17408
+constexpr uint32_t kSmE      = (kTcStages * kTcStageEnt + kTcMirror) * 16;
 constexpr uint32_t kSmCodes  = kTcSpan / 4 + 128;                              //  8320
 constexpr uint32_t kSmB      = kTcMaxN * (2 * (kMaxLen / 4)) * 16;             // 131072
 constexpr uint32_t kSmBars   = 32 * 8;
@@ -325,7 +330,9 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     const uint32_t bars   = smem_u32(sBars);
     const uint32_t eFull  = bars, eEmpty = bars + 8 * 8, tFull = bars + 16 * 8, tEmpty = bars + 20 * 8;
     const uint32_t cBar   = bars + 24 * 8, bBar = bars + 25 * 8;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a lane-0 broadcast: tells ptxas the role branches below are warp-uniform, which is what
+    // lets it use the uniform datapath (descriptors, barrier addresses) inside them
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, kTcProducers); mbar_init(eEmpty + 8 * i, 1); }
@@ -369,6 +376,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         const uint32_t w0 = sp * kTcSpan;
         const uint32_t nwin = min(kTcSpan, blk.n_payload - w0);
         const uint32_t nT = (nwin + 127) >> 7;
+        const uint32_t nSt = nT / kTcStageTiles + 1;            // E stages of the item: nT tiles + one halo tile
         const bool newTile = ((int32_t)t != curTile);
         curTile = (int32_t)t;
 
@@ -387,67 +395,86 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         if (warp < kTcProducers) {
             // ===================== producers: codes -> E ring (warp p fills entries 32p .. 32p+31 of every stage) =====================
             mbar_wait(cBar, nItem & 1, P.error_flag);
-            for (uint32_t i = 0; i <= nT; i++) {
-                const uint32_t k = kE + i, slot = k % kTcStages, ph = (k / kTcStages) & 1;
+            const uint32_t nEnt = (nT + 1) * 128;                     // entries of the item incl. one halo tile
+            for (uint32_t st = 0; st < nSt; st++) {
+                const uint32_t k = kE + st, slot = k % kTcStages, ph = (k / kTcStages) & 1;
                 mbar_wait(eEmpty + 8 * slot, ph ^ 1, P.error_flag);
-                if (warp == 0) TC_TRACE(0, i, 0);
+                if (warp == 0) TC_TRACE(0, st, 0);
                 if (!(TC_KNOCKOUT & 4)) {
 #pragma unroll
-                    for (uint32_t r = 0; r < 4 / kTcProducers; r++) {
+                    for (uint32_t r = 0; r < 4 * kTcStageTiles / kTcProducers; r++) {
                         const uint32_t e = 32 * (warp + r * kTcProducers) + lane;      // entry within the stage
-                        const uint32_t byte = 32 * i + (e >> 2);
-                        const uint32_t two = (uint32_t)sCodes[byte] | ((uint32_t)sCodes[byte + 1] << 8);
-                        const uint4 val = sLut[(two >> (2 * (e & 3))) & 15u];          // [onehot(code e) | onehot(code e+1)]
-                        *reinterpret_cast<uint4*>(sE + (slot * 128 + e) * 16) = val;
-                        if (slot == 0 && e < kTcMirror)
-                            *reinterpret_cast<uint4*>(sE + (kTcStages * 128 + e) * 16) = val;
+                        const uint32_t g = st * kTcStageEnt + e;                       // entry within the item
+                        if (g < nEnt) {
+                            const uint32_t byte = g >> 2;
+                            const uint32_t two = (uint32_t)sCodes[byte] | ((uint32_t)sCodes[byte + 1] << 8);
+                            const uint4 val = sLut[(two >> (2 * (g & 3))) & 15u];      // [onehot(code g) | onehot(code g+1)]
+                            *reinterpret_cast<uint4*>(sE + (slot * kTcStageEnt + e) * 16) = val;
+                            if (slot == 0 && e < kTcMirror)
+                                *reinterpret_cast<uint4*>(sE + (kTcStages * kTcStageEnt + e) * 16) = val;
+                        }
                     }
                 }
                 fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(eFull + 8 * slot);
-                if (warp == 0) TC_TRACE(0, i, 1);
+                if (warp == 0) TC_TRACE(0, st, 1);
             }
         } else if (warp == kTcProducers) {
             // ===================== MMA issuer =====================
+            // This warp's instruction stream is on the critical path of every tile (alone on the SM: mbarrier.try_wait 43
+            // cycles, tcgen05.commit 30, tcgen05.mma ~50 each -- tools/micro/issue_cost.cu -- and it shares its scheduler
+            // with four epilogue warps), so it is kept minimal: one eFull wait and one eEmpty commit per STAGE of
+            // kTcStageTiles tiles, one tEmpty wait and one tFull commit per tile, operands moved to uniform registers once
+            // per tile.
             if (newTile) mbar_wait(bBar, nBload & 1, P.error_flag);
+            const uint32_t n_k = __shfl_sync(0xffffffffu, tile.n_k, 0);
             // instruction descriptor: F16 x F16, D = F32 (c_format 1) or F16 (c_format 0), K-major A and B, M = 128, N = n_pad
             const uint32_t idesc = (ACC16 ? 0u : (1u << 4)) | ((tile.n_pad >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t n_k = __shfl_sync(0xffffffffu, tile.n_k, 0);
             const uint32_t nChunks = 2 * n_k;
             const uint64_t ad0 = umma_desc(smem_u32(sE), 32, 128), bd0 = umma_desc(smem_u32(sB), 128, nChunks * 128);
             const uint32_t aLo0 = (uint32_t)ad0, aHi = (uint32_t)(ad0 >> 32), bLo0 = (uint32_t)bd0, bHi = (uint32_t)(bd0 >> 32);
+            mbar_wait(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
+            uint32_t st = 0, j = 0;                                   // stage of the item / tile within the stage
             for (uint32_t i = 0; i < nT; i++) {
-                const uint32_t k = kE + i, slot = k % kTcStages, ph = (k / kTcStages) & 1;
-                const uint32_t k1 = k + 1, slot1 = k1 % kTcStages, ph1 = (k1 / kTcStages) & 1;
+                const uint32_t k = kE + st, slot = k % kTcStages;
                 const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
-                if (i == 0) mbar_wait(eFull + 8 * slot, ph, P.error_flag);     // later tiles waited for it as their halo stage
-                mbar_wait(eFull + 8 * slot1, ph1, P.error_flag);
+                const bool lastOfStage = (j + 1 == kTcStageTiles), lastTile = (i + 1 == nT);
+                if (lastOfStage) {                                    // its halo lies in the next stage
+                    const uint32_t k1 = k + 1;
+                    mbar_wait(eFull + 8 * (k1 % kTcStages), (k1 / kTcStages) & 1, P.error_flag);
+                }
                 TC_TRACE(1, i, 0);
                 mbar_wait(tEmpty + 8 * buf, tph ^ 1, P.error_flag);
                 TC_TRACE(1, i, 1);
                 tc_fence_after();
                 {
                     const uint32_t d = tmem_base + buf * kBufCols;
-                    // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[slot*128 + r + 2*kk]; one MMA = 4 entries = 64 B
+                    // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[entry0 + r + 2*kk]; one MMA = 4 entries = 64 B
                     // B: [8-column group][chunk] blocks of 128 B: one MMA = 2 chunks = 256 B
-                    uint32_t alo = aLo0 + slot * 128, blo = bLo0;          // address fields are in 16-byte units
-                    const bool leader = elect_one();
-                    if (leader && !(TC_KNOCKOUT & 2)) umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
-                    for (uint32_t m = 1; m < ((TC_KNOCKOUT & 2) ? 0u : n_k); m++) {
-                        alo += 4; blo += 16;
-                        if (leader) umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
-                    }
-                    if (leader) {
-                        umma_commit(eEmpty + 8 * slot);       // stage k is dead once tile i (and i-1 before it) completed
+                    uint32_t alo = aLo0 + slot * kTcStageEnt + j * 128, blo = bLo0;          // address fields are in 16-byte units
+                    // ONE branch around the whole chain (not a predicate per instruction): inside it ptxas moves the operands
+                    // to uniform registers once and steps the descriptors with UIADD3 between back-to-back UTCHMMAs.
+                    if (elect_one()) {
+                        if (!(TC_KNOCKOUT & 2)) {
+                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+#pragma unroll 1
+                            for (uint32_t m = 1; m < n_k; m++) {
+                                alo += 4; blo += 16;
+                                umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
+                            }
+                        }
+                        // MMAs complete in issue order: once the last tile of a stage is done, so is every reader of the stage
+                        // (its own tiles and the halo read of the stage before).  The item's last tile also frees its halo stage.
+                        if (lastOfStage || lastTile) umma_commit(eEmpty + 8 * slot);
+                        if (lastOfStage && lastTile) umma_commit(eEmpty + 8 * ((k + 1) % kTcStages));
                         umma_commit(tFull + 8 * buf);
                     }
                 }
                 TC_TRACE(1, i, 2);
                 __syncwarp();
+                if (lastOfStage) { j = 0; st++; } else j++;
             }
-            if (elect_one()) umma_commit(eEmpty + 8 * ((kE + nT) % kTcStages));   // the halo stage
-            __syncwarp();
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
             const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
@@ -493,7 +520,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 if (warp == kTcEpiWarp0) TC_TRACE(2, i, 3); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 3);
             }
         }
-        kE += nT + 1;
+        kE += nSt;
         kT += nT;
         nItem++;
         if (newTile) nBload++;

@@ -4,7 +4,9 @@ set -e
 cd "$(dirname "$0")/.."
 V=blamm_b200/lib/variants
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared blamm_b200/csrc/b200scan.cu"
+if [ -n "$VARSET" ]; then eval "declare -A VAR=( $VARSET )"; else
 declare -A VAR=( [base]="" [ko_prod]="-DTC_KNOCKOUT=4" [ko_push]="-DTC_KNOCKOUT=8" [ko_prod_push]="-DTC_KNOCKOUT=12" [ko_mma_push]="-DTC_KNOCKOUT=10" )
+fi
 if [ "$1" = build ]; then
   mkdir -p $V
   for k in "${!VAR[@]}"; do $NV ${VAR[$k]} $EXTRA -o $V/$k.so & done; wait; ls -la $V
