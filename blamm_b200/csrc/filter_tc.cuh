@@ -84,7 +84,7 @@ static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N colu
 static_assert((4 * TC_STAGE_TILES) % TC_PRODUCERS == 0 && TC_STAGE_TILES >= 1 && TC_STAGE_TILES <= 8 && TC_EPI_WARPS % (4 * TC_EPI_GROUPS) == 0 && (TC_EPI_GROUPS & (TC_EPI_GROUPS - 1)) == 0 && TC_BUFS % TC_EPI_GROUPS == 0, "warp role split");
 constexpr uint32_t kTcEpiGroups = TC_EPI_GROUPS;
 constexpr uint32_t kRawBlock   = 64;         // raw entries per block (an epilogue warp reserves a block at a time)
-constexpr uint32_t kRawWords   = 40;         // 32 TMEM words + {window, first column} + padding = 160 B per entry (32 B aligned)
+constexpr uint32_t kRawWords   = 4;          // {window, first column, sign mask of 32 (FP32) / 64 (FP16) accumulators} = 16 B per entry
 
 struct TcTile {
     uint32_t col0;      // first sorted column
@@ -235,25 +235,38 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 
-// a & b & c as ONE opaque lop3: keeps the reduction a tree (nvcc otherwise re-associates the ANDs into a
-// 16-deep dependent chain, which a warp can only issue every ~4.5 cycles).
-__device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
+// Sign bits of the 32 words one tcgen05.ld delivered, compacted into two mask words (bit = 1 <=> accumulator negative).
+// PRMT in sign-replication mode turns the signs of two words into 0x00 / 0xFF bytes, one LOP3 ((r & C_t) | acc) files
+// them under bit t of each byte.  Opaque asm keeps the two accumulation chains per mask exactly as written (nvcc would
+// re-associate them into one long dependent chain).
+//   FP16 accumulators (.pack::16b: word k = columns 2k | 2k+1): 64 columns; bit 8*b + t of mask w <-> column 32w + 4t + b
+//   FP32 accumulators (word k = column k):                      32 columns; bit 8*b + t of mask w <-> column 16w + 2t + b, b < 2
+//                                                               (bits 16..31 of both masks stay 1)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-// AND of 32 TMEM words as a depth-4 tree of 3-input LOP3s.  A sign bit of the result (bit 31; with FP16
-// accumulators also bit 15) is set <=> every accumulator in that position is negative.
-__device__ __forceinline__ uint32_t and_tree32(const uint32_t (&v)[32]) {
-    const uint32_t t0 = and3(v[0], v[1], v[2]),    t1 = and3(v[3], v[4], v[5]),    t2 = and3(v[6], v[7], v[8]);
-    const uint32_t t3 = and3(v[9], v[10], v[11]),  t4 = and3(v[12], v[13], v[14]), t5 = and3(v[15], v[16], v[17]);
-    const uint32_t t6 = and3(v[18], v[19], v[20]), t7 = and3(v[21], v[22], v[23]), t8 = and3(v[24], v[25], v[26]);
-    const uint32_t t9 = and3(v[27], v[28], v[29]), t10 = and3(v[30], v[31], 0xffffffffu);
-    const uint32_t u0 = and3(t0, t1, t2), u1 = and3(t3, t4, t5), u2 = and3(t6, t7, t8), u3 = and3(t9, t10, 0xffffffffu);
-    return and3(and3(u0, u1, u2), u3, 0xffffffffu);
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {      // (a & b) | c
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
-template <bool ACC16> __device__ __forceinline__ bool any_nonneg(uint32_t a) {
-    return ACC16 ? ((a & 0x80008000u) != 0x80008000u) : ((int32_t)a >= 0);
+template <bool ACC16> __device__ __forceinline__ void sign_masks(const uint32_t (&v)[32], uint32_t& m0, uint32_t& m1) {
+    constexpr uint32_t sel = ACC16 ? 0xFDB9u : 0xFBFBu;          // sign(byte 1, 3, 5, 7)  /  sign(byte 3, 7, 3, 7)
+    constexpr uint32_t c0 = ACC16 ? 0x01010101u : 0x00000101u, init = ACC16 ? 0u : 0xFFFF0000u;
+    uint32_t m[2];
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        uint32_t ea = init, eb = 0u;
+#pragma unroll
+        for (int t = 0; t < 8; t += 2) {
+            ea = and_or(prmt(v[16 * w + 2 * t],     v[16 * w + 2 * t + 1], sel), c0 << t,       ea);
+            eb = and_or(prmt(v[16 * w + 2 * t + 2], v[16 * w + 2 * t + 3], sel), c0 << (t + 1), eb);
+        }
+        m[w] = ea | eb;
+    }
+    m0 = m[0]; m1 = m[1];
 }
 
 // Per-epilogue-warp cursor into the raw-entry blocks.  next/left/blk are warp-uniform; `spare` (meaningful in lane 0) is
@@ -273,31 +286,22 @@ __device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, 
     rc.next = P.raw + (size_t)min(rc.blk, P.blk_cap) * (kRawBlock * kRawWords);
     rc.left = kRawBlock;
 }
-// Predicated raw-entry store (no branch, no divergence): four 256-bit stores of the lane's 32 words + {window, column}.
-__device__ __forceinline__ void st_entry_pred(bool p, uint32_t* d, const uint32_t (&v)[32], uint32_t win, uint32_t col) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %35, 0;\n"
-                 "@q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
-                 "@q st.global.v8.b32 [%0+32], {%9, %10, %11, %12, %13, %14, %15, %16};\n"
-                 "@q st.global.v8.b32 [%0+64], {%17, %18, %19, %20, %21, %22, %23, %24};\n"
-                 "@q st.global.v8.b32 [%0+96], {%25, %26, %27, %28, %29, %30, %31, %32};\n"
-                 "@q st.global.v2.b32 [%0+128], {%33, %34};\n}"
-                 ::"l"(d), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
-                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
-                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]),
-                   "r"(win), "r"(col), "r"((uint32_t)p) : "memory");
+// Predicated raw-entry store (no branch, no divergence): one 128-bit store of {window, first column, mask, mask}.
+__device__ __forceinline__ void st_entry_pred(bool p, uint32_t* d, uint32_t win, uint32_t col, uint32_t m0, uint32_t m1) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %5, 0;\n@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n}"
+                 ::"l"(d), "r"(win), "r"(col), "r"(m0), "r"(m1), "r"((uint32_t)p) : "memory");
 }
-// Lanes with c0 / c1 append the 32 words of chunk 0 / chunk 1 (+ {window, first column}) to the warp's current block:
-// one pair of ballots, one cursor update, predicated fire-and-forget stores (~2e-4 of the accumulators are candidates).
-__device__ __forceinline__ void raw_push2(RawCursor& rc, const TcParams& P, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+// Lanes with c0 / c1 append the entry of chunk 0 / chunk 1 to the warp's current block: one pair of ballots, one cursor
+// update, predicated fire-and-forget stores (~2e-4 of the accumulators are candidates, i.e. about every other call).
+__device__ __forceinline__ void raw_push2(RawCursor& rc, const TcParams& P, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1,
                                           bool c0, bool c1, uint32_t win, uint32_t col0, uint32_t col1, uint32_t lane) {
     const unsigned t0 = __ballot_sync(0xffffffffu, c0), t1 = __ballot_sync(0xffffffffu, c1);
     const uint32_t n0 = __popc(t0), n = n0 + __popc(t1);
     if (n > rc.left) raw_new_block(rc, P, lane);            // n <= 64 = kRawBlock
     const uint32_t lt = (1u << lane) - 1u;
     if (!(TC_KNOCKOUT & 16)) {
-        st_entry_pred(c0, rc.next + __popc(t0 & lt) * kRawWords, v0, win, col0);
-        st_entry_pred(c1, rc.next + (n0 + __popc(t1 & lt)) * kRawWords, v1, win, col1);
+        st_entry_pred(c0, rc.next + __popc(t0 & lt) * kRawWords, win, col0, a0, a1);
+        st_entry_pred(c1, rc.next + (n0 + __popc(t1 & lt)) * kRawWords, win, col1, b0, b1);
     }
     rc.next += n * kRawWords;
     rc.left -= n;
@@ -506,10 +510,13 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         released = true;
                         if (warp == kTcEpiWarp0) TC_TRACE(2, i, 2); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 2);
                     }
-                    // both reductions first (independent trees interleave in the issue slots), then ONE test and ONE vote
-                    const uint32_t a0 = and_tree32(v0), a1 = has1 ? and_tree32(v1) : 0xffffffffu;
-                    if (!(TC_KNOCKOUT & 8) && __any_sync(0xffffffffu, winOk && any_nonneg<ACC16>(a0 & a1)))
-                        raw_push2(rawc, P, v0, v1, winOk && any_nonneg<ACC16>(a0), has1 && winOk && any_nonneg<ACC16>(a1), win0 + lane,
+                    // both compactions first (independent chains interleave in the issue slots), then ONE test and ONE vote
+                    uint32_t a0, a1, b0 = 0xffffffffu, b1 = 0xffffffffu;
+                    sign_masks<ACC16>(v0, a0, a1);
+                    if (has1) sign_masks<ACC16>(v1, b0, b1);
+                    const bool c0 = winOk && (a0 & a1) != 0xffffffffu, c1 = winOk && (b0 & b1) != 0xffffffffu;
+                    if (!(TC_KNOCKOUT & 8) && __any_sync(0xffffffffu, c0 || c1))
+                        raw_push2(rawc, P, a0, a1, b0, b1, c0, c1, win0 + lane,
                                   tile.col0 + wc * kColsPerWord, tile.col0 + (wc + step) * kColsPerWord, lane);
                 }
                 if (!released) {                                      // this warp owns no chunk of such a narrow tile

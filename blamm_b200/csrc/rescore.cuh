@@ -8,17 +8,17 @@
 
 namespace b200 {
 
-// Raw entries of the tensor-core filter -> (position, sorted column) candidates.  One warp per block of entries; lane k
-// tests word k of an entry (FP32 accumulators: word k = column first + k; FP16 via .pack::16b: word k = columns
-// first + 2k in the low half and first + 2k + 1 in the high half; candidate <=> sign bit clear).  Candidates are staged
-// in shared memory and appended with one global atomic per >= 256 of them.
+// Raw entries of the tensor-core filter -> (position, sorted column) candidates.  One thread per entry slot
+// {window, first column, mask0, mask1}; a zero mask bit is a candidate (bit layout: filter_tc.cuh, sign_masks).  A warp's
+// candidates are staged in shared memory and appended with one global atomic per >= 256 of them.
 template <bool ACC16>
 __global__ void __launch_bounds__(256)
 expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count, const unsigned int* __restrict__ n_blocks_ptr,
               uint32_t blk_cap, Cand* __restrict__ cand, unsigned long long* n_cand, unsigned long long cand_cap,
               const uint32_t* __restrict__ has_zero)
 {
-    __shared__ Cand s_stage[8][512];      // per-warp staging (a trip adds <= 256): one global atomic per >= 256 candidates
+    constexpr uint32_t kStage = 640;
+    __shared__ Cand s_stage[8][kStage];   // per-warp staging: one global atomic per >= 256 candidates
     if (__ldg(has_zero) != 0) return;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t nb = min(*n_blocks_ptr, blk_cap);
@@ -34,40 +34,38 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
         __syncwarp();
         n = 0;
     };
-    const uint32_t lt = (1u << lane) - 1u;
-    // Each warp takes 4 consecutive entry slots (block, e) per trip and issues all their loads before using any
-    // (the kernel is latency bound otherwise); slots beyond a block's count are skipped.
+    auto column = [](uint32_t first, uint32_t w, uint32_t bit) {
+        return ACC16 ? first + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first + 16 * w + 2 * (bit & 7u) + (bit >> 3);
+    };
     const unsigned long long slots = (unsigned long long)nb * kRawBlock;
-    for (unsigned long long s0 = ((unsigned long long)blockIdx.x * 8 + wib) * 4; s0 < slots; s0 += (unsigned long long)gridDim.x * 8 * 4) {
-        const uint32_t b = (uint32_t)(s0 / kRawBlock), e0 = (uint32_t)(s0 % kRawBlock);       // kRawBlock % 4 == 0: same block
-        const uint32_t cnt = __ldg(blk_count + b);
-        uint32_t w[4], pos[4], first[4];
+    const uint4* ent = reinterpret_cast<const uint4*>(raw);
+    for (unsigned long long s0 = ((unsigned long long)blockIdx.x * 8 + wib) * 32; s0 < slots; s0 += (unsigned long long)gridDim.x * 8 * 32) {
+        const uint32_t b = (uint32_t)(s0 / kRawBlock), e = (uint32_t)(s0 % kRawBlock) + lane;     // kRawBlock % 32 == 0: same block
+        const bool live = e < __ldg(blk_count + b);
+        uint4 x = make_uint4(0u, 0u, 0xffffffffu, 0xffffffffu);
+        if (live) x = __ldg(ent + s0 + lane);
+        uint32_t z0 = ~x.z, z1 = ~x.w;
+        const uint32_t c = __popc(z0) + __popc(z1);
+        uint32_t incl = c;                                   // inclusive warp scan
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t* ent = raw + (s0 + k) * kRawWords;
-            const bool live = e0 + k < cnt;
-            w[k] = live ? __ldg(ent + lane) : 0x80008000u;           // all-negative: no candidate
-            pos[k] = live ? __ldg(ent + 32) : 0u;
-            first[k] = live ? __ldg(ent + 33) : 0u;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += y; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        if (n + total > kStage) flush();
+        Cand cd; cd.pos = x.x;
+        if (total <= kStage) {
+            uint32_t o = n + incl - c;
+            while (z0) { const uint32_t bit = __ffs(z0) - 1; z0 &= z0 - 1; cd.col = column(x.y, 0, bit); st[o++] = cd; }
+            while (z1) { const uint32_t bit = __ffs(z1) - 1; z1 &= z1 - 1; cd.col = column(x.y, 1, bit); st[o++] = cd; }
+            n += total;
+            if (n > 256) flush();
+        } else {                                             // more than 32 candidates per entry on average: straight to global
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_cand, (unsigned long long)total);
+            unsigned long long o = __shfl_sync(0xffffffffu, base, 0) + incl - c;
+            while (z0) { const uint32_t bit = __ffs(z0) - 1; z0 &= z0 - 1; cd.col = column(x.y, 0, bit); if (o < cand_cap) cand[o] = cd; o++; }
+            while (z1) { const uint32_t bit = __ffs(z1) - 1; z1 &= z1 - 1; cd.col = column(x.y, 1, bit); if (o < cand_cap) cand[o] = cd; o++; }
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (e0 + k >= cnt) break;                                 // warp-uniform
-            Cand cd; cd.pos = pos[k];
-            if (ACC16) {
-                const bool lo = !(w[k] & 0x8000u), hi = !(w[k] & 0x80000000u);
-                const unsigned blo = __ballot_sync(0xffffffffu, lo), bhi = __ballot_sync(0xffffffffu, hi);
-                if (lo) { cd.col = first[k] + 2 * lane;     st[n + __popc(blo & lt)] = cd; }
-                if (hi) { cd.col = first[k] + 2 * lane + 1; st[n + __popc(blo) + __popc(bhi & lt)] = cd; }
-                n += __popc(blo) + __popc(bhi);
-            } else {
-                const bool c = (int32_t)w[k] >= 0;
-                const unsigned bb = __ballot_sync(0xffffffffu, c);
-                if (c) { cd.col = first[k] + lane; st[n + __popc(bb & lt)] = cd; }
-                n += __popc(bb);
-            }
-        }
-        if (n > 256) flush();
     }
     if (n) flush();
 }
