@@ -84,7 +84,7 @@ static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N colu
 static_assert((4 * TC_STAGE_TILES) % TC_PRODUCERS == 0 && TC_STAGE_TILES >= 1 && TC_STAGE_TILES <= 8 && TC_EPI_WARPS % (4 * TC_EPI_GROUPS) == 0 && (TC_EPI_GROUPS & (TC_EPI_GROUPS - 1)) == 0 && TC_BUFS % TC_EPI_GROUPS == 0, "warp role split");
 constexpr uint32_t kTcEpiGroups = TC_EPI_GROUPS;
 constexpr uint32_t kRawBlock   = 64;         // raw entries per block (an epilogue warp reserves a block at a time)
-constexpr uint32_t kRawWords   = 4;          // {window, first column, sign mask of 32 (FP32) / 64 (FP16) accumulators} = 16 B per entry
+constexpr uint32_t kRawWords   = 8;          // {window, column of chunk 0, 2 sign words, column of chunk 1, 2 sign words, -} = 32 B per entry
 
 struct TcTile {
     uint32_t col0;      // first sorted column
@@ -235,38 +235,38 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 
-// Sign bits of the 32 words one tcgen05.ld delivered, compacted into two mask words (bit = 1 <=> accumulator negative).
-// PRMT in sign-replication mode turns the signs of two words into 0x00 / 0xFF bytes, one LOP3 ((r & C_t) | acc) files
-// them under bit t of each byte.  Opaque asm keeps the two accumulation chains per mask exactly as written (nvcc would
-// re-associate them into one long dependent chain).
-//   FP16 accumulators (.pack::16b: word k = columns 2k | 2k+1): 64 columns; bit 8*b + t of mask w <-> column 32w + 4t + b
-//   FP32 accumulators (word k = column k):                      32 columns; bit 8*b + t of mask w <-> column 16w + 2t + b, b < 2
-//                                                               (bits 16..31 of both masks stay 1)
+// Sign bits of the 32 words one tcgen05.ld delivered, compacted into two words.  PRMT in sign-replication mode (ALU pipe)
+// turns the signs of two words into 0x00 / 0xFF bytes r_t; an IMAD (FMA pipe, otherwise idle here) accumulates
+// X = sum_t r_t * 2^t.  With M_b = sum_t 2^t [accumulator (t, b) negative] that is X = sum_b 255 * M_b * 256^b (mod 2^32),
+// which rescore.cuh: decode_sign_word() inverts; all negative <=> X == kAllNegative.  (An AND/OR accumulation would put
+// all 34 operations per chunk on the half-rate ALU pipe, which the epilogue warps then saturate.)
+//   FP16 accumulators (.pack::16b: word k = columns 2k | 2k+1): 64 columns per chunk; (t, b) of word w <-> column 32w + 4t + b
+//   FP32 accumulators (word k = column k):                      32 columns per chunk; (t, b) of word w <-> column 16w + 2t + b, b < 2
+constexpr uint32_t kAllNegative = 0xFFFFFF01u;
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {      // (a & b) | c
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {         // a * b + c, kept a multiply-add
     uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-template <bool ACC16> __device__ __forceinline__ void sign_masks(const uint32_t (&v)[32], uint32_t& m0, uint32_t& m1) {
+template <bool ACC16> __device__ __forceinline__ void sign_words(const uint32_t (&v)[32], uint32_t& x0, uint32_t& x1) {
     constexpr uint32_t sel = ACC16 ? 0xFDB9u : 0xFBFBu;          // sign(byte 1, 3, 5, 7)  /  sign(byte 3, 7, 3, 7)
-    constexpr uint32_t c0 = ACC16 ? 0x01010101u : 0x00000101u, init = ACC16 ? 0u : 0xFFFF0000u;
-    uint32_t m[2];
+    uint32_t x[2];
 #pragma unroll
     for (int w = 0; w < 2; w++) {
-        uint32_t ea = init, eb = 0u;
+        uint32_t ea = prmt(v[16 * w], v[16 * w + 1], sel), eb = 0u;           // two independent chains
 #pragma unroll
-        for (int t = 0; t < 8; t += 2) {
-            ea = and_or(prmt(v[16 * w + 2 * t],     v[16 * w + 2 * t + 1], sel), c0 << t,       ea);
-            eb = and_or(prmt(v[16 * w + 2 * t + 2], v[16 * w + 2 * t + 3], sel), c0 << (t + 1), eb);
+        for (int t = 1; t < 8; t += 2) {
+            eb = imad(prmt(v[16 * w + 2 * t], v[16 * w + 2 * t + 1], sel), 1u << t, eb);
+            if (t + 1 < 8) ea = imad(prmt(v[16 * w + 2 * t + 2], v[16 * w + 2 * t + 3], sel), 1u << (t + 1), ea);
         }
-        m[w] = ea | eb;
+        x[w] = ea + eb;
     }
-    m0 = m[0]; m1 = m[1];
+    x0 = x[0]; x1 = x[1];
 }
 
 // Per-epilogue-warp cursor into the raw-entry blocks.  next/left/blk are warp-uniform; `spare` (meaningful in lane 0) is
@@ -286,23 +286,18 @@ __device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, 
     rc.next = P.raw + (size_t)min(rc.blk, P.blk_cap) * (kRawBlock * kRawWords);
     rc.left = kRawBlock;
 }
-// Predicated raw-entry store (no branch, no divergence): one 128-bit store of {window, first column, mask, mask}.
-__device__ __forceinline__ void st_entry_pred(bool p, uint32_t* d, uint32_t win, uint32_t col, uint32_t m0, uint32_t m1) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %5, 0;\n@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n}"
-                 ::"l"(d), "r"(win), "r"(col), "r"(m0), "r"(m1), "r"((uint32_t)p) : "memory");
-}
-// Lanes with c0 / c1 append the entry of chunk 0 / chunk 1 to the warp's current block: one pair of ballots, one cursor
-// update, predicated fire-and-forget stores (~2e-4 of the accumulators are candidates, i.e. about every other call).
-__device__ __forceinline__ void raw_push2(RawCursor& rc, const TcParams& P, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1,
-                                          bool c0, bool c1, uint32_t win, uint32_t col0, uint32_t col1, uint32_t lane) {
-    const unsigned t0 = __ballot_sync(0xffffffffu, c0), t1 = __ballot_sync(0xffffffffu, c1);
-    const uint32_t n0 = __popc(t0), n = n0 + __popc(t1);
-    if (n > rc.left) raw_new_block(rc, P, lane);            // n <= 64 = kRawBlock
-    const uint32_t lt = (1u << lane) - 1u;
-    if (!(TC_KNOCKOUT & 16)) {
-        st_entry_pred(c0, rc.next + __popc(t0 & lt) * kRawWords, win, col0, a0, a1);
-        st_entry_pred(c1, rc.next + (n0 + __popc(t1 & lt)) * kRawWords, win, col1, b0, b1);
-    }
+// Lanes whose window has a candidate in either of the warp's two chunks append one entry {window, column of chunk 0, its two
+// sign masks, column of chunk 1, its two sign masks} to the warp's current block.  `t` is the ballot of those lanes (non-zero):
+// one cursor update and one predicated, fire-and-forget 256-bit store (~2e-4 of the accumulators are candidates, so this
+// runs for about every other tile of every warp).
+__device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, unsigned t, bool c, uint32_t win, uint32_t col0, uint32_t a0, uint32_t a1,
+                                         uint32_t col1, uint32_t b0, uint32_t b1, uint32_t lane) {
+    const uint32_t n = __popc(t);
+    if (n > rc.left) raw_new_block(rc, P, lane);            // n <= 32 <= kRawBlock
+    uint32_t* d = rc.next + __popc(t & ((1u << lane) - 1u)) * kRawWords;
+    if (!(TC_KNOCKOUT & 16))
+        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %8, 0;\n@q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %7};\n}"
+                     ::"l"(d), "r"(win), "r"(col0), "r"(a0), "r"(a1), "r"(col1), "r"(b0), "r"(b1), "r"((uint32_t)c) : "memory");
     rc.next += n * kRawWords;
     rc.left -= n;
 }
@@ -511,13 +506,13 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         if (warp == kTcEpiWarp0) TC_TRACE(2, i, 2); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 2);
                     }
                     // both compactions first (independent chains interleave in the issue slots), then ONE test and ONE vote
-                    uint32_t a0, a1, b0 = 0xffffffffu, b1 = 0xffffffffu;
-                    sign_masks<ACC16>(v0, a0, a1);
-                    if (has1) sign_masks<ACC16>(v1, b0, b1);
-                    const bool c0 = winOk && (a0 & a1) != 0xffffffffu, c1 = winOk && (b0 & b1) != 0xffffffffu;
-                    if (!(TC_KNOCKOUT & 8) && __any_sync(0xffffffffu, c0 || c1))
-                        raw_push2(rawc, P, a0, a1, b0, b1, c0, c1, win0 + lane,
-                                  tile.col0 + wc * kColsPerWord, tile.col0 + (wc + step) * kColsPerWord, lane);
+                    uint32_t a0, a1, b0 = kAllNegative, b1 = kAllNegative;
+                    sign_words<ACC16>(v0, a0, a1);
+                    if (has1) sign_words<ACC16>(v1, b0, b1);
+                    const bool c = winOk && (((a0 ^ kAllNegative) | (a1 ^ kAllNegative) | (b0 ^ kAllNegative) | (b1 ^ kAllNegative)) != 0u);
+                    const unsigned t = (TC_KNOCKOUT & 8) ? 0u : __ballot_sync(0xffffffffu, c);
+                    if (t) raw_push(rawc, P, t, c, win0 + lane, tile.col0 + wc * kColsPerWord, a0, a1,
+                                    tile.col0 + (wc + step) * kColsPerWord, b0, b1, lane);
                 }
                 if (!released) {                                      // this warp owns no chunk of such a narrow tile
                     tc_fence_before();

@@ -9,8 +9,25 @@
 namespace b200 {
 
 // Raw entries of the tensor-core filter -> (position, sorted column) candidates.  One thread per entry slot
-// {window, first column, mask0, mask1}; a zero mask bit is a candidate (bit layout: filter_tc.cuh, sign_masks).  A warp's
-// candidates are staged in shared memory and appended with one global atomic per >= 256 of them.
+// {window, column of chunk 0, mask, mask, column of chunk 1, mask, mask, -}; sign words are decoded to masks whose zero bits are the
+// candidates (filter_tc.cuh: sign_words).  A warp's candidates are staged in shared memory and appended with one global atomic per
+// >= 256 of them.
+// Inverse of filter_tc.cuh: sign_words().  X = sum_b 255 * M_b * 256^b (mod 2^32)  ->  M_0 | M_1 << 8 | M_2 << 16 | M_3 << 24
+// (bit 8b + t set <=> accumulator (t, b) negative).  255 M = 256 M - M, so X = -M_0 + (M_0 - M_1) 256 + (M_1 - M_2) 256^2 + ...
+// and the bytes peel off from the bottom.  FP32 accumulators only fill b < 2 (the upper bytes repeat them).
+template <bool ACC16> __device__ __forceinline__ uint32_t decode_sign_word(uint32_t x)
+{
+    const uint32_t m0 = (0u - x) & 255u;
+    const uint32_t y1 = (x + m0) >> 8;                               // (M_0 - M_1) + (M_1 - M_2) 256 + (M_2 - M_3) 256^2  mod 2^24
+    const uint32_t m1 = (m0 - y1) & 255u;
+    if (!ACC16) return m0 | (m1 << 8) | 0xFFFF0000u;
+    const uint32_t y2 = ((y1 - (m0 - m1)) & 0xFFFFFFu) >> 8;         // (M_1 - M_2) + (M_2 - M_3) 256  mod 2^16
+    const uint32_t m2 = (m1 - y2) & 255u;
+    const uint32_t y3 = ((y2 - (m1 - m2)) & 0xFFFFu) >> 8;           // (M_2 - M_3)  mod 2^8
+    const uint32_t m3 = (m2 - y3) & 255u;
+    return m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
+}
+
 template <bool ACC16>
 __global__ void __launch_bounds__(256)
 expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count, const unsigned int* __restrict__ n_blocks_ptr,
@@ -42,29 +59,32 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
     for (unsigned long long s0 = ((unsigned long long)blockIdx.x * 8 + wib) * 32; s0 < slots; s0 += (unsigned long long)gridDim.x * 8 * 32) {
         const uint32_t b = (uint32_t)(s0 / kRawBlock), e = (uint32_t)(s0 % kRawBlock) + lane;     // kRawBlock % 32 == 0: same block
         const bool live = e < __ldg(blk_count + b);
-        uint4 x = make_uint4(0u, 0u, 0xffffffffu, 0xffffffffu);
-        if (live) x = __ldg(ent + s0 + lane);
-        uint32_t z0 = ~x.z, z1 = ~x.w;
-        const uint32_t c = __popc(z0) + __popc(z1);
+        uint4 x = make_uint4(0u, 0u, kAllNegative, kAllNegative), y = make_uint4(0u, kAllNegative, kAllNegative, 0u);
+        if (live) { x = __ldg(ent + 2 * (s0 + lane)); y = __ldg(ent + 2 * (s0 + lane) + 1); }
+        uint32_t z[4] = {~decode_sign_word<ACC16>(x.z), ~decode_sign_word<ACC16>(x.w), ~decode_sign_word<ACC16>(y.y), ~decode_sign_word<ACC16>(y.z)};
+        const uint32_t first[2] = {x.y, y.x};
+        const uint32_t c = __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
         uint32_t incl = c;                                   // inclusive warp scan
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += y; }
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += u; }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) continue;
         if (n + total > kStage) flush();
         Cand cd; cd.pos = x.x;
         if (total <= kStage) {
             uint32_t o = n + incl - c;
-            while (z0) { const uint32_t bit = __ffs(z0) - 1; z0 &= z0 - 1; cd.col = column(x.y, 0, bit); st[o++] = cd; }
-            while (z1) { const uint32_t bit = __ffs(z1) - 1; z1 &= z1 - 1; cd.col = column(x.y, 1, bit); st[o++] = cd; }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(first[q >> 1], q & 1, bit); st[o++] = cd; }
             n += total;
             if (n > 256) flush();
-        } else {                                             // more than 32 candidates per entry on average: straight to global
+        } else {                                             // more than 20 candidates per entry on average: straight to global
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(n_cand, (unsigned long long)total);
             unsigned long long o = __shfl_sync(0xffffffffu, base, 0) + incl - c;
-            while (z0) { const uint32_t bit = __ffs(z0) - 1; z0 &= z0 - 1; cd.col = column(x.y, 0, bit); if (o < cand_cap) cand[o] = cd; o++; }
-            while (z1) { const uint32_t bit = __ffs(z1) - 1; z1 &= z1 - 1; cd.col = column(x.y, 1, bit); if (o < cand_cap) cand[o] = cd; o++; }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(first[q >> 1], q & 1, bit); if (o < cand_cap) cand[o] = cd; o++; }
         }
     }
     if (n) flush();
