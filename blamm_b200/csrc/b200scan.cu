@@ -45,7 +45,8 @@ struct Slot {
     bool in_flight = false, resident = false;
     uint64_t n_total = 0, n_payload = 0, n_frag = 0;
     bool packed_zero_known = false;               // submit_packed: has_zero decided on the host
-    cudaEvent_t ev[8] = {};                       // 0 start, 1 after h2d, 2 after pack, 3 after score, 4 after rescore, 5 after counters d2h, 6/7 hit d2h
+    cudaEvent_t ev[9] = {};                       // upload stream: 0 start, 1 after h2d, 2 after pack; compute stream: 8 scoring starts,
+                                                  // 3 after score, 4 after rescore, 5 after counters d2h; copy stream: 6/7 hit d2h
     b200scan_timing timing = {};
 };
 
@@ -56,6 +57,7 @@ struct b200scan_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // hit downloads: overlap the next block's kernels
+    cudaStream_t up_stream = nullptr;        // block uploads + packing: overlap the previous block's kernels
     uint64_t max_block = 0;
     int engine = B200SCAN_ENGINE_AUTO;
     std::string err;
@@ -385,7 +387,7 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     return B200SCAN_OK;
 }
 
-int reset_counters(b200scan_ctx* ctx, Slot& s, bool keep_has_zero)
+int reset_counters(b200scan_ctx* ctx, Slot& s, bool keep_has_zero, cudaStream_t st)
 {
     // [0] n_cand [1] n_hits: zero.  [2] = {has_zero, error}: keep has_zero on re-runs.  [3] work counter: zero.
     CU(cudaMemsetAsync(s.d_counters, 0, 16, ctx->stream));
@@ -411,7 +413,7 @@ int check_common(b200scan_ctx* ctx, int slot, uint64_t n_total, uint64_t n_paylo
     return B200SCAN_OK;
 }
 
-int stage_frags(b200scan_ctx* ctx, Slot& s, const uint64_t* frag, uint64_t n_frag)
+int stage_frags(b200scan_ctx* ctx, Slot& s, const uint64_t* frag, uint64_t n_frag, cudaStream_t st)
 {
     if (n_frag > s.frag_cap) {
         size_t cap = std::max<size_t>(n_frag * 2, 1 << 16);
@@ -420,7 +422,7 @@ int stage_frags(b200scan_ctx* ctx, Slot& s, const uint64_t* frag, uint64_t n_fra
         s.frag_cap = cap;
     }
     for (uint64_t i = 0; i < n_frag; i++) s.h_frag[i] = (uint32_t)frag[i];
-    if (n_frag) CU(cudaMemcpyAsync(s.d_frag, s.h_frag, n_frag * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_frag) CU(cudaMemcpyAsync(s.d_frag, s.h_frag, n_frag * 4, cudaMemcpyHostToDevice, st));
     return B200SCAN_OK;
 }
 
@@ -428,6 +430,9 @@ int finish_submit(b200scan_ctx* ctx, Slot& s)
 {
     s.timing.kernel_launches = 0;
     int launches = 0;
+    // the block was uploaded and packed on the upload stream (behind the kernels of the other slot's block)
+    CU(cudaStreamWaitEvent(ctx->stream, s.ev[2], 0));
+    CU(cudaEventRecord(s.ev[8], ctx->stream));
     int rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
     if (rc) return rc;
     s.timing.kernel_launches += launches;
@@ -489,6 +494,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
                        return bail(e_ == cudaErrorMemoryAllocation ? B200SCAN_ENOMEM : B200SCAN_ECUDA); } } while (0)
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) g_margin16_scale = atof(e);
@@ -540,6 +546,7 @@ void b200scan_destroy(b200scan_ctx* c)
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg);
     dfree(c->d_hist); dfree(c->d_hmin); dfree(c->d_hwid); dfree(c->d_htiles);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -586,7 +593,7 @@ int b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64
     Slot& s = ctx->slot[slot];
     s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag;
     s.timing = b200scan_timing{};
-    CU(cudaEventRecord(s.ev[0], ctx->stream));
+    CU(cudaEventRecord(s.ev[0], ctx->up_stream));
     // pinned caller memory goes straight to the device; pageable memory is staged through the slot's pinned buffer
     const void* src = block;
     cudaPointerAttributes pa;
@@ -595,19 +602,19 @@ int b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64
         std::memcpy(s.h_ascii, block, n_total);
         src = s.h_ascii;
     }
-    if (n_total) CU(cudaMemcpyAsync(s.d_ascii, src, n_total, cudaMemcpyHostToDevice, ctx->stream));
-    rc = stage_frags(ctx, s, frag_starts, n_frag);
+    if (n_total) CU(cudaMemcpyAsync(s.d_ascii, src, n_total, cudaMemcpyHostToDevice, ctx->up_stream));
+    rc = stage_frags(ctx, s, frag_starts, n_frag, ctx->up_stream);
     if (rc) return rc;
-    rc = reset_counters(ctx, s, false);
+    rc = reset_counters(ctx, s, false, ctx->up_stream);
     if (rc) return rc;
-    CU(cudaEventRecord(s.ev[1], ctx->stream));
+    CU(cudaEventRecord(s.ev[1], ctx->up_stream));
     if (n_total) {
         const unsigned threads = (unsigned)((n_total + 31) / 32);
-        pack_ascii_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(s.d_ascii, (uint32_t)n_total, lowercase_mode == B200SCAN_LOWER_FOLD,
+        pack_ascii_kernel<<<(threads + 255) / 256, 256, 0, ctx->up_stream>>>(s.d_ascii, (uint32_t)n_total, lowercase_mode == B200SCAN_LOWER_FOLD,
                                                                           s.d_codes, s.d_zmask, reinterpret_cast<uint32_t*>(s.d_counters + 2));
         CU(cudaGetLastError());
     }
-    CU(cudaEventRecord(s.ev[2], ctx->stream));
+    CU(cudaEventRecord(s.ev[2], ctx->up_stream));
     rc = finish_submit(ctx, s);
     if (rc == B200SCAN_OK && n_total) s.timing.kernel_launches += 1;
     return rc;
@@ -623,25 +630,25 @@ int b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2, 
     Slot& s = ctx->slot[slot];
     s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag;
     s.timing = b200scan_timing{};
-    CU(cudaEventRecord(s.ev[0], ctx->stream));
+    CU(cudaEventRecord(s.ev[0], ctx->up_stream));
     const size_t cw = (n_total + 15) / 16, zw = (n_total + 31) / 32;
     // pageable sources: cudaMemcpyAsync stages them itself and returns once the source may be reused
-    if (cw) CU(cudaMemcpyAsync(s.d_codes, codes2, cw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (cw) CU(cudaMemcpyAsync(s.d_codes, codes2, cw * 4, cudaMemcpyHostToDevice, ctx->up_stream));
     uint32_t hz = 0;
     if (zero_mask) {
         for (size_t i = 0; i < zw && !hz; i++) {
             uint32_t live = (i + 1 == zw && (n_total & 31)) ? ((1u << (n_total & 31)) - 1u) : 0xffffffffu;
             if (zero_mask[i] & live) hz = 1;
         }
-        if (hz) CU(cudaMemcpyAsync(s.d_zmask, zero_mask, zw * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (hz) CU(cudaMemcpyAsync(s.d_zmask, zero_mask, zw * 4, cudaMemcpyHostToDevice, ctx->up_stream));
     }
-    rc = stage_frags(ctx, s, frag_starts, n_frag);
+    rc = stage_frags(ctx, s, frag_starts, n_frag, ctx->up_stream);
     if (rc) return rc;
-    rc = reset_counters(ctx, s, false);
+    rc = reset_counters(ctx, s, false, ctx->up_stream);
     if (rc) return rc;
-    if (hz) CU(cudaMemsetAsync(s.d_counters + 2, 1, 1, ctx->stream));      // has_zero = 1 (little endian)
-    CU(cudaEventRecord(s.ev[1], ctx->stream));
-    CU(cudaEventRecord(s.ev[2], ctx->stream));
+    if (hz) CU(cudaMemsetAsync(s.d_counters + 2, 1, 1, ctx->up_stream));      // has_zero = 1 (little endian)
+    CU(cudaEventRecord(s.ev[1], ctx->up_stream));
+    CU(cudaEventRecord(s.ev[2], ctx->up_stream));
     return finish_submit(ctx, s);
 }
 
@@ -703,9 +710,9 @@ int b200scan_hist_block_ascii(b200scan_ctx* ctx, const char* block, uint64_t n_t
     if (n_total == 0 || n_payload == 0) return B200SCAN_OK;
     std::memcpy(s.h_ascii, block, n_total);
     CU(cudaMemcpyAsync(s.d_ascii, s.h_ascii, n_total, cudaMemcpyHostToDevice, ctx->stream));
-    rc = stage_frags(ctx, s, frag_starts, n_frag);
+    rc = stage_frags(ctx, s, frag_starts, n_frag, ctx->stream);
     if (rc) return rc;
-    rc = reset_counters(ctx, s, false);
+    rc = reset_counters(ctx, s, false, ctx->stream);
     if (rc) return rc;
     const unsigned threads = (unsigned)((n_total + 31) / 32);
     pack_ascii_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(s.d_ascii, (uint32_t)n_total, lowercase_mode == B200SCAN_LOWER_FOLD,
@@ -782,7 +789,7 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
                 s.hit_cap = want;
             }
         }
-        int rc = reset_counters(ctx, s, true);
+        int rc = reset_counters(ctx, s, true, ctx->stream);
         if (rc) return rc;
         int launches = 0;
         rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
@@ -800,7 +807,7 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
     CU(cudaEventSynchronize(s.ev[7]));
     cudaEventElapsedTime(&s.timing.h2d_ms, s.ev[0], s.ev[1]);
     cudaEventElapsedTime(&s.timing.pack_ms, s.ev[1], s.ev[2]);
-    cudaEventElapsedTime(&s.timing.score_ms, s.ev[2], s.ev[3]);
+    cudaEventElapsedTime(&s.timing.score_ms, s.ev[8], s.ev[3]);
     cudaEventElapsedTime(&s.timing.rescore_ms, s.ev[3], s.ev[4]);
     cudaEventElapsedTime(&s.timing.d2h_ms, s.ev[6], s.ev[7]);
     if (hits) *hits = s.h_hits;
@@ -820,7 +827,7 @@ int b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total
     for (auto& e : ev) CU(cudaEventCreate(&e));
     int rc = B200SCAN_OK;
     for (int i = 0; i < iters && rc == B200SCAN_OK; i++) {
-        rc = reset_counters(ctx, s, true);
+        rc = reset_counters(ctx, s, true, ctx->stream);
         if (rc) break;
         CU(cudaEventRecord(ev[3 * i], ctx->stream));
         rc = launch_scoring(ctx, s, ev[3 * i + 1], ev[3 * i + 2], nullptr);
