@@ -433,47 +433,47 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             const uint32_t nChunks = 2 * n_k;
             const uint64_t ad0 = umma_desc(smem_u32(sE), 32, 128), bd0 = umma_desc(smem_u32(sB), 128, nChunks * 128);
             const uint32_t aLo0 = (uint32_t)ad0, aHi = (uint32_t)(ad0 >> 32), bLo0 = (uint32_t)bd0, bHi = (uint32_t)(bd0 >> 32);
-            mbar_wait(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
-            uint32_t st = 0, j = 0;                                   // stage of the item / tile within the stage
-            for (uint32_t i = 0; i < nT; i++) {
-                const uint32_t k = kE + st, slot = k % kTcStages;
-                const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
-                const bool lastOfStage = (j + 1 == kTcStageTiles), lastTile = (i + 1 == nT);
-                if (lastOfStage) {                                    // its halo lies in the next stage
-                    const uint32_t k1 = k + 1;
-                    mbar_wait(eFull + 8 * (k1 % kTcStages), (k1 / kTcStages) & 1, P.error_flag);
-                }
-                TC_TRACE(1, i, 0);
-                mbar_wait(tEmpty + 8 * buf, tph ^ 1, P.error_flag);
-                TC_TRACE(1, i, 1);
-                tc_fence_after();
-                {
+            // The whole tile loop runs in ONE elected lane, inside one branch: there ptxas moves the loop state to uniform
+            // registers once per item and steps descriptors / barrier addresses with UIADD3 (predicating each tcgen05
+            // instruction instead costs 5-7 R2UR moves in front of every one of them).
+            if (elect_one()) {
+                mbar_wait(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
+                uint32_t st = 0, j = 0;                                   // stage of the item / tile within the stage
+#pragma unroll 1
+                for (uint32_t i = 0; i < nT; i++) {
+                    const uint32_t k = kE + st, slot = k % kTcStages;
+                    const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
+                    const bool lastOfStage = (j + 1 == kTcStageTiles), lastTile = (i + 1 == nT);
+                    if (lastOfStage) {                                    // its halo lies in the next stage
+                        const uint32_t k1 = k + 1;
+                        mbar_wait(eFull + 8 * (k1 % kTcStages), (k1 / kTcStages) & 1, P.error_flag);
+                    }
+                    TC_TRACE(1, i, 0);
+                    mbar_wait(tEmpty + 8 * buf, tph ^ 1, P.error_flag);
+                    TC_TRACE(1, i, 1);
+                    tc_fence_after();
                     const uint32_t d = tmem_base + buf * kBufCols;
                     // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[entry0 + r + 2*kk]; one MMA = 4 entries = 64 B
                     // B: [8-column group][chunk] blocks of 128 B: one MMA = 2 chunks = 256 B
                     uint32_t alo = aLo0 + slot * kTcStageEnt + j * 128, blo = bLo0;          // address fields are in 16-byte units
-                    // ONE branch around the whole chain (not a predicate per instruction): inside it ptxas moves the operands
-                    // to uniform registers once and steps the descriptors with UIADD3 between back-to-back UTCHMMAs.
-                    if (elect_one()) {
-                        if (!(TC_KNOCKOUT & 2)) {
-                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+                    if (!(TC_KNOCKOUT & 2)) {
+                        umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
 #pragma unroll 1
-                            for (uint32_t m = 1; m < n_k; m++) {
-                                alo += 4; blo += 16;
-                                umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
-                            }
+                        for (uint32_t m = 1; m < n_k; m++) {
+                            alo += 4; blo += 16;
+                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
                         }
-                        // MMAs complete in issue order: once the last tile of a stage is done, so is every reader of the stage
-                        // (its own tiles and the halo read of the stage before).  The item's last tile also frees its halo stage.
-                        if (lastOfStage || lastTile) umma_commit(eEmpty + 8 * slot);
-                        if (lastOfStage && lastTile) umma_commit(eEmpty + 8 * ((k + 1) % kTcStages));
-                        umma_commit(tFull + 8 * buf);
                     }
+                    // MMAs complete in issue order: once the last tile of a stage is done, so is every reader of the stage
+                    // (its own tiles and the halo read of the stage before).  The item's last tile also frees its halo stage.
+                    if (lastOfStage || lastTile) umma_commit(eEmpty + 8 * slot);
+                    if (lastOfStage && lastTile) umma_commit(eEmpty + 8 * ((k + 1) % kTcStages));
+                    umma_commit(tFull + 8 * buf);
+                    TC_TRACE(1, i, 2);
+                    if (lastOfStage) { j = 0; st++; } else j++;
                 }
-                TC_TRACE(1, i, 2);
-                __syncwarp();
-                if (lastOfStage) { j = 0; st++; } else j++;
             }
+            __syncwarp();
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
             const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
