@@ -18,24 +18,23 @@
 //    the epilogue's ALU work), else FP32.
 //  * The tensor pass is a CONSERVATIVE FILTER: weights are  fp16_round_up(W[j][b] - thr'/L)  with
 //    thr' = thr - margin, so  acc >= 0  whenever the exact FP32 score >= thr (b200scan.cu: build_tc_tiles).
-//    The epilogue only tests sign bits (AND-reduction, half a LOP3 per score) and appends (pos, col)
-//    candidates; rescore.cuh then recomputes those few scores exactly.  R never exists.
+//    The epilogue only looks at sign bits (one PRMT + one IMAD per four scores) and appends raw entries;
+//    rescore.cuh expands them to (pos, col) candidates and recomputes those few scores exactly.  R never exists.
 //
 // Roofline: tensor pipe.  One tcgen05.mma (M=128, N, K=16) covers 4 motif positions of N columns for 128
-// windows and takes N/2 cycles; the epilogue must drain 128 x N FP32 accumulators per tile from TMEM.
+// windows and takes N/2 cycles; the epilogue must drain 128 x N accumulators per tile from TMEM.
 //
 // Warp roles (608 threads, 1 CTA/SM, persistent with an atomic work counter):
-//   warps 0..1   producers: codes -> E ring (8 stages of 128 entries + mirrored halo) through a 16-entry one-hot LUT,
-//                64 entries of every stage each (a single producer warp needed ~650 cycles per stage and set the pace)
-//   warp 2       TMEM allocation; one elected lane issues tcgen05.mma / tcgen05.commit (B/codes bulk loads: thread 0)
+//   warps 0..1   producers: codes -> E ring (3 stages of 4 tiles = 512 entries + mirrored halo) through a 16-entry one-hot LUT
+//   warp 2       TMEM allocation; ONE elected lane runs the whole issue loop: tcgen05.mma chains and tcgen05.commit, one
+//                eFull wait / eEmpty commit per stage, one tEmpty wait / tFull commit per tile (B/codes bulk loads: thread 0)
 //   warps 3..18  epilogue: TWO independent groups of 8 warps, group g owns TMEM buffer g (even / odd window tiles).
 //                Within a group two warps share each TMEM lane quarter and split the tile's 32-word chunks:
-//                tcgen05.ld 32x32b.x32 into registers, RELEASE the TMEM buffer at once, tree-shaped AND of the sign
-//                bits.  A lane that saw a non-negative accumulator stores its 32 words + {window, column} as one raw
-//                entry in global memory (blocks of 64 entries reserved ahead of time, predicated fire-and-forget
-//                stores).  Because a buffer is released right after the load, a group has a whole buffer round trip
-//                (~1100 cycles) for its ~650 cycles of work per tile: candidate pushes land in slack instead of
-//                delaying the next MMAs (with one group of 8 warps every tile paid for its slowest warp).
+//                tcgen05.ld 32x32b.x32 into registers, RELEASE the TMEM buffer at once, compact the sign bits of the 32
+//                words into two sign words (PRMT on the ALU pipe + IMAD on the FMA pipe).  A lane that saw a non-negative
+//                accumulator stores {window, column, sign words} as one 32-byte raw entry in global memory (blocks of 64
+//                entries reserved ahead of time, one predicated fire-and-forget store).  Because a buffer is released
+//                right after the load, candidate pushes land in slack instead of delaying the next MMAs.
 //   expand_kernel (rescore.cuh) later turns raw entries into (position, column) candidates for the exact rescorer.
 #pragma once
 #include "common.cuh"

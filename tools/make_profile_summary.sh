@@ -40,3 +40,16 @@ for r in rows[2:]:
     for k in want: print('   %-72s %-10s %s'%(k,u.get(k,''),d.get(k,'')))
 "; } > profiles/${R}_ncu_summary.txt
 wc -l profiles/${R}_ncu_summary.txt
+# DRAM traffic of the dominant kernel -> profiles/${R}_filter_traffic.json (bench.py reports it as roofline.traffic)
+ncu -i gpurun_out/prof_filter.ncu-rep --page raw --csv 2>/dev/null | python3 -c "
+import csv, sys, json
+rows = list(csv.reader(sys.stdin)); d = dict(zip(rows[0], rows[2])); u = dict(zip(rows[0], rows[1]))
+scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+def b(k): return float(d[k].replace(',', '')) * scale[u[k]]
+rd, wr = b('dram__bytes_read.sum'), b('dram__bytes_write.sum')
+t = float(d['gpu__time_duration.sum'].replace(',', '')) * {'ms': 1.0, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[u['gpu__time_duration.sum']]
+json.dump({'kernel': d['Kernel Name'].split('(')[0], 'workload': 'bench.py default (1800 columns x 100 Mbp)', 'dram_bytes_read': rd, 'dram_bytes_write': wr,
+           'gpu_time_ms_under_ncu': t, 'tensor_pipe_active_pct': float(d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']),
+           'source': 'ncu --set full --clock-control none, profiles/${R}_ncu_summary.txt', 'traffic_bytes_per_launch': rd + wr}, open('profiles/${R}_filter_traffic.json', 'w'), indent=1)
+print(open('profiles/${R}_filter_traffic.json').read())
+"
