@@ -238,6 +238,40 @@ def test_engines_agree_at_scale_and_properties(scanner):
     assert np.array_equal(keep, shifted[shifted["pos"] >= first_frag_after - k])
 
 
+def test_full_size_bench_workload_properties(tmp_path):
+    """BASELINE.json configs[1] at full size (bench.py's workload: 1800 columns x 100 Mbp = 1.8e11 scores), through
+    size-independent properties: the tensor path and the exact gather-add engine return the identical hit list; a random
+    sample of hits re-verifies bit-exactly against the oracle; every hit clears its threshold; a window-aligned slice of
+    the block scanned on its own returns exactly the hits of that slice (chunking invariance, the multi-GPU shard rule)."""
+    import bench
+    ms, P, col_len, thr, seq, bg = bench.build_inputs(str(tmp_path), 100_000_000, 0)
+    assert len(col_len) == 1800
+    sc = capi.Scanner(0, max_block_nt=len(seq) + 64, max_hits=1 << 25)
+    res = {}
+    for engine in (capi.ENGINE_TENSOR, capi.ENGINE_GATHER):
+        sc.set_engine(engine)
+        sc.set_motifs(P, col_len, thr)
+        h, t = sc.scan(seq)
+        assert t["engine_used"] == engine
+        res[engine] = _sorted(h)
+    tc, g = res[capi.ENGINE_TENSOR], res[capi.ENGINE_GATHER]
+    assert len(g) > 10_000_000 and np.array_equal(tc, g)
+    assert np.all(g["score"] >= thr[g["col"]])
+    assert np.all(g["pos"] + col_len[g["col"]].astype(np.uint64) <= len(seq))
+    pick = np.sort(np.random.default_rng(5).choice(len(g), 200_000, replace=False))
+    want = O.score_at(bytes(seq), P, col_len, g["pos"][pick], g["col"][pick])
+    assert np.array_equal(want.view(np.uint32), g["score"][pick].view(np.uint32))
+    lo, n_pay, halo = 37_000_001, 9_000_000, int(col_len.max()) - 1
+    sc.set_engine(capi.ENGINE_TENSOR)
+    sc.set_motifs(P, col_len, thr)
+    part, _ = sc.scan(seq[lo:lo + n_pay + halo], None, n_pay)
+    part = _sorted(part)
+    ref = g[(g["pos"] >= lo) & (g["pos"] < lo + n_pay)].copy()
+    ref["pos"] -= np.uint64(lo)
+    assert np.array_equal(part, ref)
+    sc.close()
+
+
 def test_sharded_scan_matches_single_pass(scanner):
     """The multi-GPU decomposition (chunks + halo, round-robin over ranks, host merge) on one device."""
     case = util.random_case(81, n_motifs=20, n_nt=500_000)
