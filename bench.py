@@ -285,7 +285,7 @@ def main() -> None:
             sc.flush_l2()
             a, b, nh = sc.rerun_resident(0, 1)
             tot_ms += a; k_ms += b
-            assert nh == n_hits, "resident re-run changed the hit count"
+            assert nh == n_hits or os.environ.get("B200_BENCH_DIAG"), "resident re-run changed the hit count"     # DIAG: knock-out builds (tools/variants.sh)
         barrier()
         # ---- timed: end to end from pinned host memory through the C ABI, the way the CLI drives it: the two slots of
         #      the context alternate, so the hit download of block k overlaps the kernels of block k+1 ----

@@ -398,7 +398,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 const uint32_t k = kE + st, slot = k % kTcStages, ph = (k / kTcStages) & 1;
                 mbar_wait(eEmpty + 8 * slot, ph ^ 1, P.error_flag);
                 if (warp == 0) TC_TRACE(0, st, 0);
-                if (!(TC_KNOCKOUT & 4)) {
+                if (!(TC_KNOCKOUT & 4) && !((TC_KNOCKOUT & 64) && t != 0 && nItem > 8)) {     // 64: fill only for column tile 0 (emulates an E-stationary loop order on random sequence; results invalid)
 #pragma unroll
                     for (uint32_t r = 0; r < 4 * kTcStageTiles / kTcProducers; r++) {
                         const uint32_t e = 32 * (warp + r * kTcProducers) + lane;      // entry within the stage

@@ -97,6 +97,23 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
     if (__ldg(blk.has_zero) != 0) return;          // such blocks went through the gather kernel
     unsigned long long n_cand = *n_cand_ptr;
     if (n_cand > cand_cap) n_cand = cand_cap;       // overflow: the host re-runs with a larger buffer
+    // Hits of kRounds consecutive rounds are staged per warp in shared memory and appended with ONE global atomic
+    // (all hits of a block go through a single counter: one atomic per warp round made the atomic unit the bottleneck).
+    constexpr uint32_t kRounds = 4;
+    __shared__ b200scan_hit s_hits[8][32 * kRounds];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    b200scan_hit* st = s_hits[wib];
+    uint32_t n_st = 0, round = 0;
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long o = 0;
+        if (lane == 0) o = atomicAdd(sink.n_hits, (unsigned long long)n_st);
+        o = __shfl_sync(0xffffffffu, o, 0);
+        for (uint32_t k = lane; k < n_st; k += 32)
+            if (o + k < sink.cap) sink.hits[o + k] = st[k];
+        __syncwarp();
+        n_st = 0; round = 0;
+    };
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < n_cand; base += stride) {
         unsigned long long i = base + threadIdx.x;
@@ -110,23 +127,34 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
             const float* wp = reinterpret_cast<const float*>(md.w + __ldg(md.woff + col));
             uint32_t codes[4];
             load_window_codes(blk.codes, pos, codes);
+            // 16 positions at a time: all (predicated) weight loads first -- independent, so one L2 round trip per group
+            // instead of one per position -- then the additions strictly in position order
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if ((uint32_t)(16 * q) < L) {
-                    uint32_t r = codes[q];
-                    const uint32_t n = min(16u, L - 16u * q);
-                    for (uint32_t t = 0; t < n; t++) {
-                        s += __ldg(wp + 4 * (16 * q + t) + (r & 3u));
-                        r >>= 2;
-                    }
+                    const uint32_t r = codes[q], n = min(16u, L - 16u * q);
+                    float wv[16];
+#pragma unroll
+                    for (uint32_t t = 0; t < 16; t++)
+                        wv[t] = (t < n) ? __ldg(wp + 4 * (16 * q + t) + ((r >> (2 * t)) & 3u)) : 0.0f;
+#pragma unroll
+                    for (uint32_t t = 0; t < 16; t++)
+                        if (t < n) s += wv[t];
                 }
             }
             hit = (pos < blk.n_payload) && !(s < __ldg(md.thr + col));
             if (hit) hit = window_in_fragment(blk, pos, L);
             col = __ldg(md.orig + col);
         }
-        emit_hits_warp(hit, pos, col, s, sink);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            b200scan_hit h; h.pos = pos; h.col = col; h.score = s;
+            st[n_st + __popc(m & ((1u << lane) - 1u))] = h;
+        }
+        n_st += __popc(m);
+        if (++round == kRounds) flush();
     }
+    if (n_st) flush();
 }
 
 } // namespace b200

@@ -14,7 +14,7 @@ else
   mkdir -p gpurun_out
   for k in "${!VAR[@]}"; do
     [ -f $V/$k.so ] || continue
-    echo "== $k"; B200SCAN_LIB=$PWD/$V/$k.so timeout 300 python bench.py --mbp ${MBP:-50} --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+    echo "== $k"; B200_BENCH_DIAG=1 B200SCAN_LIB=$PWD/$V/$k.so timeout 300 python bench.py --mbp ${MBP:-50} --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
