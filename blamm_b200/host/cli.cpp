@@ -5,9 +5,12 @@
 
 #include <algorithm>
 #include <atomic>
+#include <charconv>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <deque>
 #include <fstream>
@@ -20,7 +23,28 @@ using namespace std;
 
 namespace blamm {
 
-int formatScore(char* dst, float v) { return snprintf(dst, 32, "%g", (double)v); }
+// operator<<(ostream&, float) of the reference (pwmscan.cpp:93) == printf("%g").  std::to_chars in general format with
+// precision 6 is specified to give exactly that conversion (checked against snprintf on 4e7 floats) at a fifth of the cost.
+int formatScore(char* dst, float v)
+{
+    if (!std::isfinite(v)) return snprintf(dst, 32, "%g", (double)v);
+    return (int)(std::to_chars(dst, dst + 32, (double)v, std::chars_format::general, 6).ptr - dst);
+}
+
+namespace {
+struct PhaseTimer {            // BLAMM_B200_TIMING=1: wall-clock seconds per phase on stderr (sums over threads where noted)
+    bool on = getenv("BLAMM_B200_TIMING") != nullptr;
+    std::mutex m; std::vector<std::pair<std::string, double>> acc;
+    void add(const char* what, double s) {
+        if (!on) return;
+        std::lock_guard<std::mutex> l(m);
+        for (auto& a : acc) if (a.first == what) { a.second += s; return; }
+        acc.emplace_back(what, s);
+    }
+    void report() { if (on) for (auto& a : acc) fprintf(stderr, "[timing] %-28s %8.3f s\n", a.first.c_str(), a.second); }
+} gTimer;
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}
 
 // =========================================================================================================
 // dict  (reference dict.cpp:53-115)
@@ -204,62 +228,111 @@ struct ScanShared {
     const MotifSet* motifs = nullptr;
     const Species* species = nullptr;
     ofstream* os = nullptr;
-    mutex outMutex;
     uint64_t totMatches = 0;
     size_t formatThreads = 1;
+    size_t maxNameLen = 0;                      // longest "<sequence>\tblamm\t<motif>" prefix, for sizing the text buffers
     // job queue (producer = FASTA reader, consumers = one thread per GPU)
     mutex qMutex; condition_variable qCv;
     deque<unique_ptr<Job>> queue; bool done = false; size_t maxQueue = 2;
+    // output queue (producers = the GPU threads, consumer = one writer thread): the file write of block k overlaps the
+    // formatting of block k+1 (the reference formats outside and writes inside its output mutex, pwmscan.cpp:88-101)
+    mutex oMutex; condition_variable oCv;
+    deque<vector<string>> outQueue; bool outDone = false; size_t maxOut = 4;
     string error; atomic<bool> failed{false};
 };
 
 // hits of one block -> text lines (reference format: pwmscan.cpp:88-95), in (position, column) order.
 // The block is cut into position ranges; each formatting thread sorts and formats its range, the pieces are
-// written in order under the output mutex (the reference formats outside and writes inside its mutex too, :99).
+// handed to the writer thread in order.
 void formatRange(const ScanShared& sh, const Job& job, std::vector<b200scan_hit>& hits, std::string& text)
 {
     sort(hits.begin(), hits.end(), [](const b200scan_hit& a, const b200scan_hit& b) {
         return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; });
-    text.reserve(hits.size() * 56);
-    char num[64];
+    // worst-case line: names + 2 positions of <= 20 digits + score (<= 16) + 5 tabs + strand + "\t.\t.\n"
+    text.resize(hits.size() * (sh.maxNameLen + 72));
+    char* const base = &text[0];
+    char* p = base;
     size_t f = 0;
     for (const auto& h : hits) {
         while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= h.pos) f++;
         const Fragment& fr = job.frags[f];
         const uint64_t seqPos = fr.seqPos + (h.pos - fr.streamPos);
         const Motif& m = sh.motifs->motifs[h.col];
-        text += sh.species->seqNames.at(fr.seqIdx);
-        text += "\tblamm\t";
-        text += m.name;
-        text += '\t';
-        text.append(num, snprintf(num, sizeof num, "%llu\t%llu\t", (unsigned long long)seqPos, (unsigned long long)(seqPos + m.size())));
-        text.append(num, formatScore(num, h.score));
-        text += '\t';
-        text += m.revComp ? '-' : '+';
-        text += "\t.\t.\n";
+        const string& sn = sh.species->seqNames.at(fr.seqIdx);
+        memcpy(p, sn.data(), sn.size()); p += sn.size();
+        memcpy(p, "\tblamm\t", 7); p += 7;
+        memcpy(p, m.name.data(), m.name.size()); p += m.name.size();
+        *p++ = '\t';
+        p = to_chars(p, p + 24, (unsigned long long)seqPos).ptr; *p++ = '\t';
+        p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size())).ptr; *p++ = '\t';
+        p += formatScore(p, h.score);
+        *p++ = '\t'; *p++ = m.revComp ? '-' : '+';
+        memcpy(p, "\t.\t.\n", 5); p += 5;
     }
+    text.resize((size_t)(p - base));
 }
 
 void writeHits(ScanShared& sh, const Job& job, const b200scan_hit* hits, uint64_t n)
 {
+    double t0 = now();
     const size_t T = std::max<size_t>(1, std::min<size_t>(sh.formatThreads, n / 50000 + 1));
     vector<vector<b200scan_hit>> part(T);
     if (T == 1) part[0].assign(hits, hits + n);
     else {
+        // position ranges of equal width; counting and scattering are themselves split over the threads (hit order from
+        // the device is arbitrary, so every thread scans its slice of the list and appends to per-(thread, range) bins)
         const uint64_t span = job.nPayload / T + 1;
-        vector<size_t> cnt(T, 0);
-        for (uint64_t i = 0; i < n; i++) cnt[hits[i].pos / span]++;
-        for (size_t t = 0; t < T; t++) part[t].reserve(cnt[t]);
-        for (uint64_t i = 0; i < n; i++) part[hits[i].pos / span].push_back(hits[i]);
+        vector<vector<vector<b200scan_hit>>> bins(T, vector<vector<b200scan_hit>>(T));
+        vector<thread> pool;
+        auto scatter = [&](size_t t) {
+            const uint64_t lo = n * t / T, hi = n * (t + 1) / T;
+            for (auto& b : bins[t]) b.reserve((hi - lo) / T + (hi - lo) / (4 * T) + 16);
+            for (uint64_t i = lo; i < hi; i++) bins[t][hits[i].pos / span].push_back(hits[i]);
+        };
+        for (size_t t = 1; t < T; t++) pool.emplace_back(scatter, t);
+        scatter(0);
+        for (auto& th : pool) th.join();
+        pool.clear();
+        auto gather = [&](size_t r) {
+            size_t c = 0;
+            for (size_t t = 0; t < T; t++) c += bins[t][r].size();
+            part[r].reserve(c);
+            for (size_t t = 0; t < T; t++) part[r].insert(part[r].end(), bins[t][r].begin(), bins[t][r].end());
+        };
+        for (size_t r = 1; r < T; r++) pool.emplace_back(gather, r);
+        gather(0);
+        for (auto& th : pool) th.join();
     }
+    gTimer.add("partition hits (wall)", now() - t0); t0 = now();
     vector<string> text(T);
     vector<thread> pool;
     for (size_t t = 1; t < T; t++) pool.emplace_back(formatRange, cref(sh), cref(job), ref(part[t]), ref(text[t]));
     formatRange(sh, job, part[0], text[0]);
     for (auto& th : pool) th.join();
-    lock_guard<mutex> lock(sh.outMutex);
+    gTimer.add("sort + format (wall)", now() - t0); t0 = now();
+    unique_lock<mutex> lock(sh.oMutex);
+    sh.oCv.wait(lock, [&] { return sh.outQueue.size() < sh.maxOut || sh.failed; });
     sh.totMatches += n;
-    for (const auto& t : text) sh.os->write(t.data(), (streamsize)t.size());
+    sh.outQueue.push_back(std::move(text));
+    sh.oCv.notify_all();
+    gTimer.add("wait for writer (wall)", now() - t0);
+}
+
+void writerThread(ScanShared& sh)
+{
+    for (;;) {
+        vector<string> text;
+        {
+            unique_lock<mutex> l(sh.oMutex);
+            sh.oCv.wait(l, [&] { return !sh.outQueue.empty() || sh.outDone; });
+            if (sh.outQueue.empty()) return;
+            text = std::move(sh.outQueue.front()); sh.outQueue.pop_front();
+            sh.oCv.notify_all();
+        }
+        const double t0 = now();
+        for (const auto& t : text) sh.os->write(t.data(), (streamsize)t.size());
+        gTimer.add("file write (writer thread)", now() - t0);
+    }
 }
 
 void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, int engine, bool foldLower)
@@ -270,7 +343,9 @@ void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, 
         if (!sh.failed.exchange(true)) sh.error = what;
         sh.qCv.notify_all();
     };
+    double t0 = now();
     if (b200scan_create(&ctx, dev, maxBlock, maxHits) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(nullptr)); return; }
+    gTimer.add("b200scan_create (per GPU)", now() - t0);
     const auto len = sh.motifs->colLen();
     const auto thr = sh.motifs->colThr();
     if (b200scan_set_engine(ctx, engine) != B200SCAN_OK ||
@@ -281,7 +356,9 @@ void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, 
     int slot = 0;
     auto collect = [&](int s) -> bool {
         const b200scan_hit* hits = nullptr; uint64_t n = 0;
+        const double tc = now();
         if (b200scan_collect(ctx, s, &hits, &n, nullptr) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
+        gTimer.add("b200scan_collect (wait GPU)", now() - tc);
         writeHits(sh, *inFlight[s], hits, n);
         inFlight[s].reset();
         return true;
@@ -306,7 +383,9 @@ void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, 
         if (inFlight[slot] && !collect(slot)) break;     // overlap: format block k-1 while the GPU scores block k
     }
     for (int s = 0; s < B200SCAN_NUM_SLOTS && !sh.failed; s++) { if (inFlight[slot]) collect(slot); slot ^= 1; }
+    t0 = now();
     b200scan_destroy(ctx);
+    gTimer.add("b200scan_destroy (per GPU)", now() - t0);
 }
 
 } // namespace
@@ -353,6 +432,7 @@ int runScan(int argc, char** argv)
     if (relSpec && pSpec) throw runtime_error("Specify either the relative or p-value threshold, not both.");
 
     cout << "Welcome to blamm -- PWM scan module" << endl;
+    const double tStart = now();
     Settings settings;
     settings.print();
 
@@ -400,9 +480,16 @@ int runScan(int argc, char** argv)
             ofsCutoff << sp.name << "\t" << m.name << "\t" << m.minScore() << "\t" << m.threshold << "\t" << m.maxScore() << endl;
         }
 
+        gTimer.add("setup: dict, motifs, thresholds", now() - tStart);
         ScanShared sh;
         sh.motifs = &mc; sh.species = &sp; sh.os = &os;
         sh.formatThreads = std::max<size_t>(1, numThreads / (size_t)nDev);
+        size_t sl = 0, ml = 0;
+        for (const auto& n : sp.seqNames) sl = max(sl, n.size());
+        for (const auto& m : mc.motifs) ml = max(ml, m.name.size());
+        sh.maxNameLen = sl + ml;
+        thread writer(writerThread, ref(sh));
+        auto stopWriter = [&] { { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; } sh.oCv.notify_all(); writer.join(); };
         const uint64_t maxBlock = min<uint64_t>(chunk, max<uint64_t>(sp.totSeqLen, 1024)) + halo + 64;
         vector<thread> workers;
         // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block)
@@ -412,11 +499,14 @@ int runScan(int argc, char** argv)
         try {
             FastaStream fs(sp.files, sp.totSeqLen);
             FastaStream::Chunk c;
-            while (!sh.failed && fs.next(maxBlock - halo - 64, halo, c)) {
+            for (;;) {
+                double tr = now();
+                if (sh.failed || !fs.next(maxBlock - halo - 64, halo, c)) break;
                 unique_ptr<Job> job(new Job);
                 job->chars.assign(c.chars, c.chars + c.nTotal);
                 job->fragStarts = c.fragStarts; job->frags = c.frags;
                 job->nTotal = c.nTotal; job->nPayload = c.nPayload;
+                gTimer.add("FASTA read + filter (reader)", now() - tr);
                 unique_lock<mutex> l(sh.qMutex);
                 sh.qCv.wait(l, [&] { return sh.queue.size() < sh.maxQueue || sh.failed; });
                 sh.queue.push_back(std::move(job));
@@ -427,11 +517,13 @@ int runScan(int argc, char** argv)
             { lock_guard<mutex> l(sh.qMutex); sh.done = true; sh.failed = true; }
             sh.qCv.notify_all();
             for (auto& w : workers) w.join();
+            stopWriter();
             throw;
         }
         { lock_guard<mutex> l(sh.qMutex); sh.done = true; }
         sh.qCv.notify_all();
         for (auto& w : workers) w.join();
+        stopWriter();
         if (sh.failed) throw runtime_error(sh.error.empty() ? "scan failed" : sh.error);
         cout << "Progress... 100%  " << endl;
         totMatches += sh.totMatches;
@@ -439,6 +531,8 @@ int runScan(int argc, char** argv)
     os.close();
     ofsCutoff.close();
     cout << "\nWrote " << totMatches << " matches to " << outputFilename << ".\n";
+    gTimer.add("total (scan module)", now() - tStart);
+    gTimer.report();
     return EXIT_SUCCESS;
 }
 

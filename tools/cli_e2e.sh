@@ -17,12 +17,12 @@ synth.write_fasta("subset.fa", [("chr%d" % (i + 1), seq[i * q:i * q + m]) for i 
 open("genome.mf", "w").write("syn\tgenome.fa\n"); open("subset.mf", "w").write("syn\tsubset.fa\n")
 PY
 B=$ROOT/blamm_b200/lib/blamm-b200; R=$ROOT/oracle/_ref/blamm
-export OPENBLAS_NUM_THREADS=1
+export OPENBLAS_NUM_THREADS=1 BLAMM_B200_TIMING=1
 t() { local s=$(date +%s.%N); "$@" > log.txt 2>&1 || { cat log.txt; exit 1; }; python -c "print('%.2f' % ($(date +%s.%N) - $s))"; }
 echo "dict   b200: $(t $B dict genome.mf) s"
 echo "hist   b200: $(t $B hist motifs.jaspar genome.mf) s"
 echo "scan   b200 ($MBP Mbp x 1800 cols, -rc -pt 1e-4, $GPUS GPU): $(t $B scan -rc -pt 0.0001 -g $GPUS -o occ_full.txt motifs.jaspar genome.mf) s; $(wc -l < occ_full.txt) lines, $(du -m occ_full.txt | cut -f1) MB"
-tail -2 log.txt
+grep timing log.txt; tail -2 log.txt
 $B dict subset.mf > /dev/null; cp genome.mf.dict /dev/null
 # the subset has its own background -> its own histograms / thresholds; both programs read the same files
 $R dict subset.mf > /dev/null; $R hist motifs.jaspar subset.mf > /dev/null
