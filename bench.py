@@ -59,13 +59,44 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock, power and clock-event (throttle) reasons of one GPU, sampled DURING the timed region: an NVML thread
+    (10 ms period, device addressed by PCI bus id so CUDA_VISIBLE_DEVICES cannot confuse it); if pynvml is unusable,
+    the `nvidia-smi --query-gpu ... -lms` loop of the profiling recipe."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.f, self.p = gpu_index, None, None
+    def __init__(self, gpu_index: int, pci_bus_id: str = None):
+        self.idx, self.bus, self.f, self.p = gpu_index, pci_bus_id, None, None
+        self.rows, self.thread, self.stop_flag, self.nv, self.h = [], None, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, reasons))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
 
     def start(self):
+        if self.nv:
+            import threading
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -74,6 +105,20 @@ class ClockSampler:
             self.p = None
 
     def stop(self) -> dict:
+        if self.nv:
+            nv = self.nv
+            self.stop_flag.set(); self.thread.join()
+            if not self.rows:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            busy = [r[0] for r in self.rows if r[1] > 200.0] or [r[0] for r in self.rows]
+            bits = 0
+            for r in self.rows:
+                bits |= r[2]
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            return {"sm_mhz": float(statistics.median(busy)), "sm_max_mhz": float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                    "reasons": [n for n, b in names if bits & b], "samples": len(self.rows), "power_w_max": max(r[1] for r in self.rows),
+                    "source": "nvml, 10 ms period"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -91,7 +136,36 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[5 + k].strip() == "Active" for r in rows)]
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(rows[0][2]), "reasons": reasons, "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows)}
+                "power_w_max": max(float(r[3]) for r in rows), "source": "nvidia-smi -lms 100"}
+
+
+def pci_bus_id(device_index: int) -> str:
+    import torch
+    p = torch.cuda.get_device_properties(device_index)
+    try:
+        return "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(bus: str) -> str:
+    """Pin this rank (and so its pinned host buffers, first touch) to the CPUs of the GPU's NUMA node: with one process per
+    GPU the hit downloads of all ranks otherwise meet on one socket's memory controllers."""
+    try:
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus[-12:].lower()).read())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:
+        return "numa: unbound (%s)" % type(e).__name__
+    return "numa: unbound"
 
 
 def build_inputs(workdir: str, n_nt: int, rank: int):
@@ -245,6 +319,8 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the scan path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    bus = pci_bus_id(local_rank)
+    numa = bind_to_gpu_numa_node(bus) if bus else "numa: unknown bus id"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -276,7 +352,7 @@ def main() -> None:
             hits, t_e2e = sc.collect(0, copy=False)
         n_hits = len(hits)
 
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank, bus)
         # ---- timed: device-resident steps (CUDA events on the scan stream), L2 flushed between steps ----
         barrier()
         sampler.start()
@@ -324,7 +400,7 @@ def main() -> None:
                 "config": {"workload": "configs[1]: JASPAR-like %d PWMs x2 strands (%d columns, sum L = %d) x %.0f Mbp synthetic uniform ACGT per GPU, "
                                        "-rc -pt 1e-4 (real JASPAR CORE unavailable offline)" % (N_MOTIFS, n_cols, sum_len, args.mbp),
                            "engine": engine_used, "parallelism": "chunk-sharded x%d, no collective" % world,
-                           "l2": "flushed between steps (256 MiB memset outside the event pairs)", "hits_per_step": int(n_hits),
+                           "l2": "flushed between steps (256 MiB memset outside the event pairs)", "host_binding": numa, "hits_per_step": int(n_hits),
                            "candidates_per_step": int(t_e2e["n_candidates"])},
                 "gpu_launches": int(launches_per_pass * args.steps * 2 + args.steps),
                 "clocks": clocks,
