@@ -299,6 +299,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mbp", type=float, default=100.0, help="Mbp per GPU")
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "gather"])
+    ap.add_argument("--acc", type=int, default=0, choices=[0, 16, 32], help="tensor filter accumulators: 0 = automatic (diagnostic)")
     ap.add_argument("--cpu-sample-nt", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -343,6 +344,8 @@ def main() -> None:
         ctypes.memmove(host_ptr, seq.ctypes.data, n_nt)
         sc = capi.Scanner(local_rank, max_block_nt=n_nt + 64, max_hits=max(1 << 20, int(2.2e-4 * n_nt * n_cols)))
         sc.set_engine({"auto": capi.ENGINE_AUTO, "tensor": capi.ENGINE_TENSOR, "gather": capi.ENGINE_GATHER}[args.engine])
+        if args.acc:
+            sc.set_tensor_accumulator(args.acc)
         sc.set_motifs(P, col_len, thr)
         scores_per_step = n_nt * n_cols
 

@@ -72,8 +72,9 @@ struct b200scan_ctx {
     float4* d_w = nullptr;  uint32_t *d_woff = nullptr, *d_len = nullptr, *d_orig = nullptr;  float* d_thr = nullptr;
     GatherTile* d_gtiles = nullptr;  std::vector<GatherTile> gtiles;  size_t gather_smem = 0;
     TcTile* d_ttiles = nullptr;  std::vector<TcTile> ttiles;  uint8_t* d_bimg = nullptr;
+    uint32_t n_tiles16 = 0;       // ttiles[0 .. n_tiles16) use FP16 accumulators, the rest FP32
     bool tc_usable = false;
-    bool tc_acc16 = false;        // FP16 accumulators in TMEM (else FP32)
+    int  tc_acc_bits = 32;        // accumulators of the tensor tiles: 16, 32, or 0 when tiles differ
     int  acc_pref = 0;            // 0 auto, 16, 32 (b200scan_set_tensor_accumulator)
     double cand_inflation = 0;    // mean margin over columns (diagnostic)
     uint8_t* d_flush = nullptr;
@@ -245,28 +246,38 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
         return f;
     };
 
-    bool acc16 = ctx->acc_pref != 32 && max_len <= (uint32_t)kMaxLen;
-    double margin_sum = 0;
+    // Accumulator type PER TILE: FP16 accumulators (half the epilogue work) where every column of the tile keeps its margin
+    // <= 2 score units, FP32 otherwise -- a few long or extreme motifs then cost their own tile, not the whole set.
+    const bool try16 = ctx->acc_pref != 32 && max_len <= (uint32_t)kMaxLen;
     std::vector<Folded> folded(n_cols);
-    for (int pass = 0; pass < 2; pass++) {
-        bool ok = true; margin_sum = 0;
-        for (int32_t sc = 0; sc < n_cols; sc++) {
-            folded[sc] = fold((uint32_t)sc, acc16);
-            if (!folded[sc].always) { margin_sum += folded[sc].margin; if (acc16 && folded[sc].margin > 2.0) ok = false; }
-        }
-        if (ok || !acc16) break;
-        if (ctx->acc_pref == 16) break;      // forced: keep FP16 accumulators, the margins stay rigorous (just looser)
-        acc16 = false;
-    }
-    if (acc16) for (auto& f : folded) if (!f.always && f.margin > 1e8) { f.always = true; }
-
+    for (int32_t sc = 0; sc < n_cols; sc++) folded[sc] = fold((uint32_t)sc, try16);
     std::vector<std::pair<uint32_t, uint32_t>> cuts;
-    plan_tc_tiles(len, acc16, cuts);
+    plan_tc_tiles(len, try16, cuts);
+    std::vector<uint32_t> tile_acc16(cuts.size(), 0);
+    for (size_t ti = 0; ti < cuts.size(); ti++) {
+        bool ok = try16;
+        if (ok && ctx->acc_pref != 16)
+            for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++)
+                if (!folded[sc].always && folded[sc].margin > 2.0) { ok = false; break; }
+        tile_acc16[ti] = ok ? 1u : 0u;
+        for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++) {
+            if (!ok && try16) folded[sc] = fold(sc, false);
+            // forced FP16 accumulators: a column whose bound did not converge goes to the exact rescorer wholesale
+            if (ok && !folded[sc].always && folded[sc].margin > 1e8) folded[sc].always = true;
+        }
+    }
+    double margin_sum = 0;
+    for (const auto& f : folded) if (!f.always) margin_sum += f.margin;
+    uint32_t n16 = 0;
+    for (uint32_t a : tile_acc16) n16 += a;
+
     std::vector<TcTile> tt;
     std::vector<uint8_t> bimg;
     bool tc_ok = true;
-    for (auto& cut : cuts) {
+    for (size_t ti = 0; ti < cuts.size(); ti++) {
+        const auto& cut = cuts[ti];
         TcTile t{};
+        t.acc16 = tile_acc16[ti];
         t.col0 = cut.first; t.n_cols = cut.second - cut.first;
         t.n_pad = (t.n_cols + 63) / 64 * 64;
         t.n_k = (len[cut.second - 1] + 3) / 4;
@@ -294,8 +305,10 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
         }
         tt.push_back(t);
     }
+    std::stable_partition(tt.begin(), tt.end(), [](const TcTile& t) { return t.acc16 != 0; });
+    ctx->n_tiles16 = n16;
     if (max_len > (uint32_t)kMaxLen) tc_ok = false;
-    ctx->tc_acc16 = acc16;
+    ctx->tc_acc_bits = (n16 == cuts.size()) ? 16 : (n16 == 0 ? 32 : 0);
     ctx->cand_inflation = n_cols ? margin_sum / n_cols : 0;
 
     // ---- upload ----
@@ -346,6 +359,7 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     HitSink sink{s.d_hits, s.d_counters + 1, s.hit_cap};
     unsigned int* err = reinterpret_cast<unsigned int*>(s.d_counters + 2) + 1;
     unsigned int* work = reinterpret_cast<unsigned int*>(s.d_counters + 3);
+    unsigned int* work2 = reinterpret_cast<unsigned int*>(s.d_counters + 4);      // work counter of the FP32-accumulator instance
     int n = 0;
     if (s.n_payload == 0) {                          // nothing to score (empty block): keep the event protocol intact
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
@@ -361,16 +375,26 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
         tp.work_counter = work; tp.raw = ctx->d_raw; tp.blk_count = ctx->d_blk_count; tp.n_blocks = work + 1; tp.blk_cap = ctx->blk_cap;
         tp.error_flag = err;
         tp.trace = ctx->d_trace;
-        if (ctx->tc_acc16) filter_tc_kernel<true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
-        else filter_tc_kernel<false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+        // one instance per accumulator type over its share of the tiles (FP16 tiles are stored first); both append to the same
+        // raw-entry blocks, each has its own work counter
+        if (ctx->n_tiles16) {
+            tp.tiles = ctx->d_ttiles; tp.n_tiles = ctx->n_tiles16; tp.work_counter = work;
+            filter_tc_kernel<true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+            n++;
+        }
+        if (ctx->n_tiles16 < ctx->ttiles.size()) {
+            tp.tiles = ctx->d_ttiles + ctx->n_tiles16; tp.n_tiles = (uint32_t)ctx->ttiles.size() - ctx->n_tiles16; tp.work_counter = work2;
+            filter_tc_kernel<false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+            n++;
+        }
+        n--;
         n++;
         if (ctx->engine == B200SCAN_ENGINE_AUTO) {     // blocks with a zero mask: exact gather-add (kernel exits at once otherwise)
             gather_scan_kernel<true><<<ggrid, kGatherThreads, ctx->gather_smem, ctx->stream>>>(md, blk, ctx->d_gtiles, sink, 1);
             n++;
         }
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
-        if (ctx->tc_acc16) expand_kernel<true><<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
-        else expand_kernel<false><<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
+        expand_kernel<<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
         n++;
         rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(md, blk, ctx->d_cand, s.d_counters, ctx->cand_cap, sink);
         n++;
@@ -389,11 +413,12 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
 
 int reset_counters(b200scan_ctx* ctx, Slot& s, bool keep_has_zero, cudaStream_t st)
 {
-    // [0] n_cand [1] n_hits: zero.  [2] = {has_zero, error}: keep has_zero on re-runs.  [3] work counter: zero.
-    CU(cudaMemsetAsync(s.d_counters, 0, 16, ctx->stream));
-    if (keep_has_zero) CU(cudaMemsetAsync(reinterpret_cast<uint32_t*>(s.d_counters + 2) + 1, 0, 4, ctx->stream));
-    else CU(cudaMemsetAsync(s.d_counters + 2, 0, 8, ctx->stream));
-    CU(cudaMemsetAsync(s.d_counters + 3, 0, 8, ctx->stream));
+    // [0] n_cand [1] n_hits: zero.  [2] = {has_zero, error}: keep has_zero on re-runs.  [3] {work counter, raw blocks} [4] second work counter: zero.
+    // (all on the caller's stream `st`: on a first submit that is the upload stream, where the pack kernel then sets has_zero)
+    CU(cudaMemsetAsync(s.d_counters, 0, 16, st));
+    if (keep_has_zero) CU(cudaMemsetAsync(reinterpret_cast<uint32_t*>(s.d_counters + 2) + 1, 0, 4, st));
+    else CU(cudaMemsetAsync(s.d_counters + 2, 0, 8, st));
+    CU(cudaMemsetAsync(s.d_counters + 3, 0, 16, st));               // both work counters and the block counter
     return B200SCAN_OK;
 }
 
@@ -513,7 +538,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
         CUB(cudaMemset(s.d_zmask, 0, nb / 8 + kPadBytes));
         CUB(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * max_hits));
         s.hit_cap = max_hits;
-        CUB(cudaMalloc(&s.d_counters, 32));
+        CUB(cudaMalloc(&s.d_counters, 64));
         CUB(cudaMemset(s.d_counters, 0, 32));
         for (auto& e : s.ev) CUB(cudaEventCreate(&e));
     }
@@ -878,7 +903,7 @@ int b200scan_flush_l2(b200scan_ctx* ctx)
 int b200scan_tensor_info(const b200scan_ctx* ctx, int32_t* accumulator_bits, double* mean_margin)
 {
     if (!ctx) return B200SCAN_EINVAL;
-    if (accumulator_bits) *accumulator_bits = ctx->tc_acc16 ? 16 : 32;
+    if (accumulator_bits) *accumulator_bits = ctx->tc_acc_bits;
     if (mean_margin) *mean_margin = ctx->cand_inflation;
     return B200SCAN_OK;
 }

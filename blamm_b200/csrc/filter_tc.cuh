@@ -92,6 +92,8 @@ struct TcTile {
     uint32_t n_k;       // MMAs per 128-window tile = ceil(Lmax / 4)
     uint32_t b_off;     // byte offset of the tile's B image in TcParams::bimg
     uint32_t b_bytes;   // n_pad * (2*n_k) * 16
+    uint32_t acc16;     // 1: FP16 accumulators (filter_tc_kernel<true>), 0: FP32 -- chosen per tile by the host's error bound; the host
+                        // launches one kernel instance per accumulator type over its share of the tiles
 };
 
 struct TcParams {
@@ -242,6 +244,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 //   FP16 accumulators (.pack::16b: word k = columns 2k | 2k+1): 64 columns per chunk; (t, b) of word w <-> column 32w + 4t + b
 //   FP32 accumulators (word k = column k):                      32 columns per chunk; (t, b) of word w <-> column 16w + 2t + b, b < 2
 constexpr uint32_t kAllNegative = 0xFFFFFF01u;
+constexpr uint32_t kRawFp32Flag = 0x80000000u;     // set in a raw entry's column words when its tile used FP32 accumulators
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -510,8 +513,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     if (has1) sign_words<ACC16>(v1, b0, b1);
                     const bool c = winOk && (((a0 ^ kAllNegative) | (a1 ^ kAllNegative) | (b0 ^ kAllNegative) | (b1 ^ kAllNegative)) != 0u);
                     const unsigned t = (TC_KNOCKOUT & 8) ? 0u : __ballot_sync(0xffffffffu, c);
-                    if (t) raw_push(rawc, P, t, c, win0 + lane, tile.col0 + wc * kColsPerWord, a0, a1,
-                                    tile.col0 + (wc + step) * kColsPerWord, b0, b1, lane);
+                    if (t) raw_push(rawc, P, t, c, win0 + lane, (tile.col0 + wc * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), a0, a1,
+                                    (tile.col0 + (wc + step) * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), b0, b1, lane);
                 }
                 if (!released) {                                      // this warp owns no chunk of such a narrow tile
                     tc_fence_before();

@@ -15,12 +15,12 @@ namespace b200 {
 // Inverse of filter_tc.cuh: sign_words().  X = sum_b 255 * M_b * 256^b (mod 2^32)  ->  M_0 | M_1 << 8 | M_2 << 16 | M_3 << 24
 // (bit 8b + t set <=> accumulator (t, b) negative).  255 M = 256 M - M, so X = -M_0 + (M_0 - M_1) 256 + (M_1 - M_2) 256^2 + ...
 // and the bytes peel off from the bottom.  FP32 accumulators only fill b < 2 (the upper bytes repeat them).
-template <bool ACC16> __device__ __forceinline__ uint32_t decode_sign_word(uint32_t x)
+__device__ __forceinline__ uint32_t decode_sign_word(bool acc16, uint32_t x)
 {
     const uint32_t m0 = (0u - x) & 255u;
     const uint32_t y1 = (x + m0) >> 8;                               // (M_0 - M_1) + (M_1 - M_2) 256 + (M_2 - M_3) 256^2  mod 2^24
     const uint32_t m1 = (m0 - y1) & 255u;
-    if (!ACC16) return m0 | (m1 << 8) | 0xFFFF0000u;
+    if (!acc16) return m0 | (m1 << 8) | 0xFFFF0000u;
     const uint32_t y2 = ((y1 - (m0 - m1)) & 0xFFFFFFu) >> 8;         // (M_1 - M_2) + (M_2 - M_3) 256  mod 2^16
     const uint32_t m2 = (m1 - y2) & 255u;
     const uint32_t y3 = ((y2 - (m1 - m2)) & 0xFFFFu) >> 8;           // (M_2 - M_3)  mod 2^8
@@ -28,7 +28,6 @@ template <bool ACC16> __device__ __forceinline__ uint32_t decode_sign_word(uint3
     return m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
 }
 
-template <bool ACC16>
 __global__ void __launch_bounds__(256)
 expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count, const unsigned int* __restrict__ n_blocks_ptr,
               uint32_t blk_cap, Cand* __restrict__ cand, unsigned long long* n_cand, unsigned long long cand_cap,
@@ -51,8 +50,8 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
         __syncwarp();
         n = 0;
     };
-    auto column = [](uint32_t first, uint32_t w, uint32_t bit) {
-        return ACC16 ? first + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first + 16 * w + 2 * (bit & 7u) + (bit >> 3);
+    auto column = [](bool acc16, uint32_t first, uint32_t w, uint32_t bit) {
+        return acc16 ? first + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first + 16 * w + 2 * (bit & 7u) + (bit >> 3);
     };
     const unsigned long long slots = (unsigned long long)nb * kRawBlock;
     const uint4* ent = reinterpret_cast<const uint4*>(raw);
@@ -61,8 +60,9 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
         const bool live = e < __ldg(blk_count + b);
         uint4 x = make_uint4(0u, 0u, kAllNegative, kAllNegative), y = make_uint4(0u, kAllNegative, kAllNegative, 0u);
         if (live) { x = __ldg(ent + 2 * (s0 + lane)); y = __ldg(ent + 2 * (s0 + lane) + 1); }
-        uint32_t z[4] = {~decode_sign_word<ACC16>(x.z), ~decode_sign_word<ACC16>(x.w), ~decode_sign_word<ACC16>(y.y), ~decode_sign_word<ACC16>(y.z)};
-        const uint32_t first[2] = {x.y, y.x};
+        const bool acc16 = !(x.y & kRawFp32Flag);                 // the tile's accumulator type travels in the column words
+        uint32_t z[4] = {~decode_sign_word(acc16, x.z), ~decode_sign_word(acc16, x.w), ~decode_sign_word(acc16, y.y), ~decode_sign_word(acc16, y.z)};
+        const uint32_t first[2] = {x.y & ~kRawFp32Flag, y.x & ~kRawFp32Flag};
         const uint32_t c = __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
         uint32_t incl = c;                                   // inclusive warp scan
 #pragma unroll
@@ -75,7 +75,7 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
             uint32_t o = n + incl - c;
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(first[q >> 1], q & 1, bit); st[o++] = cd; }
+                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(acc16, first[q >> 1], q & 1, bit); st[o++] = cd; }
             n += total;
             if (n > 256) flush();
         } else {                                             // more than 20 candidates per entry on average: straight to global
@@ -84,7 +84,7 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
             unsigned long long o = __shfl_sync(0xffffffffu, base, 0) + incl - c;
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(first[q >> 1], q & 1, bit); if (o < cand_cap) cand[o] = cd; o++; }
+                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(acc16, first[q >> 1], q & 1, bit); if (o < cand_cap) cand[o] = cd; o++; }
         }
     }
     if (n) flush();

@@ -146,6 +146,41 @@ def test_max_length_and_many_columns(scanner, engine):
     scanner.set_tensor_accumulator(0)
 
 
+def test_accumulator_type_is_chosen_per_tile(scanner):
+    """Short motifs keep FP16 accumulators while a tile of long motifs with extreme weights (error bound > 2 score
+    units) falls back to FP32: the set is 'mixed' (tensor_info reports 0) and the hit list still equals the oracle's."""
+    case = util.random_case(91, n_motifs=150, n_nt=300_000, len_range=(6, 12))
+    rng = np.random.default_rng(92)
+    n_short, ldp = case["P"].shape[0], 4 * 64
+    P = np.zeros((n_short + 8, ldp), dtype=np.float32)
+    P[:n_short, :case["P"].shape[1]] = case["P"]
+    col_len = np.concatenate([case["col_len"], np.full(8, 64, dtype=case["col_len"].dtype)])
+    thr = np.concatenate([case["thr"], np.zeros(8, dtype=np.float32)])
+    codes = np.frombuffer(bytes(case["chars"][:4096]), dtype=np.uint8)
+    lut = np.zeros(256, dtype=np.int64); lut[ord("C")] = 1; lut[ord("G")] = 2; lut[ord("T")] = 3
+    for k in range(8):                                   # weights in [-20, 2]; the window at 100 + 37 k scores the maximum
+        W = rng.uniform(-20.0, -1.0, size=(64, 4)).astype(np.float32)
+        best = lut[codes[100 + 37 * k: 164 + 37 * k]]
+        W[np.arange(64), best] = rng.uniform(0.5, 2.0, size=64).astype(np.float32)
+        P[n_short + k, :] = W.reshape(-1)
+        thr[n_short + k] = np.float32(-400.0)            # ~2 sigma above the mean window score: thousands of hits per column
+    scanner.set_engine(capi.ENGINE_TENSOR)
+    scanner.set_tensor_accumulator(0)
+    scanner.set_motifs(P, col_len, thr)
+    assert scanner.tensor_info()["accumulator_bits"] == 0, scanner.tensor_info()
+    hits, t = scanner.scan(case["chars"], case["frag_start"][1:])
+    want = _oracle_hits(dict(case, P=P, col_len=col_len, thr=thr))
+    assert (hits["col"] >= n_short).sum() > 100
+    _assert_same(hits, *want)
+    for bits in (16, 32):                                # forcing either type everywhere changes nothing
+        scanner.set_tensor_accumulator(bits)
+        scanner.set_motifs(P, col_len, thr)
+        assert scanner.tensor_info()["accumulator_bits"] == bits
+        h2, _ = scanner.scan(case["chars"], case["frag_start"][1:])
+        _assert_same(h2, *want)
+    scanner.set_tensor_accumulator(0)
+
+
 def test_packed_submit_and_zero_mask(scanner):
     case = util.random_case(41, n_motifs=10, n_nt=50_000)
     chars = case["chars"]
@@ -202,6 +237,27 @@ def test_double_buffered_slots_and_state_errors(scanner):
         scanner.collect(0)                                   # nothing in flight
     with pytest.raises(capi.ScanError):
         scanner.submit_ascii(0, a["chars"], frag_starts=np.array([5, 5], dtype=np.uint64))   # not ascending
+
+
+def test_pipelined_lower_case_block_keeps_zero_mask(scanner):
+    """A lower-case block submitted on slot 1 while slot 0's kernels are still running: its upload, counter reset and
+    packing run on the upload stream, and the has_zero flag the pack kernel raises must survive until the scan of that
+    block (AUTO then routes it through the exact gather-add kernel with BLAS-path semantics)."""
+    big = util.random_case(61, n_motifs=60, n_nt=24_000_000, len_range=(6, 14), with_gaps=False)
+    small = util.random_case(62, n_motifs=60, n_nt=300_000, len_range=(6, 14), lower=True)
+    for c in (big, small):
+        c["P"], c["col_len"] = big["P"], big["col_len"]
+        c["thr"] = np.maximum(big["thr"], 8.0).astype(np.float32)
+    scanner.set_engine(capi.ENGINE_AUTO)
+    scanner.set_motifs(big["P"], big["col_len"], big["thr"])
+    for _ in range(3):
+        scanner.submit_ascii(0, big["chars"])
+        scanner.submit_ascii(1, small["chars"], frag_starts=small["frag_start"][1:])
+        h0, t0 = scanner.collect(0)
+        h1, t1 = scanner.collect(1)
+        assert t0["engine_used"] == capi.ENGINE_TENSOR and t1["engine_used"] == capi.ENGINE_GATHER
+        _assert_same(h1, *_oracle_hits(small))
+    assert len(h0) > 1000
 
 
 def test_engines_agree_at_scale_and_properties(scanner):
