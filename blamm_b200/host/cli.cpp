@@ -249,7 +249,7 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<b200scan_hit>
     sort(hits.begin(), hits.end(), [](const b200scan_hit& a, const b200scan_hit& b) {
         return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; });
     // worst-case line: names + 2 positions of <= 20 digits + score (<= 16) + 5 tabs + strand + "\t.\t.\n"
-    text.resize(hits.size() * (sh.maxNameLen + 72));
+    text.resize(hits.size() * (sh.maxNameLen + 96) + 64);
     char* const base = &text[0];
     char* p = base;
     size_t f = 0;
