@@ -21,6 +21,11 @@ $(LIBDIR)/libb200scan_trace.so: $(CSRC)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -DB200_TRACE -shared blamm_b200/csrc/b200scan.cu -o $@
 
+# diagnostic build with per-role cycle totals (tools/tc_phase.py); never used by the product
+$(LIBDIR)/libb200scan_phase.so: $(CSRC)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -DB200_PHASE -shared blamm_b200/csrc/b200scan.cu -o $@
+
 $(LIBDIR)/libblammhost.so: $(HSRC) blamm_b200/host/host_abi.cpp $(HHDR)
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(CXXFLAGS) -shared $(HSRC) blamm_b200/host/host_abi.cpp -o $@

@@ -542,7 +542,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
         CUB(cudaMemset(s.d_counters, 0, 32));
         for (auto& e : s.ev) CUB(cudaEventCreate(&e));
     }
-#ifdef B200_TRACE
+#if defined(B200_TRACE) || defined(B200_PHASE)
     CUB(cudaMalloc(&c->d_trace, 4 * kTraceTiles * 4 * 8));
     CUB(cudaMemset(c->d_trace, 0, 4 * kTraceTiles * 4 * 8));
 #endif
@@ -879,7 +879,7 @@ int b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total
     return rc;
 }
 
-#ifdef B200_TRACE
+#if defined(B200_TRACE) || defined(B200_PHASE)
 int b200scan_debug_trace(b200scan_ctx* ctx, unsigned long long* out, int n)
 {
     if (!ctx || !out) return B200SCAN_EINVAL;

@@ -111,11 +111,25 @@ struct TcParams {
 };
 
 constexpr uint32_t kTraceTiles = 256;
-#ifdef B200_TRACE
+#if defined(B200_TRACE) && !defined(B200_PHASE)
 #define TC_TRACE(role, tile_i, ev) do { if (blockIdx.x == 0 && nItem == 0 && lane == 0 && (tile_i) < kTraceTiles) \
         P.trace[((role) * kTraceTiles + (tile_i)) * 4 + (ev)] = (unsigned long long)clock64(); } while (0)
 #else
 #define TC_TRACE(role, tile_i, ev) do {} while (0)
+#endif
+// B200_PHASE builds (diagnostic, tools/tc_phase.py): per-role cycle totals over the whole launch, accumulated in registers
+// (two clock reads per phase, no memory traffic until the kernel ends).  P.trace[16 * role + k], summed over all CTAs:
+//   role 0 producer warp 0:   0 waiting for a free E stage   1 filling            3 stages
+//   role 1 issuer:            0 waiting for E stages         1 waiting for TMEM   2 issuing + commits   3 tiles
+//   role 2 epilogue, group 0: 0 waiting for tFull            1 tcgen05.ld phase   2 compaction + push   3 tiles
+#ifdef B200_PHASE
+#define PH_MARK()   do { ph_t = clock64(); } while (0)
+#define PH_ACC(k)   do { const long long n_ = clock64(); ph_a[k] += n_ - ph_t; ph_t = n_; } while (0)
+#define PH_COUNT()  do { ph_a[3]++; } while (0)
+#else
+#define PH_MARK()   do {} while (0)
+#define PH_ACC(k)   do {} while (0)
+#define PH_COUNT()  do {} while (0)
 #endif
 
 // shared memory carve-up (bytes)
@@ -352,6 +366,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     tc_fence_after();
     const uint32_t tmem_base = sMisc[1];
 
+    long long ph_t = 0, ph_a[4] = {0, 0, 0, 0};   // B200_PHASE only (dead otherwise)
+    (void)ph_t; (void)ph_a;
     uint32_t kE = 0;            // E stages produced / consumed so far (every role advances identically)
     uint32_t kT = 0;            // window tiles so far
     uint32_t nItem = 0, nBload = 0;
@@ -399,7 +415,9 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             const uint32_t nEnt = (nT + 1) * 128;                     // entries of the item incl. one halo tile
             for (uint32_t st = 0; st < nSt; st++) {
                 const uint32_t k = kE + st, slot = k % kTcStages, ph = (k / kTcStages) & 1;
+                PH_MARK();
                 mbar_wait(eEmpty + 8 * slot, ph ^ 1, P.error_flag);
+                PH_ACC(0);
                 if (warp == 0) TC_TRACE(0, st, 0);
                 if (!(TC_KNOCKOUT & 4) && !((TC_KNOCKOUT & 64) && t != 0 && nItem > 8)) {     // 64: fill only for column tile 0 (emulates an E-stationary loop order on random sequence; results invalid)
 #pragma unroll
@@ -419,6 +437,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(eFull + 8 * slot);
+                PH_ACC(1); PH_COUNT();
                 if (warp == 0) TC_TRACE(0, st, 1);
             }
         } else if (warp == kTcProducers) {
@@ -446,12 +465,15 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     const uint32_t k = kE + st, slot = k % kTcStages;
                     const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
                     const bool lastOfStage = (j + 1 == kTcStageTiles), lastTile = (i + 1 == nT);
+                    PH_MARK();
                     if (lastOfStage) {                                    // its halo lies in the next stage
                         const uint32_t k1 = k + 1;
                         mbar_wait(eFull + 8 * (k1 % kTcStages), (k1 / kTcStages) & 1, P.error_flag);
                     }
                     TC_TRACE(1, i, 0);
+                    PH_ACC(0);
                     mbar_wait(tEmpty + 8 * buf, tph ^ 1, P.error_flag);
+                    PH_ACC(1);
                     TC_TRACE(1, i, 1);
                     tc_fence_after();
                     const uint32_t d = tmem_base + buf * kBufCols;
@@ -471,6 +493,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     if (lastOfStage || lastTile) umma_commit(eEmpty + 8 * slot);
                     if (lastOfStage && lastTile) umma_commit(eEmpty + 8 * ((k + 1) % kTcStages));
                     umma_commit(tFull + 8 * buf);
+                    PH_ACC(2); PH_COUNT();
                     TC_TRACE(1, i, 2);
                     if (lastOfStage) { j = 0; st++; } else j++;
                 }
@@ -484,7 +507,9 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             uint32_t kt = kT + i0, win0 = w0 + 128 * i0 + 32 * eQ;    // running tile index; window of lane 0
             for (uint32_t i = i0; i < nT; i += kTcEpiGroups, kt += kTcEpiGroups, win0 += 128 * kTcEpiGroups) {
                 const uint32_t buf = kt % kBufs, tph = (kt / kBufs) & 1;
+                PH_MARK();
                 mbar_wait(tFull + 8 * buf, tph, P.error_flag);
+                PH_ACC(0);
                 if (warp == kTcEpiWarp0) TC_TRACE(2, i, 0); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 0);
                 tc_fence_after();
                 const bool winOk = win0 + lane < blk.n_payload;
@@ -504,6 +529,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tEmpty + 8 * buf);
+                        PH_ACC(1);
                         released = true;
                         if (warp == kTcEpiWarp0) TC_TRACE(2, i, 2); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 2);
                     }
@@ -521,6 +547,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tEmpty + 8 * buf);
                 }
+                PH_ACC(2); PH_COUNT();
                 if (warp == kTcEpiWarp0) TC_TRACE(2, i, 3); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 3);
             }
         }
@@ -531,6 +558,12 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         __syncthreads();          // item boundary: every role is done with sCodes / sB / the pipelines are drained
     }
 
+#ifdef B200_PHASE
+    if (lane == 0 && (warp == 0 || warp == kTcProducers || warp == kTcEpiWarp0)) {
+        const uint32_t role = warp == 0 ? 0u : (warp == kTcProducers ? 1u : 2u);
+        for (int k = 0; k < 4; k++) atomicAdd(P.trace + 16 * role + k, (unsigned long long)ph_a[k]);
+    }
+#endif
     if (warp >= kTcEpiWarp0 && lane == 0) {                                          // close the open block and the unused spare
         if (rawc.blk < P.blk_cap) P.blk_count[rawc.blk] = kRawBlock - rawc.left;
         if (rawc.spare < P.blk_cap) P.blk_count[rawc.spare] = 0;
