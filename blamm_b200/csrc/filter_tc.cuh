@@ -76,7 +76,8 @@ constexpr int      kTcThreads  = 32 * (kTcProducers + 1 + kTcEpiWarps);
 constexpr uint32_t kTcSpan     = TC_SPAN;    // windows per work item
 constexpr uint32_t kTcStageTiles = TC_STAGE_TILES;
 constexpr uint32_t kTcStageEnt = 128 * kTcStageTiles;          // entries per E stage
-constexpr uint32_t kTcStages   = 8 / kTcStageTiles < 3 ? 3 : 8 / kTcStageTiles;     // E ring stages (<= 8: barrier map), ring of >= 8 tiles
+constexpr uint32_t kTcStages   = kTcStageTiles >= 4 ? 4 : 8 / kTcStageTiles;        // E ring stages: a power of two <= 8 (barrier map), ring of >= 8 tiles
+static_assert((kTcStages & (kTcStages - 1)) == 0 && (TC_BUFS & (TC_BUFS - 1)) == 0, "ring and buffer counts are powers of two (the issuer steps them with masks)");
 constexpr uint32_t kTcMirror   = 64;         // entries mirrored past the ring end (>= 2*(2*nK_max-1))
 constexpr uint32_t kTcMaxN     = TC_MAXN;     // columns per tile; 2 accumulator buffers of kTcMaxN TMEM columns per CTA
 static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N columns x CTAs per SM must fit 512 columns");
@@ -459,27 +460,26 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             // instruction instead costs 5-7 R2UR moves in front of every one of them).
             if (elect_one()) {
                 mbar_wait(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
-                uint32_t st = 0, j = 0;                                   // stage of the item / tile within the stage
+                // loop state is stepped incrementally (adds and masks only: every instruction of this lane is on the critical path)
+                uint32_t j = 0, kCur = kE, kt = kT;                      // tile within the stage, stage counter, tile counter
+                uint32_t aOff = (kE % kTcStages) * kTcStageEnt;          // first E entry of the tile, in ring entries
 #pragma unroll 1
-                for (uint32_t i = 0; i < nT; i++) {
-                    const uint32_t k = kE + st, slot = k % kTcStages;
-                    const uint32_t kt = kT + i, buf = kt % kBufs, tph = (kt / kBufs) & 1;
-                    const bool lastOfStage = (j + 1 == kTcStageTiles), lastTile = (i + 1 == nT);
+                for (uint32_t left = nT; left != 0; left--) {
+                    const uint32_t buf = kt % kBufs;
+                    const bool lastOfStage = (j + 1 == kTcStageTiles), lastTile = (left == 1);
                     PH_MARK();
-                    if (lastOfStage) {                                    // its halo lies in the next stage
-                        const uint32_t k1 = k + 1;
-                        mbar_wait(eFull + 8 * (k1 % kTcStages), (k1 / kTcStages) & 1, P.error_flag);
-                    }
-                    TC_TRACE(1, i, 0);
+                    if (lastOfStage)                                      // its halo lies in the next stage
+                        mbar_wait(eFull + 8 * ((kCur + 1) % kTcStages), ((kCur + 1) / kTcStages) & 1, P.error_flag);
+                    TC_TRACE(1, nT - left, 0);
                     PH_ACC(0);
-                    mbar_wait(tEmpty + 8 * buf, tph ^ 1, P.error_flag);
+                    mbar_wait(tEmpty + 8 * buf, ((kt / kBufs) & 1) ^ 1, P.error_flag);
                     PH_ACC(1);
-                    TC_TRACE(1, i, 1);
+                    TC_TRACE(1, nT - left, 1);
                     tc_fence_after();
                     const uint32_t d = tmem_base + buf * kBufCols;
                     // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[entry0 + r + 2*kk]; one MMA = 4 entries = 64 B
                     // B: [8-column group][chunk] blocks of 128 B: one MMA = 2 chunks = 256 B
-                    uint32_t alo = aLo0 + slot * kTcStageEnt + j * 128, blo = bLo0;          // address fields are in 16-byte units
+                    uint32_t alo = aLo0 + aOff, blo = bLo0;               // address fields are in 16-byte units = entries
                     if (!(TC_KNOCKOUT & 2)) {
                         umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
 #pragma unroll 1
@@ -490,12 +490,14 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     }
                     // MMAs complete in issue order: once the last tile of a stage is done, so is every reader of the stage
                     // (its own tiles and the halo read of the stage before).  The item's last tile also frees its halo stage.
-                    if (lastOfStage || lastTile) umma_commit(eEmpty + 8 * slot);
-                    if (lastOfStage && lastTile) umma_commit(eEmpty + 8 * ((k + 1) % kTcStages));
+                    if (lastOfStage || lastTile) umma_commit(eEmpty + 8 * (kCur % kTcStages));
+                    if (lastOfStage && lastTile) umma_commit(eEmpty + 8 * ((kCur + 1) % kTcStages));
                     umma_commit(tFull + 8 * buf);
                     PH_ACC(2); PH_COUNT();
-                    TC_TRACE(1, i, 2);
-                    if (lastOfStage) { j = 0; st++; } else j++;
+                    TC_TRACE(1, nT - left, 2);
+                    aOff = (aOff + 128) % (kTcStages * kTcStageEnt);
+                    kt++;
+                    if (lastOfStage) { j = 0; kCur++; } else j++;
                 }
             }
             __syncwarp();
