@@ -181,6 +181,23 @@ def test_accumulator_type_is_chosen_per_tile(scanner):
     scanner.set_tensor_accumulator(0)
 
 
+@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+def test_many_short_fragments(scanner, engine):
+    """120,000 sequences of 1 .. 40 characters in one block (most shorter than the motifs): the fragment rule of
+    SeqBlock::getRemainingSeqLen decides almost every window."""
+    case = util.random_case(33, n_motifs=30, n_nt=2_400_000, len_range=(5, 24), with_gaps=False)
+    rng = np.random.default_rng(34)
+    starts = np.cumsum(rng.integers(1, 41, size=120_000)).astype(np.uint64)
+    case["frag_start"] = np.concatenate([np.zeros(1, dtype=np.uint64), starts[starts < len(case["chars"]) - 1]])
+    case["thr"] = np.minimum(case["thr"], 6.0).astype(np.float32)
+    scanner.set_engine(engine)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    hits, t = scanner.scan(case["chars"], case["frag_start"][1:])
+    want = _oracle_hits(case)
+    assert len(want[0]) > 1000
+    _assert_same(hits, *want)
+
+
 def test_packed_submit_and_zero_mask(scanner):
     case = util.random_case(41, n_motifs=10, n_nt=50_000)
     chars = case["chars"]
