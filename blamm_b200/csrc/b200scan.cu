@@ -73,6 +73,7 @@ struct b200scan_ctx {
     GatherTile* d_gtiles = nullptr;  std::vector<GatherTile> gtiles;  size_t gather_smem = 0;
     TcTile* d_ttiles = nullptr;  std::vector<TcTile> ttiles;  uint8_t* d_bimg = nullptr;
     uint32_t n_tiles16 = 0;       // ttiles[0 .. n_tiles16) use FP16 accumulators, the rest FP32
+    TcTile* d_ttiles_z = nullptr;  uint8_t* d_bimg_z = nullptr;  uint32_t n_tiles16_z = 0;     // the same for blocks with zero-contribution characters
     bool tc_usable = false;
     int  tc_acc_bits = 32;        // accumulators of the tensor tiles: 16, 32, or 0 when tiles differ
     int  acc_pref = 0;            // 0 auto, 16, 32 (b200scan_set_tensor_accumulator)
@@ -191,7 +192,7 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     //     M_k = largest possible prefix), so |D_k| <= B_k = max(M_k, R_k, 0).  Allowing a rounding of one FP16 ulp
     //     (2^-10 relative: covers round-to-nearest and truncation) on EVERY internal add of the 4 products and the
     //     old accumulator:  |e2| <= 2^-10 * 4 * sum_k (B_{k-1} + A_k),  A_k = sum of max|y_j| over the step.
-    struct Folded { std::vector<uint16_t> y; double margin; bool always; };
+    struct Folded { std::vector<uint16_t> y; double margin; bool always; uint16_t bias = 0; };
     auto fold = [&](uint32_t sc, bool acc16) {
         const uint32_t L = len[sc];
         Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false;
@@ -246,74 +247,137 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
         return f;
     };
 
+    // Blocks with zero-contribution characters (lower case under the reference's BLAS-path semantics, sequence.cpp:312-319)
+    // use a second image: the weights are NOT shifted by a threshold share (a masked position must add exactly 0); instead
+    // one extra leading MMA step adds the bias  b = fp16_up(-(thr - margin))  to every window through a constant one-hot
+    // operand.  acc = b + sum y_j >= score - thr + margin as before, for either sign of the threshold, and a fully masked
+    // window gets acc = b < 0 instead of a spurious candidate.  FP16 accumulation: D_0 = b exactly; for a true hit the
+    // partial sum after position step k lies in [-R_k, b + M_k] with M_k / R_k built from max(y, 0) (a masked position
+    // contributes 0), so |D_k| <= max(R_k, |b| + M_k) and the same per-add ulp bound applies.
+    auto fold_z = [&](uint32_t sc, bool acc16) {
+        const uint32_t L = len[sc];
+        Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false; f.bias = 0;
+        double A = 0;
+        bool finite = std::isfinite(thr_s[sc]);
+        std::vector<double> ymax(L), yabs(L);
+        for (uint32_t j = 0; j < L; j++) {
+            const float4 v = w[woff[sc] + j];
+            const float a4[4] = {v.x, v.y, v.z, v.w};
+            double m = 0, mx = 0, ma = 0;                      // mx starts at 0: the masked contribution
+            for (uint32_t o = 0; o < 4; o++) {
+                if (!std::isfinite(a4[o])) { finite = false; continue; }
+                m = std::max(m, std::fabs((double)a4[o]));
+                if (std::fabs((double)a4[o]) > 30000.0) { finite = false; continue; }
+                const uint16_t h = half_round_up((double)a4[o]);
+                f.y[4 * j + o] = h;
+                __half hh; std::memcpy(&hh, &h, 2);
+                const double yr = (double)__half2float(hh);
+                mx = std::max(mx, yr); ma = std::max(ma, std::fabs(yr));
+            }
+            A += m; ymax[j] = mx; yabs[j] = ma;
+        }
+        if (!finite || std::fabs((double)thr_s[sc]) > 30000.0) { f.always = true; return f; }
+        const double e1 = (L - 1) * std::ldexp(A, -24);
+        double margin = 1e-3 + e1 + L * std::ldexp(A + std::fabs((double)thr_s[sc]) + 1.0, -18);
+        const uint32_t nk = (L + 3) / 4;
+        std::vector<double> pre(nk + 1, 0.0), suf(nk + 1, 0.0);
+        for (uint32_t k = 1; k <= nk; k++) { pre[k] = pre[k - 1]; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) pre[k] += ymax[j]; }
+        for (uint32_t k = nk; k-- > 0;) { suf[k] = suf[k + 1]; for (uint32_t j = 4 * k; j < std::min(L, 4 * (k + 1)); j++) suf[k] += ymax[j]; }
+        for (int iter = 0; iter < 6; iter++) {
+            f.bias = half_round_up(-((double)thr_s[sc] - margin));
+            f.margin = margin;
+            if (!acc16) return f;
+            __half hb; std::memcpy(&hb, &f.bias, 2);
+            const double babs = std::fabs((double)__half2float(hb));
+            double sum = 0;
+            for (uint32_t k = 1; k <= nk; k++) {
+                double Ak = 0; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) Ak += yabs[j];
+                sum += std::max(suf[k - 1], babs + pre[k - 1]) + Ak;
+            }
+            const double need = 1e-3 + e1 + g_margin16_scale * std::ldexp(4.0 * sum, -10);
+            if (need <= margin) return f;
+            margin = need * 1.02;
+        }
+        f.margin = 1e9;           // did not converge: FP32 accumulators for this tile
+        return f;
+    };
+
     // Accumulator type PER TILE: FP16 accumulators (half the epilogue work) where every column of the tile keeps its margin
     // <= 2 score units, FP32 otherwise -- a few long or extreme motifs then cost their own tile, not the whole set.
     const bool try16 = ctx->acc_pref != 32 && max_len <= (uint32_t)kMaxLen;
-    std::vector<Folded> folded(n_cols);
-    for (int32_t sc = 0; sc < n_cols; sc++) folded[sc] = fold((uint32_t)sc, try16);
     std::vector<std::pair<uint32_t, uint32_t>> cuts;
     plan_tc_tiles(len, try16, cuts);
-    std::vector<uint32_t> tile_acc16(cuts.size(), 0);
-    for (size_t ti = 0; ti < cuts.size(); ti++) {
-        bool ok = try16;
-        if (ok && ctx->acc_pref != 16)
-            for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++)
-                if (!folded[sc].always && folded[sc].margin > 2.0) { ok = false; break; }
-        tile_acc16[ti] = ok ? 1u : 0u;
-        for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++) {
-            if (!ok && try16) folded[sc] = fold(sc, false);
-            // forced FP16 accumulators: a column whose bound did not converge goes to the exact rescorer wholesale
-            if (ok && !folded[sc].always && folded[sc].margin > 1e8) folded[sc].always = true;
-        }
-    }
-    double margin_sum = 0;
-    for (const auto& f : folded) if (!f.always) margin_sum += f.margin;
-    uint32_t n16 = 0;
-    for (uint32_t a : tile_acc16) n16 += a;
-
-    std::vector<TcTile> tt;
-    std::vector<uint8_t> bimg;
     bool tc_ok = true;
-    for (size_t ti = 0; ti < cuts.size(); ti++) {
-        const auto& cut = cuts[ti];
-        TcTile t{};
-        t.acc16 = tile_acc16[ti];
-        t.col0 = cut.first; t.n_cols = cut.second - cut.first;
-        t.n_pad = (t.n_cols + 63) / 64 * 64;
-        t.n_k = (len[cut.second - 1] + 3) / 4;
-        const uint32_t nChunks = 2 * t.n_k;
-        t.b_off = (uint32_t)bimg.size();
-        t.b_bytes = t.n_pad * nChunks * 16;
-        bimg.resize(bimg.size() + t.b_bytes, 0);
-        uint16_t* img = reinterpret_cast<uint16_t*>(bimg.data() + t.b_off);
-        auto at = [&](uint32_t n, uint32_t j, uint32_t o) -> uint16_t& {        // column n (tile-local), position j, letter o
-            const uint32_t kk = j >> 1;
-            return img[(((n >> 3) * nChunks + kk) * 8 + (n & 7)) * 8 + (j & 1) * 4 + o];
-        };
-        for (uint32_t n = 0; n < t.n_pad; n++) {
-            if (n >= t.n_cols) {                         // padding column: can never reach acc >= 0
-                for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0xFBFFu;   // -65504
-                continue;
+    double margin_sum = 0;
+    // zmode 0: blocks without zero-contribution characters; zmode 1: with (bias step first, see fold_z)
+    auto build_image = [&](int zmode, std::vector<TcTile>& tt, std::vector<uint8_t>& bimg, uint32_t& n16) {
+        std::vector<Folded> folded(n_cols);
+        for (int32_t sc = 0; sc < n_cols; sc++) folded[sc] = zmode ? fold_z((uint32_t)sc, try16) : fold((uint32_t)sc, try16);
+        std::vector<uint32_t> tile_acc16(cuts.size(), 0);
+        for (size_t ti = 0; ti < cuts.size(); ti++) {
+            bool ok = try16;
+            if (ok && ctx->acc_pref != 16)
+                for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++)
+                    if (!folded[sc].always && folded[sc].margin > 2.0) { ok = false; break; }
+            tile_acc16[ti] = ok ? 1u : 0u;
+            for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++) {
+                if (!ok && try16) folded[sc] = zmode ? fold_z(sc, false) : fold(sc, false);
+                // forced FP16 accumulators: a column whose bound did not converge goes to the exact rescorer wholesale
+                if (ok && !folded[sc].always && folded[sc].margin > 1e8) folded[sc].always = true;
             }
-            const Folded& f = folded[t.col0 + n];
-            if (f.always) {                              // degenerate column: every window goes to the exact rescorer
-                for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0x3C00u;      // acc = +1
-                continue;
-            }
-            for (uint32_t j = 0; j < len[t.col0 + n]; j++)
-                for (uint32_t o = 0; o < 4; o++) at(n, j, o) = f.y[4 * j + o];
         }
-        tt.push_back(t);
-    }
-    std::stable_partition(tt.begin(), tt.end(), [](const TcTile& t) { return t.acc16 != 0; });
-    ctx->n_tiles16 = n16;
+        if (!zmode) for (const auto& f : folded) if (!f.always) margin_sum += f.margin;
+        n16 = 0;
+        for (uint32_t a : tile_acc16) n16 += a;
+        tt.clear(); bimg.clear();
+        for (size_t ti = 0; ti < cuts.size(); ti++) {
+            const auto& cut = cuts[ti];
+            TcTile t{};
+            t.acc16 = tile_acc16[ti];
+            t.col0 = cut.first; t.n_cols = cut.second - cut.first;
+            t.n_pad = (t.n_cols + 63) / 64 * 64;
+            t.n_k = (len[cut.second - 1] + 3) / 4 + (zmode ? 1u : 0u);      // MMA steps per window tile (zmode: + the bias step)
+            const uint32_t nChunks = 2 * t.n_k;
+            t.b_off = (uint32_t)bimg.size();
+            t.b_bytes = t.n_pad * nChunks * 16;
+            bimg.resize(bimg.size() + t.b_bytes, 0);
+            uint16_t* img = reinterpret_cast<uint16_t*>(bimg.data() + t.b_off);
+            auto at = [&](uint32_t n, uint32_t j, uint32_t o) -> uint16_t& {        // column n (tile-local), position j, letter o
+                const uint32_t kk = (j >> 1) + (zmode ? 2u : 0u);
+                return img[(((n >> 3) * nChunks + kk) * 8 + (n & 7)) * 8 + (j & 1) * 4 + o];
+            };
+            auto bias = [&](uint32_t n) -> uint16_t& { return img[(((n >> 3) * nChunks) * 8 + (n & 7)) * 8]; };   // zmode: chunk 0, half 0
+            for (uint32_t n = 0; n < t.n_pad; n++) {
+                if (n >= t.n_cols) {                         // padding column: can never reach acc >= 0
+                    if (zmode) bias(n) = 0xFBFFu; else for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0xFBFFu;   // -65504
+                    continue;
+                }
+                const Folded& f = folded[t.col0 + n];
+                if (f.always) {                              // degenerate column: every window goes to the exact rescorer
+                    if (zmode) bias(n) = 0x3C00u; else for (uint32_t o = 0; o < 4; o++) at(n, 0, o) = 0x3C00u;   // acc = +1
+                    continue;
+                }
+                if (zmode) bias(n) = f.bias;
+                for (uint32_t j = 0; j < len[t.col0 + n]; j++)
+                    for (uint32_t o = 0; o < 4; o++) at(n, j, o) = f.y[4 * j + o];
+            }
+            tt.push_back(t);
+        }
+        std::stable_partition(tt.begin(), tt.end(), [](const TcTile& t) { return t.acc16 != 0; });
+    };
+    std::vector<TcTile> tt, tt_z;
+    std::vector<uint8_t> bimg, bimg_z;
+    uint32_t n16 = 0, n16_z = 0;
+    build_image(0, tt, bimg, n16);
+    build_image(1, tt_z, bimg_z, n16_z);
+    ctx->n_tiles16 = n16; ctx->n_tiles16_z = n16_z;
     if (max_len > (uint32_t)kMaxLen) tc_ok = false;
     ctx->tc_acc_bits = (n16 == cuts.size()) ? 16 : (n16 == 0 ? 32 : 0);
     ctx->cand_inflation = n_cols ? margin_sum / n_cols : 0;
 
     // ---- upload ----
     dfree(ctx->d_w); dfree(ctx->d_woff); dfree(ctx->d_len); dfree(ctx->d_orig); dfree(ctx->d_thr);
-    dfree(ctx->d_gtiles); dfree(ctx->d_ttiles); dfree(ctx->d_bimg);
+    dfree(ctx->d_gtiles); dfree(ctx->d_ttiles); dfree(ctx->d_bimg); dfree(ctx->d_ttiles_z); dfree(ctx->d_bimg_z);
     CU(cudaMalloc(&ctx->d_w, sizeof(float4) * (sum_len + 80)));       // slack: the rescorer never reads past len, but keep loads in bounds
     CU(cudaMemset(ctx->d_w, 0, sizeof(float4) * (sum_len + 80)));
     CU(cudaMalloc(&ctx->d_woff, 4 * n_cols)); CU(cudaMalloc(&ctx->d_len, 4 * n_cols));
@@ -321,6 +385,8 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     CU(cudaMalloc(&ctx->d_gtiles, sizeof(GatherTile) * gt.size()));
     CU(cudaMalloc(&ctx->d_ttiles, sizeof(TcTile) * tt.size()));
     CU(cudaMalloc(&ctx->d_bimg, bimg.size() + 128));
+    CU(cudaMalloc(&ctx->d_ttiles_z, sizeof(TcTile) * tt_z.size()));
+    CU(cudaMalloc(&ctx->d_bimg_z, bimg_z.size() + 128));
     CU(cudaMemcpy(ctx->d_w, w.data(), sizeof(float4) * sum_len, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_woff, woff.data(), 4 * n_cols, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_len, len.data(), 4 * n_cols, cudaMemcpyHostToDevice));
@@ -329,6 +395,8 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     CU(cudaMemcpy(ctx->d_gtiles, gt.data(), sizeof(GatherTile) * gt.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_ttiles, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_bimg, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_ttiles_z, tt_z.data(), sizeof(TcTile) * tt_z.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_bimg_z, bimg_z.data(), bimg_z.size(), cudaMemcpyHostToDevice));
     ctx->gtiles = gt; ctx->ttiles = tt;
     ctx->h_len_sorted = len; ctx->h_woff_sorted = woff; ctx->h_orig_sorted = orig;
     ctx->hist_bins = 0;
@@ -370,28 +438,30 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     const dim3 ggrid((unsigned)((s.n_payload + kGatherSpan - 1) / kGatherSpan), (unsigned)ctx->gtiles.size());
     if (want_tc) {
         TcParams tp;
-        tp.bimg = ctx->d_bimg; tp.tiles = ctx->d_ttiles; tp.n_tiles = (uint32_t)ctx->ttiles.size();
         tp.n_spans = (uint32_t)((s.n_payload + kTcSpan - 1) / kTcSpan);
         tp.work_counter = work; tp.raw = ctx->d_raw; tp.blk_count = ctx->d_blk_count; tp.n_blocks = work + 1; tp.blk_cap = ctx->blk_cap;
         tp.error_flag = err;
         tp.trace = ctx->d_trace;
-        // one instance per accumulator type over its share of the tiles (FP16 tiles are stored first); both append to the same
-        // raw-entry blocks, each has its own work counter
-        if (ctx->n_tiles16) {
-            tp.tiles = ctx->d_ttiles; tp.n_tiles = ctx->n_tiles16; tp.work_counter = work;
-            filter_tc_kernel<true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
-            n++;
-        }
-        if (ctx->n_tiles16 < ctx->ttiles.size()) {
-            tp.tiles = ctx->d_ttiles + ctx->n_tiles16; tp.n_tiles = (uint32_t)ctx->ttiles.size() - ctx->n_tiles16; tp.work_counter = work2;
-            filter_tc_kernel<false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
-            n++;
-        }
-        n--;
-        n++;
-        if (ctx->engine == B200SCAN_ENGINE_AUTO) {     // blocks with a zero mask: exact gather-add (kernel exits at once otherwise)
-            gather_scan_kernel<true><<<ggrid, kGatherThreads, ctx->gather_smem, ctx->stream>>>(md, blk, ctx->d_gtiles, sink, 1);
-            n++;
+        // One instance per accumulator type over its share of the tiles (FP16 tiles are stored first), and that for both
+        // kinds of block: plain ACGT, or with zero-contribution characters (the instance that does not match the block's
+        // has_zero flag returns at once).  All append to the same raw-entry blocks; each accumulator type has its own work counter.
+        const uint32_t n_tiles = (uint32_t)ctx->ttiles.size();
+        for (int z = 0; z < 2; z++) {
+            const TcTile* tiles = z ? ctx->d_ttiles_z : ctx->d_ttiles;
+            const uint32_t n16 = z ? ctx->n_tiles16_z : ctx->n_tiles16;
+            tp.bimg = z ? ctx->d_bimg_z : ctx->d_bimg;
+            if (n16) {
+                tp.tiles = tiles; tp.n_tiles = n16; tp.work_counter = work;
+                if (z) filter_tc_kernel<true, true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+                else   filter_tc_kernel<true, false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+                n++;
+            }
+            if (n16 < n_tiles) {
+                tp.tiles = tiles + n16; tp.n_tiles = n_tiles - n16; tp.work_counter = work2;
+                if (z) filter_tc_kernel<false, true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+                else   filter_tc_kernel<false, false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+                n++;
+            }
         }
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
         expand_kernel<<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
@@ -520,8 +590,10 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
-    CUB(cudaFuncSetAttribute(filter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    CUB(cudaFuncSetAttribute(filter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) g_margin16_scale = atof(e);
     CUB(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
@@ -568,7 +640,7 @@ void b200scan_destroy(b200scan_ctx* c)
     }
     dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_flush);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
-    dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg);
+    dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg); dfree(c->d_ttiles_z); dfree(c->d_bimg_z);
     dfree(c->d_hist); dfree(c->d_hmin); dfree(c->d_hwid); dfree(c->d_htiles);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
@@ -777,8 +849,6 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
         const unsigned long long n_cand = s.h_counters[0], nh = s.h_counters[1];
         const uint32_t has_zero = (uint32_t)(s.h_counters[2] & 0xffffffffu), errflag = (uint32_t)(s.h_counters[2] >> 32);
         if (errflag) return fail(ctx, B200SCAN_ECUDA, "kernel reported error flag 0x%08x", errflag);
-        if (ctx->engine == B200SCAN_ENGINE_TENSOR && has_zero)
-            return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR cannot score a block with zero-contribution characters (use AUTO)");
         if (ctx->engine == B200SCAN_ENGINE_TENSOR && !ctx->tc_usable)
             return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR unavailable for this motif set");
         const uint32_t n_blocks = (uint32_t)(s.h_counters[3] >> 32);
@@ -786,7 +856,8 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
         const bool cand_over = raw_over || n_cand > ctx->cand_cap, hit_over = nh > s.hit_cap;
         if (!cand_over && !hit_over) {
             s.timing.n_candidates = n_cand; s.timing.n_hits = nh;
-            s.timing.engine_used = (has_zero || ctx->engine == B200SCAN_ENGINE_GATHER || !ctx->tc_usable) ? B200SCAN_ENGINE_GATHER : B200SCAN_ENGINE_TENSOR;
+            s.timing.engine_used = (ctx->engine == B200SCAN_ENGINE_GATHER || !ctx->tc_usable) ? B200SCAN_ENGINE_GATHER : B200SCAN_ENGINE_TENSOR;
+            (void)has_zero;
             break;
         }
         if (attempt >= 4) return fail(ctx, B200SCAN_ECUDA, "hit buffers still too small after regrowing");

@@ -136,10 +136,12 @@ constexpr uint32_t kTraceTiles = 256;
 // shared memory carve-up (bytes)
 constexpr uint32_t kSmE      = (kTcStages * kTcStageEnt + kTcMirror) * 16;
 constexpr uint32_t kSmCodes  = kTcSpan / 4 + 128;                              //  8320
-constexpr uint32_t kSmB      = kTcMaxN * (2 * (kMaxLen / 4)) * 16;             // 131072
+constexpr uint32_t kSmB      = kTcMaxN * (2 * (kMaxLen / 4 + 1)) * 16;         // 139264: up to 16 position steps + the bias step of masked blocks
+constexpr uint32_t kSmZ      = kTcSpan / 8 + 64;                               //   4160: zero-mask bits of the span (masked blocks only)
+constexpr uint32_t kSmOnes   = 144 * 16;                                       //   2304: constant operand of the bias step
 constexpr uint32_t kSmBars   = 32 * 8;
 constexpr uint32_t kSmLut    = 16 * 16;                                        //   256: E entry for every (code, next code)
-constexpr uint32_t kTcSmemBytes = kSmE + kSmCodes + kSmB + kSmBars + kSmLut + 128;
+constexpr uint32_t kTcSmemBytes = kSmE + kSmCodes + kSmB + kSmBars + kSmLut + kSmZ + kSmOnes + 128;
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -322,7 +324,10 @@ __device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, unsig
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <bool ACC16>
+// ZMASK = false: blocks of plain upper-case ACGT.  ZMASK = true: blocks with zero-contribution characters (lower case under the
+// reference's BLAS-path semantics): their E entries are zeroed, the B image carries unshifted weights and one leading bias step
+// (b200scan.cu: fold_z).  Each instance returns at once when the block is not of its kind.
+template <bool ACC16, bool ZMASK>
 __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm)
 filter_tc_kernel(TcParams P, BlockDev blk)
 {
@@ -332,7 +337,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     constexpr uint32_t kEpiPerQ = kTcEpiWarps / 4 / kTcEpiGroups;      // warps sharing one TMEM lane quarter of one tile
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    if (__ldg(blk.has_zero) != 0) return;                       // zero-mask blocks take the gather kernel
+    if ((__ldg(blk.has_zero) != 0) != ZMASK) return;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t*  sE     = smem;
@@ -342,6 +347,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     // barrier map: [0..7] e_full, [8..15] e_empty, [16..19] t_full, [20..23] t_empty, [24] codes, [25] B
     volatile uint32_t* sMisc = reinterpret_cast<volatile uint32_t*>(sBars + 28);   // [0] work item, [1] tmem base
     uint4* sLut = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sBars) + kSmBars);
+    uint8_t* sZ = reinterpret_cast<uint8_t*>(sLut) + kSmLut;
+    uint4* sOnes = reinterpret_cast<uint4*>(sZ + kSmZ);
 
     const uint32_t bars   = smem_u32(sBars);
     const uint32_t eFull  = bars, eEmpty = bars + 8 * 8, tFull = bars + 16 * 8, tEmpty = bars + 20 * 8;
@@ -362,6 +369,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         const uint32_t v0 = 0x3C00u << (16 * (c0 & 1)), v1 = 0x3C00u << (16 * (c1 & 1));
         sLut[threadIdx.x] = make_uint4((c0 & 2) ? 0u : v0, (c0 & 2) ? v0 : 0u, (c1 & 2) ? 0u : v1, (c1 & 2) ? v1 : 0u);
     }
+    if (ZMASK && threadIdx.x < kSmOnes / 16) sOnes[threadIdx.x] = make_uint4(0x00003C00u, 0u, 0u, 0u);      // [1.0, 0, ..., 0] in every row
+    if (ZMASK) fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -400,9 +409,10 @@ filter_tc_kernel(TcParams P, BlockDev blk)
 
         if (threadIdx.x == 0) {
             // 2-bit codes of the span + one halo stage (+16 B so the last entry can see its successor)
-            const uint32_t cbytes = (nT + 1) * 32 + 16;
-            mbar_expect_tx(cBar, cbytes);
+            const uint32_t cbytes = (nT + 1) * 32 + 16, zbytes = ZMASK ? (nT + 1) * 16 + 16 : 0u;
+            mbar_expect_tx(cBar, cbytes + zbytes);
             bulk_g2s(smem_u32(sCodes), reinterpret_cast<const uint8_t*>(blk.codes) + (w0 >> 2), cbytes, cBar);
+            if (ZMASK) bulk_g2s(smem_u32(sZ), reinterpret_cast<const uint8_t*>(blk.zmask) + (w0 >> 3), zbytes, cBar);
             if (newTile) {
                 mbar_expect_tx(bBar, tile.b_bytes);
                 for (uint32_t off = 0; off < tile.b_bytes; off += 32768)
@@ -428,7 +438,12 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         if (g < nEnt) {
                             const uint32_t byte = g >> 2;
                             const uint32_t two = (uint32_t)sCodes[byte] | ((uint32_t)sCodes[byte + 1] << 8);
-                            const uint4 val = sLut[(two >> (2 * (g & 3))) & 15u];      // [onehot(code g) | onehot(code g+1)]
+                            uint4 val = sLut[(two >> (2 * (g & 3))) & 15u];            // [onehot(code g) | onehot(code g+1)]
+                            if (ZMASK) {                                               // a masked character contributes an all-zero row
+                                const uint32_t zz = ((uint32_t)sZ[g >> 3] | ((uint32_t)sZ[(g >> 3) + 1] << 8)) >> (g & 7);
+                                if (zz & 1u) { val.x = 0u; val.y = 0u; }
+                                if (zz & 2u) { val.z = 0u; val.w = 0u; }
+                            }
                             *reinterpret_cast<uint4*>(sE + (slot * kTcStageEnt + e) * 16) = val;
                             if (slot == 0 && e < kTcMirror)
                                 *reinterpret_cast<uint4*>(sE + (kTcStages * kTcStageEnt + e) * 16) = val;
@@ -455,6 +470,9 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             const uint32_t nChunks = 2 * n_k;
             const uint64_t ad0 = umma_desc(smem_u32(sE), 32, 128), bd0 = umma_desc(smem_u32(sB), 128, nChunks * 128);
             const uint32_t aLo0 = (uint32_t)ad0, aHi = (uint32_t)(ad0 >> 32), bLo0 = (uint32_t)bd0, bHi = (uint32_t)(bd0 >> 32);
+            const uint32_t aLoOnes = (uint32_t)umma_desc(smem_u32(sOnes), 32, 128);      // ZMASK: rows of [1, 0, ..., 0]
+            const uint32_t n_pos = ZMASK ? n_k - 1 : n_k;                                  // position steps (ZMASK: n_k counts the bias step too)
+            (void)aLoOnes;
             // The whole tile loop runs in ONE elected lane, inside one branch: there ptxas moves the loop state to uniform
             // registers once per item and steps descriptors / barrier addresses with UIADD3 (predicating each tcgen05
             // instruction instead costs 5-7 R2UR moves in front of every one of them).
@@ -481,9 +499,15 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     // B: [8-column group][chunk] blocks of 128 B: one MMA = 2 chunks = 256 B
                     uint32_t alo = aLo0 + aOff, blo = bLo0;               // address fields are in 16-byte units = entries
                     if (!(TC_KNOCKOUT & 2)) {
-                        umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+                        if (ZMASK) {                                      // step 0: D = bias (constant one-hot rows x chunk 0 of B)
+                            umma_f16_lohi(d, aLoOnes, aHi, blo, bHi, idesc, 0u);
+                            blo += 16;
+                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
+                        } else {
+                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+                        }
 #pragma unroll 1
-                        for (uint32_t m = 1; m < n_k; m++) {
+                        for (uint32_t m = 1; m < n_pos; m++) {
                             alo += 4; blo += 16;
                             umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
                         }

@@ -35,7 +35,7 @@ expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk
 {
     constexpr uint32_t kStage = 640;
     __shared__ Cand s_stage[8][kStage];   // per-warp staging: one global atomic per >= 256 candidates
-    if (__ldg(has_zero) != 0) return;
+    (void)has_zero;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t nb = min(*n_blocks_ptr, blk_cap);
     Cand* st = s_stage[wib];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256)
 rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
                const unsigned long long* __restrict__ n_cand_ptr, unsigned long long cand_cap, HitSink sink)
 {
-    if (__ldg(blk.has_zero) != 0) return;          // such blocks went through the gather kernel
+    const bool masked = __ldg(blk.has_zero) != 0;   // block with zero-contribution characters: such positions add exactly 0
     unsigned long long n_cand = *n_cand_ptr;
     if (n_cand > cand_cap) n_cand = cand_cap;       // overflow: the host re-runs with a larger buffer
     // Hits of kRounds consecutive rounds are staged per warp in shared memory and appended with ONE global atomic
@@ -125,8 +125,9 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
             pos = c.pos; col = c.col;
             const uint32_t L = __ldg(md.len + col);
             const float* wp = reinterpret_cast<const float*>(md.w + __ldg(md.woff + col));
-            uint32_t codes[4];
+            uint32_t codes[4], zm[2] = {0u, 0u};
             load_window_codes(blk.codes, pos, codes);
+            if (masked) load_window_zmask(blk.zmask, pos, zm);
             // 16 positions at a time: all (predicated) weight loads first -- independent, so one L2 round trip per group
             // instead of one per position -- then the additions strictly in position order
 #pragma unroll
@@ -139,7 +140,7 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
                         wv[t] = (t < n) ? __ldg(wp + 4 * (16 * q + t) + ((r >> (2 * t)) & 3u)) : 0.0f;
 #pragma unroll
                     for (uint32_t t = 0; t < 16; t++)
-                        if (t < n) s += wv[t];
+                        if (t < n && !((zm[q >> 1] >> (16 * (q & 1) + t)) & 1u)) s += wv[t];
                 }
             }
             hit = (pos < blk.n_payload) && !(s < __ldg(md.thr + col));

@@ -64,10 +64,6 @@ def test_golden_cases(scanner, golden, engine, case_name, mode_key):
             c = fs.next(20000, halo)            # several chunks per group: exercises the halo hand-over
             if c is None:
                 break
-            if engine == capi.ENGINE_TENSOR and any(ch in c["chars"] for ch in b"acgt"):
-                with pytest.raises(capi.ScanError):
-                    scanner.scan(c["chars"], c["frag_start"][1:], c["n_payload"])
-                return
             hits, t = scanner.scan(c["chars"], c["frag_start"][1:], c["n_payload"])
             f = np.searchsorted(c["frag_start"], hits["pos"], side="right") - 1
             for h, fi in zip(hits, f):
@@ -111,7 +107,37 @@ def test_lower_case_semantics(scanner, lower):
     scanner.set_motifs(case["P"], case["col_len"], case["thr"])
     hits, t = scanner.scan(case["chars"], case["frag_start"][1:], lower=lower)
     _assert_same(hits, *_oracle_hits(case, lower_fold=(lower == capi.LOWER_FOLD)))
-    assert t["engine_used"] == (capi.ENGINE_GATHER if lower == capi.LOWER_ZERO else capi.ENGINE_TENSOR)
+    assert t["engine_used"] == capi.ENGINE_TENSOR        # masked blocks have their own tensor instance (bias step, zeroed rows)
+
+
+@pytest.mark.parametrize("engine,acc", [(capi.ENGINE_GATHER, 0), (capi.ENGINE_TENSOR, 16), (capi.ENGINE_TENSOR, 32)])
+@pytest.mark.parametrize("seed", [5, 6])
+def test_soft_masked_blocks_bit_exact(scanner, engine, acc, seed):
+    """Soft-masked sequence (half of it lower case, in runs of 1 .. 3000, as repeat-masked genomes are): lower-case
+    characters contribute exactly 0 (the reference's BLAS path, sequence.cpp:312-319), negative and positive thresholds."""
+    case = util.random_case(seed, n_motifs=40, n_nt=700_000, len_range=(5, 40))
+    rng = np.random.default_rng(seed + 100)
+    chars = case["chars"].copy()
+    p = 0
+    while p < len(chars):
+        run = int(rng.integers(1, 3000))
+        if rng.random() < 0.5:
+            chars[p:p + run] |= 0x20                     # lower case
+        p += run
+    case["chars"] = chars
+    thr = case["thr"].copy()
+    thr[::8] = np.float32(-1.5)                          # every 8th column: negative threshold (fully masked windows score 0 >= thr)
+    thr[1::3] = np.minimum(thr[1::3], 4.0)
+    case["thr"] = thr
+    scanner.set_engine(engine)
+    scanner.set_tensor_accumulator(acc)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    hits, t = scanner.scan(case["chars"], case["frag_start"][1:])
+    scanner.set_tensor_accumulator(0)
+    want = _oracle_hits(case)
+    assert len(want[0]) > 10_000
+    _assert_same(hits, *want)
+    assert t["engine_used"] == engine
 
 
 @pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
@@ -219,7 +245,7 @@ def test_packed_submit_and_zero_mask(scanner):
     hits, t = scanner.collect(1)
     low = chars.copy(); low[1000:2000] = np.frombuffer(bytes(low[1000:2000]).lower(), dtype=np.uint8)
     _assert_same(hits, *_oracle_hits(dict(case, chars=low)))
-    assert t["engine_used"] == capi.ENGINE_GATHER
+    assert t["engine_used"] == capi.ENGINE_TENSOR
 
 
 @pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
@@ -259,7 +285,7 @@ def test_double_buffered_slots_and_state_errors(scanner):
 def test_pipelined_lower_case_block_keeps_zero_mask(scanner):
     """A lower-case block submitted on slot 1 while slot 0's kernels are still running: its upload, counter reset and
     packing run on the upload stream, and the has_zero flag the pack kernel raises must survive until the scan of that
-    block (AUTO then routes it through the exact gather-add kernel with BLAS-path semantics)."""
+    block (its tensor instance zeroes the rows of masked characters; without the flag they would score as upper case)."""
     big = util.random_case(61, n_motifs=60, n_nt=24_000_000, len_range=(6, 14), with_gaps=False)
     small = util.random_case(62, n_motifs=60, n_nt=300_000, len_range=(6, 14), lower=True)
     for c in (big, small):
@@ -272,7 +298,7 @@ def test_pipelined_lower_case_block_keeps_zero_mask(scanner):
         scanner.submit_ascii(1, small["chars"], frag_starts=small["frag_start"][1:])
         h0, t0 = scanner.collect(0)
         h1, t1 = scanner.collect(1)
-        assert t0["engine_used"] == capi.ENGINE_TENSOR and t1["engine_used"] == capi.ENGINE_GATHER
+        assert t0["engine_used"] == capi.ENGINE_TENSOR and t1["engine_used"] == capi.ENGINE_TENSOR
         _assert_same(h1, *_oracle_hits(small))
     assert len(h0) > 1000
 
