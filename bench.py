@@ -300,6 +300,7 @@ def main() -> None:
     ap.add_argument("--mbp", type=float, default=100.0, help="Mbp per GPU")
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "gather"])
     ap.add_argument("--acc", type=int, default=0, choices=[0, 16, 32], help="tensor filter accumulators: 0 = automatic (diagnostic)")
+    ap.add_argument("--softmask", type=float, default=0.0, help="diagnostic: fraction of the sequence turned lower case (runs of 1..3000), scored with BLAS-path semantics")
     ap.add_argument("--cpu-sample-nt", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -335,6 +336,14 @@ def main() -> None:
     work = tempfile.mkdtemp(prefix="bench_b200_")
     try:
         ms, P, col_len, thr, seq, bg = build_inputs(work, n_nt, rank)
+        if args.softmask > 0:
+            rng = np.random.default_rng(7 + rank)
+            p = 0
+            while p < n_nt:
+                run = int(rng.integers(1, 3000))
+                if rng.random() < args.softmask:
+                    seq[p:p + run] |= 0x20
+                p += run
         n_cols, sum_len = len(col_len), int(col_len.sum())
         L = capi.scan_lib()
         host_ptr = L.b200scan_host_alloc(n_nt + 64)                 # pinned host block (the e2e input)
@@ -401,7 +410,7 @@ def main() -> None:
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "configs[1]: JASPAR-like %d PWMs x2 strands (%d columns, sum L = %d) x %.0f Mbp synthetic uniform ACGT per GPU, "
-                                       "-rc -pt 1e-4 (real JASPAR CORE unavailable offline)" % (N_MOTIFS, n_cols, sum_len, args.mbp),
+                                       "-rc -pt 1e-4 (real JASPAR CORE unavailable offline)%s" % (N_MOTIFS, n_cols, sum_len, args.mbp, (", %.0f %% soft-masked" % (100 * args.softmask)) if args.softmask > 0 else ""),
                            "engine": engine_used, "parallelism": "chunk-sharded x%d, no collective" % world,
                            "l2": "flushed between steps (256 MiB memset outside the event pairs)", "host_binding": numa, "hits_per_step": int(n_hits),
                            "candidates_per_step": int(t_e2e["n_candidates"])},

@@ -58,9 +58,9 @@ extern "C" {
 #define B200SCAN_NUM_SLOTS      2  /* submit/collect double buffering */
 
 /* scoring engines (b200scan_set_engine) */
-#define B200SCAN_ENGINE_AUTO    0  /* tensor-core filter + exact rescore; gather-add for blocks with a zero-mask */
+#define B200SCAN_ENGINE_AUTO    0  /* tensor-core filter + exact rescore (gather-add only if the motif set is unusable for it) */
 #define B200SCAN_ENGINE_GATHER  1  /* shared-memory gather-add, every score in exact reference order */
-#define B200SCAN_ENGINE_TENSOR  2  /* tcgen05 filter + exact rescore (fails with ESTATE on a zero-mask block) */
+#define B200SCAN_ENGINE_TENSOR  2  /* tcgen05 filter + exact rescore, also for blocks with zero-contribution characters   */
 
 /* how lower-case acgt is scored (b200scan_submit_ascii) */
 #define B200SCAN_LOWER_ZERO     0  /* BLAS-path semantics: valid character, contributes 0 (sequence.cpp:312-319) */
