@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # End-to-end CLI run on the GPU box: FASTA in -> occurrences.txt out, next to the reference binary on a subset
-# (same inputs, sorted outputs compared byte for byte).  usage: tools/cli_e2e.sh [Mbp] [subset Mbp] [gpus]
+# (same inputs, sorted outputs compared byte for byte).  usage: [SOFTMASK=0.5] tools/cli_e2e.sh [Mbp] [subset Mbp] [gpus]
+# SOFTMASK = fraction of the sequence written in lower case (runs of 1..3000), as in repeat-masked genomes
 set -e
 cd "$(dirname "$0")/.."
 ROOT=$PWD; MBP=${1:-100}; SUB=${2:-8}; GPUS=${3:-1}
@@ -11,6 +12,14 @@ from blamm_b200 import synth
 synth.make_jaspar_like("motifs.jaspar", 900, 2024)
 n = int($MBP * 1e6); q = n // 4
 seq = synth.random_acgt(n, 4242)
+soft = float("${SOFTMASK:-0}")
+if soft > 0:
+    import numpy as np
+    rng = np.random.default_rng(9); p = 0
+    while p < n:
+        run = int(rng.integers(1, 3000))
+        if rng.random() < soft: seq[p:p + run] |= 0x20
+        p += run
 synth.write_fasta("genome.fa", [("chr%d" % (i + 1), seq[i * q:(i + 1) * q]) for i in range(4)])
 m = int($SUB * 1e6) // 4
 synth.write_fasta("subset.fa", [("chr%d" % (i + 1), seq[i * q:i * q + m]) for i in range(4)])
