@@ -259,11 +259,11 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
         Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false; f.bias = 0;
         double A = 0;
         bool finite = std::isfinite(thr_s[sc]);
-        std::vector<double> ymax(L), yabs(L);
+        std::vector<double> ymax(L), ymin(L), yabs(L);
         for (uint32_t j = 0; j < L; j++) {
             const float4 v = w[woff[sc] + j];
             const float a4[4] = {v.x, v.y, v.z, v.w};
-            double m = 0, mx = 0, ma = 0;                      // mx starts at 0: the masked contribution
+            double m = 0, mx = 0, mn = 0, ma = 0;              // mx / mn start at 0: the masked contribution
             for (uint32_t o = 0; o < 4; o++) {
                 if (!std::isfinite(a4[o])) { finite = false; continue; }
                 m = std::max(m, std::fabs((double)a4[o]));
@@ -272,27 +272,33 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                 f.y[4 * j + o] = h;
                 __half hh; std::memcpy(&hh, &h, 2);
                 const double yr = (double)__half2float(hh);
-                mx = std::max(mx, yr); ma = std::max(ma, std::fabs(yr));
+                mx = std::max(mx, yr); mn = std::min(mn, yr); ma = std::max(ma, std::fabs(yr));
             }
-            A += m; ymax[j] = mx; yabs[j] = ma;
+            A += m; ymax[j] = mx; ymin[j] = mn; yabs[j] = ma;
         }
         if (!finite || std::fabs((double)thr_s[sc]) > 30000.0) { f.always = true; return f; }
         const double e1 = (L - 1) * std::ldexp(A, -24);
         double margin = 1e-3 + e1 + L * std::ldexp(A + std::fabs((double)thr_s[sc]) + 1.0, -18);
         const uint32_t nk = (L + 3) / 4;
-        std::vector<double> pre(nk + 1, 0.0), suf(nk + 1, 0.0);
-        for (uint32_t k = 1; k <= nk; k++) { pre[k] = pre[k - 1]; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) pre[k] += ymax[j]; }
+        // prefix maxima / minima and suffix maxima of the position sums at the step boundaries
+        std::vector<double> pre(nk + 1, 0.0), pmin(nk + 1, 0.0), suf(nk + 1, 0.0);
+        for (uint32_t k = 1; k <= nk; k++) {
+            pre[k] = pre[k - 1]; pmin[k] = pmin[k - 1];
+            for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) { pre[k] += ymax[j]; pmin[k] += ymin[j]; }
+        }
         for (uint32_t k = nk; k-- > 0;) { suf[k] = suf[k + 1]; for (uint32_t j = 4 * k; j < std::min(L, 4 * (k + 1)); j++) suf[k] += ymax[j]; }
         for (int iter = 0; iter < 6; iter++) {
             f.bias = half_round_up(-((double)thr_s[sc] - margin));
             f.margin = margin;
             if (!acc16) return f;
             __half hb; std::memcpy(&hb, &f.bias, 2);
-            const double babs = std::fabs((double)__half2float(hb));
+            const double b = (double)__half2float(hb);
             double sum = 0;
             for (uint32_t k = 1; k <= nk; k++) {
                 double Ak = 0; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) Ak += yabs[j];
-                sum += std::max(suf[k - 1], babs + pre[k - 1]) + Ak;
+                // D_{k-1} lies in [max(-R, b + Pmin), b + Pmax] for a window that ends up >= 0
+                const double hi = b + pre[k - 1], lo = std::max(-suf[k - 1], b + pmin[k - 1]);
+                sum += std::max(std::fabs(hi), std::fabs(lo)) + Ak;
             }
             const double need = 1e-3 + e1 + g_margin16_scale * std::ldexp(4.0 * sum, -10);
             if (need <= margin) return f;
