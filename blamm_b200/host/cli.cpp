@@ -335,22 +335,26 @@ void writerThread(ScanShared& sh)
     }
 }
 
-void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, int engine, bool foldLower)
+// `ctxSlot` persists across the species groups of a run: the context (CUDA initialisation, pinned and device buffers,
+// ~0.7 s) is created by the first group that uses the device and only re-loaded with motifs afterwards.
+void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, int engine, bool foldLower, b200scan_ctx** ctxSlot)
 {
-    b200scan_ctx* ctx = nullptr;
+    b200scan_ctx*& ctx = *ctxSlot;
     auto die = [&](const string& what) {
         lock_guard<mutex> l(sh.qMutex);
         if (!sh.failed.exchange(true)) sh.error = what;
         sh.qCv.notify_all();
     };
     double t0 = now();
-    if (b200scan_create(&ctx, dev, maxBlock, maxHits) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(nullptr)); return; }
-    gTimer.add("b200scan_create (per GPU)", now() - t0);
+    if (!ctx) {
+        if (b200scan_create(&ctx, dev, maxBlock, maxHits) != B200SCAN_OK) { ctx = nullptr; die(string("CUDA error: ") + b200scan_last_error(nullptr)); return; }
+        gTimer.add("b200scan_create (per GPU)", now() - t0);
+    }
     const auto len = sh.motifs->colLen();
     const auto thr = sh.motifs->colThr();
     if (b200scan_set_engine(ctx, engine) != B200SCAN_OK ||
         b200scan_set_motifs(ctx, sh.motifs->P().data(), sh.motifs->ldp(), (int32_t)len.size(), len.data(), thr.data()) != B200SCAN_OK) {
-        die(string("CUDA error: ") + b200scan_last_error(ctx)); b200scan_destroy(ctx); return;
+        die(string("CUDA error: ") + b200scan_last_error(ctx)); return;
     }
     unique_ptr<Job> inFlight[B200SCAN_NUM_SLOTS];
     int slot = 0;
@@ -383,9 +387,6 @@ void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, 
         if (inFlight[slot] && !collect(slot)) break;     // overlap: format block k-1 while the GPU scores block k
     }
     for (int s = 0; s < B200SCAN_NUM_SLOTS && !sh.failed; s++) { if (inFlight[slot]) collect(slot); slot ^= 1; }
-    t0 = now();
-    b200scan_destroy(ctx);
-    gTimer.add("b200scan_destroy (per GPU)", now() - t0);
 }
 
 } // namespace
@@ -465,6 +466,15 @@ int runScan(int argc, char** argv)
     if (const char* e = getenv("BLAMM_B200_CHUNK")) chunk = max<uint64_t>(strtoull(e, nullptr, 10), 1024);
     const uint64_t halo = mc.maxLen() - 1;
     uint64_t totMatches = 0;
+    // one context per device for the whole run, sized for the largest group
+    uint64_t maxTot = 1024;
+    for (const auto& sp : sc.species) maxTot = max<uint64_t>(maxTot, sp.totSeqLen);
+    const uint64_t maxBlock = min<uint64_t>(chunk, maxTot) + halo + 64;
+    struct CtxPool {
+        vector<b200scan_ctx*> ctx;
+        ~CtxPool() { const double t0 = now(); for (auto c : ctx) if (c) b200scan_destroy(c); gTimer.add("b200scan_destroy (all GPUs)", now() - t0); }
+    } pool;
+    pool.ctx.assign((size_t)nDev, nullptr);
 
     for (const auto& sp : sc.species) {
         cout << "Scanning species: " << sp.name;
@@ -490,12 +500,11 @@ int runScan(int argc, char** argv)
         sh.maxNameLen = sl + ml;
         thread writer(writerThread, ref(sh));
         auto stopWriter = [&] { { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; } sh.oCv.notify_all(); writer.join(); };
-        const uint64_t maxBlock = min<uint64_t>(chunk, max<uint64_t>(sp.totSeqLen, 1024)) + halo + 64;
         vector<thread> workers;
         // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block)
         const double rate = pSpec ? std::min(1.0, 3.0 * pvalue) : 2e-4;
         const uint64_t maxHits = std::max<uint64_t>(1 << 20, (uint64_t)(rate * (double)maxBlock * (double)mc.motifs.size()));
-        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), d, maxBlock, maxHits, engine, foldLower);
+        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), d, maxBlock, maxHits, engine, foldLower, &pool.ctx[(size_t)d]);
         try {
             FastaStream fs(sp.files, sp.totSeqLen);
             FastaStream::Chunk c;
