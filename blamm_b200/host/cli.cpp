@@ -476,6 +476,7 @@ int runScan(int argc, char** argv)
     } pool;
     pool.ctx.assign((size_t)nDev, nullptr);
 
+    double tSetup = tStart;
     for (const auto& sp : sc.species) {
         cout << "Scanning species: " << sp.name;
         sp.printNuclProb(settings.pseudocount);
@@ -490,7 +491,7 @@ int runScan(int argc, char** argv)
             ofsCutoff << sp.name << "\t" << m.name << "\t" << m.minScore() << "\t" << m.threshold << "\t" << m.maxScore() << endl;
         }
 
-        gTimer.add("setup: dict, motifs, thresholds", now() - tStart);
+        gTimer.add("setup: dict, motifs, thresholds", now() - tSetup);
         ScanShared sh;
         sh.motifs = &mc; sh.species = &sp; sh.os = &os;
         sh.formatThreads = std::max<size_t>(1, numThreads / (size_t)nDev);
@@ -536,6 +537,7 @@ int runScan(int argc, char** argv)
         if (sh.failed) throw runtime_error(sh.error.empty() ? "scan failed" : sh.error);
         cout << "Progress... 100%  " << endl;
         totMatches += sh.totMatches;
+        tSetup = now();
     }
     os.close();
     ofsCutoff.close();
