@@ -20,6 +20,9 @@
 //    thr' = thr - margin, so  acc >= 0  whenever the exact FP32 score >= thr (b200scan.cu: build_tc_tiles).
 //    The epilogue only looks at sign bits (one PRMT + one IMAD per four scores) and appends raw entries;
 //    rescore.cuh expands them to (pos, col) candidates and recomputes those few scores exactly.  R never exists.
+//  * Blocks with zero-contribution characters (lower case under the reference's BLAS-path semantics) run the ZMASK = true
+//    instance: masked characters become all-zero operand rows, the weights stay unshifted and one leading MMA step adds the
+//    bias -(thr - margin) through a constant one-hot operand (b200scan.cu: fold_z).
 //
 // Roofline: tensor pipe.  One tcgen05.mma (M=128, N, K=16) covers 4 motif positions of N columns for 128
 // windows and takes N/2 cycles; the epilogue must drain 128 x N accumulators per tile from TMEM.
