@@ -76,6 +76,7 @@ struct b200scan_ctx {
     TcTile* d_ttiles_z = nullptr;  uint8_t* d_bimg_z = nullptr;  uint32_t n_tiles16_z = 0;     // the same for blocks with zero-contribution characters
     bool tc_usable = false;
     int  tc_acc_bits = 32;        // accumulators of the tensor tiles: 16, 32, or 0 when tiles differ
+    bool pair_mode = false;       // filter launched as CTA pairs (cta_group::2 MMAs)
     int  acc_pref = 0;            // 0 auto, 16, 32 (b200scan_set_tensor_accumulator)
     double cand_inflation = 0;    // mean margin over columns (diagnostic)
     uint8_t* d_flush = nullptr;
@@ -444,7 +445,6 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     const dim3 ggrid((unsigned)((s.n_payload + kGatherSpan - 1) / kGatherSpan), (unsigned)ctx->gtiles.size());
     if (want_tc) {
         TcParams tp;
-        tp.n_spans = (uint32_t)((s.n_payload + kTcSpan - 1) / kTcSpan);
         tp.work_counter = work; tp.raw = ctx->d_raw; tp.blk_count = ctx->d_blk_count; tp.n_blocks = work + 1; tp.blk_cap = ctx->blk_cap;
         tp.error_flag = err;
         tp.trace = ctx->d_trace;
@@ -452,20 +452,33 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
         // kinds of block: plain ACGT, or with zero-contribution characters (the instance that does not match the block's
         // has_zero flag returns at once).  All append to the same raw-entry blocks; each accumulator type has its own work counter.
         const uint32_t n_tiles = (uint32_t)ctx->ttiles.size();
+        using FilterFn = void (*)(TcParams, BlockDev);
+        static const FilterFn kFilter[2][2][2] = {       // [FP16 accumulators][masked block][CTA pair]
+            {{filter_tc_kernel<false, false, false>, filter_tc_kernel<false, false, true>}, {filter_tc_kernel<false, true, false>, filter_tc_kernel<false, true, true>}},
+            {{filter_tc_kernel<true, false, false>, filter_tc_kernel<true, false, true>}, {filter_tc_kernel<true, true, false>, filter_tc_kernel<true, true, true>}}};
+        const int pair = ctx->pair_mode ? 1 : 0;
+        tp.n_spans = (uint32_t)((s.n_payload + (pair ? 2 : 1) * (uint64_t)kTcSpan - 1) / ((pair ? 2 : 1) * (uint64_t)kTcSpan));
+        auto launch = [&](int acc16, int z) -> cudaError_t {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(pair ? 2u * (unsigned)(ctx->sm_count / 2) : (unsigned)(ctx->sm_count * kTcCtasPerSm));
+            cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmemBytes; cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = pair ? 1 : 0;
+            return cudaLaunchKernelEx(&cfg, kFilter[acc16][z][pair], tp, blk);
+        };
         for (int z = 0; z < 2; z++) {
             const TcTile* tiles = z ? ctx->d_ttiles_z : ctx->d_ttiles;
             const uint32_t n16 = z ? ctx->n_tiles16_z : ctx->n_tiles16;
             tp.bimg = z ? ctx->d_bimg_z : ctx->d_bimg;
             if (n16) {
                 tp.tiles = tiles; tp.n_tiles = n16; tp.work_counter = work;
-                if (z) filter_tc_kernel<true, true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
-                else   filter_tc_kernel<true, false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+                CU(launch(1, z));
                 n++;
             }
             if (n16 < n_tiles) {
                 tp.tiles = tiles + n16; tp.n_tiles = n_tiles - n16; tp.work_counter = work2;
-                if (z) filter_tc_kernel<false, true><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
-                else   filter_tc_kernel<false, false><<<ctx->sm_count * kTcCtasPerSm, kTcThreads, kTcSmemBytes, ctx->stream>>>(tp, blk);
+                CU(launch(0, z));
                 n++;
             }
         }
@@ -596,10 +609,15 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
-    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    if (const char* e = getenv("B200SCAN_PAIR")) c->pair_mode = atoi(e) != 0;
     if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) g_margin16_scale = atof(e);
     CUB(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));

@@ -247,6 +247,47 @@ template <bool ACC16> __device__ __forceinline__ void tmem_ld_words(uint32_t tad
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: one issuer drives the tensor cores of two SMs (M = 256: each CTA supplies its own 128
+// window rows and half of the B columns); completion is multicast to the barriers of both CTAs; the peer CTA signals the leader's
+// barriers through the cluster shared window.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {        // address of the same smem location in CTA `rank`
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t raddr) {           // cluster-scope release: orders this CTA's smem writes
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_cta(uint32_t raddr) {       // default (CTA-scope) semantics: no cluster-wide fence; enough when
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");   // only tcgen05 operations are being ordered (TMEM hand-back)
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t raddr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}"
+                 ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {          // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <bool PAIR> __device__ __forceinline__ void umma_x(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma2_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc); else umma_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc);
+}
+template <bool PAIR> __device__ __forceinline__ void commit_x(uint32_t bar) { if (PAIR) umma2_commit(bar); else umma_commit(bar); }
+
 // K-major, no-swizzle ("interleave") shared memory descriptor: rows 16 B apart inside an 8-row core matrix,
 // 8-row groups SBO apart, the two 16-byte K-chunks of one K=16 MMA LBO apart (cute mma_traits_sm100.hpp,
 // canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units; version = 1 on sm_100).
@@ -330,10 +371,13 @@ __device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, unsig
 // ZMASK = false: blocks of plain upper-case ACGT.  ZMASK = true: blocks with zero-contribution characters (lower case under the
 // reference's BLAS-path semantics): their E entries are zeroed, the B image carries unshifted weights and one leading bias step
 // (b200scan.cu: fold_z).  Each instance returns at once when the block is not of its kind.
-template <bool ACC16, bool ZMASK>
+// PAIR = true: launched as clusters of two CTAs (same TPC).  The pair takes an item of 2 * kTcSpan windows together -- rank 0 the
+// first half of its window tiles, rank 1 the second -- and rank 0's issuer lane drives both tensor cores with cta_group::2 MMAs.
+template <bool ACC16, bool ZMASK, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm)
 filter_tc_kernel(TcParams P, BlockDev blk)
 {
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     constexpr uint32_t kBufs    = TC_BUFS;              // TMEM accumulator buffers
     constexpr uint32_t kBufCols = kTcMaxN;              // TMEM columns per buffer: one accumulator per column, FP32 or FP16
     constexpr uint32_t kColsPerWord = ACC16 ? 2 : 1;
@@ -361,12 +405,14 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, kTcProducers); mbar_init(eEmpty + 8 * i, 1); }
-        for (uint32_t i = 0; i < kBufs; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, kTcEpiWarps / kTcEpiGroups); }
+        // PAIR: eFull / tEmpty of the leader collect the arrivals of both CTAs; eEmpty / tFull are signalled in both by multicast commits
+        for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, (PAIR ? 2u : 1u) * kTcProducers); mbar_init(eEmpty + 8 * i, 1); }
+        for (uint32_t i = 0; i < kBufs; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, (PAIR ? 2u : 1u) * kTcEpiWarps / kTcEpiGroups); }
         mbar_init(cBar, 1); mbar_init(bBar, 1);
         fence_mbar_init();
     }
-    if (warp == kTcProducers) tmem_alloc(smem_u32(const_cast<uint32_t*>(&sMisc[1])), kBufs * kBufCols);
+    if (PAIR) cluster_sync();                    // both CTAs are resident and past their barrier initialisation
+    if (warp == kTcProducers) { if (PAIR) tmem_alloc2(smem_u32(const_cast<uint32_t*>(&sMisc[1])), kBufs * kBufCols); else tmem_alloc(smem_u32(const_cast<uint32_t*>(&sMisc[1])), kBufs * kBufCols); }
     if (threadIdx.x < 16) {                      // one-hot FP16 (1.0 = 0x3C00) of code c in halves 0..3, of the next code in 4..7
         const uint32_t c0 = threadIdx.x & 3, c1 = threadIdx.x >> 2;
         const uint32_t v0 = 0x3C00u << (16 * (c0 & 1)), v1 = 0x3C00u << (16 * (c1 & 1));
@@ -376,8 +422,12 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     if (ZMASK) fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = sMisc[1];
+    // the leader's copies of the barriers that collect arrivals from both CTAs (for rank 0 these map to its own)
+    const uint32_t eFullL = PAIR ? mapa_u32(eFull, 0) : eFull, tEmptyL = PAIR ? mapa_u32(tEmpty, 0) : tEmpty;
+    (void)eFullL; (void)tEmptyL;
 
     long long ph_t = 0, ph_a[4] = {0, 0, 0, 0};   // B200_PHASE only (dead otherwise)
     (void)ph_t; (void)ph_a;
@@ -396,16 +446,26 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     uint32_t eLaneAddr = tmem_base + ((32 * eQ) << 16);
     asm volatile("" : "+r"(eQ), "+r"(eGroup), "+r"(eWc0), "+r"(eLaneAddr));
 
+    constexpr uint32_t kSpan = PAIR ? 2 * kTcSpan : kTcSpan;       // windows per item (P.n_spans counts these)
     while (true) {
-        if (threadIdx.x == 0) sMisc[0] = atomicAdd(P.work_counter, 1u);
-        __syncthreads();
+        if (threadIdx.x == 0 && rank == 0) {
+            const uint32_t it = atomicAdd(P.work_counter, 1u);
+            sMisc[0] = it;
+            if (PAIR) st_cluster_u32(mapa_u32(smem_u32(const_cast<uint32_t*>(&sMisc[0])), 1), it);     // the peer works on the same item
+        }
+        if (PAIR) cluster_sync(); else __syncthreads();
         const uint32_t item = sMisc[0];
         if (item >= nItems) break;
         const uint32_t t = item / P.n_spans, sp = item % P.n_spans;
         const TcTile tile = P.tiles[t];
-        const uint32_t w0 = sp * kTcSpan;
-        const uint32_t nwin = min(kTcSpan, blk.n_payload - w0);
-        const uint32_t nT = (nwin + 127) >> 7;
+        const uint32_t wItem = sp * kSpan;
+        const uint32_t nTall = (min(kSpan, blk.n_payload - wItem) + 127) >> 7;          // window tiles of the item
+        // PAIR: rank 0 takes the first ceil(nTall / 2) tiles, rank 1 the rest; both run nT iterations in lockstep (rank 1's last one
+        // may be a phantom whose results are dropped)
+        const uint32_t nT = PAIR ? (nTall + 1) >> 1 : nTall;
+        const uint32_t myTiles = PAIR ? (rank ? nTall - nT : nT) : nTall;
+        const uint32_t w0 = wItem + (rank ? 128 * nT : 0u);
+        (void)myTiles;
         const uint32_t nSt = nT / kTcStageTiles + 1;            // E stages of the item: nT tiles + one halo tile
         const bool newTile = ((int32_t)t != curTile);
         curTile = (int32_t)t;
@@ -416,16 +476,18 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             mbar_expect_tx(cBar, cbytes + zbytes);
             bulk_g2s(smem_u32(sCodes), reinterpret_cast<const uint8_t*>(blk.codes) + (w0 >> 2), cbytes, cBar);
             if (ZMASK) bulk_g2s(smem_u32(sZ), reinterpret_cast<const uint8_t*>(blk.zmask) + (w0 >> 3), zbytes, cBar);
-            if (newTile) {
-                mbar_expect_tx(bBar, tile.b_bytes);
-                for (uint32_t off = 0; off < tile.b_bytes; off += 32768)
-                    bulk_g2s(smem_u32(sB) + off, P.bimg + tile.b_off + off, min(32768u, tile.b_bytes - off), bBar);
+            if (newTile) {                                    // PAIR: each CTA holds half of the tile's columns (a contiguous half of the image)
+                const uint32_t bBytes = PAIR ? tile.b_bytes / 2 : tile.b_bytes, bOff = tile.b_off + rank * bBytes;
+                mbar_expect_tx(bBar, bBytes);
+                for (uint32_t off = 0; off < bBytes; off += 32768)
+                    bulk_g2s(smem_u32(sB) + off, P.bimg + bOff + off, min(32768u, bBytes - off), bBar);
             }
         }
 
         if (warp < kTcProducers) {
             // ===================== producers: codes -> E ring (warp p fills entries 32p .. 32p+31 of every stage) =====================
             mbar_wait(cBar, nItem & 1, P.error_flag);
+            if (PAIR && newTile) mbar_wait(bBar, nBload & 1, P.error_flag);      // PAIR: a stage reported full also vouches for this CTA's half of B
             const uint32_t nEnt = (nT + 1) * 128;                     // entries of the item incl. one halo tile
             for (uint32_t st = 0; st < nSt; st++) {
                 const uint32_t k = kE + st, slot = k % kTcStages, ph = (k / kTcStages) & 1;
@@ -455,7 +517,9 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 }
                 fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(eFull + 8 * slot);
+                // (PAIR: the stage lives in this CTA's shared memory and is read by this SM's tensor core; fence.proxy.async above made it
+                //  visible to that proxy, so the arrival on the leader's barrier needs no cluster-wide release fence -- which costs ~600 cycles)
+                if (lane == 0) { if (PAIR) mbar_arrive_cluster_cta(eFullL + 8 * slot); else mbar_arrive(eFull + 8 * slot); }
                 PH_ACC(1); PH_COUNT();
                 if (warp == 0) TC_TRACE(0, st, 1);
             }
@@ -466,10 +530,10 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             // with four epilogue warps), so it is kept minimal: one eFull wait and one eEmpty commit per STAGE of
             // kTcStageTiles tiles, one tEmpty wait and one tFull commit per tile, operands moved to uniform registers once
             // per tile.
-            if (newTile) mbar_wait(bBar, nBload & 1, P.error_flag);
+            if (!PAIR && newTile) mbar_wait(bBar, nBload & 1, P.error_flag);
             const uint32_t n_k = __shfl_sync(0xffffffffu, tile.n_k, 0);
-            // instruction descriptor: F16 x F16, D = F32 (c_format 1) or F16 (c_format 0), K-major A and B, M = 128, N = n_pad
-            const uint32_t idesc = (ACC16 ? 0u : (1u << 4)) | ((tile.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+            // instruction descriptor: F16 x F16, D = F32 (c_format 1) or F16 (c_format 0), K-major A and B, M = 128 (256 for a CTA pair), N = n_pad
+            const uint32_t idesc = (ACC16 ? 0u : (1u << 4)) | ((tile.n_pad >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
             const uint32_t nChunks = 2 * n_k;
             const uint64_t ad0 = umma_desc(smem_u32(sE), 32, 128), bd0 = umma_desc(smem_u32(sB), 128, nChunks * 128);
             const uint32_t aLo0 = (uint32_t)ad0, aHi = (uint32_t)(ad0 >> 32), bLo0 = (uint32_t)bd0, bHi = (uint32_t)(bd0 >> 32);
@@ -479,7 +543,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             // The whole tile loop runs in ONE elected lane, inside one branch: there ptxas moves the loop state to uniform
             // registers once per item and steps descriptors / barrier addresses with UIADD3 (predicating each tcgen05
             // instruction instead costs 5-7 R2UR moves in front of every one of them).
-            if (elect_one()) {
+            if (rank == 0 && elect_one()) {           // PAIR: the leader's lane issues for both CTAs
                 mbar_wait(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
                 // loop state is stepped incrementally (adds and masks only: every instruction of this lane is on the critical path)
                 uint32_t j = 0, kCur = kE, kt = kT;                      // tile within the stage, stage counter, tile counter
@@ -503,23 +567,23 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     uint32_t alo = aLo0 + aOff, blo = bLo0;               // address fields are in 16-byte units = entries
                     if (!(TC_KNOCKOUT & 2)) {
                         if (ZMASK) {                                      // step 0: D = bias (constant one-hot rows x chunk 0 of B)
-                            umma_f16_lohi(d, aLoOnes, aHi, blo, bHi, idesc, 0u);
+                            umma_x<PAIR>(d, aLoOnes, aHi, blo, bHi, idesc, 0u);
                             blo += 16;
-                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
+                            umma_x<PAIR>(d, alo, aHi, blo, bHi, idesc, 1u);
                         } else {
-                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+                            umma_x<PAIR>(d, alo, aHi, blo, bHi, idesc, 0u);
                         }
 #pragma unroll 1
                         for (uint32_t m = 1; m < n_pos; m++) {
                             alo += 4; blo += 16;
-                            umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u);
+                            umma_x<PAIR>(d, alo, aHi, blo, bHi, idesc, 1u);
                         }
                     }
                     // MMAs complete in issue order: once the last tile of a stage is done, so is every reader of the stage
                     // (its own tiles and the halo read of the stage before).  The item's last tile also frees its halo stage.
-                    if (lastOfStage || lastTile) umma_commit(eEmpty + 8 * (kCur % kTcStages));
-                    if (lastOfStage && lastTile) umma_commit(eEmpty + 8 * ((kCur + 1) % kTcStages));
-                    umma_commit(tFull + 8 * buf);
+                    if (lastOfStage || lastTile) commit_x<PAIR>(eEmpty + 8 * (kCur % kTcStages));
+                    if (lastOfStage && lastTile) commit_x<PAIR>(eEmpty + 8 * ((kCur + 1) % kTcStages));
+                    commit_x<PAIR>(tFull + 8 * buf);
                     PH_ACC(2); PH_COUNT();
                     TC_TRACE(1, nT - left, 2);
                     aOff = (aOff + 128) % (kTcStages * kTcStageEnt);
@@ -541,7 +605,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 PH_ACC(0);
                 if (warp == kTcEpiWarp0) TC_TRACE(2, i, 0); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 0);
                 tc_fence_after();
-                const bool winOk = win0 + lane < blk.n_payload;
+                const bool winOk = (!PAIR || i < myTiles) && win0 + lane < blk.n_payload;
                 const uint32_t taddr = eLaneAddr + buf * kBufCols;
                 // this warp owns the 32-word chunks sub, sub + kEpiPerQ, sub + 2 kEpiPerQ, ... of the tile, taken two at a
                 // time (both loads in flight).  As soon as its LAST loads have landed in registers the warp hands the
@@ -557,7 +621,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     if (wc + 2 * step >= nWords) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tEmpty + 8 * buf);
+                        if (lane == 0) { if (PAIR) mbar_arrive_cluster_cta(tEmptyL + 8 * buf); else mbar_arrive(tEmpty + 8 * buf); }
                         PH_ACC(1);
                         released = true;
                         if (warp == kTcEpiWarp0) TC_TRACE(2, i, 2); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 2);
@@ -574,7 +638,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 if (!released) {                                      // this warp owns no chunk of such a narrow tile
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tEmpty + 8 * buf);
+                    if (lane == 0) { if (PAIR) mbar_arrive_cluster_cta(tEmptyL + 8 * buf); else mbar_arrive(tEmpty + 8 * buf); }
                 }
                 PH_ACC(2); PH_COUNT();
                 if (warp == kTcEpiWarp0) TC_TRACE(2, i, 3); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 3);
@@ -584,7 +648,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         kT += nT;
         nItem++;
         if (newTile) nBload++;
-        __syncthreads();          // item boundary: every role is done with sCodes / sB / the pipelines are drained
+        if (PAIR) cluster_sync(); else __syncthreads();          // item boundary: every role (of both CTAs) is done with sCodes / sB, the pipelines are drained
     }
 
 #ifdef B200_PHASE
@@ -599,7 +663,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kTcProducers) tmem_dealloc(tmem_base, kBufs * kBufCols);
+    if (PAIR) cluster_sync();
+    if (warp == kTcProducers) { if (PAIR) tmem_dealloc2(tmem_base, kBufs * kBufCols); else tmem_dealloc(tmem_base, kBufs * kBufCols); }
 }
 
 } // namespace b200

@@ -224,6 +224,22 @@ def test_many_short_fragments(scanner, engine):
     _assert_same(hits, *want)
 
 
+def test_cta_pair_kernel_matches(monkeypatch):
+    """The optional CTA-pair instance of the filter (B200SCAN_PAIR=1: cta_group::2 MMAs issued by one lane for two SMs,
+    completion multicast to both CTAs, hand-backs through the cluster shared window) returns the same hit lists."""
+    monkeypatch.setenv("B200SCAN_PAIR", "1")
+    sc = capi.Scanner(0, max_block_nt=1 << 22, max_hits=1 << 22)
+    try:
+        for seed, lower in ((3, False), (12, True)):
+            case = util.random_case(seed, n_motifs=120, n_nt=3_000_001, len_range=(5, 40), lower=lower)
+            sc.set_engine(capi.ENGINE_TENSOR)
+            sc.set_motifs(case["P"], case["col_len"], case["thr"])
+            hits, t = sc.scan(case["chars"], case["frag_start"][1:])
+            _assert_same(hits, *_oracle_hits(case))
+    finally:
+        sc.close()
+
+
 def test_packed_submit_and_zero_mask(scanner):
     case = util.random_case(41, n_motifs=10, n_nt=50_000)
     chars = case["chars"]
