@@ -56,6 +56,9 @@ namespace b200 {
 #ifndef TC_PRODUCERS
 #define TC_PRODUCERS 2
 #endif
+#ifndef TC_MMA_WARPS
+#define TC_MMA_WARPS 1        // issuer warps; 2 (experimental, single-CTA instances only): issuer m takes the tiles whose running index is m mod 2
+#endif
 #ifndef TC_STAGE_TILES
 #define TC_STAGE_TILES 4      // 128-window tiles per E stage: the issuer pays one eFull wait and one eEmpty commit per stage
 #endif
@@ -71,8 +74,10 @@ namespace b200 {
 constexpr uint32_t kTcEpiWarps = TC_EPI_WARPS;                 // per TMEM lane quarter: kTcEpiWarps / 4
 constexpr uint32_t kTcCtasPerSm = TC_CTAS_PER_SM;             // co-resident CTAs share the SM's 512 TMEM columns
 constexpr uint32_t kTcProducers = TC_PRODUCERS;                         // warps filling the E ring, 32 entries of every stage each
-constexpr uint32_t kTcEpiWarp0 = kTcProducers + 1;            // first epilogue warp (warp kTcProducers issues the MMAs)
-constexpr int      kTcThreads  = 32 * (kTcProducers + 1 + kTcEpiWarps);
+constexpr uint32_t kTcMmaWarps = TC_MMA_WARPS;
+constexpr uint32_t kTcEpiWarp0 = kTcProducers + kTcMmaWarps;  // first epilogue warp (warps kTcProducers .. issue the MMAs)
+constexpr int      kTcThreads  = 32 * (kTcProducers + kTcMmaWarps + kTcEpiWarps);
+static_assert(TC_MMA_WARPS == 1 || TC_MMA_WARPS == 2, "one or two issuer warps");
 #ifndef TC_SPAN
 #define TC_SPAN 32768
 #endif
@@ -406,7 +411,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
 
     if (threadIdx.x == 0) {
         // PAIR: eFull / tEmpty of the leader collect the arrivals of both CTAs; eEmpty / tFull are signalled in both by multicast commits
-        for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, (PAIR ? 2u : 1u) * kTcProducers); mbar_init(eEmpty + 8 * i, 1); }
+        for (uint32_t i = 0; i < kTcStages; i++) { mbar_init(eFull + 8 * i, (PAIR ? 2u : 1u) * kTcProducers); mbar_init(eEmpty + 8 * i, kTcMmaWarps); }
         for (uint32_t i = 0; i < kBufs; i++) { mbar_init(tFull + 8 * i, 1); mbar_init(tEmpty + 8 * i, (PAIR ? 2u : 1u) * kTcEpiWarps / kTcEpiGroups); }
         mbar_init(cBar, 1); mbar_init(bBar, 1);
         fence_mbar_init();
@@ -523,8 +528,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 PH_ACC(1); PH_COUNT();
                 if (warp == 0) TC_TRACE(0, st, 1);
             }
-        } else if (warp == kTcProducers) {
-            // ===================== MMA issuer =====================
+        } else if (warp < kTcEpiWarp0) {
+            // ===================== MMA issuer(s) =====================
             // This warp's instruction stream is on the critical path of every tile (alone on the SM: mbarrier.try_wait 43
             // cycles, tcgen05.commit 30, tcgen05.mma ~50 each -- tools/micro/issue_cost.cu -- and it shares its scheduler
             // with four epilogue warps), so it is kept minimal: one eFull wait and one eEmpty commit per STAGE of
@@ -543,6 +548,38 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             // The whole tile loop runs in ONE elected lane, inside one branch: there ptxas moves the loop state to uniform
             // registers once per item and steps descriptors / barrier addresses with UIADD3 (predicating each tcgen05
             // instruction instead costs 5-7 R2UR moves in front of every one of them).
+            if (kTcMmaWarps == 2) {
+                // Two issuers, four or two TMEM buffers: issuer m takes the tiles with running index = m (mod 2).  A commit only tracks
+                // the issuing thread's MMAs, so eEmpty counts two arrivals per stage: stage s is read by tiles 4s-1 .. 4s+3 (clipped
+                // to the item); its last reader commits for its issuer, the reader before it for the other, a lone reader for both.
+                const uint32_t mw = warp - kTcProducers;
+                if (elect_one()) {
+                    for (uint32_t i = (mw - kT) & 1u; i < nT; i += 2) {
+                        const uint32_t st = i / kTcStageTiles, j = i % kTcStageTiles, k = kE + st, kt = kT + i, buf = kt % kBufs;
+                        if (i < 2 || j < 2) mbar_wait(eFull + 8 * (k % kTcStages), (k / kTcStages) & 1, P.error_flag);       // this issuer's first tile in the stage
+                        if (j + 1 == kTcStageTiles) mbar_wait(eFull + 8 * ((k + 1) % kTcStages), ((k + 1) / kTcStages) & 1, P.error_flag);
+                        mbar_wait(tEmpty + 8 * buf, ((kt / kBufs) & 1) ^ 1, P.error_flag);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + buf * kBufCols;
+                        uint32_t alo = aLo0 + (k % kTcStages) * kTcStageEnt + j * 128, blo = bLo0;
+                        if (!(TC_KNOCKOUT & 2)) {
+                            if (ZMASK) { umma_f16_lohi(d, aLoOnes, aHi, blo, bHi, idesc, 0u); blo += 16; umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u); }
+                            else umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+#pragma unroll 1
+                            for (uint32_t m = 1; m < n_pos; m++) { alo += 4; blo += 16; umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u); }
+                        }
+                        auto free_stage = [&](uint32_t s2) {
+                            const uint32_t lo = s2 ? kTcStageTiles * s2 - 1 : 0u, hi = min(kTcStageTiles * s2 + kTcStageTiles - 1, nT - 1);
+                            const uint32_t bar = eEmpty + 8 * ((kE + s2) % kTcStages);
+                            if (i == hi) { umma_commit(bar); if (hi == lo) umma_commit(bar); }
+                            else if (i + 1 == hi) umma_commit(bar);
+                        };
+                        free_stage(st);
+                        if (j + 1 == kTcStageTiles && st + 1 < nSt) free_stage(st + 1);
+                        umma_commit(tFull + 8 * buf);
+                    }
+                }
+            } else
             if (rank == 0 && elect_one()) {           // PAIR: the leader's lane issues for both CTAs
                 mbar_wait(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
                 // loop state is stepped incrementally (adds and masks only: every instruction of this lane is on the critical path)
