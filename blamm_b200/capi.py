@@ -86,6 +86,7 @@ def host_lib() -> ctypes.CDLL:
         L.blamm_motifs_write_histograms.argtypes = [vp, _u64p, ctypes.c_float, u64, u64, ctypes.c_char_p, ctypes.c_char_p]
         L.blamm_fasta_open.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, u64, ctypes.POINTER(vp)]
         L.blamm_fasta_close.argtypes = [vp]; L.blamm_fasta_close.restype = None
+        L.blamm_fasta_set_parallel.argtypes = [vp, ctypes.c_uint, u64]
         L.blamm_fasta_next.argtypes = [vp, u64, u64, ctypes.POINTER(vp), _u64p, _u64p, _u64p, ctypes.POINTER(vp),
                                        ctypes.POINTER(vp), ctypes.POINTER(vp), _u64p]
         L.blamm_fasta_num_sequences.argtypes = [vp]
@@ -273,11 +274,13 @@ class MotifSet:
 class FastaStream:
     """FastaBatch mirror: filtered stream of a group's FASTA files, chunk by chunk."""
 
-    def __init__(self, files: Sequence[str], max_filtered: int = 2 ** 63):
+    def __init__(self, files: Sequence[str], max_filtered: int = 2 ** 63, threads: int = 1, segment_bytes: int = 0):
         self._L = host_lib()
         self._h = ctypes.c_void_p()
         arr = (ctypes.c_char_p * len(files))(*[f.encode() for f in files])
         if self._L.blamm_fasta_open(arr, len(files), max_filtered, ctypes.byref(self._h)) != 0:
+            raise HostError(self._L.blamm_host_last_error().decode())
+        if (threads != 1 or segment_bytes) and self._L.blamm_fasta_set_parallel(self._h, threads, segment_bytes) != 0:
             raise HostError(self._L.blamm_host_last_error().decode())
 
     def __del__(self):

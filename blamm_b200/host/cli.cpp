@@ -44,6 +44,13 @@ struct PhaseTimer {            // BLAMM_B200_TIMING=1: wall-clock seconds per ph
     void report() { if (on) for (auto& a : acc) fprintf(stderr, "[timing] %-28s %8.3f s\n", a.first.c_str(), a.second); }
 } gTimer;
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// FASTA parser threads: -t where the module has it, else the host's cores; BLAMM_B200_INGEST_THREADS overrides (1 = serial)
+unsigned ingestThreads(size_t wanted = 0)
+{
+    if (const char* e = getenv("BLAMM_B200_INGEST_THREADS")) return (unsigned)std::max(1, atoi(e));
+    const size_t t = wanted ? wanted : std::thread::hardware_concurrency();
+    return (unsigned)std::min<size_t>(std::max<size_t>(t, 1), 64);
+}
 }
 
 // =========================================================================================================
@@ -89,8 +96,9 @@ int runDict(int argc, char** argv)
         cout << "Computing nucleotide composition for " << s.name << " ...";
         cout.flush();
         FastaStream fs(s.files);
+        fs.setParallel(ingestThreads());
         FastaStream::Chunk c;
-        while (fs.next(1 << 24, 0, c)) {}
+        while (fs.next(64 << 20, 0, c)) {}
         s.nuclCounts = fs.counts();
         s.totSeqLen = s.nuclCounts[0] + s.nuclCounts[1] + s.nuclCounts[2] + s.nuclCounts[3];
         s.seqNames = fs.seqNames();
@@ -170,6 +178,7 @@ int runHist(int argc, char** argv)
             check(b200scan_set_motifs(ctx, mc.P().data(), mc.ldp(), (int32_t)len.size(), len.data(), thr.data()));
             check(b200scan_hist_begin(ctx, mn.data(), mx.data(), (uint32_t)numBins));
             FastaStream fs(sp.files, maxLength);
+            fs.setParallel(ingestThreads());
             FastaStream::Chunk c;
             while (fs.next(chunk, halo, c)) {
                 check(b200scan_hist_block_ascii(ctx, c.chars, c.nTotal, c.nPayload, c.fragStarts.data(), c.fragStarts.size(), B200SCAN_LOWER_ZERO));
@@ -218,7 +227,7 @@ static void scanUsage()
 namespace {
 
 struct Job {
-    vector<char> chars;
+    unique_ptr<char[]> chars;                      // not a vector: no zero fill before the parallel copy
     vector<uint64_t> fragStarts;
     vector<Fragment> frags;
     uint64_t nTotal = 0, nPayload = 0;
@@ -378,7 +387,7 @@ void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, 
             sh.qCv.notify_all();
         }
         if (inFlight[slot] && !collect(slot)) break;
-        if (b200scan_submit_ascii(ctx, slot, job->chars.data(), job->nTotal, job->nPayload, job->fragStarts.data(),
+        if (b200scan_submit_ascii(ctx, slot, job->chars.get(), job->nTotal, job->nPayload, job->fragStarts.data(),
                                   job->fragStarts.size(), foldLower ? B200SCAN_LOWER_FOLD : B200SCAN_LOWER_ZERO) != B200SCAN_OK) {
             die(string("CUDA error: ") + b200scan_last_error(ctx)); break;
         }
@@ -508,12 +517,14 @@ int runScan(int argc, char** argv)
         for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), d, maxBlock, maxHits, engine, foldLower, &pool.ctx[(size_t)d]);
         try {
             FastaStream fs(sp.files, sp.totSeqLen);
+            fs.setParallel(ingestThreads(numThreads));
             FastaStream::Chunk c;
             for (;;) {
                 double tr = now();
                 if (sh.failed || !fs.next(maxBlock - halo - 64, halo, c)) break;
                 unique_ptr<Job> job(new Job);
-                job->chars.assign(c.chars, c.chars + c.nTotal);
+                job->chars.reset(new char[c.nTotal]);
+                fs.copyChunk(c, job->chars.get());
                 job->fragStarts = c.fragStarts; job->frags = c.frags;
                 job->nTotal = c.nTotal; job->nPayload = c.nPayload;
                 gTimer.add("FASTA read + filter (reader)", now() - tr);

@@ -98,10 +98,17 @@ struct SpeciesSet {
 struct Fragment { uint64_t streamPos; uint64_t seqIdx; uint64_t seqPos; };
 
 // Filtered stream of one group, produced chunk by chunk (reference: FastaBatch, sequence.cpp:123-293).
+// The files are mmap'ed and parsed in waves of byte segments, one segment per thread; a segment is parsed without
+// knowing the record it starts in (record index and in-record position relative to a carry-in), and a short serial
+// stitch resolves the carries, merges fragments across segment borders and applies the maxFiltered cut.
 class FastaStream {
 public:
     FastaStream(const std::vector<std::string>& files, uint64_t maxFiltered = UINT64_MAX);
     ~FastaStream();
+    FastaStream(const FastaStream&) = delete;
+    FastaStream& operator=(const FastaStream&) = delete;
+    // Parser threads (>= 1) and, for tests, a forced segment size in bytes (0 = sized from the request).
+    void setParallel(unsigned threads, size_t segmentBytes = 0);
     // Next chunk: up to `payload` new characters followed by up to `halo` characters that will open the next
     // chunk.  Returns false when the stream is exhausted.  chunk.chars stays valid until the next call.
     struct Chunk {
@@ -112,6 +119,7 @@ public:
         std::vector<Fragment> frags;               // chunk-relative fragment table, frags[0].streamPos == 0
     };
     bool next(uint64_t payload, uint64_t halo, Chunk& out);
+    void copyChunk(const Chunk& c, char* dst);     // c.chars[0, nTotal) -> dst on the parser threads
     const std::vector<Fragment>& fragments() const { return frags_; }
     const std::vector<std::string>& seqNames() const { return names_; }
     uint64_t filteredLength() const { return streamLen_; }
@@ -119,21 +127,32 @@ public:
     void locate(uint64_t streamPos, uint64_t& seqIdx, uint64_t& seqPos) const;
     // nucleotide counts of everything consumed so far (dict module, species.cpp:32-61)
     const std::array<uint64_t, 4>& counts() const { return counts_; }
+    struct Segment;                                // one parsed byte range (sequence.cpp)
+    struct Pool;                                   // the parser threads (sequence.cpp)
 private:
-    bool fill(uint64_t want);                      // append filtered characters until buf_ holds `want`
+    bool fill(uint64_t want);                      // append filtered characters until `want` are buffered
     bool openNext();
+    void wave(uint64_t need);                      // parse the next byte range of the current file
+    void stitch(Segment& s, const char* p, size_t n, bool midLine);
+    void reserveBuf(size_t n);
     std::vector<std::string> files_;
     size_t fileIdx_ = 0;
     const char* map_ = nullptr; size_t mapLen_ = 0, mapPos_ = 0; int fd_ = -1;
+    bool posMidLine_ = false;                      // mapPos_ lies inside a sequence line (a long line was split)
     uint64_t maxFiltered_, streamLen_ = 0;
     uint64_t curSeqLen_ = 0;                       // position inside the current record
     bool haveLast_ = false; uint64_t lastSeq_ = 0, lastPosPlus1_ = 0;
     uint64_t pendingDrop_ = 0;
-    std::vector<char> buf_; uint64_t bufStart_ = 0;        // filtered characters [bufStart_, bufStart_+buf_.size())
+    // filtered characters [bufStart_, bufStart_ + bufLen_) live at buf_[bufHead_ ...]; plain malloc'ed storage so
+    // that growing it does not zero-fill what the copy threads overwrite anyway
+    char* buf_ = nullptr; size_t bufCap_ = 0, bufHead_ = 0, bufLen_ = 0; uint64_t bufStart_ = 0;
     std::vector<Fragment> frags_;
     std::vector<std::string> names_;
     std::array<uint64_t, 4> counts_{{0, 0, 0, 0}};
     bool eof_ = false;
+    unsigned threads_ = 1; size_t forcedSegment_ = 0;
+    std::vector<std::unique_ptr<Segment>> segs_;   // reused from wave to wave
+    std::unique_ptr<Pool> pool_;
 };
 
 // "%g" with 6 significant digits == ostream << float (pwmscan.cpp:94)

@@ -109,6 +109,10 @@ int blamm_fasta_open(const char* const* files, int n, uint64_t maxFiltered, blam
     });
 }
 void blamm_fasta_close(blamm_fasta* f) { delete f; }
+int blamm_fasta_set_parallel(blamm_fasta* f, unsigned threads, uint64_t segmentBytes)
+{
+    return guarded([&] { f->fs->setParallel(threads, (size_t)segmentBytes); });
+}
 
 int blamm_fasta_next(blamm_fasta* f, uint64_t payload, uint64_t halo, const char** chars, uint64_t* nTotal, uint64_t* nPayload,
                      uint64_t* streamStart, const uint64_t** fs, const uint64_t** fq, const uint64_t** fp, uint64_t* nFrag)

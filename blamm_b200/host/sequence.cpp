@@ -2,14 +2,23 @@
 #include "host.h"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <numeric>
 #include <set>
 #include <sstream>
+#include <thread>
+#include <cstdlib>
 
 #include <fcntl.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -103,6 +112,12 @@ void SpeciesSet::addFile(const std::string& group, const std::string& fasta)
 // advances the position inside the record.  Kept characters of all records and files are concatenated; a new
 // fragment starts whenever a kept character does not directly follow the previous kept one in the same
 // record.  The stream stops after maxFiltered kept characters (the dictionary's TOT_SEQ_LENGTH).
+//
+// Structure: the reference parses line by line under a mutex (sequence.cpp:274-293).  Here a *wave* cuts the next
+// byte range of the mmap'ed file into one segment per thread (at line starts; a line longer than 4 KB is split in
+// the middle), every segment is parsed independently into its own buffer with record indices and in-record
+// positions relative to an unknown carry-in, and a serial stitch over the segments' few fragments and names
+// resolves the carries.  The kept characters are then copied into the stream buffer in parallel.
 // ---------------------------------------------------------------------------------------------------------
 static const struct ValidTable {
     uint8_t v[256];
@@ -110,13 +125,201 @@ static const struct ValidTable {
                    v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; }
 } kValid;
 
+// First index >= i (and <= len) whose character is not KEPT (ACGTacgt) / not dropped: 16 characters per step with
+// SSE2 (baseline x86-64), bytes elsewhere.
+#if defined(__SSE2__)
+static inline unsigned keptMask16(const char* p)
+{
+    const __m128i u = _mm_or_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(p)), _mm_set1_epi8(0x20));
+    const __m128i k = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('a')), _mm_cmpeq_epi8(u, _mm_set1_epi8('c'))),
+                                   _mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('g')), _mm_cmpeq_epi8(u, _mm_set1_epi8('t'))));
+    return (unsigned)_mm_movemask_epi8(k);
+}
+#endif
+template <bool KEPT>
+static inline size_t runEnd(const char* line, size_t i, size_t len)
+{
+#if defined(__SSE2__)
+    while (i + 16 <= len) {
+        const unsigned m = KEPT ? ~keptMask16(line + i) & 0xFFFFu : keptMask16(line + i);    // bits that end the run
+        if (m) return i + (size_t)__builtin_ctz(m);
+        i += 16;
+    }
+#endif
+    while (i < len && (kValid.v[(uint8_t)line[i]] != 4) == KEPT) i++;
+    return i;
+}
+
+// A, C, G, T counts of a run of kept characters.  (c >> 1) & 3 is 0 for Aa, 1 for Cc, 3 for Gg, 2 for Tt, so two bit
+// planes of eight characters at a time give the C, G and T counts in byte lanes; A is the remainder.
+static void countRun(const char* s, size_t n, uint64_t cnt[4])
+{
+    const uint64_t kOnes = 0x0101010101010101ull;
+    uint64_t c = 0, g = 0, t = 0;
+    size_t i = 0;
+    while (i + 8 <= n) {
+        uint64_t ac = 0, ag = 0, at = 0;
+        const size_t stop = std::min(n - (n - i) % 8, i + 8 * 255);
+        for (; i < stop; i += 8) {
+            uint64_t w;
+            std::memcpy(&w, s + i, 8);
+            const uint64_t b1 = (w >> 1) & kOnes, b2 = (w >> 2) & kOnes;
+            ac += b1 & ~b2; ag += b1 & b2; at += b2 & ~b1;
+        }
+        // horizontal sums of the byte lanes (each lane <= 255)
+        auto hsum = [](uint64_t v) {
+            v = (v & 0x00FF00FF00FF00FFull) + ((v >> 8) & 0x00FF00FF00FF00FFull);
+            v = (v & 0x0000FFFF0000FFFFull) + ((v >> 16) & 0x0000FFFF0000FFFFull);
+            return (v & 0xFFFFFFFFull) + (v >> 32);
+        };
+        c += hsum(ac); g += hsum(ag); t += hsum(at);
+    }
+    for (; i < n; i++) {
+        const unsigned k = ((unsigned char)s[i] >> 1) & 3;
+        c += k == 1; g += k == 3; t += k == 2;
+    }
+    cnt[0] += n - c - g - t; cnt[1] += c; cnt[2] += g; cnt[3] += t;
+}
+
+// One parsed byte range.  Records are numbered relative to the segment: 0 = the record that was open when the segment
+// began (its index and the position reached in it are the carry-in), k = the k-th header line inside the segment.
+struct FastaStream::Segment {
+    struct Frag { uint64_t off; uint32_t rec; uint64_t pos; };     // off = offset into `chars`
+    std::unique_ptr<char[]> chars; size_t cap = 0, nKept = 0;
+    std::vector<Frag> frags;
+    std::vector<std::string> names;
+    uint64_t seqLenEnd = 0;              // in-record position at the end (to be added to the carry-in if names is empty)
+    bool haveLast = false; uint32_t lastRec = 0; uint64_t lastPosPlus1 = 0;
+    uint64_t counts[4] = {0, 0, 0, 0};
+    bool seqBeforeHeader = false;        // a non-empty sequence line belongs to record 0
+    const char* src = nullptr; size_t srcLen = 0; bool midLine = false;
+    size_t dstOff = 0;                   // where the kept characters go in the stream buffer (set by the stitch)
+
+    // limit = how many characters may still be kept; like the reference, the cut is tested before every line
+    void parse(const char* p, size_t n, bool startsMidLine, uint64_t limit)
+    {
+        if (cap < n) { chars.reset(new char[n]); cap = n; }
+        nKept = 0; frags.clear(); names.clear(); seqLenEnd = 0; haveLast = false; lastRec = 0; lastPosPlus1 = 0;
+        counts[0] = counts[1] = counts[2] = counts[3] = 0; seqBeforeHeader = false;
+        char* dst = chars.get();
+        uint32_t rec = 0;
+        uint64_t seqLen = 0;
+        size_t at = 0;
+        bool mid = startsMidLine;
+        while (at < n && nKept < limit) {
+            const char* line = p + at;
+            const char* nl = static_cast<const char*>(memchr(line, '\n', n - at));
+            const size_t len = nl ? (size_t)(nl - line) : n - at;
+            at += len + (nl ? 1 : 0);
+            const bool lineStart = !mid;
+            mid = false;
+            if (len == 0) continue;
+            if (lineStart && line[0] == '>') {
+                seqLen = 0; rec++;
+                size_t b = 1;
+                while (b < len && isspace((unsigned char)line[b])) b++;
+                size_t e = b;
+                while (e < len && !isspace((unsigned char)line[e])) e++;
+                names.emplace_back(line + b, e - b);
+                continue;
+            }
+            if (rec == 0) seqBeforeHeader = true;
+            size_t i = 0;
+            while (i < len) {
+                i = runEnd<false>(line, i, len);                                 // a run of dropped characters
+                const size_t j = runEnd<true>(line, i, len);
+                if (j == i) break;
+                size_t run = j - i;
+                if (nKept + run > limit) run = (size_t)(limit - nKept);
+                if (run) {
+                    const uint64_t pos = seqLen + i;
+                    if (!(haveLast && lastRec == rec && lastPosPlus1 == pos)) frags.push_back(Frag{nKept, rec, pos});
+                    std::memcpy(dst + nKept, line + i, run);
+                    countRun(line + i, run, counts);
+                    nKept += run;
+                    haveLast = true; lastRec = rec; lastPosPlus1 = pos + run;
+                }
+                i = j;
+            }
+            seqLen += len;
+        }
+        seqLenEnd = seqLen;
+    }
+};
+
+// The parser threads of one stream.  They live as long as the stream (a wave lasts a few milliseconds: threads created
+// per wave would mostly still be waiting for a core when it ends); run(n, fn) executes fn(0..n-1) on them and on the
+// caller and rethrows the first exception.
+struct FastaStream::Pool {
+    explicit Pool(unsigned helpers) { for (unsigned t = 0; t < helpers; t++) threads.emplace_back([this] { loop(); }); }
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> l(m); stop = true; }
+        wake.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    void run(size_t n, const std::function<void(size_t)>& fn)
+    {
+        if (n == 0) return;
+        if (n == 1 || threads.empty()) { for (size_t i = 0; i < n; i++) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> l(m);
+            job = &fn; jobSize = n; nextIdx = 0; busy = threads.size(); err = nullptr; generation++;
+        }
+        wake.notify_all();
+        work();
+        std::unique_lock<std::mutex> l(m);
+        idle.wait(l, [&] { return busy == 0; });
+        job = nullptr;
+        if (err) std::rethrow_exception(err);
+    }
+private:
+    void work()
+    {
+        try { for (size_t i; (i = nextIdx.fetch_add(1)) < jobSize;) (*job)(i); }
+        catch (...) { std::lock_guard<std::mutex> l(m); if (!err) err = std::current_exception(); }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m);
+                wake.wait(l, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            work();
+            std::lock_guard<std::mutex> l(m);
+            if (--busy == 0) idle.notify_one();
+        }
+    }
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable wake, idle;
+    const std::function<void(size_t)>* job = nullptr;
+    size_t jobSize = 0, busy = 0;
+    std::atomic<size_t> nextIdx{0};
+    uint64_t generation = 0;
+    bool stop = false;
+    std::exception_ptr err;
+};
+
 FastaStream::FastaStream(const std::vector<std::string>& files, uint64_t maxFiltered)
-    : files_(files), maxFiltered_(maxFiltered) {}
+    : files_(files), maxFiltered_(maxFiltered), pool_(new Pool(0)) {}
 
 FastaStream::~FastaStream()
 {
     if (map_) munmap(const_cast<char*>(map_), mapLen_);
     if (fd_ >= 0) close(fd_);
+    std::free(buf_);
+}
+
+void FastaStream::setParallel(unsigned threads, size_t segmentBytes)
+{
+    threads_ = std::max(1u, threads);
+    forcedSegment_ = segmentBytes;
+    pool_.reset(new Pool(threads_ - 1));
 }
 
 bool FastaStream::openNext()
@@ -129,7 +332,7 @@ bool FastaStream::openNext()
         if (fd_ < 0) throw std::runtime_error("Could not open file: " + f);
         struct stat st;
         if (fstat(fd_, &st) != 0) throw std::runtime_error("Could not open file: " + f);
-        mapLen_ = (size_t)st.st_size; mapPos_ = 0;
+        mapLen_ = (size_t)st.st_size; mapPos_ = 0; posMidLine_ = false;
         if (mapLen_ == 0) { close(fd_); fd_ = -1; continue; }
         void* p = mmap(nullptr, mapLen_, PROT_READ, MAP_PRIVATE, fd_, 0);
         if (p == MAP_FAILED) throw std::runtime_error("Could not map file: " + f);
@@ -140,70 +343,125 @@ bool FastaStream::openNext()
     return false;
 }
 
+void FastaStream::reserveBuf(size_t n)
+{
+    if (n <= bufCap_) return;
+    const size_t cap = std::max(n, bufCap_ + bufCap_ / 2);
+    char* p = static_cast<char*>(std::realloc(buf_, cap));
+    if (!p) throw std::bad_alloc();
+    buf_ = p; bufCap_ = cap;
+}
+
+// Serial part of a wave: give segment s its place in the stream.  p/n/midLine describe its bytes again because a
+// segment that crosses the maxFiltered cut is re-parsed with the cut (the reference stops reading lines there, so
+// headers behind the cut are not registered either).
+void FastaStream::stitch(Segment& s, const char* p, size_t n, bool midLine)
+{
+    if (streamLen_ >= maxFiltered_) { eof_ = true; return; }
+    if (s.nKept > maxFiltered_ - streamLen_) s.parse(p, n, midLine, maxFiltered_ - streamLen_);
+    if (s.seqBeforeHeader && names_.empty()) throw std::runtime_error("Input file does not appear to be in fasta format\n");
+    const uint64_t carrySeq = names_.empty() ? 0 : names_.size() - 1, carryLen = curSeqLen_, firstNew = names_.size();
+    auto recOf = [&](uint32_t rec) { return rec == 0 ? carrySeq : firstNew + rec - 1; };
+    auto posOf = [&](uint32_t rec, uint64_t pos) { return rec == 0 ? carryLen + pos : pos; };
+    for (size_t k = 0; k < s.frags.size(); k++) {
+        const auto& f = s.frags[k];
+        const uint64_t seq = recOf(f.rec), pos = posOf(f.rec, f.pos);
+        if (k == 0 && haveLast_ && lastSeq_ == seq && lastPosPlus1_ == pos) continue;     // continues the open fragment
+        frags_.push_back(Fragment{streamLen_ + f.off, seq, pos});
+    }
+    if (s.haveLast) { haveLast_ = true; lastSeq_ = recOf(s.lastRec); lastPosPlus1_ = posOf(s.lastRec, s.lastPosPlus1); }
+    curSeqLen_ = s.names.empty() ? carryLen + s.seqLenEnd : s.seqLenEnd;
+    for (auto& nm : s.names) names_.push_back(std::move(nm));
+    for (int i = 0; i < 4; i++) counts_[i] += s.counts[i];
+    s.dstOff = bufHead_ + bufLen_;
+    bufLen_ += s.nKept;
+    streamLen_ += s.nKept;
+}
+
+void FastaStream::wave(uint64_t need)
+{
+    // FASTA carries 1/60 of line ends; a short wave is simply followed by another one
+    const size_t left = mapLen_ - mapPos_;
+    need = std::min<uint64_t>(need, 1ull << 40);
+    const uint64_t needBytes = need + need / 32 + 4096;
+    // four segments per thread: a thread that wakes up late (or never gets a core) costs a quarter of a share, not a whole one
+    const size_t parts = threads_ > 1 ? 4 * (size_t)threads_ : 1;
+    size_t segBytes = forcedSegment_;
+    if (!segBytes) segBytes = (size_t)std::min<uint64_t>(std::max<uint64_t>(needBytes / parts + 1, 256 << 10), 64 << 20);
+    size_t nSeg = forcedSegment_ ? threads_ : (size_t)std::min<uint64_t>(parts, (needBytes + segBytes - 1) / segBytes);
+    nSeg = std::max<size_t>(1, std::min(nSeg, (left + segBytes - 1) / segBytes));
+
+    // segment borders: line starts, except that a sequence line longer than 4 KB is cut in the middle
+    struct Cut { size_t at; bool mid; };
+    std::vector<Cut> cuts{{mapPos_, posMidLine_}};
+    for (size_t k = 1; k <= nSeg; k++) {
+        const Cut prev = cuts.back();
+        const size_t x = std::min(mapLen_, mapPos_ + k * segBytes);
+        if (x <= prev.at) continue;
+        if (x == mapLen_) { cuts.push_back(Cut{x, false}); break; }
+        const char* q = static_cast<const char*>(memrchr(map_ + prev.at, '\n', x - prev.at));
+        if (q) {
+            const size_t lineStart = (size_t)(q - map_) + 1;
+            if (map_[lineStart] == '>' || x - lineStart <= 4096) { if (lineStart > prev.at) cuts.push_back(Cut{lineStart, false}); }
+            else cuts.push_back(Cut{x, true});
+        } else if (!prev.mid && map_[prev.at] == '>') {
+            // inside a header line that began at the previous border: the border moves behind it
+            const char* e = static_cast<const char*>(memchr(map_ + x, '\n', mapLen_ - x));
+            cuts.push_back(Cut{e ? (size_t)(e - map_) + 1 : mapLen_, false});
+        } else cuts.push_back(Cut{x, true});
+    }
+    const size_t n = cuts.size() - 1;
+    if (n == 0) { mapPos_ = mapLen_; return; }
+    while (segs_.size() < n) segs_.emplace_back(new Segment);
+    pool_->run(n, [&](size_t k) {
+        Segment& s = *segs_[k];
+        s.src = map_ + cuts[k].at; s.srcLen = cuts[k + 1].at - cuts[k].at; s.midLine = cuts[k].mid;
+        s.parse(s.src, s.srcLen, s.midLine, UINT64_MAX);
+    });
+    size_t used = 0, total = 0;
+    for (; used < n && !eof_; used++) total += segs_[used]->nKept;      // upper bound before the cut
+    // compact the buffer, make room, then place the segments
+    if (bufHead_) { std::memmove(buf_, buf_ + bufHead_, bufLen_); bufHead_ = 0; }
+    reserveBuf(bufLen_ + total);
+    used = 0;
+    for (; used < n; used++) {
+        Segment& s = *segs_[used];
+        stitch(s, s.src, s.srcLen, s.midLine);
+        if (eof_) break;
+    }
+    pool_->run(used, [&](size_t k) {
+        const Segment& s = *segs_[k];
+        if (s.nKept) std::memcpy(buf_ + s.dstOff, s.chars.get(), s.nKept);
+    });
+    mapPos_ = cuts[n].at; posMidLine_ = cuts[n].mid;
+}
+
 bool FastaStream::fill(uint64_t want)
 {
-    while (buf_.size() < want && !eof_) {
+    while (bufLen_ < want && !eof_) {
         if (streamLen_ >= maxFiltered_) { eof_ = true; break; }
         if (!map_ || mapPos_ >= mapLen_) {
             if (!openNext()) { eof_ = true; break; }
         }
-        // one line
-        const char* line = map_ + mapPos_;
-        const char* nl = static_cast<const char*>(memchr(line, '\n', mapLen_ - mapPos_));
-        const size_t len = nl ? (size_t)(nl - line) : mapLen_ - mapPos_;
-        mapPos_ += len + (nl ? 1 : 0);
-        if (len == 0) continue;
-        if (line[0] == '>') {
-            curSeqLen_ = 0;
-            size_t b = 1;
-            while (b < len && isspace((unsigned char)line[b])) b++;
-            size_t e = b;
-            while (e < len && !isspace((unsigned char)line[e])) e++;
-            names_.emplace_back(line + b, e - b);
-            continue;
-        }
-        if (names_.empty()) throw std::runtime_error("Input file does not appear to be in fasta format\n");
-        const uint64_t seq = names_.size() - 1;
-        size_t i = 0;
-        while (i < len) {
-            // skip a run of invalid characters
-            while (i < len && kValid.v[(uint8_t)line[i]] == 4) i++;
-            size_t j = i;
-            while (j < len && kValid.v[(uint8_t)line[j]] != 4) j++;
-            if (j == i) break;
-            size_t run = j - i;
-            if (streamLen_ + run > maxFiltered_) run = (size_t)(maxFiltered_ - streamLen_);
-            if (run) {
-                const uint64_t pos = curSeqLen_ + i;
-                if (!(haveLast_ && lastSeq_ == seq && lastPosPlus1_ == pos))
-                    frags_.push_back(Fragment{streamLen_, seq, pos});
-                buf_.insert(buf_.end(), line + i, line + i + run);
-                for (size_t k = i; k < i + run; k++) counts_[kValid.v[(uint8_t)line[k]]]++;
-                streamLen_ += run;
-                haveLast_ = true; lastSeq_ = seq; lastPosPlus1_ = pos + run;
-            }
-            i = j;
-        }
-        curSeqLen_ += len;
+        wave(std::min<uint64_t>(want - bufLen_, maxFiltered_ - streamLen_));
     }
-    return !buf_.empty();
+    return bufLen_ != 0;
 }
 
 bool FastaStream::next(uint64_t payload, uint64_t halo, Chunk& out)
 {
     // drop what the previous chunk reported as payload; its halo becomes the head of this chunk
     if (pendingDrop_) {
-        const uint64_t drop = std::min<uint64_t>(pendingDrop_, buf_.size());
-        buf_.erase(buf_.begin(), buf_.begin() + drop);
-        bufStart_ += drop;
+        const uint64_t drop = std::min<uint64_t>(pendingDrop_, bufLen_);
+        bufHead_ += drop; bufLen_ -= drop; bufStart_ += drop;
         pendingDrop_ = 0;
     }
     fill(payload + halo);
     // like the reference, a trailing chunk made only of the previous halo is still a chunk (its windows
     // were not reported yet); the stream ends when nothing is left at all (sequence.cpp:274-293)
-    if (buf_.empty()) { out = Chunk(); return false; }
-    out.chars = buf_.data();
-    out.nTotal = std::min<uint64_t>(buf_.size(), payload + halo);
+    if (bufLen_ == 0) { out = Chunk(); return false; }
+    out.chars = buf_ + bufHead_;
+    out.nTotal = std::min<uint64_t>(bufLen_, payload + halo);
     out.nPayload = std::min<uint64_t>(out.nTotal, payload);
     out.streamStart = bufStart_;
     pendingDrop_ = out.nPayload;
@@ -226,6 +484,12 @@ bool FastaStream::next(uint64_t payload, uint64_t halo, Chunk& out)
         frags_.erase(frags_.begin(), keep);
     }
     return true;
+}
+
+void FastaStream::copyChunk(const Chunk& c, char* dst)
+{
+    const size_t slice = 1 << 20, n = (size_t)((c.nTotal + slice - 1) / slice);
+    pool_->run(n, [&](size_t k) { std::memcpy(dst + k * slice, c.chars + k * slice, std::min<size_t>(slice, c.nTotal - k * slice)); });
 }
 
 void FastaStream::locate(uint64_t streamPos, uint64_t& seqIdx, uint64_t& seqPos) const

@@ -38,6 +38,9 @@ int  blamm_motifs_write_histograms(blamm_motifs* m, const uint64_t bg[4], float 
 
 int  blamm_fasta_open(const char* const* files, int n_files, uint64_t max_filtered, blamm_fasta** out);
 void blamm_fasta_close(blamm_fasta* f);
+/* Parser threads (the reference reads under one mutex, sequence.cpp:274-293); segment_bytes = 0 sizes the per-thread
+ * byte segments from the request, any other value forces it (tests). */
+int  blamm_fasta_set_parallel(blamm_fasta* f, unsigned threads, uint64_t segment_bytes);
 /* Next chunk (payload + halo).  Returns 1 if a chunk was produced, 0 at the end, -1 on error.  Pointers stay
  * valid until the next call.  frag_* describe the chunk-relative fragment table (entry 0 starts at 0). */
 int  blamm_fasta_next(blamm_fasta* f, uint64_t payload, uint64_t halo, const char** chars, uint64_t* n_total,

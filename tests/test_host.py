@@ -103,6 +103,101 @@ def test_fasta_stream_matches_oracle(golden, case, payload, halo):
             assert (int(wq[0]), int(wp[0])) == (q, p)
 
 
+def _collect_stream(fs, payload, halo):
+    """Whole stream of a FastaStream: payload characters and every fragment the chunks report, in global coordinates."""
+    chars, frag, pos = bytearray(), set(), 0
+    while True:
+        c = fs.next(payload, halo)
+        if c is None:
+            break
+        assert c["stream_start"] == pos and c["frag_start"][0] == 0
+        for s, q, p in zip(c["frag_start"], c["frag_seq"], c["frag_pos"]):
+            if s < c["n_payload"]:
+                frag.add((pos + int(s), int(q), int(p)))
+        chars += c["chars"][:c["n_payload"]]
+        pos += c["n_payload"]
+    return bytes(chars), frag
+
+
+def _check_against_oracle(files, max_filtered, threads, segment_bytes, payload, halo):
+    want = O.build_stream(files, max_filtered)
+    fs = capi.FastaStream(files, max_filtered, threads=threads, segment_bytes=segment_bytes)
+    chars, frag = _collect_stream(fs, payload, halo)
+    assert chars == want.chars
+    # the reference reads header lines lazily (sequence.cpp:216-228): past the length cut none is registered, while the
+    # oracle lists every header of the files
+    names = fs.seq_names()
+    assert names == want.seq_names[:len(names)] and (len(names) == len(want.seq_names) or len(chars) == max_filtered)
+    assert len(names) > int(want.frag_seq.max(initial=0)) or not len(chars)
+    counts = [chars.upper().count(c) for c in b"ACGT"]
+    assert fs.counts() == counts
+    true = set(zip(want.frag_start.tolist(), want.frag_seq.tolist(), want.frag_pos.tolist()))
+    assert true <= frag
+    extra = sorted(frag - true)          # chunk heads only: same coordinates as the oracle's mapping
+    if extra:
+        wq, wp = O.stream_to_seq(want, np.array([e[0] for e in extra], dtype=np.uint64))
+        assert [(int(a), int(b)) for a, b in zip(wq, wp)] == [(e[1], e[2]) for e in extra]
+
+
+@pytest.mark.parametrize("case", ["example", "edge"])
+@pytest.mark.parametrize("threads,segment_bytes", [(4, 7), (3, 64), (8, 1000), (5, 0)])
+def test_parallel_ingest_matches_oracle_on_golden_inputs(golden, case, threads, segment_bytes):
+    """The wave parser (segments parsed blind, carries resolved by the stitch) gives the reference's stream
+    (FastaBatch, sequence.cpp:142-293) whatever the segmentation -- including the dictionary's length cut."""
+    d = os.path.join(golden, case)
+    for sp in O.load_dict(os.path.join(d, "sequences.mf.dict")):
+        files = [os.path.join(d, f) for f in sp.files]
+        for cut in (sp.tot_len, max(sp.tot_len // 3, 1), 2 ** 62):
+            _check_against_oracle(files, cut, threads, segment_bytes, 1000, 22)
+
+
+def _nasty_fasta(tmp_path, seed):
+    """Files that exercise every border rule: lines far longer than the 4 KB split limit, CRLF, blank lines, N runs,
+    lower case, a header longer than a segment, a header at the very end, no trailing newline, a second file that
+    continues the open record without a header."""
+    rng = np.random.default_rng(seed)
+
+    def seq(n):
+        s = rng.choice(np.frombuffer(b"ACGTacgtNnRY-", dtype=np.uint8), size=n,
+                       p=[.2, .2, .2, .2, .03, .03, .03, .03, .02, .02, .01, .01, .02]).tobytes()
+        return s
+
+    f1 = b">chr1 first record\n" + seq(30_000) + b"\n" + seq(100) + b"\r\n\n\n" + seq(5000) + b"\n"
+    f1 += b">" + b"h" * 3000 + b" " + b"x" * 9000 + b"\n" + b"N" * 7000 + b"\n" + seq(12_345) + b"\n>empty\n>chr3\n"
+    for _ in range(200):
+        f1 += seq(int(rng.integers(0, 80))) + b"\n"
+    f1 += seq(20_000)                                   # no trailing newline
+    f2 = seq(777) + b"\n>chr4\tdescription\n" + seq(9000) + b"\n>last"
+    a, b = tmp_path / "a.fa", tmp_path / "b.fa"
+    a.write_bytes(f1)
+    b.write_bytes(f2)
+    return [str(a), str(b)]
+
+
+@pytest.mark.parametrize("threads,segment_bytes", [(1, 0), (2, 1), (4, 13), (4, 4097), (7, 5000), (8, 0), (3, 1 << 16)])
+def test_parallel_ingest_border_rules(tmp_path, threads, segment_bytes):
+    files = _nasty_fasta(tmp_path, 11)
+    total = len(O.build_stream(files).chars)
+    for cut in (2 ** 62, total, total - 1, 30_001, 29_999, 1):
+        _check_against_oracle(files, cut, threads, segment_bytes, 10_000, 34)
+
+
+def test_parallel_ingest_is_independent_of_threads_at_size(tmp_path):
+    """4 MB of 60-column FASTA with N runs: 1, 3 and 8 threads with request-sized segments give identical chunks."""
+    p = tmp_path / "g.fa"
+    seq = synth.random_acgt(4_000_000, 5)
+    for a in (100_000, 1_234_567, 3_999_000):
+        seq[a:a + 777] = ord("N")
+    synth.write_fasta(str(p), [("chrA", seq[:1_500_000]), ("chrB desc", seq[1_500_000:1_500_050]), ("chrC", seq[1_500_050:])])
+    ref = None
+    for threads in (1, 3, 8):
+        fs = capi.FastaStream([str(p)], threads=threads)
+        got = _collect_stream(fs, 700_000, 34) + (fs.seq_names(), fs.counts())
+        ref = ref or got
+        assert got == ref
+    assert ref[0] == O.build_stream([str(p)]).chars
+
+
 def test_fasta_rejects_headerless_input(tmp_path):
     p = tmp_path / "bad.fa"
     p.write_text("ACGT\n>late\nACGT\n")
