@@ -427,6 +427,82 @@ def test_cli_end_to_end_example(golden, tmp_path):
             assert open(work / "PWMthresholds.txt").read() == open(os.path.join(golden, "example", "PWMthresholds_pt_rc.txt")).read()
 
 
+def test_config4_many_columns_absolute_threshold(tmp_path):
+    """BASELINE.json configs[3] in shape: 10,000 PWMs of length 6-30 with -rc (20,000 columns, 80 column tiles) and an
+    absolute threshold, at 2 Mnt.  The oracle scans a prefix in full; beyond it the tensor path must equal the exact
+    gather-add engine hit for hit, and a sample of hits re-verifies bit-exactly against the oracle."""
+    mf = str(tmp_path / "m10k.jaspar")
+    synth.make_jaspar_like(mf, 10000, 77, uniform_len=(6, 30))
+    seq = synth.random_acgt(2_000_000, 99)
+    ms = capi.MotifSet(mf, revcompl=True)
+    P, col_len, is_rc = ms.generate_matrix(synth.counts_of(seq))
+    thr = ms.thresholds("at", 12.0)
+    assert len(col_len) == 20000 and int(col_len.min()) == 6 and int(col_len.max()) == 30
+    sc = capi.Scanner(0, max_block_nt=len(seq) + 64, max_hits=1 << 23)
+    try:
+        res = {}
+        for engine in (capi.ENGINE_TENSOR, capi.ENGINE_GATHER):
+            sc.set_engine(engine)
+            sc.set_motifs(P, col_len, thr)
+            h, t = sc.scan(seq)
+            assert t["engine_used"] == engine
+            res[engine] = _sorted(h)
+        tc, g = res[capi.ENGINE_TENSOR], res[capi.ENGINE_GATHER]
+        assert len(g) > 100_000 and np.array_equal(tc, g)
+        assert np.all(g["score"] >= thr[g["col"]])
+        assert np.all(g["pos"] + col_len[g["col"]].astype(np.uint64) <= len(seq))
+        pick = np.sort(np.random.default_rng(6).choice(len(g), 100_000, replace=False))
+        want = O.score_at(bytes(seq), P, col_len, g["pos"][pick], g["col"][pick])
+        assert np.array_equal(want.view(np.uint32), g["score"][pick].view(np.uint32))
+        # full oracle scan of a prefix (every column): identical set, bit-identical scores
+        n = 6000
+        pos, col, score = O.scan_stream(bytes(seq[:n]), np.zeros(1, np.uint64), P, col_len, thr)
+        sc.set_engine(capi.ENGINE_TENSOR)
+        h, _ = sc.scan(seq[:n])
+        _assert_same(h, pos, col, score)
+        assert np.array_equal(_sorted(h), tc[tc["pos"] + col_len[tc["col"]].astype(np.uint64) <= n])
+    finally:
+        sc.close()
+
+
+def test_config3_many_groups_cli(tmp_path):
+    """BASELINE.json configs[2] in shape: several manifest groups with distinct backgrounds (the matrix P and the p-value
+    thresholds are rebuilt per group), more than one FASTA file per group, N runs and soft-masked stretches, scanned by the
+    CLI in small chunks with a parallel reader -- against the oracle's restatement of the whole `blamm scan`."""
+    cli = os.path.join(lib_dir(), "blamm-b200")
+    work = tmp_path / "c3"
+    os.makedirs(work / "hist")
+    synth.make_jaspar_like(str(work / "motifs.jaspar"), 40, 31)
+    rng = np.random.default_rng(8)
+    manifest = []
+    for gidx, gc in enumerate((0.36, 0.41, 0.44, 0.48, 0.52)):
+        probs = ((1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2)
+        for f in range(1 + gidx % 2):
+            seq = synth.random_acgt(150_000 + 10_000 * gidx, 100 + 10 * gidx + f, probs)
+            for _ in range(4):
+                a = int(rng.integers(0, len(seq) - 5000))
+                seq[a:a + int(rng.integers(1, 3000))] = ord("N")
+                b = int(rng.integers(0, len(seq) - 5000))
+                seq[b:b + int(rng.integers(1, 4000))] |= 0x20
+            cut = len(seq) // 3
+            name = "g%d_%d.fa" % (gidx, f)
+            synth.write_fasta(str(work / name), [("g%dchr%d" % (gidx, 2 * f + 1), seq[:cut]), ("g%dchr%d extra" % (gidx, 2 * f + 2), seq[cut:])])
+            manifest.append("group%d\t%s\n" % (gidx, name))
+    open(work / "seq.mf", "w").write("".join(manifest))
+    env = dict(os.environ, BLAMM_B200_CHUNK="50000", BLAMM_B200_INGEST_THREADS="4")
+    for args in (["dict", "seq.mf"], ["hist", "-H", "hist", "motifs.jaspar", "seq.mf"]):
+        subprocess.run([cli] + args, cwd=work, env=env, check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([cli, "scan", "-rc", "-pt", "0.0005", "-H", "hist", "motifs.jaspar", "seq.mf"], cwd=work, env=env,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want, details = O.scan("motifs.jaspar", "seq.mf", "pt", 0.0005, True, histdir="hist", base_dir=str(work))
+    assert len(details) == 5 and all(len(d["pos"]) > 500 for d in details)
+    # distinct backgrounds -> distinct thresholds per group
+    assert not np.array_equal(details[0]["thr"], details[4]["thr"])
+    got = sorted(open(work / "occurrences.txt").read().splitlines(True))
+    assert got == sorted(want)
+
+
 @pytest.mark.parametrize("lower", [capi.LOWER_ZERO, capi.LOWER_FOLD])
 def test_empirical_histogram_matches_oracle(scanner, lower):
     """b200scan_hist_* (the `blamm hist -e` epilogue on the GPU) against the oracle: every bin identical, including
