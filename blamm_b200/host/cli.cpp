@@ -14,10 +14,12 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <mutex>
 #include <sstream>
 #include <thread>
+#include <unordered_map>
 
 using namespace std;
 
@@ -345,8 +347,9 @@ void writerThread(ScanShared& sh)
 }
 
 // `ctxSlot` persists across the species groups of a run: the context (CUDA initialisation, pinned and device buffers,
-// ~0.7 s) is created by the first group that uses the device and only re-loaded with motifs afterwards.
-void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, int engine, bool foldLower, b200scan_ctx** ctxSlot)
+// ~0.7 s) is created once, on its own thread, while the host still loads histograms and parses the first chunk (`ready`
+// carries the error text of a failed creation); every group only re-loads it with its motifs.
+void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctxSlot, shared_future<string> ready)
 {
     b200scan_ctx*& ctx = *ctxSlot;
     auto die = [&](const string& what) {
@@ -354,10 +357,11 @@ void deviceWorker(ScanShared& sh, int dev, uint64_t maxBlock, uint64_t maxHits, 
         if (!sh.failed.exchange(true)) sh.error = what;
         sh.qCv.notify_all();
     };
-    double t0 = now();
-    if (!ctx) {
-        if (b200scan_create(&ctx, dev, maxBlock, maxHits) != B200SCAN_OK) { ctx = nullptr; die(string("CUDA error: ") + b200scan_last_error(nullptr)); return; }
-        gTimer.add("b200scan_create (per GPU)", now() - t0);
+    {   // the context is being created since the start of the run (runScan: CtxPool), normally it is ready by now
+        const double t0 = now();
+        const string err = ready.get();
+        gTimer.add("wait for b200scan_create", now() - t0);
+        if (!err.empty() || !ctx) { die(err.empty() ? "CUDA error: no context" : err); return; }
     }
     const auto len = sh.motifs->colLen();
     const auto thr = sh.motifs->colThr();
@@ -443,6 +447,8 @@ int runScan(int argc, char** argv)
 
     cout << "Welcome to blamm -- PWM scan module" << endl;
     const double tStart = now();
+    // CUDA start-up (driver initialisation grows with the number of GPUs in the box) overlaps the loading of the inputs
+    future<int> devCount = async(launch::async, [] { return b200scan_device_count(); });
     Settings settings;
     settings.print();
 
@@ -462,7 +468,7 @@ int runScan(int argc, char** argv)
     else if (relSpec) cout << "Relative motif score threshold set to: " << relThr << endl;
     else cout << "P-value motif score threshold set to: " << pvalue << endl;
 
-    int nDev = b200scan_device_count();
+    int nDev = devCount.get();
     if (nDev == 0) throw runtime_error("CUDA error: no sm_100 devices found. Aborting...");
     if (gpusWanted > 0) nDev = min(nDev, gpusWanted);
     cout << "Using " << nDev << " GPU devices" << endl;
@@ -479,21 +485,59 @@ int runScan(int argc, char** argv)
     uint64_t maxTot = 1024;
     for (const auto& sp : sc.species) maxTot = max<uint64_t>(maxTot, sp.totSeqLen);
     const uint64_t maxBlock = min<uint64_t>(chunk, maxTot) + halo + 64;
+    // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block)
+    const double rate = pSpec ? std::min(1.0, 3.0 * pvalue) : 2e-4;
+    const uint64_t maxHits = std::max<uint64_t>(1 << 20, (uint64_t)(rate * (double)maxBlock * (double)mc.motifs.size()));
     struct CtxPool {
         vector<b200scan_ctx*> ctx;
-        ~CtxPool() { const double t0 = now(); for (auto c : ctx) if (c) b200scan_destroy(c); gTimer.add("b200scan_destroy (all GPUs)", now() - t0); }
+        vector<shared_future<string>> ready;
+        ~CtxPool()
+        {
+            for (auto& r : ready) if (r.valid()) r.wait();
+            const double t0 = now();
+            for (auto c : ctx) if (c) b200scan_destroy(c);
+            gTimer.add("b200scan_destroy (all GPUs)", now() - t0);
+        }
     } pool;
     pool.ctx.assign((size_t)nDev, nullptr);
+    for (int d = 0; d < nDev; d++)
+        pool.ready.push_back(async(launch::async, [&pool, d, maxBlock, maxHits]() -> string {
+            const double t0 = now();
+            if (b200scan_create(&pool.ctx[(size_t)d], d, maxBlock, maxHits) != B200SCAN_OK) {
+                pool.ctx[(size_t)d] = nullptr;
+                return string("CUDA error: ") + b200scan_last_error(nullptr);
+            }
+            gTimer.add("b200scan_create (per GPU)", now() - t0);
+            return string();
+        }).share());
 
     double tSetup = tStart;
     for (const auto& sp : sc.species) {
         cout << "Scanning species: " << sp.name;
         sp.printNuclProb(settings.pseudocount);
         mc.generateMatrix(sp.nuclCounts, settings.pseudocount);
-        for (auto& m : mc.motifs) {
+        if (pSpec) {
+            // a reverse complement and the permutations of a motif read the histogram of their base name (motif.h:256-267,
+            // pwmscan.cpp:607-611): every file is parsed once, on -t threads; the first missing file is reported as before
+            vector<string> base; unordered_map<string, size_t> slotOf;
+            for (const auto& m : mc.motifs) if (slotOf.emplace(m.baseName(), base.size()).second) base.push_back(m.baseName());
+            vector<float> cutoff(base.size()); vector<string> err(base.size());
+            atomic<size_t> nextBase(0);
+            auto load = [&] {
+                for (size_t i; (i = nextBase.fetch_add(1)) < base.size();) {
+                    try { ScoreHistogram h; h.load(histdir, "hist_" + sp.name + "_" + base[i]); cutoff[i] = h.scoreCutoff(pvalue); }
+                    catch (const exception& e) { err[i] = e.what(); }
+                }
+            };
+            vector<thread> loaders;
+            for (size_t t = 1; t < min<size_t>(numThreads, 16); t++) loaders.emplace_back(load);
+            load();
+            for (auto& t : loaders) t.join();
+            for (const auto& e : err) if (!e.empty()) throw runtime_error(e);
+            for (auto& m : mc.motifs) m.threshold = cutoff[slotOf[m.baseName()]];
+        } else for (auto& m : mc.motifs) {
             if (absSpec) m.threshold = absThr;
-            else if (relSpec) { const float mx = m.maxScore(), mn = m.minScore(); m.threshold = relThr * (mx - mn) + mn; }
-            else { ScoreHistogram h; h.load(histdir, "hist_" + sp.name + "_" + m.baseName()); m.threshold = h.scoreCutoff(pvalue); }
+            else { const float mx = m.maxScore(), mn = m.minScore(); m.threshold = relThr * (mx - mn) + mn; }
         }
         for (const auto& m : mc.motifs) {
             if (m.size() > 15) continue;                 // the reference lists only short motifs (pwmscan.cpp:620)
@@ -511,10 +555,7 @@ int runScan(int argc, char** argv)
         thread writer(writerThread, ref(sh));
         auto stopWriter = [&] { { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; } sh.oCv.notify_all(); writer.join(); };
         vector<thread> workers;
-        // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block)
-        const double rate = pSpec ? std::min(1.0, 3.0 * pvalue) : 2e-4;
-        const uint64_t maxHits = std::max<uint64_t>(1 << 20, (uint64_t)(rate * (double)maxBlock * (double)mc.motifs.size()));
-        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), d, maxBlock, maxHits, engine, foldLower, &pool.ctx[(size_t)d]);
+        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), engine, foldLower, &pool.ctx[(size_t)d], pool.ready[(size_t)d]);
         try {
             FastaStream fs(sp.files, sp.totSeqLen);
             fs.setParallel(ingestThreads(numThreads));
