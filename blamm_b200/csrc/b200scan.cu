@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -24,6 +25,7 @@ namespace {
 
 thread_local std::string g_create_error;
 double g_margin16_scale = 1.0;        // debug knob (env B200SCAN_MARGIN16_SCALE): scales the FP16-accumulation error bound
+double g_i8_max_overshoot = 16.0;     // INT8 operands for a tile iff every column's WORST-CASE overshoot (L / scale, score units) stays below (env B200SCAN_I8_MAX_OVERSHOOT; 0 = never).  Measured on the bench set the mean overshoot is far below the bound: 1.20 candidates per hit with every tile on INT8, against 1.44 for FP16 accumulators
 
 constexpr uint32_t kPadBytes = 16384;             // slack behind every device sequence buffer (window / span over-reads)
 constexpr size_t   kGatherSmemW = 64 * 1024;      // FP32 weights per gather column tile
@@ -72,12 +74,13 @@ struct b200scan_ctx {
     float4* d_w = nullptr;  uint32_t *d_woff = nullptr, *d_len = nullptr, *d_orig = nullptr;  float* d_thr = nullptr;
     GatherTile* d_gtiles = nullptr;  std::vector<GatherTile> gtiles;  size_t gather_smem = 0;
     TcTile* d_ttiles = nullptr;  std::vector<TcTile> ttiles;  uint8_t* d_bimg = nullptr;
-    uint32_t n_tiles16 = 0;       // ttiles[0 .. n_tiles16) use FP16 accumulators, the rest FP32
-    TcTile* d_ttiles_z = nullptr;  uint8_t* d_bimg_z = nullptr;  uint32_t n_tiles16_z = 0;     // the same for blocks with zero-contribution characters
+    uint32_t n_tiles8 = 0;        // ttiles[0 .. n_tiles8) use INT8 operands,
+    uint32_t n_tiles16 = 0;       // the next n_tiles16 FP16 operands with FP16 accumulators, the rest FP32 accumulators
+    TcTile* d_ttiles_z = nullptr;  uint8_t* d_bimg_z = nullptr;  uint32_t n_tiles16_z = 0, n_tiles8_z = 0;     // the same for blocks with zero-contribution characters
     bool tc_usable = false;
     int  tc_acc_bits = 32;        // accumulators of the tensor tiles: 16, 32, or 0 when tiles differ
     bool pair_mode = false;       // filter launched as CTA pairs (cta_group::2 MMAs)
-    int  acc_pref = 0;            // 0 auto, 16, 32 (b200scan_set_tensor_accumulator)
+    int  acc_pref = 0;            // 0 auto, 8 (INT8 operands), 16, 32 (b200scan_set_tensor_accumulator)
     double cand_inflation = 0;    // mean margin over columns (diagnostic)
     uint8_t* d_flush = nullptr;
     unsigned long long* d_trace = nullptr;   // B200_TRACE builds only
@@ -126,7 +129,7 @@ uint16_t half_round_up(double x)
 // greedy zero-area tiling of P (MotifContainer::generateMatrixTiles, motif.cpp:482-540) -- like there, the
 // split is a pure performance device and cannot change results.
 // ---------------------------------------------------------------------------------------------------------
-void plan_tc_tiles(const std::vector<uint32_t>& len_sorted, bool acc16, std::vector<std::pair<uint32_t, uint32_t>>& out)
+void plan_tc_tiles(const std::vector<uint32_t>& len_sorted, bool acc16, uint32_t pos_per_mma, std::vector<std::pair<uint32_t, uint32_t>>& out)
 {
     const uint32_t n = (uint32_t)len_sorted.size();
     // epilogue cycles per column per 128-window tile (ALU-pipe bound, from ncu: profiles/), MMA = n_k * N / 2
@@ -135,7 +138,7 @@ void plan_tc_tiles(const std::vector<uint32_t>& len_sorted, bool acc16, std::vec
     std::vector<uint32_t> from(n + 1, 0);
     best[0] = 0;
     for (uint32_t j = 1; j <= n; j++) {
-        const uint32_t nk = (len_sorted[j - 1] + 3) / 4;
+        const uint32_t nk = (len_sorted[j - 1] + pos_per_mma - 1) / pos_per_mma;
         for (uint32_t i = (j > kTcMaxN ? j - kTcMaxN : 0); i < j; i++) {
             const uint32_t npad = ((j - i) + 63) / 64 * 64;
             const double c = best[i] + std::max(nk * npad * 0.5, kEpiPerCol * npad) + kFixed;
@@ -193,7 +196,8 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     //     M_k = largest possible prefix), so |D_k| <= B_k = max(M_k, R_k, 0).  Allowing a rounding of one FP16 ulp
     //     (2^-10 relative: covers round-to-nearest and truncation) on EVERY internal add of the 4 products and the
     //     old accumulator:  |e2| <= 2^-10 * 4 * sum_k (B_{k-1} + A_k),  A_k = sum of max|y_j| over the step.
-    struct Folded { std::vector<uint16_t> y; double margin; bool always; uint16_t bias = 0; };
+    struct Folded { std::vector<uint16_t> y; double margin; bool always; uint16_t bias = 0;
+                    std::vector<int8_t> q; int32_t qbias = 0; bool never = false; };      // INT8 operands (fold_i8)
     auto fold = [&](uint32_t sc, bool acc16) {
         const uint32_t L = len[sc];
         Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false;
@@ -309,19 +313,88 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
         return f;
     };
 
+    // INT8 operands (filter_tc_kernel<.., I8 = true>: eight positions per MMA, exact S32 accumulation).  With x_j the FP32
+    // weights a window picks, S their real sum and s the reference's in-order FP32 sum (|s - S| <= e1), a hit s >= thr has
+    // S >= thr' = thr - e1 - 1e-3.  The integer weights are  q_j[b] = max(-127, ceil(scale * (x_j[b] - share_j)))  with
+    // sum_j share_j = thr':  acc = sum q_j >= scale * (S - thr') >= 0 -- rounding up and clamping up can only ADD candidates,
+    // so no accumulation margin is needed at all; what it costs is an overshoot of < 1 / scale per position.
+    //   share_j = best_j - c, c = slack / L, slack = sum_j best_j - thr'  (every position's best letter gets the same value c),
+    //   scale = 127 / max(c, slack - c + 1/8):  a letter that loses more than the whole slack kills a window on its own; it may
+    //   clamp at -127, everything milder is represented to 1 / scale.  |acc| <= 127 L < 2^15.
+    // zmode (blocks with zero-contribution characters): unshifted weights q = ceil(scale * x), the bias step adds
+    //   B = max(-4064, ceil(-scale * thr')) spread over the 32 K rows of one MMA; a masked position contributes exactly 0;
+    //   slack is taken over max(best_j, 0).  Returns the worst-case overshoot L / scale (score units) as `margin`.
+    auto fold_i8 = [&](uint32_t sc, int zmode) {
+        const uint32_t L = len[sc];
+        Folded f; f.q.assign(4 * L, 0); f.margin = 0; f.always = false;
+        double A = 0, smax = 0, pmax = 0;
+        bool finite = std::isfinite(thr_s[sc]);
+        std::vector<double> best(L);
+        for (uint32_t j = 0; j < L; j++) {
+            const float4 v = w[woff[sc] + j];
+            const float a4[4] = {v.x, v.y, v.z, v.w};
+            double m = 0, b = -1e300;
+            for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); b = std::max(b, (double)a); }
+            A += m; best[j] = zmode ? std::max(b, 0.0) : b; smax += best[j]; pmax = std::max(pmax, b);
+        }
+        if (!finite || A > 1e6 || std::fabs((double)thr_s[sc]) > 1e6) { f.always = true; return f; }
+        const double thrp = (double)thr_s[sc] - (L - 1) * std::ldexp(A, -24) - 1e-3;
+        const double slack = smax - thrp;
+        if (slack < 0) { f.never = true; return f; }                   // no window can reach the threshold
+        const double c = slack / L;
+        const double scale = zmode ? 127.0 / std::max(std::max(pmax, 0.0) + 1e-9, slack + 0.125)
+                                   : 127.0 / std::max(c + 1e-9, slack - c + 0.125);
+        if (!(scale > 1e-3) || L / scale > 64.0) { f.always = true; f.margin = 1e9; return f; }      // threshold far below the best score: INT8 cannot resolve it (auto mode then keeps FP16 operands)
+        for (uint32_t j = 0; j < L; j++) {
+            const float4 v = w[woff[sc] + j];
+            const float a4[4] = {v.x, v.y, v.z, v.w};
+            const double share = zmode ? 0.0 : best[j] - c;
+            for (uint32_t o = 0; o < 4; o++) {
+                const double q = std::ceil(scale * ((double)a4[o] - share));
+                f.q[4 * j + o] = (int8_t)std::min(127.0, std::max(-127.0, q));      // q <= 127 by the choice of scale (min: guards the last ulp)
+                if (q > 127.0) { f.always = true; f.margin = 1e9; return f; }
+            }
+        }
+        if (zmode) {
+            const double b = std::ceil(-scale * thrp);
+            if (b > 4064.0) { f.always = true; f.margin = 1e9; return f; }
+            f.qbias = (int32_t)std::max(-4064.0, b);
+        }
+        f.margin = L / scale;
+        return f;
+    };
+
     // Accumulator type PER TILE: FP16 accumulators (half the epilogue work) where every column of the tile keeps its margin
     // <= 2 score units, FP32 otherwise -- a few long or extreme motifs then cost their own tile, not the whole set.
+    // Operand type PER TILE as well: INT8 operands (half the MMAs) where the worst-case overshoot of every column of the tile
+    // stays <= g_i8_max_overshoot score units (the bound is pessimistic, see its definition; it guards the exact rescorer
+    // against columns whose threshold lies far below their best score); the FP16-operand kinds otherwise.  acc_pref 8 forces
+    // INT8 everywhere, 16 / 32 exclude it.
     const bool try16 = ctx->acc_pref != 32 && max_len <= (uint32_t)kMaxLen;
+    const bool try8 = (ctx->acc_pref == 0 || ctx->acc_pref == 8) && max_len <= (uint32_t)kMaxLen && g_i8_max_overshoot > 0;
     std::vector<std::pair<uint32_t, uint32_t>> cuts;
-    plan_tc_tiles(len, try16, cuts);
+    plan_tc_tiles(len, try16, try8 ? 8u : 4u, cuts);
     bool tc_ok = true;
     double margin_sum = 0;
     // zmode 0: blocks without zero-contribution characters; zmode 1: with (bias step first, see fold_z)
-    auto build_image = [&](int zmode, std::vector<TcTile>& tt, std::vector<uint8_t>& bimg, uint32_t& n16) {
+    auto build_image = [&](int zmode, std::vector<TcTile>& tt, std::vector<uint8_t>& bimg, uint32_t& n16, uint32_t& n8) {
         std::vector<Folded> folded(n_cols);
         for (int32_t sc = 0; sc < n_cols; sc++) folded[sc] = zmode ? fold_z((uint32_t)sc, try16) : fold((uint32_t)sc, try16);
-        std::vector<uint32_t> tile_acc16(cuts.size(), 0);
+        std::vector<uint32_t> tile_acc16(cuts.size(), 0);      // 1 FP16 accumulators, 0 FP32, 2 INT8 operands
         for (size_t ti = 0; ti < cuts.size(); ti++) {
+            if (try8) {
+                std::vector<Folded> f8;
+                bool ok8 = true;
+                for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second && ok8; sc++) {
+                    f8.push_back(fold_i8(sc, zmode));
+                    if (ctx->acc_pref != 8 && !f8.back().never && f8.back().margin > g_i8_max_overshoot) ok8 = false;     // (a non-finite column has margin 0: 'always' under every kind)
+                }
+                if (ok8) {
+                    for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++) folded[sc] = std::move(f8[sc - cuts[ti].first]);
+                    tile_acc16[ti] = 2u;
+                    continue;
+                }
+            }
             bool ok = try16;
             if (ok && ctx->acc_pref != 16)
                 for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++)
@@ -333,9 +406,9 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                 if (ok && !folded[sc].always && folded[sc].margin > 1e8) folded[sc].always = true;
             }
         }
-        if (!zmode) for (const auto& f : folded) if (!f.always) margin_sum += f.margin;
-        n16 = 0;
-        for (uint32_t a : tile_acc16) n16 += a;
+        if (!zmode) for (const auto& f : folded) if (!f.always && !f.never && f.margin < 1e8) margin_sum += f.margin;
+        n16 = 0; n8 = 0;
+        for (uint32_t a : tile_acc16) { n16 += (a == 1u); n8 += (a == 2u); }
         tt.clear(); bimg.clear();
         for (size_t ti = 0; ti < cuts.size(); ti++) {
             const auto& cut = cuts[ti];
@@ -343,11 +416,34 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
             t.acc16 = tile_acc16[ti];
             t.col0 = cut.first; t.n_cols = cut.second - cut.first;
             t.n_pad = (t.n_cols + 63) / 64 * 64;
-            t.n_k = (len[cut.second - 1] + 3) / 4 + (zmode ? 1u : 0u);      // MMA steps per window tile (zmode: + the bias step)
+            const uint32_t ppm = t.acc16 == 2u ? 8u : 4u;                    // positions per MMA
+            t.n_k = (len[cut.second - 1] + ppm - 1) / ppm + (zmode ? 1u : 0u);      // MMA steps per window tile (zmode: + the bias step)
             const uint32_t nChunks = 2 * t.n_k;
             t.b_off = (uint32_t)bimg.size();
             t.b_bytes = t.n_pad * nChunks * 16;
             bimg.resize(bimg.size() + t.b_bytes, 0);
+            if (t.acc16 == 2u) {
+                // INT8 image: [8-column group][chunk][8 columns][16 bytes = 4 positions x ACGT]; zmode: chunks 0-1 = the bias step
+                int8_t* img8 = reinterpret_cast<int8_t*>(bimg.data() + t.b_off);
+                auto at8 = [&](uint32_t n, uint32_t kk, uint32_t byte) -> int8_t& { return img8[(((n >> 3) * nChunks + kk) * 8 + (n & 7)) * 16 + byte]; };
+                for (uint32_t n = 0; n < t.n_pad; n++) {
+                    const Folded* f = n < t.n_cols ? &folded[t.col0 + n] : nullptr;
+                    if (!f || f->never || f->always) {                   // padding / unreachable column: acc < 0 for every window; degenerate column: acc > 0
+                        const int8_t v = (f && f->always) ? 1 : -127;
+                        if (zmode) at8(n, 0, 0) = v; else for (uint32_t o = 0; o < 4; o++) at8(n, 0, o) = v;
+                        continue;
+                    }
+                    if (zmode) {                                         // bias spread over the 32 K rows of the bias step
+                        const int32_t b = f->qbias, each = b / 32, rem = b - 32 * each;       // |each| <= 127; rem has the sign of b
+                        for (uint32_t r = 0; r < 32; r++)
+                            at8(n, r >> 4, r & 15) = (int8_t)(each + ((int32_t)r < std::abs(rem) ? (rem > 0 ? 1 : -1) : 0));
+                    }
+                    for (uint32_t j = 0; j < len[t.col0 + n]; j++)
+                        for (uint32_t o = 0; o < 4; o++) at8(n, (j >> 2) + (zmode ? 2u : 0u), (j & 3) * 4 + o) = f->q[4 * j + o];
+                }
+                tt.push_back(t);
+                continue;
+            }
             uint16_t* img = reinterpret_cast<uint16_t*>(bimg.data() + t.b_off);
             auto at = [&](uint32_t n, uint32_t j, uint32_t o) -> uint16_t& {        // column n (tile-local), position j, letter o
                 const uint32_t kk = (j >> 1) + (zmode ? 2u : 0u);
@@ -370,16 +466,19 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
             }
             tt.push_back(t);
         }
-        std::stable_partition(tt.begin(), tt.end(), [](const TcTile& t) { return t.acc16 != 0; });
+        // launch order: INT8 tiles, FP16-accumulator tiles, FP32-accumulator tiles
+        std::stable_sort(tt.begin(), tt.end(), [](const TcTile& a, const TcTile& b) {
+            auto rank = [](uint32_t k) { return k == 2u ? 0 : (k == 1u ? 1 : 2); };
+            return rank(a.acc16) < rank(b.acc16); });
     };
     std::vector<TcTile> tt, tt_z;
     std::vector<uint8_t> bimg, bimg_z;
-    uint32_t n16 = 0, n16_z = 0;
-    build_image(0, tt, bimg, n16);
-    build_image(1, tt_z, bimg_z, n16_z);
-    ctx->n_tiles16 = n16; ctx->n_tiles16_z = n16_z;
+    uint32_t n16 = 0, n16_z = 0, n8 = 0, n8_z = 0;
+    build_image(0, tt, bimg, n16, n8);
+    build_image(1, tt_z, bimg_z, n16_z, n8_z);
+    ctx->n_tiles16 = n16; ctx->n_tiles16_z = n16_z; ctx->n_tiles8 = n8; ctx->n_tiles8_z = n8_z;
     if (max_len > (uint32_t)kMaxLen) tc_ok = false;
-    ctx->tc_acc_bits = (n16 == cuts.size()) ? 16 : (n16 == 0 ? 32 : 0);
+    ctx->tc_acc_bits = (n8 == cuts.size()) ? 8 : (n16 == cuts.size()) ? 16 : (n16 == 0 && n8 == 0 ? 32 : 0);
     ctx->cand_inflation = n_cols ? margin_sum / n_cols : 0;
 
     // ---- upload ----
@@ -458,6 +557,8 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
             {{filter_tc_kernel<true, false, false>, filter_tc_kernel<true, false, true>}, {filter_tc_kernel<true, true, false>, filter_tc_kernel<true, true, true>}}};
         const int pair = ctx->pair_mode ? 1 : 0;
         tp.n_spans = (uint32_t)((s.n_payload + (pair ? 2 : 1) * (uint64_t)kTcSpan - 1) / ((pair ? 2 : 1) * (uint64_t)kTcSpan));
+        static const FilterFn kFilter8[2] = {filter_tc_kernel<true, false, false, true>, filter_tc_kernel<true, true, false, true>};     // INT8 operands [masked block]
+        unsigned int* work3 = work2 + 1;                                               // work counter of the INT8 instance
         auto launch = [&](int acc16, int z) -> cudaError_t {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(pair ? 2u * (unsigned)(ctx->sm_count / 2) : (unsigned)(ctx->sm_count * kTcCtasPerSm));
@@ -465,19 +566,32 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = pair ? 1 : 0;
+            if (acc16 == 2) {                                  // INT8 instances are single-CTA
+                cfg.gridDim = dim3((unsigned)(ctx->sm_count * kTcCtasPerSm)); cfg.numAttrs = 0;
+                return cudaLaunchKernelEx(&cfg, kFilter8[z], tp, blk);
+            }
             return cudaLaunchKernelEx(&cfg, kFilter[acc16][z][pair], tp, blk);
         };
         for (int z = 0; z < 2; z++) {
             const TcTile* tiles = z ? ctx->d_ttiles_z : ctx->d_ttiles;
-            const uint32_t n16 = z ? ctx->n_tiles16_z : ctx->n_tiles16;
+            const uint32_t n8 = z ? ctx->n_tiles8_z : ctx->n_tiles8, n16 = z ? ctx->n_tiles16_z : ctx->n_tiles16;
             tp.bimg = z ? ctx->d_bimg_z : ctx->d_bimg;
+            if (n8) {
+                // (a pair launch counts spans of 2 * kTcSpan windows; the INT8 instance is single-CTA)
+                const uint32_t spans = tp.n_spans;
+                tp.n_spans = (uint32_t)((s.n_payload + (uint64_t)kTcSpan - 1) / (uint64_t)kTcSpan);
+                tp.tiles = tiles; tp.n_tiles = n8; tp.work_counter = work3;
+                CU(launch(2, z));
+                tp.n_spans = spans;
+                n++;
+            }
             if (n16) {
-                tp.tiles = tiles; tp.n_tiles = n16; tp.work_counter = work;
+                tp.tiles = tiles + n8; tp.n_tiles = n16; tp.work_counter = work;
                 CU(launch(1, z));
                 n++;
             }
-            if (n16 < n_tiles) {
-                tp.tiles = tiles + n16; tp.n_tiles = n_tiles - n16; tp.work_counter = work2;
+            if (n8 + n16 < n_tiles) {
+                tp.tiles = tiles + n8 + n16; tp.n_tiles = n_tiles - n8 - n16; tp.work_counter = work2;
                 CU(launch(0, z));
                 n++;
             }
@@ -592,13 +706,25 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     if (!out) return B200SCAN_EINVAL;
     *out = nullptr;
     if (max_block_nt == 0 || max_block_nt > 0xF0000000ull) return fail(nullptr, B200SCAN_EINVAL, "max_block_nt must be in (0, 2^32)");
+    // B200SCAN_TIMING=1: wall-clock phases of the creation on stderr (CUDA start-up dominates short runs)
+    const bool timing = getenv("B200SCAN_TIMING") != nullptr;
+    auto tPrev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200scan_create] %-34s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tPrev).count());
+        tPrev = t;
+    };
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, B200SCAN_ENODEVICE, "no CUDA device (this library has no CPU path)");
+    lap("cudaGetDeviceCount");
     if (device < 0 || device >= ndev) return fail(nullptr, B200SCAN_ENODEVICE, "device %d out of range (%d devices)", device, ndev);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(nullptr, B200SCAN_ENODEVICE, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
     CU(cudaSetDevice(device));
+    CU(cudaFree(nullptr));
+    lap("device properties + primary context");
 
     b200scan_ctx* c = new b200scan_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->max_block = max_block_nt;
@@ -619,14 +745,19 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     CUB(cudaFuncSetAttribute(filter_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     if (const char* e = getenv("B200SCAN_PAIR")) c->pair_mode = atoi(e) != 0;
     if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) g_margin16_scale = atof(e);
+    if (const char* e = getenv("B200SCAN_I8_MAX_OVERSHOOT")) g_i8_max_overshoot = atof(e);
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
+    lap("streams + kernel attributes");
     if (max_hits == 0) max_hits = 1 << 20;
     const size_t nb = (size_t)max_block_nt;
     for (auto& s : c->slot) {
         CUB(cudaMallocHost(&s.h_ascii, nb + 64));
         CUB(cudaMallocHost(&s.h_hits, sizeof(b200scan_hit) * max_hits));
         CUB(cudaMallocHost(&s.h_counters, 32));
+        lap("pinned buffers of a slot");
         CUB(cudaMalloc(&s.d_ascii, nb + kPadBytes));
         CUB(cudaMalloc(&s.d_codes, nb / 4 + kPadBytes));
         CUB(cudaMalloc(&s.d_zmask, nb / 8 + kPadBytes));
@@ -637,6 +768,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
         CUB(cudaMalloc(&s.d_counters, 64));
         CUB(cudaMemset(s.d_counters, 0, 32));
         for (auto& e : s.ev) CUB(cudaEventCreate(&e));
+        lap("device buffers of a slot");
     }
 #if defined(B200_TRACE) || defined(B200_PHASE)
     CUB(cudaMalloc(&c->d_trace, 4 * kTraceTiles * 4 * 8));
@@ -647,6 +779,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     c->blk_cap = (uint32_t)std::max<unsigned long long>(c->cand_cap / kRawBlock + 4096, 8192);
     CUB(cudaMalloc(&c->d_raw, ((size_t)c->blk_cap + 1) * kRawBlock * kRawWords * 4));     // + the sacrificial overflow block
     CUB(cudaMalloc(&c->d_blk_count, (size_t)c->blk_cap * 4));
+    lap("candidate / raw buffers");
 #undef CUB
     *out = c;
     return B200SCAN_OK;
@@ -683,7 +816,7 @@ int b200scan_set_engine(b200scan_ctx* ctx, int engine)
 int b200scan_set_tensor_accumulator(b200scan_ctx* ctx, int bits)
 {
     if (!ctx) return B200SCAN_EINVAL;
-    if (bits != 0 && bits != 16 && bits != 32) return fail(ctx, B200SCAN_EINVAL, "accumulator must be 0 (auto), 16 or 32");
+    if (bits != 0 && bits != 8 && bits != 16 && bits != 32) return fail(ctx, B200SCAN_EINVAL, "accumulator must be 0 (auto), 8 (INT8 operands), 16 or 32");
     ctx->acc_pref = bits;
     return B200SCAN_OK;
 }

@@ -288,8 +288,16 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {          // arrives
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-template <bool PAIR> __device__ __forceinline__ void umma_x(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
-    if (PAIR) umma2_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc); else umma_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc);
+// kind::i8 (UTCIMMA): signed 8-bit operands, K = 32 per instruction, S32 accumulators
+__device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n}"
+                 ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <bool PAIR, bool I8> __device__ __forceinline__ void umma_x(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
+    if (I8) umma_i8_lohi(d, alo, ahi, blo, bhi, idesc, acc);
+    else if (PAIR) umma2_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc); else umma_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc);
 }
 template <bool PAIR> __device__ __forceinline__ void commit_x(uint32_t bar) { if (PAIR) umma2_commit(bar); else umma_commit(bar); }
 
@@ -378,10 +386,16 @@ __device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, unsig
 // (b200scan.cu: fold_z).  Each instance returns at once when the block is not of its kind.
 // PAIR = true: launched as clusters of two CTAs (same TPC).  The pair takes an item of 2 * kTcSpan windows together -- rank 0 the
 // first half of its window tiles, rank 1 the second -- and rank 0's issuer lane drives both tensor cores with cta_group::2 MMAs.
-template <bool ACC16, bool ZMASK, bool PAIR>
+// I8 = true: INT8 operands (tcgen05.mma.kind::i8, K = 32: EIGHT motif positions per instruction instead of four).  An E entry
+// then holds the one-hot bytes of four consecutive positions, E8[p] = [oh(p) oh(p+1) oh(p+2) oh(p+3)] with oh(c) = 1 << 8c, and
+// "window r, K-chunk kk" is E8[g0 + r + 4 kk] (LBO = 64 B); the weights are integers  ceil(scale * (w - share))  clamped to
+// [-127, 127] (b200scan.cu: fold_i8), the S32 accumulators are exact and stay inside +-2^15, so tcgen05.ld.pack::16b delivers
+// their low halves as S16 and the FP16-accumulator epilogue (sign bits only) is reused unchanged (ACC16 = true).
+template <bool ACC16, bool ZMASK, bool PAIR, bool I8 = false>
 __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm)
 filter_tc_kernel(TcParams P, BlockDev blk)
 {
+    static_assert(!I8 || (ACC16 && !PAIR && TC_MMA_WARPS == 1), "INT8 operands: packed epilogue, single CTA, one issuer");
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     constexpr uint32_t kBufs    = TC_BUFS;              // TMEM accumulator buffers
     constexpr uint32_t kBufCols = kTcMaxN;              // TMEM columns per buffer: one accumulator per column, FP32 or FP16
@@ -423,7 +437,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         const uint32_t v0 = 0x3C00u << (16 * (c0 & 1)), v1 = 0x3C00u << (16 * (c1 & 1));
         sLut[threadIdx.x] = make_uint4((c0 & 2) ? 0u : v0, (c0 & 2) ? v0 : 0u, (c1 & 2) ? 0u : v1, (c1 & 2) ? v1 : 0u);
     }
-    if (ZMASK && threadIdx.x < kSmOnes / 16) sOnes[threadIdx.x] = make_uint4(0x00003C00u, 0u, 0u, 0u);      // [1.0, 0, ..., 0] in every row
+    if (ZMASK && threadIdx.x < kSmOnes / 16)                                                                // FP16: [1.0, 0, ..., 0] in every row; INT8: all ones
+        sOnes[threadIdx.x] = I8 ? make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u) : make_uint4(0x00003C00u, 0u, 0u, 0u);
     if (ZMASK) fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -508,11 +523,22 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         if (g < nEnt) {
                             const uint32_t byte = g >> 2;
                             const uint32_t two = (uint32_t)sCodes[byte] | ((uint32_t)sCodes[byte + 1] << 8);
-                            uint4 val = sLut[(two >> (2 * (g & 3))) & 15u];            // [onehot(code g) | onehot(code g+1)]
+                            uint4 val;
+                            if (I8) {                                                  // one-hot bytes of codes g .. g+3
+                                const uint32_t c4 = two >> (2 * (g & 3));
+                                val = make_uint4(1u << (8 * (c4 & 3u)), 1u << (8 * ((c4 >> 2) & 3u)), 1u << (8 * ((c4 >> 4) & 3u)), 1u << (8 * ((c4 >> 6) & 3u)));
+                            } else val = sLut[(two >> (2 * (g & 3))) & 15u];           // [onehot(code g) | onehot(code g+1)]
                             if (ZMASK) {                                               // a masked character contributes an all-zero row
                                 const uint32_t zz = ((uint32_t)sZ[g >> 3] | ((uint32_t)sZ[(g >> 3) + 1] << 8)) >> (g & 7);
-                                if (zz & 1u) { val.x = 0u; val.y = 0u; }
-                                if (zz & 2u) { val.z = 0u; val.w = 0u; }
+                                if (I8) {
+                                    if (zz & 1u) val.x = 0u;
+                                    if (zz & 2u) val.y = 0u;
+                                    if (zz & 4u) val.z = 0u;
+                                    if (zz & 8u) val.w = 0u;
+                                } else {
+                                    if (zz & 1u) { val.x = 0u; val.y = 0u; }
+                                    if (zz & 2u) { val.z = 0u; val.w = 0u; }
+                                }
                             }
                             *reinterpret_cast<uint4*>(sE + (slot * kTcStageEnt + e) * 16) = val;
                             if (slot == 0 && e < kTcMirror)
@@ -538,11 +564,14 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             if (!PAIR && newTile) mbar_wait(bBar, nBload & 1, P.error_flag);
             const uint32_t n_k = __shfl_sync(0xffffffffu, tile.n_k, 0);
             // instruction descriptor: F16 x F16, D = F32 (c_format 1) or F16 (c_format 0), K-major A and B, M = 128 (256 for a CTA pair), N = n_pad
-            const uint32_t idesc = (ACC16 ? 0u : (1u << 4)) | ((tile.n_pad >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
+            // (INT8: signed 8-bit A and B -- a_format = b_format = 1 -- and D = S32, c_format 2)
+            const uint32_t idesc = (I8 ? ((2u << 4) | (1u << 7) | (1u << 10)) : (ACC16 ? 0u : (1u << 4))) | ((tile.n_pad >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
             const uint32_t nChunks = 2 * n_k;
-            const uint64_t ad0 = umma_desc(smem_u32(sE), 32, 128), bd0 = umma_desc(smem_u32(sB), 128, nChunks * 128);
+            // the two 16-byte K-chunks of one MMA are 2 entries apart for FP16 (2 positions per entry), 4 for INT8 (4 positions per entry)
+            constexpr uint32_t kChunkEnt = I8 ? 4u : 2u, kStepEnt = 2 * kChunkEnt;
+            const uint64_t ad0 = umma_desc(smem_u32(sE), 16 * kChunkEnt, 128), bd0 = umma_desc(smem_u32(sB), 128, nChunks * 128);
             const uint32_t aLo0 = (uint32_t)ad0, aHi = (uint32_t)(ad0 >> 32), bLo0 = (uint32_t)bd0, bHi = (uint32_t)(bd0 >> 32);
-            const uint32_t aLoOnes = (uint32_t)umma_desc(smem_u32(sOnes), 32, 128);      // ZMASK: rows of [1, 0, ..., 0]
+            const uint32_t aLoOnes = (uint32_t)umma_desc(smem_u32(sOnes), 16 * kChunkEnt, 128);      // ZMASK: constant rows (the bias step)
             const uint32_t n_pos = ZMASK ? n_k - 1 : n_k;                                  // position steps (ZMASK: n_k counts the bias step too)
             (void)aLoOnes;
             // The whole tile loop runs in ONE elected lane, inside one branch: there ptxas moves the loop state to uniform
@@ -566,7 +595,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                             if (ZMASK) { umma_f16_lohi(d, aLoOnes, aHi, blo, bHi, idesc, 0u); blo += 16; umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u); }
                             else umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
 #pragma unroll 1
-                            for (uint32_t m = 1; m < n_pos; m++) { alo += 4; blo += 16; umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u); }
+                            for (uint32_t m = 1; m < n_pos; m++) { alo += kStepEnt; blo += 16; umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u); }
                         }
                         auto free_stage = [&](uint32_t s2) {
                             const uint32_t lo = s2 ? kTcStageTiles * s2 - 1 : 0u, hi = min(kTcStageTiles * s2 + kTcStageTiles - 1, nT - 1);
@@ -604,16 +633,16 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     uint32_t alo = aLo0 + aOff, blo = bLo0;               // address fields are in 16-byte units = entries
                     if (!(TC_KNOCKOUT & 2)) {
                         if (ZMASK) {                                      // step 0: D = bias (constant one-hot rows x chunk 0 of B)
-                            umma_x<PAIR>(d, aLoOnes, aHi, blo, bHi, idesc, 0u);
+                            umma_x<PAIR, I8>(d, aLoOnes, aHi, blo, bHi, idesc, 0u);
                             blo += 16;
-                            umma_x<PAIR>(d, alo, aHi, blo, bHi, idesc, 1u);
+                            umma_x<PAIR, I8>(d, alo, aHi, blo, bHi, idesc, 1u);
                         } else {
-                            umma_x<PAIR>(d, alo, aHi, blo, bHi, idesc, 0u);
+                            umma_x<PAIR, I8>(d, alo, aHi, blo, bHi, idesc, 0u);
                         }
 #pragma unroll 1
                         for (uint32_t m = 1; m < n_pos; m++) {
-                            alo += 4; blo += 16;
-                            umma_x<PAIR>(d, alo, aHi, blo, bHi, idesc, 1u);
+                            alo += kStepEnt; blo += 16;
+                            umma_x<PAIR, I8>(d, alo, aHi, blo, bHi, idesc, 1u);
                         }
                     }
                     // MMAs complete in issue order: once the last tile of a stage is done, so is every reader of the stage

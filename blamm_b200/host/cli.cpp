@@ -594,8 +594,7 @@ int runScan(int argc, char** argv)
     os.close();
     ofsCutoff.close();
     cout << "\nWrote " << totMatches << " matches to " << outputFilename << ".\n";
-    gTimer.add("total (scan module)", now() - tStart);
-    gTimer.report();
+    gTimer.add("scan module before teardown", now() - tStart);
     return EXIT_SUCCESS;
 }
 
@@ -620,7 +619,14 @@ int main(int argc, char** argv)
     try {
         if (cmd == "dict") { int rc = blamm::runDict(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
         if (cmd == "hist") { int rc = blamm::runHist(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
-        if (cmd == "scan") { int rc = blamm::runScan(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
+        if (cmd == "scan") {
+            const double t0 = blamm::now();
+            int rc = blamm::runScan(argc, argv);
+            blamm::gTimer.add("scan module incl. teardown", blamm::now() - t0);
+            blamm::gTimer.report();
+            if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl;
+            return rc;
+        }
     } catch (const exception& e) {
         cerr << e.what() << endl;
         return EXIT_FAILURE;

@@ -21,6 +21,10 @@ hits, t = sc.scan(seq)
 assert L.b200scan_debug_trace(sc._ctx, buf, 64) == 0
 a = np.frombuffer(buf, dtype=np.uint64).astype(np.float64).reshape(4, 16)
 print("score kernel %.2f ms (phase build; the product build has no clock reads), %d hits" % (t["score_ms"], len(hits)))
+d = sc.describe()
+tiles_per_sm = a[1, 3] / d["sm_count"]
+print("column tiles %d, %s; window tiles issued %.0f = %.0f per SM -> %.0f cycles of kernel time per tile at 1.965 GHz" % (
+    d["n_tiles"], sc.tensor_info(), a[1, 3], tiles_per_sm, t["score_ms"] * 1e-3 * 1.965e9 / tiles_per_sm))
 names = {0: ("producer warp 0 (per 4-tile stage)", ["wait for a free E stage", "fill"]),
          1: ("issuer (per tile)", ["wait for E stages", "wait for the TMEM buffer", "issue MMAs + commits"]),
          2: ("epilogue warp, group 0 (per tile of its buffer = every 2nd tile)", ["wait for tFull", "tcgen05.ld phase until release", "sign compaction + push"])}
