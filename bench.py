@@ -400,6 +400,10 @@ def main() -> None:
         tot_ms, k_ms, e2e_ms = stats.tolist()
         launches_per_pass = t_e2e["kernel_launches"] - 1           # the e2e pass also launches the pack kernel
         engine_used = "tensor+rescore" if t_e2e["engine_used"] == capi.ENGINE_TENSOR else "gather"
+        kinds = {8: "int8 operands, s32 accumulators (tcgen05.mma.kind::i8)", 16: "fp16 operands, fp16 accumulators (kind::f16)",
+                 32: "fp16 operands, fp32 accumulators (kind::f16)", 0: "mixed per column tile (int8 / fp16)"}
+        operands = kinds.get(sc.tensor_info()["accumulator_bits"], "?") if engine_used != "gather" else "fp32 gather-add"
+        int8_pipe = engine_used != "gather" and sc.tensor_info()["accumulator_bits"] in (8, 0)
 
         if rank == 0:
             burst, sustained, how = peaks()
@@ -411,7 +415,7 @@ def main() -> None:
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "configs[1]: JASPAR-like %d PWMs x2 strands (%d columns, sum L = %d) x %.0f Mbp synthetic uniform ACGT per GPU, "
                                        "-rc -pt 1e-4 (real JASPAR CORE unavailable offline)%s" % (N_MOTIFS, n_cols, sum_len, args.mbp, (", %.0f %% soft-masked" % (100 * args.softmask)) if args.softmask > 0 else ""),
-                           "engine": engine_used, "parallelism": "chunk-sharded x%d, no collective" % world,
+                           "engine": engine_used, "operands": operands, "parallelism": "chunk-sharded x%d, no collective" % world,
                            "l2": "flushed between steps (256 MiB memset outside the event pairs)", "host_binding": numa, "hits_per_step": int(n_hits),
                            "candidates_per_step": int(t_e2e["n_candidates"])},
                 "gpu_launches": int(launches_per_pass * args.steps * 2 + args.steps),
@@ -424,6 +428,11 @@ def main() -> None:
                              "kernel": "filter_tc_kernel" if engine_used != "gather" else "gather_scan_kernel",
                              "kernel_ms": k_ms / args.steps, "algorithmic_flops_per_launch": flops_per_launch},
             }
+            if int8_pipe:
+                # The INT8 pipe has no measured peak in MEASURED_PEAKS.json: `peak` stays the measured bf16 number (what the
+                # FP16-operand instance of the same kernel runs against); the INT8 pipe's nominal dense rate is twice that.
+                line["roofline"]["pipe"] = "int8 tensor pipe (UTCIMMA); nominal dense peak = 2 x bf16"
+                line["roofline"]["frac_of_int8_nominal"] = achieved / (2.0 * burst)
             if world == 1 and not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline(work, seq, n_cols, min(args.cpu_sample_nt, n_nt))
             print(json.dumps(line), flush=True)

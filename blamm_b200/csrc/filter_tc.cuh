@@ -395,7 +395,7 @@ template <bool ACC16, bool ZMASK, bool PAIR, bool I8 = false>
 __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm)
 filter_tc_kernel(TcParams P, BlockDev blk)
 {
-    static_assert(!I8 || (ACC16 && !PAIR && TC_MMA_WARPS == 1), "INT8 operands: packed epilogue, single CTA, one issuer");
+    static_assert(!I8 || (ACC16 && !PAIR), "INT8 operands: packed epilogue, single CTA");
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     constexpr uint32_t kBufs    = TC_BUFS;              // TMEM accumulator buffers
     constexpr uint32_t kBufCols = kTcMaxN;              // TMEM columns per buffer: one accumulator per column, FP32 or FP16
@@ -592,10 +592,10 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         const uint32_t d = tmem_base + buf * kBufCols;
                         uint32_t alo = aLo0 + (k % kTcStages) * kTcStageEnt + j * 128, blo = bLo0;
                         if (!(TC_KNOCKOUT & 2)) {
-                            if (ZMASK) { umma_f16_lohi(d, aLoOnes, aHi, blo, bHi, idesc, 0u); blo += 16; umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u); }
-                            else umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 0u);
+                            if (ZMASK) { umma_x<false, I8>(d, aLoOnes, aHi, blo, bHi, idesc, 0u); blo += 16; umma_x<false, I8>(d, alo, aHi, blo, bHi, idesc, 1u); }
+                            else umma_x<false, I8>(d, alo, aHi, blo, bHi, idesc, 0u);
 #pragma unroll 1
-                            for (uint32_t m = 1; m < n_pos; m++) { alo += kStepEnt; blo += 16; umma_f16_lohi(d, alo, aHi, blo, bHi, idesc, 1u); }
+                            for (uint32_t m = 1; m < n_pos; m++) { alo += kStepEnt; blo += 16; umma_x<false, I8>(d, alo, aHi, blo, bHi, idesc, 1u); }
                         }
                         auto free_stage = [&](uint32_t s2) {
                             const uint32_t lo = s2 ? kTcStageTiles * s2 - 1 : 0u, hi = min(kTcStageTiles * s2 + kTcStageTiles - 1, nT - 1);

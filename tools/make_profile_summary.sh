@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/.."
 R=${1:-r01}
 cp gpurun_out/launches.csv profiles/${R}_launches_bench.csv
-{ echo "# Round ${R#r} ncu summaries (B200, bench.py default workload: 1800 columns x 100 Mbp, FP16-accumulator tensor filter)"
+{ echo "# Round ${R#r} ncu summaries (B200, bench.py default workload: 1800 columns x 100 Mbp, INT8-operand tensor filter: tcgen05.mma.kind::i8, S32 accumulators read back with pack::16b)"
 echo "# commands: tools/gpu_prof.sh; raw metrics via 'ncu -i <rep> --page raw --csv', hot SASS via tools/ncu_top.py"
 echo; echo "## launch list of 'python bench.py --steps 2 --warmup 3' (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised -> compare SHARES)"
 python3 - <<'PY'
@@ -20,7 +20,7 @@ for r in data:
 tot=sum(sum(v) for v in agg.values())
 for k,v in agg.items(): print('%-40s launches=%3d  mean %8.3f ms  share of GPU time %5.1f%%'%(k,len(v),sum(v)/len(v)/1e6,100*sum(v)/tot))
 PY
-echo; echo "## filter_tc_kernel<1> (ncu --set full --clock-control none), one launch = 100 Mbp x 1800 columns"
+echo; echo "## filter_tc_kernel<ACC16 = true, ZMASK = false, PAIR = false, I8 = true> (ncu --set full --clock-control none), one launch = 100 Mbp x 1800 columns"
 python3 tools/ncu_top.py gpurun_out/prof_filter.ncu-rep 25
 ncu -i gpurun_out/prof_filter.ncu-rep --page raw --csv 2>/dev/null | python3 -c "
 import csv,sys
