@@ -103,13 +103,14 @@ const char* b200scan_last_error(const b200scan_ctx* ctx);   /* ctx may be NULL: 
 
 int  b200scan_set_engine(b200scan_ctx* ctx, int engine);
 
-/* Accumulator type of the tensor-core filter: 0 = automatic (per column tile: FP16 accumulators in TMEM when the
- * error bound computed in b200scan_set_motifs allows it for every column of the tile, else FP32), 16 or 32 to force
- * one everywhere.  Takes effect at the next b200scan_set_motifs.  Results do not depend on it (the filter is
+/* Operand / accumulator kind of the tensor-core filter: 0 = automatic (per column tile: INT8 operands with exact S32
+ * accumulation where the integer weights resolve every column of the tile; else FP16 operands with FP16 accumulators in
+ * TMEM when the error bound computed in b200scan_set_motifs allows it, else FP32 accumulators); 8, 16 or 32 to force
+ * one kind everywhere.  Takes effect at the next b200scan_set_motifs.  Results do not depend on it (the filter is
  * conservative, scores are re-summed exactly). */
 int  b200scan_set_tensor_accumulator(b200scan_ctx* ctx, int bits);
-/* What the last b200scan_set_motifs chose (16, 32, or 0 when the tiles differ), and the mean safety margin (score units)
- * folded into the filter. */
+/* What the last b200scan_set_motifs chose (8, 16, 32, or 0 when the tiles differ), and the mean safety margin (score
+ * units) folded into the filter (INT8: the mean worst-case overshoot of the integer weights). */
 int  b200scan_tensor_info(const b200scan_ctx* ctx, int32_t* accumulator_bits, double* mean_margin);
 
 /* Motif matrix of the current species: P is column-major with leading dimension ldp >= 4*max(col_len),
