@@ -208,6 +208,60 @@ def test_accumulator_type_is_chosen_per_tile(scanner):
     scanner.set_tensor_accumulator(0)
 
 
+@pytest.mark.parametrize("lower", [False, True])
+def test_int8_filter_at_the_edges_of_its_bound(scanner, lower):
+    """The INT8 instance rounds and clamps its integer weights UP, so it must never lose a hit -- also where its
+    quantisation is at its limits: thresholds exactly at, one ulp below and above the best attainable score (slack 0:
+    scale at its maximum, every other letter clamps), thresholds just below that (a single mild mismatch allowed),
+    extreme weights (-60 ... +8: clamped letters), thresholds far below the best score (INT8 cannot resolve them: forced
+    INT8 sends every window to the exact rescorer), negative thresholds, and lengths 1, 8, 9, 64 around the 8-position MMA step."""
+    rng = np.random.default_rng(321)
+    n_nt = 400_000
+    chars = synth.random_acgt(n_nt, 77)
+    lut = np.zeros(256, dtype=np.int64); lut[ord("C")] = 1; lut[ord("G")] = 2; lut[ord("T")] = 3
+    codes = lut[chars]
+    lens = [1, 2, 7, 8, 9, 15, 16, 17, 24, 25, 33, 64] * 4
+    ldp = 4 * 64
+    P = np.zeros((len(lens), ldp), dtype=np.float32)
+    thr = np.zeros(len(lens), dtype=np.float32)
+    for c, L in enumerate(lens):
+        kind = c // 12
+        W = rng.uniform(-6.0, 1.9, size=(L, 4)).astype(np.float32)
+        if kind == 1:
+            W = rng.uniform(-60.0, 8.0, size=(L, 4)).astype(np.float32)
+        at = int(rng.integers(0, n_nt - 64))                     # plant the column's best window in the sequence
+        W[np.arange(L), codes[at:at + L]] = rng.uniform(0.4, 2.0, size=L).astype(np.float32) * (4.0 if kind == 1 else 1.0)
+        P[c, :4 * L] = W.reshape(-1)
+        best = np.float32(0.0)
+        for j in range(L):                                       # the reference's in-order FP32 sum of the best letters
+            best = np.float32(best + W[j].max())
+        if kind == 0:
+            thr[c] = [best, np.nextafter(best, np.float32(-np.inf)), np.nextafter(best, np.float32(np.inf))][c % 3]
+        elif kind == 1:
+            thr[c] = np.float32(best - rng.uniform(0.0, 3.0))
+        elif kind == 2:
+            thr[c] = np.float32(best - (0.5 + 0.25 * L))
+        else:
+            thr[c] = np.float32(-1.0 - 0.1 * L) if L > 2 else np.float32(0.3)
+    col_len = np.array(lens, dtype=np.int32)
+    if lower:
+        chars = chars.copy()
+        chars[1000:200_000:3] |= 0x20
+    case = dict(P=P, col_len=col_len, thr=thr, chars=chars, frag_start=np.array([0, 5, 300_001], dtype=np.uint64))
+    want = _oracle_hits(case)
+    assert len(want[0]) > 1000
+    big = capi.Scanner(0, max_block_nt=1 << 20, max_hits=1 << 23)
+    try:
+        for bits in (8, 0):
+            big.set_engine(capi.ENGINE_TENSOR)
+            big.set_tensor_accumulator(bits)
+            big.set_motifs(P, col_len, thr)
+            hits, t = big.scan(chars, case["frag_start"][1:])
+            _assert_same(hits, *want)
+    finally:
+        big.close()
+
+
 @pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
 def test_many_short_fragments(scanner, engine):
     """120,000 sequences of 1 .. 40 characters in one block (most shorter than the motifs): the fragment rule of
