@@ -301,6 +301,7 @@ def main() -> None:
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "gather"])
     ap.add_argument("--acc", type=int, default=0, choices=[0, 16, 32], help="tensor filter accumulators: 0 = automatic (diagnostic)")
     ap.add_argument("--softmask", type=float, default=0.0, help="diagnostic: fraction of the sequence turned lower case (runs of 1..3000), scored with BLAS-path semantics")
+    ap.add_argument("--hits", type=int, default=12, choices=[12, 16], help="hit record format of the run (b200scan_set_hit_format): 12 = b200scan_hit12, what the CLI uses")
     ap.add_argument("--cpu-sample-nt", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -355,6 +356,7 @@ def main() -> None:
         sc.set_engine({"auto": capi.ENGINE_AUTO, "tensor": capi.ENGINE_TENSOR, "gather": capi.ENGINE_GATHER}[args.engine])
         if args.acc:
             sc.set_tensor_accumulator(args.acc)
+        sc.set_hit_format(args.hits)
         sc.set_motifs(P, col_len, thr)
         scores_per_step = n_nt * n_cols
 
@@ -386,9 +388,9 @@ def main() -> None:
         for k in range(1, args.steps):
             sc.submit_ascii(k % 2, host_ptr, n_total=n_nt, n_payload=n_nt)
             hits, t_e2e = sc.collect((k - 1) % 2, copy=False)
-            d2h += len(hits) * 16 + 32
+            d2h += len(hits) * args.hits + 32
         hits, t_e2e = sc.collect((args.steps - 1) % 2, copy=False)
-        d2h += len(hits) * 16 + 32
+        d2h += len(hits) * args.hits + 32
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         barrier()
@@ -416,7 +418,7 @@ def main() -> None:
                 "config": {"workload": "configs[1]: JASPAR-like %d PWMs x2 strands (%d columns, sum L = %d) x %.0f Mbp synthetic uniform ACGT per GPU, "
                                        "-rc -pt 1e-4 (real JASPAR CORE unavailable offline)%s" % (N_MOTIFS, n_cols, sum_len, args.mbp, (", %.0f %% soft-masked" % (100 * args.softmask)) if args.softmask > 0 else ""),
                            "engine": engine_used, "operands": operands, "parallelism": "chunk-sharded x%d, no collective" % world,
-                           "l2": "flushed between steps (256 MiB memset outside the event pairs)", "host_binding": numa, "hits_per_step": int(n_hits),
+                           "l2": "flushed between steps (256 MiB memset outside the event pairs)", "host_binding": numa, "hits_per_step": int(n_hits), "hit_record_bytes": args.hits,
                            "candidates_per_step": int(t_e2e["n_candidates"])},
                 "gpu_launches": int(launches_per_pass * args.steps * 2 + args.steps),
                 "clocks": clocks,

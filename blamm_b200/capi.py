@@ -18,6 +18,8 @@ LOWER_ZERO, LOWER_FOLD = 0, 1
 NUM_SLOTS = 2
 
 HIT_DTYPE = np.dtype([("pos", "<u8"), ("col", "<u4"), ("score", "<f4")])
+HIT12_DTYPE = np.dtype([("pos", "<u4"), ("col", "<u4"), ("score", "<f4")])      # b200scan_hit12
+HITS_16, HITS_12 = 16, 12
 
 
 class Timing(ctypes.Structure):
@@ -56,6 +58,8 @@ def scan_lib() -> ctypes.CDLL:
         L.b200scan_submit_ascii.argtypes = [vp, ctypes.c_int, vp, u64, u64, vp, u64, ctypes.c_int]
         L.b200scan_submit_packed.argtypes = [vp, ctypes.c_int, vp, vp, u64, u64, vp, u64]
         L.b200scan_collect.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), _u64p, ctypes.POINTER(Timing)]
+        L.b200scan_collect12.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), _u64p, ctypes.POINTER(Timing)]
+        L.b200scan_set_hit_format.argtypes = [vp, ctypes.c_int]
         L.b200scan_rerun_resident.argtypes = [vp, ctypes.c_int, ctypes.c_int, f32p, f32p, _u64p]
         L.b200scan_hist_begin.argtypes = [vp, vp, vp, ctypes.c_uint32]
         L.b200scan_hist_block_ascii.argtypes = [vp, vp, u64, u64, vp, u64, ctypes.c_int]
@@ -112,6 +116,8 @@ class Scanner:
         if rc != 0:
             raise ScanError(rc, (self._L.b200scan_last_error(None) or b"").decode())
         self._keep = {}
+        self._hit_format = HITS_16
+        self._slot_format = {}
 
     def close(self) -> None:
         if self._ctx:
@@ -133,6 +139,11 @@ class Scanner:
 
     def set_tensor_accumulator(self, bits: int) -> None:
         self._chk(self._L.b200scan_set_tensor_accumulator(self._ctx, bits))
+
+    def set_hit_format(self, fmt: int) -> None:
+        """HITS_16 (b200scan_hit, default) or HITS_12 (b200scan_hit12) for blocks submitted from now on."""
+        self._chk(self._L.b200scan_set_hit_format(self._ctx, fmt))
+        self._hit_format = fmt
 
     def tensor_info(self) -> dict:
         b, m = ctypes.c_int32(), ctypes.c_double()
@@ -164,6 +175,7 @@ class Scanner:
         fs = np.ascontiguousarray(frag_starts if frag_starts is not None else [], dtype=np.uint64)
         self._chk(self._L.b200scan_submit_ascii(self._ctx, slot, ptr, n_total, n_payload, fs.ctypes.data if len(fs) else None,
                                                 len(fs), lower))
+        self._slot_format[slot] = self._hit_format
 
     def submit_packed(self, slot: int, codes2: np.ndarray, zero_mask: Optional[np.ndarray], n_total: int,
                       n_payload: Optional[int] = None, frag_starts: Optional[np.ndarray] = None) -> None:
@@ -173,15 +185,20 @@ class Scanner:
         fs = np.ascontiguousarray(frag_starts if frag_starts is not None else [], dtype=np.uint64)
         self._chk(self._L.b200scan_submit_packed(self._ctx, slot, codes2.ctypes.data, None if zm is None else zm.ctypes.data,
                                                  n_total, n_payload, fs.ctypes.data if len(fs) else None, len(fs)))
+        self._slot_format[slot] = self._hit_format
 
-    def collect(self, slot: int, copy: bool = True) -> Tuple[np.ndarray, dict]:
+    def collect(self, slot: int, copy: bool = True, fmt: Optional[int] = None) -> Tuple[np.ndarray, dict]:
+        """Hits of the block on `slot`, as HIT_DTYPE or HIT12_DTYPE records -- the format the block was submitted under
+        (`fmt` overrides the choice of the collecting function: only the state tests do that)."""
         hp, n, t = ctypes.c_void_p(), ctypes.c_uint64(), Timing()
-        self._chk(self._L.b200scan_collect(self._ctx, slot, ctypes.byref(hp), ctypes.byref(n), ctypes.byref(t)))
+        fmt = self._slot_format.get(slot, self._hit_format) if fmt is None else fmt
+        fn, dt = (self._L.b200scan_collect12, HIT12_DTYPE) if fmt == HITS_12 else (self._L.b200scan_collect, HIT_DTYPE)
+        self._chk(fn(self._ctx, slot, ctypes.byref(hp), ctypes.byref(n), ctypes.byref(t)))
         self._keep.pop(slot, None)
         if n.value == 0:
-            return np.zeros(0, dtype=HIT_DTYPE), t.as_dict()
-        raw = (ctypes.c_uint8 * (n.value * HIT_DTYPE.itemsize)).from_address(hp.value)
-        hits = np.frombuffer(raw, dtype=HIT_DTYPE)
+            return np.zeros(0, dtype=dt), t.as_dict()
+        raw = (ctypes.c_uint8 * (n.value * dt.itemsize)).from_address(hp.value)
+        hits = np.frombuffer(raw, dtype=dt)
         return (hits.copy() if copy else hits), t.as_dict()
 
     def scan(self, block, frag_starts=None, n_payload=None, lower: int = LOWER_ZERO, slot: int = 0) -> Tuple[np.ndarray, dict]:

@@ -47,6 +47,7 @@ struct Slot {
     bool in_flight = false, resident = false;
     uint64_t n_total = 0, n_payload = 0, n_frag = 0;
     bool packed_zero_known = false;               // submit_packed: has_zero decided on the host
+    int  hit_bytes = B200SCAN_HITS_16;            // record format of the block in flight / resident (b200scan_set_hit_format)
     cudaEvent_t ev[9] = {};                       // upload stream: 0 start, 1 after h2d, 2 after pack; compute stream: 8 scoring starts,
                                                   // 3 after score, 4 after rescore, 5 after counters d2h; copy stream: 6/7 hit d2h
     b200scan_timing timing = {};
@@ -62,6 +63,7 @@ struct b200scan_ctx {
     cudaStream_t up_stream = nullptr;        // block uploads + packing: overlap the previous block's kernels
     uint64_t max_block = 0;
     int engine = B200SCAN_ENGINE_AUTO;
+    int hit_format = B200SCAN_HITS_16;
     std::string err;
     Slot slot[B200SCAN_NUM_SLOTS];
     // candidates are shared by the slots (stream order serialises filter -> rescore per block)
@@ -530,7 +532,7 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
 {
     const MotifDev md = motif_dev(ctx);
     const BlockDev blk = block_dev(s);
-    HitSink sink{s.d_hits, s.d_counters + 1, s.hit_cap};
+    HitSink sink{s.d_hits, s.d_counters + 1, s.hit_cap, s.hit_bytes == B200SCAN_HITS_12 ? 1u : 0u};
     unsigned int* err = reinterpret_cast<unsigned int*>(s.d_counters + 2) + 1;
     unsigned int* work = reinterpret_cast<unsigned int*>(s.d_counters + 3);
     unsigned int* work2 = reinterpret_cast<unsigned int*>(s.d_counters + 4);      // work counter of the FP32-accumulator instance
@@ -657,6 +659,7 @@ int stage_frags(b200scan_ctx* ctx, Slot& s, const uint64_t* frag, uint64_t n_fra
 int finish_submit(b200scan_ctx* ctx, Slot& s)
 {
     s.timing.kernel_launches = 0;
+    s.hit_bytes = ctx->hit_format;
     int launches = 0;
     // the block was uploaded and packed on the upload stream (behind the kernels of the other slot's block)
     CU(cudaStreamWaitEvent(ctx->stream, s.ev[2], 0));
@@ -992,12 +995,15 @@ int b200scan_hist_read(b200scan_ctx* ctx, uint64_t* counts, uint64_t n_counts)
     return B200SCAN_OK;
 }
 
-int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits, b200scan_timing* timing)
+static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void** hits, uint64_t* n_hits, b200scan_timing* timing)
 {
     if (!ctx) return B200SCAN_EINVAL;
     if (slot < 0 || slot >= B200SCAN_NUM_SLOTS) return fail(ctx, B200SCAN_EINVAL, "slot %d out of range", slot);
     Slot& s = ctx->slot[slot];
     if (!s.in_flight) return fail(ctx, B200SCAN_ESTATE, "slot %d has nothing to collect", slot);
+    if (s.hit_bytes != want_bytes)
+        return fail(ctx, B200SCAN_ESTATE, "slot %d was submitted with %d-byte hit records: collect it with %s", slot, s.hit_bytes,
+                    s.hit_bytes == B200SCAN_HITS_12 ? "b200scan_collect12" : "b200scan_collect");
     CU(cudaSetDevice(ctx->device));
     s.in_flight = false;
     for (int attempt = 0;; attempt++) {
@@ -1055,7 +1061,7 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
     // the scan of this slot is complete (ev[5] was waited for): download its hits on the copy stream, so that the
     // kernels of a block already submitted on the other slot keep the compute stream busy meanwhile
     CU(cudaEventRecord(s.ev[6], ctx->copy_stream));
-    if (nh) CU(cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(b200scan_hit) * nh, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (nh) CU(cudaMemcpyAsync(s.h_hits, s.d_hits, (size_t)s.hit_bytes * nh, cudaMemcpyDeviceToHost, ctx->copy_stream));
     CU(cudaEventRecord(s.ev[7], ctx->copy_stream));
     CU(cudaEventSynchronize(s.ev[7]));
     cudaEventElapsedTime(&s.timing.h2d_ms, s.ev[0], s.ev[1]);
@@ -1066,6 +1072,31 @@ int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uin
     if (hits) *hits = s.h_hits;
     if (n_hits) *n_hits = nh;
     if (timing) *timing = s.timing;
+    return B200SCAN_OK;
+}
+
+int b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits, b200scan_timing* timing)
+{
+    const void* p = nullptr;
+    const int rc = collect_impl(ctx, slot, B200SCAN_HITS_16, &p, n_hits, timing);
+    if (rc == B200SCAN_OK && hits) *hits = static_cast<const b200scan_hit*>(p);
+    return rc;
+}
+
+int b200scan_collect12(b200scan_ctx* ctx, int slot, const b200scan_hit12** hits, uint64_t* n_hits, b200scan_timing* timing)
+{
+    const void* p = nullptr;
+    const int rc = collect_impl(ctx, slot, B200SCAN_HITS_12, &p, n_hits, timing);
+    if (rc == B200SCAN_OK && hits) *hits = static_cast<const b200scan_hit12*>(p);
+    return rc;
+}
+
+int b200scan_set_hit_format(b200scan_ctx* ctx, int format)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    if (format != B200SCAN_HITS_16 && format != B200SCAN_HITS_12) return fail(ctx, B200SCAN_EINVAL, "hit format must be B200SCAN_HITS_16 or B200SCAN_HITS_12");
+    for (auto& s : ctx->slot) if (s.in_flight) return fail(ctx, B200SCAN_ESTATE, "set_hit_format while a block is in flight");
+    ctx->hit_format = format;
     return B200SCAN_OK;
 }
 

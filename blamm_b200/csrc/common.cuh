@@ -37,7 +37,16 @@ struct HitSink {
     b200scan_hit*        hits;
     unsigned long long*  n_hits;   // keeps counting past `cap` so the host can size a retry exactly
     unsigned long long   cap;
+    uint32_t             compact;  // 1: the list holds 12-byte b200scan_hit12 records
 };
+// record `idx` of the hit list in the sink's format
+__device__ __forceinline__ void store_hit(const HitSink& sink, unsigned long long idx, const b200scan_hit& h)
+{
+    if (sink.compact) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(sink.hits) + 3 * idx;
+        d[0] = (uint32_t)h.pos; d[1] = h.col; d[2] = __float_as_uint(h.score);
+    } else sink.hits[idx] = h;
+}
 
 // Window [pos, pos+L) lies wholly inside one fragment?  (SeqBlock::getRemainingSeqLen, sequence.cpp:68-79,
 // used as `m.size() > remSeqLen -> reject` in pwmscan.cpp:122-126.)
@@ -78,7 +87,7 @@ __device__ __forceinline__ void emit_hits_warp(bool pred, uint32_t pos, uint32_t
         unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
         if (idx < sink.cap) {
             b200scan_hit h; h.pos = pos; h.col = col; h.score = score;
-            sink.hits[idx] = h;
+            store_hit(sink, idx, h);
         }
     }
 }

@@ -110,7 +110,7 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
         if (lane == 0) o = atomicAdd(sink.n_hits, (unsigned long long)n_st);
         o = __shfl_sync(0xffffffffu, o, 0);
         for (uint32_t k = lane; k < n_st; k += 32)
-            if (o + k < sink.cap) sink.hits[o + k] = st[k];
+            if (o + k < sink.cap) store_hit(sink, o + k, st[k]);
         __syncwarp();
         n_st = 0; round = 0;
     };

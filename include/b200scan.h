@@ -77,6 +77,18 @@ typedef struct b200scan_hit {
     float    score;
 } b200scan_hit;
 
+/* The same occurrence as a 12-byte record: block positions always fit 32 bits (max_block_nt < 2^32).  A quarter less
+ * device->host traffic -- the hit list IS the PCIe traffic of this path (4 bytes of hits come back for every byte of
+ * sequence sent at -pt 1e-4 with 1800 columns), and on an 8-GPU box the ranks share the host link.  Selected per
+ * context with b200scan_set_hit_format and fetched with b200scan_collect12. */
+typedef struct b200scan_hit12 {
+    uint32_t pos;
+    uint32_t col;
+    float    score;
+} b200scan_hit12;
+#define B200SCAN_HITS_16 16   /* b200scan_hit records, b200scan_collect (default) */
+#define B200SCAN_HITS_12 12   /* b200scan_hit12 records, b200scan_collect12        */
+
 /* timings of the last launch on a slot, CUDA events on the context's stream (milliseconds) */
 typedef struct b200scan_timing {
     float h2d_ms;        /* host->device copy of the block (+ fragment table)          */
@@ -144,6 +156,11 @@ int  b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2,
  * the slot).  timing may be NULL. */
 int  b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits,
                       b200scan_timing* timing);
+/* Record format of the hit lists (B200SCAN_HITS_16 | B200SCAN_HITS_12) for blocks submitted from now on; no block may be
+ * in flight.  A block must be collected with the function of the format it was submitted under (else B200SCAN_ESTATE). */
+int  b200scan_set_hit_format(b200scan_ctx* ctx, int format);
+int  b200scan_collect12(b200scan_ctx* ctx, int slot, const b200scan_hit12** hits, uint64_t* n_hits,
+                        b200scan_timing* timing);
 
 /* Empirical score histograms (`blamm hist -e`, reference Histogram::histThread + extractObsScore, hist.cpp:70-140):
  * same scoring as the scan, but instead of thresholding every window that lies inside one fragment adds 1 to bin

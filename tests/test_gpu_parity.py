@@ -338,6 +338,44 @@ def test_hit_buffer_overflow_regrows(engine):
         s.close()
 
 
+@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+def test_compact_hit_records(engine):
+    """b200scan_set_hit_format(B200SCAN_HITS_12) / b200scan_collect12: the same occurrences as 12-byte records -- also
+    through the regrow path (max_hits = 1024) -- and the state errors of mixing the two formats."""
+    s = capi.Scanner(0, max_block_nt=1 << 20, max_hits=1024)
+    try:
+        case = util.random_case(71, n_motifs=12, n_nt=150_000, lower=True)
+        s.set_engine(engine)
+        s.set_motifs(case["P"], case["col_len"], case["thr"])
+        want = _oracle_hits(case)
+        s.set_hit_format(capi.HITS_12)
+        h12, _ = s.scan(case["chars"], case["frag_start"][1:])
+        assert h12.dtype == capi.HIT12_DTYPE and h12.dtype.itemsize == 12 and len(h12) > 1024
+        _assert_same(h12, *want)
+        # both slots in flight in the compact format, then back to 16-byte records
+        s.submit_ascii(0, case["chars"], frag_starts=case["frag_start"][1:])
+        fs = case["frag_start"][1:]
+        s.submit_ascii(1, case["chars"][:70_029], n_payload=70_000, frag_starts=fs[fs < 70_029])     # payload + halo of maxLen - 1
+        with pytest.raises(capi.ScanError):
+            s.set_hit_format(capi.HITS_16)                   # a block is in flight
+        with pytest.raises(capi.ScanError) as ei:
+            s.collect(0, fmt=capi.HITS_16)                   # submitted under the 12-byte format
+        assert ei.value.code != 0
+        a, _ = s.collect(0)
+        b, _ = s.collect(1)
+        _assert_same(a, *want)
+        k = want[0] < 70_000
+        _assert_same(b, want[0][k], want[1][k], want[2][k])
+        s.set_hit_format(capi.HITS_16)
+        h16, _ = s.scan(case["chars"], case["frag_start"][1:])
+        assert h16.dtype == capi.HIT_DTYPE
+        _assert_same(h16, *want)
+        with pytest.raises(capi.ScanError):
+            s.set_hit_format(13)
+    finally:
+        s.close()
+
+
 def test_double_buffered_slots_and_state_errors(scanner):
     a, b = util.random_case(61, n_motifs=8, n_nt=80_000), util.random_case(62, n_motifs=8, n_nt=70_000)
     scanner.set_engine(capi.ENGINE_AUTO)
