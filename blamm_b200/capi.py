@@ -96,6 +96,8 @@ def host_lib() -> ctypes.CDLL:
         L.blamm_fasta_num_sequences.argtypes = [vp]
         L.blamm_fasta_sequence_name.argtypes = [vp, ctypes.c_int]; L.blamm_fasta_sequence_name.restype = ctypes.c_char_p
         L.blamm_fasta_counts.argtypes = [vp, _u64p]
+        L.blamm_pack_ascii.argtypes = [vp, u64, ctypes.c_int, vp, vp]
+        L.blamm_fasta_pack.argtypes = [vp, ctypes.c_int, vp, vp]
         _host = L
     return _host
 
@@ -288,6 +290,18 @@ class MotifSet:
                                                         species.encode(), histdir.encode()))
 
 
+def pack_ascii(block, lower: int = LOWER_ZERO) -> Tuple[np.ndarray, np.ndarray, bool]:
+    """Host 2-bit packer (blamm_pack_ascii): (codes2, zero_mask, has_zero) of a block, the inputs of Scanner.submit_packed."""
+    L = host_lib()
+    buf = np.frombuffer(block, dtype=np.uint8) if isinstance(block, (bytes, bytearray)) else np.ascontiguousarray(block, dtype=np.uint8)
+    n = len(buf)
+    codes = np.zeros((n + 15) // 16, dtype=np.uint32); zm = np.zeros((n + 31) // 32, dtype=np.uint32)
+    rc = L.blamm_pack_ascii(buf.ctypes.data if n else None, n, int(lower == LOWER_FOLD), codes.ctypes.data, zm.ctypes.data)
+    if rc < 0:
+        raise HostError(L.blamm_host_last_error().decode())
+    return codes, zm, bool(rc)
+
+
 class FastaStream:
     """FastaBatch mirror: filtered stream of a group's FASTA files, chunk by chunk."""
 
@@ -320,6 +334,14 @@ class FastaStream:
 
         return dict(chars=ctypes.string_at(chars.value, nt.value), n_total=nt.value, n_payload=npay.value, stream_start=st.value,
                     frag_start=arr(fs, nf.value), frag_seq=arr(fq, nf.value), frag_pos=arr(fp, nf.value))
+
+    def pack(self, n_total: int, lower: int = LOWER_ZERO) -> Tuple[np.ndarray, np.ndarray, bool]:
+        """2-bit codes, zero mask and has_zero of the chunk the last next() returned (packed on the parser threads)."""
+        codes = np.zeros((n_total + 15) // 16, dtype=np.uint32); zm = np.zeros((n_total + 31) // 32, dtype=np.uint32)
+        rc = self._L.blamm_fasta_pack(self._h, int(lower == LOWER_FOLD), codes.ctypes.data, zm.ctypes.data)
+        if rc < 0:
+            raise HostError(self._L.blamm_host_last_error().decode())
+        return codes, zm, bool(rc)
 
     def seq_names(self) -> List[str]:
         return [self._L.blamm_fasta_sequence_name(self._h, i).decode() for i in range(self._L.blamm_fasta_num_sequences(self._h))]

@@ -230,6 +230,10 @@ namespace {
 
 struct Job {
     unique_ptr<char[]> chars;                      // not a vector: no zero fill before the parallel copy
+    // packed hand-over (default): 2 bits per character + the zero mask, produced by the parser threads (FastaStream::packChunk);
+    // `chars` stays empty.  BLAMM_B200_ASCII=1 sends the characters instead and lets the device pack them.
+    unique_ptr<uint32_t[]> codes, zmask;
+    bool hasZero = false;
     vector<uint64_t> fragStarts;
     vector<Fragment> frags;
     uint64_t nTotal = 0, nPayload = 0;
@@ -394,8 +398,12 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
             sh.qCv.notify_all();
         }
         if (inFlight[slot] && !collect(slot)) break;
-        if (b200scan_submit_ascii(ctx, slot, job->chars.get(), job->nTotal, job->nPayload, job->fragStarts.data(),
-                                  job->fragStarts.size(), foldLower ? B200SCAN_LOWER_FOLD : B200SCAN_LOWER_ZERO) != B200SCAN_OK) {
+        const int rc = job->codes
+            ? b200scan_submit_packed(ctx, slot, job->codes.get(), job->hasZero ? job->zmask.get() : nullptr, job->nTotal, job->nPayload,
+                                     job->fragStarts.data(), job->fragStarts.size())
+            : b200scan_submit_ascii(ctx, slot, job->chars.get(), job->nTotal, job->nPayload, job->fragStarts.data(),
+                                    job->fragStarts.size(), foldLower ? B200SCAN_LOWER_FOLD : B200SCAN_LOWER_ZERO);
+        if (rc != B200SCAN_OK) {
             die(string("CUDA error: ") + b200scan_last_error(ctx)); break;
         }
         inFlight[slot] = std::move(job);
@@ -562,13 +570,21 @@ int runScan(int argc, char** argv)
         try {
             FastaStream fs(sp.files, sp.totSeqLen);
             fs.setParallel(ingestThreads(numThreads));
+            const char* asciiEnv = getenv("BLAMM_B200_ASCII");
+            const bool sendAscii = asciiEnv && *asciiEnv && *asciiEnv != '0';
             FastaStream::Chunk c;
             for (;;) {
                 double tr = now();
                 if (sh.failed || !fs.next(maxBlock - halo - 64, halo, c)) break;
                 unique_ptr<Job> job(new Job);
-                job->chars.reset(new char[c.nTotal]);
-                fs.copyChunk(c, job->chars.get());
+                if (sendAscii) {
+                    job->chars.reset(new char[c.nTotal]);
+                    fs.copyChunk(c, job->chars.get());
+                } else {                                  // 0.375 byte per character crosses PCIe instead of 1 (the reference: 18)
+                    job->codes.reset(new uint32_t[(c.nTotal + 15) / 16]);
+                    job->zmask.reset(new uint32_t[(c.nTotal + 31) / 32]);
+                    job->hasZero = fs.packChunk(c, foldLower, job->codes.get(), job->zmask.get());
+                }
                 job->fragStarts = c.fragStarts; job->frags = c.frags;
                 job->nTotal = c.nTotal; job->nPayload = c.nPayload;
                 gTimer.add("FASTA read + filter (reader)", now() - tr);

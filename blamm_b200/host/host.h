@@ -120,6 +120,8 @@ public:
     };
     bool next(uint64_t payload, uint64_t halo, Chunk& out);
     void copyChunk(const Chunk& c, char* dst);     // c.chars[0, nTotal) -> dst on the parser threads
+    // c.chars[0, nTotal) -> 2-bit codes + zero mask (see packAscii) on the parser threads; true if a character contributes 0
+    bool packChunk(const Chunk& c, bool foldLower, uint32_t* codes2, uint32_t* zmask);
     const std::vector<Fragment>& fragments() const { return frags_; }
     const std::vector<std::string>& seqNames() const { return names_; }
     uint64_t filteredLength() const { return streamLen_; }
@@ -154,6 +156,14 @@ private:
     std::vector<std::unique_ptr<Segment>> segs_;   // reused from wave to wave
     std::unique_ptr<Pool> pool_;
 };
+
+// Host twin of the device packer (csrc/pack.cuh) for b200scan_submit_packed: character i -> bits 2(i % 16) of codes2[i / 16]
+// (A0 C1 G2 T3, either case) and bit i % 32 of zmask[i / 32] ("contributes zero": lower case unless foldLower -- the
+// reference's one-hot fill only recognises upper case, sequence.cpp:312-319 -- and any byte outside ACGTacgt; the padding
+// behind n in the last words is code 0 / zero 1).  codes2 holds ceil(n / 16) words, zmask ceil(n / 32).  Returns true if
+// one of the n characters has its zero bit set.  Replaces the 16 bytes of FP32 one-hot per character that
+// SeqMatrix::getNextSeqMatrix writes (sequence.cpp:306-337) by 0.375 byte.
+bool packAscii(const char* chars, uint64_t n, bool foldLower, uint32_t* codes2, uint32_t* zmask);
 
 // "%g" with 6 significant digits == ostream << float (pwmscan.cpp:94)
 int formatScore(char* dst, float v);

@@ -132,4 +132,24 @@ int blamm_fasta_num_sequences(const blamm_fasta* f) { return (int)f->fs->seqName
 const char* blamm_fasta_sequence_name(const blamm_fasta* f, int idx) { return f->fs->seqNames().at(idx).c_str(); }
 int blamm_fasta_counts(const blamm_fasta* f, uint64_t c[4]) { for (int i = 0; i < 4; i++) c[i] = f->fs->counts()[i]; return 0; }
 
+int blamm_pack_ascii(const char* chars, uint64_t n, int foldLower, uint32_t* codes2, uint32_t* zeroMask)
+{
+    int any = 0;
+    int rc = guarded([&] {
+        if ((!chars && n) || !codes2 || !zeroMask) throw std::runtime_error("blamm_pack_ascii: NULL argument");
+        any = packAscii(chars, n, foldLower != 0, codes2, zeroMask) ? 1 : 0;
+    });
+    return rc ? -1 : any;
+}
+int blamm_fasta_pack(blamm_fasta* f, int foldLower, uint32_t* codes2, uint32_t* zeroMask)
+{
+    int any = 0;
+    int rc = guarded([&] {
+        if (!f || !codes2 || !zeroMask) throw std::runtime_error("blamm_fasta_pack: NULL argument");
+        if (!f->chunk.chars) throw std::runtime_error("blamm_fasta_pack: no chunk (call blamm_fasta_next first)");
+        any = f->fs->packChunk(f->chunk, foldLower != 0, codes2, zeroMask) ? 1 : 0;
+    });
+    return rc ? -1 : any;
+}
+
 } // extern "C"

@@ -492,6 +492,80 @@ void FastaStream::copyChunk(const Chunk& c, char* dst)
     pool_->run(n, [&](size_t k) { std::memcpy(dst + k * slice, c.chars + k * slice, std::min<size_t>(slice, c.nTotal - k * slice)); });
 }
 
+// ---- 2-bit packer (the device twin is csrc/pack.cuh: same codes, same mask, same padding) -------------------------------
+// Sixteen characters per step as bit planes: with u = c & 0xDF, bit 2 of u is the high code bit and bit 1 ^ bit 2 the low one
+// (A 0x41, C 0x43, G 0x47, T 0x54 -> 0 1 2 3, the row order of the matrix); a shift brings the wanted bit of every byte to
+// bit 7, PMOVMSKB collects the sixteen of them, and one 64-bit spread interleaves the two planes into the code word.
+namespace {
+inline uint32_t interleave16(uint32_t lo, uint32_t hi)         // bit i of lo -> bit 2i, bit i of hi -> bit 2i + 1
+{
+    uint64_t x = (uint64_t)lo | ((uint64_t)hi << 32);
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x << 2)) & 0x3333333333333333ULL;
+    x = (x | (x << 1)) & 0x5555555555555555ULL;
+    return (uint32_t)x | ((uint32_t)(x >> 32) << 1);
+}
+// 16 characters -> their code word; `zero` receives the 16 "contributes zero" bits
+inline uint32_t pack16(const char* p, bool foldLower, uint32_t& zero)
+{
+    const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+    const __m128i u = _mm_and_si128(x, _mm_set1_epi8((char)0xDF));
+    // valid <=> the upper-cased byte is one of A C G T (a filtered stream holds nothing else; the test keeps the packer total:
+    // any other byte, and the zero padding behind the block, becomes code 0 with its zero bit set)
+    const __m128i v = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8(0x41)), _mm_cmpeq_epi8(u, _mm_set1_epi8(0x43))),
+                                   _mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8(0x47)), _mm_cmpeq_epi8(u, _mm_set1_epi8(0x54))));
+    const uint32_t valid = (uint32_t)_mm_movemask_epi8(v);
+    const uint32_t hi = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(u, 5)) & valid;                                   // bit 2
+    const uint32_t lo = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(_mm_xor_si128(u, _mm_srli_epi16(u, 1)), 6)) & valid;   // bit 1 ^ bit 2
+    zero = ~valid & 0xFFFFu;
+    if (!foldLower) zero |= (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(x, 2));                                      // bit 5: lower case
+    return interleave16(lo, hi);
+}
+// characters [i0, i1) of `chars` (i0 a multiple of 32) -> their code and mask words; true if a live character contributes 0
+bool packRange(const char* chars, uint64_t i0, uint64_t i1, bool foldLower, uint32_t* codes2, uint32_t* zmask)
+{
+    bool anyZero = false;
+    uint64_t base = i0;
+    for (; base + 32 <= i1; base += 32) {
+        uint32_t z0, z1;
+        codes2[base / 16] = pack16(chars + base, foldLower, z0);
+        codes2[base / 16 + 1] = pack16(chars + base + 16, foldLower, z1);
+        const uint32_t zm = z0 | (z1 << 16);
+        zmask[base / 32] = zm;
+        anyZero |= zm != 0;
+    }
+    if (base < i1) {                                            // ragged tail: zero padding (invalid: code 0, zero bit set)
+        const uint64_t n = i1 - base;
+        char tmp[32] = {0};
+        std::memcpy(tmp, chars + base, (size_t)n);
+        uint32_t z0, z1;
+        codes2[base / 16] = pack16(tmp, foldLower, z0);
+        const uint32_t c1 = pack16(tmp + 16, foldLower, z1);
+        if (n > 16) codes2[base / 16 + 1] = c1;
+        const uint32_t zm = z0 | (z1 << 16);
+        zmask[base / 32] = zm;
+        anyZero |= (zm & ((1u << n) - 1u)) != 0;
+    }
+    return anyZero;
+}
+} // namespace
+
+bool packAscii(const char* chars, uint64_t n, bool foldLower, uint32_t* codes2, uint32_t* zmask)
+{
+    return packRange(chars, 0, n, foldLower, codes2, zmask);
+}
+
+bool FastaStream::packChunk(const Chunk& c, bool foldLower, uint32_t* codes2, uint32_t* zmask)
+{
+    const size_t slice = 1 << 20, n = (size_t)((c.nTotal + slice - 1) / slice);       // a multiple of 32: whole words per slice
+    std::atomic<bool> anyZero{false};
+    pool_->run(n, [&](size_t k) {
+        if (packRange(c.chars, k * slice, std::min<uint64_t>(c.nTotal, (k + 1) * slice), foldLower, codes2, zmask)) anyZero = true;
+    });
+    return anyZero;
+}
+
 void FastaStream::locate(uint64_t streamPos, uint64_t& seqIdx, uint64_t& seqPos) const
 {
     auto it = std::upper_bound(frags_.begin(), frags_.end(), streamPos,

@@ -49,6 +49,16 @@ int  blamm_fasta_next(blamm_fasta* f, uint64_t payload, uint64_t halo, const cha
 int  blamm_fasta_num_sequences(const blamm_fasta* f);
 const char* blamm_fasta_sequence_name(const blamm_fasta* f, int idx);
 int  blamm_fasta_counts(const blamm_fasta* f, uint64_t counts[4]);
+/* 2-bit packer for b200scan_submit_packed -- replaces the FP32 one-hot fill of SeqMatrix::getNextSeqMatrix
+ * (sequence.cpp:306-337: 16 bytes per character) by 0.375 byte per character, in the layout b200scan.h documents:
+ * character i -> bits 2(i % 16) of codes2[i / 16] (A0 C1 G2 T3, either case) and bit i % 32 of zero_mask[i / 32]
+ * (set = contributes 0: lower case unless fold_lower -- the reference's fill only recognises upper case,
+ * sequence.cpp:312-319 -- and any byte outside ACGTacgt; padding behind n: code 0, bit set).  codes2 holds
+ * ceil(n / 16) words, zero_mask ceil(n / 32).  blamm_pack_ascii packs any buffer on the calling thread,
+ * blamm_fasta_pack the chunk the last blamm_fasta_next returned, on the stream's parser threads.
+ * Return 1 if one of the n characters has its zero bit set, 0 if none, -1 on error. */
+int  blamm_pack_ascii(const char* chars, uint64_t n, int fold_lower, uint32_t* codes2, uint32_t* zero_mask);
+int  blamm_fasta_pack(blamm_fasta* f, int fold_lower, uint32_t* codes2, uint32_t* zero_mask);
 
 #ifdef __cplusplus
 }

@@ -322,6 +322,28 @@ def test_packed_submit_and_zero_mask(scanner):
     assert t["engine_used"] == capi.ENGINE_TENSOR
 
 
+@pytest.mark.parametrize("lower", [capi.LOWER_ZERO, capi.LOWER_FOLD])
+def test_host_packed_block_matches_ascii_block(scanner, lower):
+    """blamm_pack_ascii (host twin of pack_ascii_kernel) + b200scan_submit_packed == b200scan_submit_ascii == oracle, for a block
+    with lower-case stretches under both lower-case rules and a length that fills neither a code nor a mask word."""
+    case = util.random_case(43, n_motifs=12, n_nt=123_457, lower=True)
+    chars = case["chars"].copy()
+    chars[90_000:90_700] |= 0x20
+    case = dict(case, chars=chars)
+    scanner.set_engine(capi.ENGINE_AUTO)
+    scanner.set_motifs(case["P"], case["col_len"], case["thr"])
+    codes, zm, has_zero = capi.pack_ascii(chars, lower)
+    assert has_zero == (lower == capi.LOWER_ZERO)
+    n = len(chars)
+    scanner.submit_packed(0, codes, zm if has_zero else None, n, n, case["frag_start"][1:])
+    scanner.submit_ascii(1, chars, frag_starts=case["frag_start"][1:], lower=lower)
+    hp, _ = scanner.collect(0)
+    ha, _ = scanner.collect(1)
+    want = _oracle_hits(case, lower_fold=(lower == capi.LOWER_FOLD))
+    _assert_same(hp, *want)
+    _assert_same(ha, *want)
+
+
 @pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
 def test_hit_buffer_overflow_regrows(engine):
     """Thresholds so low that almost every window is an occurrence: far more hits than max_hits."""
@@ -561,8 +583,11 @@ def test_config4_many_columns_absolute_threshold(tmp_path):
         sc.close()
 
 
-def test_config3_many_groups_cli(tmp_path):
-    """BASELINE.json configs[2] in shape: several manifest groups with distinct backgrounds (the matrix P and the p-value
+@pytest.mark.parametrize("handover", ["packed", "ascii"])
+def test_config3_many_groups_cli(tmp_path, handover):
+    """(`handover`: the CLI's default -- chunks packed to 2 bits by the parser threads, b200scan_submit_packed -- and
+    BLAMM_B200_ASCII=1 -- characters sent, packed on the device; the packed run is repeated with -s, lower case folded.)
+    BASELINE.json configs[2] in shape: several manifest groups with distinct backgrounds (the matrix P and the p-value
     thresholds are rebuilt per group), more than one FASTA file per group, N runs and soft-masked stretches, scanned by the
     CLI in small chunks with a parallel reader -- against the oracle's restatement of the whole `blamm scan`."""
     cli = os.path.join(lib_dir(), "blamm-b200")
@@ -585,7 +610,7 @@ def test_config3_many_groups_cli(tmp_path):
             synth.write_fasta(str(work / name), [("g%dchr%d" % (gidx, 2 * f + 1), seq[:cut]), ("g%dchr%d extra" % (gidx, 2 * f + 2), seq[cut:])])
             manifest.append("group%d\t%s\n" % (gidx, name))
     open(work / "seq.mf", "w").write("".join(manifest))
-    env = dict(os.environ, BLAMM_B200_CHUNK="50000", BLAMM_B200_INGEST_THREADS="4")
+    env = dict(os.environ, BLAMM_B200_CHUNK="50000", BLAMM_B200_INGEST_THREADS="4", BLAMM_B200_ASCII="1" if handover == "ascii" else "0")
     for args in (["dict", "seq.mf"], ["hist", "-H", "hist", "motifs.jaspar", "seq.mf"]):
         subprocess.run([cli] + args, cwd=work, env=env, check=True, stdout=subprocess.DEVNULL)
     r = subprocess.run([cli, "scan", "-rc", "-pt", "0.0005", "-H", "hist", "motifs.jaspar", "seq.mf"], cwd=work, env=env,
@@ -597,6 +622,13 @@ def test_config3_many_groups_cli(tmp_path):
     assert not np.array_equal(details[0]["thr"], details[4]["thr"])
     got = sorted(open(work / "occurrences.txt").read().splitlines(True))
     assert got == sorted(want)
+    if handover == "packed":
+        r = subprocess.run([cli, "scan", "-s", "-rc", "-pt", "0.0005", "-H", "hist", "-o", "occ_s.txt", "motifs.jaspar", "seq.mf"], cwd=work,
+                           env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        want_s, _ = O.scan("motifs.jaspar", "seq.mf", "pt", 0.0005, True, histdir="hist", base_dir=str(work), lower_fold=True)
+        got_s = sorted(open(work / "occ_s.txt").read().splitlines(True))
+        assert got_s == sorted(want_s) and got_s != got
 
 
 @pytest.mark.parametrize("lower", [capi.LOWER_ZERO, capi.LOWER_FOLD])

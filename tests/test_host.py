@@ -198,6 +198,66 @@ def test_parallel_ingest_is_independent_of_threads_at_size(tmp_path):
     assert ref[0] == O.build_stream([str(p)]).chars
 
 
+def _pack_restated(buf, fold_lower):
+    """The packing rule of include/blamm_host.h / csrc/pack.cuh, one character at a time."""
+    n = len(buf)
+    code = np.zeros(256, dtype=np.uint32); zero = np.ones(256, dtype=np.uint32)
+    for k, (u, l) in enumerate(zip(b"ACGT", b"acgt")):
+        code[u] = code[l] = k
+        zero[u] = 0
+        zero[l] = 0 if fold_lower else 1
+    m = (n + 31) // 32 * 32
+    c = np.zeros(m, dtype=np.uint32); z = np.ones(m, dtype=np.uint32)
+    c[:n] = code[buf]; z[:n] = zero[buf]
+    codes = (c.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1, dtype=np.uint64).astype(np.uint32)[:(n + 15) // 16]
+    zm = (z.reshape(-1, 32) << np.arange(32, dtype=np.uint32)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    return codes, zm, bool(z[:n].any())
+
+
+@pytest.mark.parametrize("lower", [capi.LOWER_ZERO, capi.LOWER_FOLD])
+def test_host_packer_matches_its_rule(lower):
+    """blamm_pack_ascii (the host twin of the device packer) on every length around the word sizes, mixed case, and
+    bytes that a filtered stream never holds (every byte value occurs)."""
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+    for n in [0, 1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 1000, 100_003]:
+        buf = alphabet[rng.integers(0, 8, size=n)].copy()
+        codes, zm, hz = capi.pack_ascii(buf, lower)
+        wc, wz, wh = _pack_restated(buf, lower == capi.LOWER_FOLD)
+        assert np.array_equal(codes, wc) and np.array_equal(zm, wz) and hz == wh, n
+        up = alphabet[rng.integers(0, 4, size=n)].copy()          # upper case only: no character contributes zero
+        assert capi.pack_ascii(up, lower)[2] is False
+    every = np.tile(np.arange(256, dtype=np.uint8), 5)[:1273]
+    rng.shuffle(every)
+    codes, zm, hz = capi.pack_ascii(every, lower)
+    wc, wz, wh = _pack_restated(every, lower == capi.LOWER_FOLD)
+    assert np.array_equal(codes, wc) and np.array_equal(zm, wz) and hz and wh
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_fasta_stream_packs_its_chunks(tmp_path, threads):
+    """blamm_fasta_pack: every chunk of a soft-masked FASTA (2.5 MB: several 1 MiB pack slices, ragged last chunk) packed on
+    the parser threads == the rule applied to the chunk's characters, both lower-case modes."""
+    p = tmp_path / "g.fa"
+    seq = synth.random_acgt(2_500_000, 21)
+    seq[300_000:1_200_000] |= 0x20
+    seq[2_000_000:2_000_500] = ord("N")
+    synth.write_fasta(str(p), [("chr1", seq[:1_700_000]), ("chr2", seq[1_700_000:])])
+    fs = capi.FastaStream([str(p)], threads=threads)
+    n_chunks = 0
+    while True:
+        c = fs.next(1_100_000, 29)
+        if c is None:
+            break
+        buf = np.frombuffer(c["chars"], dtype=np.uint8)
+        for lower in (capi.LOWER_ZERO, capi.LOWER_FOLD):
+            codes, zm, hz = fs.pack(c["n_total"], lower)
+            wc, wz, wh = _pack_restated(buf, lower == capi.LOWER_FOLD)
+            assert np.array_equal(codes, wc) and np.array_equal(zm, wz) and hz == wh
+        n_chunks += 1
+    assert n_chunks == 3
+
+
 def test_fasta_rejects_headerless_input(tmp_path):
     p = tmp_path / "bad.fa"
     p.write_text("ACGT\n>late\nACGT\n")
