@@ -96,6 +96,7 @@ def host_lib() -> ctypes.CDLL:
         L.blamm_fasta_num_sequences.argtypes = [vp]
         L.blamm_fasta_sequence_name.argtypes = [vp, ctypes.c_int]; L.blamm_fasta_sequence_name.restype = ctypes.c_char_p
         L.blamm_fasta_counts.argtypes = [vp, _u64p]
+        L.blamm_format_score.argtypes = [ctypes.c_float, ctypes.c_char_p]
         L.blamm_pack_ascii.argtypes = [vp, u64, ctypes.c_int, vp, vp]
         L.blamm_fasta_pack.argtypes = [vp, ctypes.c_int, vp, vp]
         _host = L

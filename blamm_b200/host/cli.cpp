@@ -17,9 +17,11 @@
 #include <future>
 #include <iostream>
 #include <mutex>
+#include <random>
 #include <sstream>
 #include <thread>
 #include <unordered_map>
+#include <unistd.h>
 
 using namespace std;
 
@@ -27,12 +29,6 @@ namespace blamm {
 
 // operator<<(ostream&, float) of the reference (pwmscan.cpp:93) == printf("%g").  std::to_chars in general format with
 // precision 6 is specified to give exactly that conversion (checked against snprintf on 4e7 floats) at a fifth of the cost.
-int formatScore(char* dst, float v)
-{
-    if (!std::isfinite(v)) return snprintf(dst, 32, "%g", (double)v);
-    return (int)(std::to_chars(dst, dst + 32, (double)v, std::chars_format::general, 6).ptr - dst);
-}
-
 namespace {
 struct PhaseTimer {            // BLAMM_B200_TIMING=1: wall-clock seconds per phase on stderr (sums over threads where noted)
     bool on = getenv("BLAMM_B200_TIMING") != nullptr;
@@ -260,11 +256,42 @@ struct ScanShared {
 // The block is cut into position ranges; each formatting thread sorts and formats its range, the pieces are
 // handed to the writer thread in order.
 // H = b200scan_hit12: the CLI asks the context for 12-byte records (a quarter less PCIe and host-memory traffic per hit).
+// (position, column) order by LSD radix sort: the hit list of a block comes back in no particular order, and a comparison sort
+// was half of the formatting time.  Digits of <= 12 bits over the column and then over the position relative to the smallest
+// one in the list (3 passes for 1800 columns and a 6 M position range); counting passes are stable.
+template <class H>
+void sortHits(std::vector<H>& hits)
+{
+    const size_t n = hits.size();
+    auto less = [](const H& a, const H& b) { return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; };
+    if (n < 4096) { sort(hits.begin(), hits.end(), less); return; }
+    uint64_t pLo = hits[0].pos, pHi = hits[0].pos; uint32_t cHi = 0;
+    for (const auto& h : hits) { pLo = min<uint64_t>(pLo, h.pos); pHi = max<uint64_t>(pHi, h.pos); cHi = max(cHi, h.col); }
+    auto bitsOf = [](uint64_t v) { unsigned b = 0; while (v) { b++; v >>= 1; } return b; };
+    std::vector<H> tmp(n);
+    H* src = hits.data(); H* dst = tmp.data();
+    std::vector<size_t> count;
+    auto passes = [&](unsigned bits, auto key) {
+        if (!bits) return;
+        const unsigned np = (bits + 11) / 12, width = (bits + np - 1) / np;
+        for (unsigned pass = 0; pass < np; pass++) {
+            const unsigned shift = pass * width; const uint64_t mask = (1ull << width) - 1;
+            count.assign((size_t)mask + 2, 0);
+            for (size_t i = 0; i < n; i++) count[((key(src[i]) >> shift) & mask) + 1]++;
+            for (size_t b = 1; b <= mask; b++) count[b] += count[b - 1];
+            for (size_t i = 0; i < n; i++) dst[count[(key(src[i]) >> shift) & mask]++] = src[i];
+            std::swap(src, dst);
+        }
+    };
+    passes(bitsOf(cHi), [](const H& h) { return (uint64_t)h.col; });
+    passes(bitsOf(pHi - pLo), [pLo](const H& h) { return (uint64_t)h.pos - pLo; });
+    if (src != hits.data()) hits.swap(tmp);
+}
+
 template <class H>
 void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, std::string& text)
 {
-    sort(hits.begin(), hits.end(), [](const H& a, const H& b) {
-        return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; });
+    sortHits(hits);
     // worst-case line: names + 2 positions of <= 20 digits + score (<= 16) + 5 tabs + strand + "\t.\t.\n"
     text.resize(hits.size() * (sh.maxNameLen + 96) + 64);
     char* const base = &text[0];
@@ -411,6 +438,78 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
         if (inFlight[slot] && !collect(slot)) break;     // overlap: format block k-1 while the GPU scores block k
     }
     for (int s = 0; s < B200SCAN_NUM_SLOTS && !sh.failed; s++) { if (inFlight[slot]) collect(slot); slot ^= 1; }
+}
+
+// `blamm-b200 selftest-writer [hits] [threads]` (no GPU): the occurrence writer -- partition, radix sort, formatting, writer
+// thread -- on a synthetic hit list of both record types, against a plain restatement (std::sort, upper_bound, snprintf "%g").
+template <class H>
+bool writerSelfTest(size_t nHits, size_t threads, const char* label)
+{
+    std::mt19937_64 rng(12345 + nHits);
+    MotifSet ms;
+    const size_t nCols = 37;
+    for (size_t c = 0; c < nCols; c++) {
+        Motif m; m.name = "MA" + to_string(1000 + c / 2) + "." + to_string(1 + c % 3); m.pfm.resize(5 + c % 17); m.revComp = c & 1;
+        ms.motifs.push_back(m);
+    }
+    Species sp; sp.name = "syn";
+    sp.seqNames = {"chr1", "chr2_with_a_longer_name", "s3"};
+    Job job;
+    job.nPayload = 3000000; job.nTotal = job.nPayload + 40;
+    job.frags = {{0, 0, 1234567890123ull}, {700001, 0, 1234567990123ull}, {1500000, 1, 0}, {1500007, 1, 19}, {2999990, 2, 5}};
+    // distinct (position, column) pairs, shuffled
+    const uint64_t universe = job.nPayload * nCols, g = max<uint64_t>(1, universe / max<size_t>(1, nHits));
+    vector<H> hits;
+    for (size_t i = 0; i < nHits && i * g < universe; i++) {
+        const uint64_t key = i * g + rng() % g;
+        H h; h.pos = (decltype(h.pos))(key / nCols); h.col = (uint32_t)(key % nCols);
+        const int kind = (int)(rng() % 8);
+        const double u = (double)(rng() % 2000001) / 1e6 - 1.0;                       // [-1, 1]
+        h.score = kind == 0 ? (float)(u * 1e-3) : kind == 1 ? (float)(u * 2e6) : kind == 2 ? (float)((int)(u * 40)) : (float)(u * 30.0);
+        hits.push_back(h);
+    }
+    shuffle(hits.begin(), hits.end(), rng);
+    // restatement
+    vector<H> inOrder(hits);
+    sort(inOrder.begin(), inOrder.end(), [](const H& a, const H& b) { return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; });
+    string want;
+    char line[512];
+    for (const auto& h : inOrder) {
+        auto it = upper_bound(job.frags.begin(), job.frags.end(), (uint64_t)h.pos, [](uint64_t p, const Fragment& f) { return p < f.streamPos; }) - 1;
+        const unsigned long long seqPos = it->seqPos + (h.pos - it->streamPos);
+        const Motif& m = ms.motifs[h.col];
+        const int n = snprintf(line, sizeof line, "%s\tblamm\t%s\t%llu\t%llu\t%g\t%c\t.\t.\n", sp.seqNames[it->seqIdx].c_str(), m.name.c_str(),
+                               seqPos, seqPos + (unsigned long long)m.size(), (double)h.score, m.revComp ? '-' : '+');
+        want.append(line, (size_t)n);
+    }
+    const string path = "/tmp/blamm_b200_selftest_" + to_string((long)getpid()) + ".txt";
+    {
+        ofstream os(path, ios::binary);
+        ScanShared sh;
+        sh.motifs = &ms; sh.species = &sp; sh.os = &os; sh.formatThreads = threads;
+        sh.maxNameLen = 23 + 8;
+        thread writer(writerThread, ref(sh));
+        writeHits(sh, job, hits.data(), hits.size());
+        { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; }
+        sh.oCv.notify_all();
+        writer.join();
+        if (sh.totMatches != hits.size()) { cerr << label << ": match count differs\n"; return false; }
+    }
+    ifstream is(path, ios::binary);
+    const string got((istreambuf_iterator<char>(is)), istreambuf_iterator<char>());
+    remove(path.c_str());
+    const bool ok = got == want;
+    cout << label << ": " << hits.size() << " hits, " << threads << " threads, " << got.size() << " bytes: " << (ok ? "identical" : "DIFFERENT") << "\n";
+    return ok;
+}
+
+int runWriterSelfTest(int argc, char** argv)
+{
+    const size_t nHits = argc > 2 ? (size_t)atoll(argv[2]) : 300000, threads = argc > 3 ? (size_t)atoll(argv[3]) : 4;
+    bool ok = writerSelfTest<b200scan_hit>(nHits, threads, "b200scan_hit  ");
+    ok = writerSelfTest<b200scan_hit12>(nHits, threads, "b200scan_hit12") && ok;
+    gTimer.report();                                   // BLAMM_B200_TIMING=1: the phases of both runs, summed
+    return ok ? EXIT_SUCCESS : EXIT_FAILURE;
 }
 
 } // namespace
@@ -638,6 +737,7 @@ int main(int argc, char** argv)
     try {
         if (cmd == "dict") { int rc = blamm::runDict(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
         if (cmd == "hist") { int rc = blamm::runHist(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
+        if (cmd == "selftest-writer") return blamm::runWriterSelfTest(argc, argv);
         if (cmd == "scan") {
             const double t0 = blamm::now();
             int rc = blamm::runScan(argc, argv);

@@ -152,4 +152,6 @@ int blamm_fasta_pack(blamm_fasta* f, int foldLower, uint32_t* codes2, uint32_t* 
     return rc ? -1 : any;
 }
 
+int blamm_format_score(float score, char* dst) { return dst ? formatScore(dst, score) : -1; }
+
 } // extern "C"

@@ -2,7 +2,9 @@
 #include "host.h"
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
+#include <cstdio>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -334,5 +336,45 @@ void MotifSet::theoreticalHistogram(const Motif& m, const std::array<float, 4>& 
         hist.setNumObservations(score, (uint64_t)(maxLength * cur[s]));
     }
 }
+
+// "%g" (precision 6) of a float, the format of `ostream << float` in the reference's writer (pwmscan.cpp:94).
+// Fast path for 1e-4 <= |v| < 1e6, i.e. the fixed notation of %g: with X = floor(log10 |v|), y = |v| * 10^(5 - X) is EXACT in
+// double arithmetic (a float has 24 significant bits and 10^k = 2^k * 5^k with 5^9 < 2^21, so the product needs at most 45
+// bits), hence nearbyint(y) -- round to nearest, ties to even -- is the correctly rounded 6-digit decimal that printf
+// produces from the exact binary value; the digits are then laid out as %f with precision 5 - X and the trailing zeros are
+// dropped.  The comparisons against the double constants 1e-4 .. 1e-1 are exact for float inputs (no float lies between
+// such a constant and the decimal it approximates).  Everything else (zero, exponent notation, non-finite) goes to
+// std::to_chars / snprintf.  tests/test_host.py checks the function against printf on random bit patterns, ties and edges.
+int formatScore(char* dst, float v)
+{
+    static const double kPow10[10] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9};
+    const double a = std::fabs((double)v);
+    if (a >= 1e-4 && a < 1e6) {
+        int X = a >= 1e2 ? (a >= 1e4 ? (a >= 1e5 ? 5 : 4) : (a >= 1e3 ? 3 : 2))
+                         : (a >= 1e0 ? (a >= 1e1 ? 1 : 0) : (a >= 1e-2 ? (a >= 1e-1 ? -1 : -2) : (a >= 1e-3 ? -3 : -4)));
+        uint32_t r = (uint32_t)std::nearbyint(a * kPow10[5 - X]);           // 100000 .. 1000000
+        if (r >= 1000000u) { r = 100000u; X++; }                            // 999999.5 -> 1.00000 x 10^(X+1)
+        if (X <= 5) {
+            char dig[6];
+            for (int i = 5; i >= 0; i--) { dig[i] = (char)('0' + r % 10); r /= 10; }
+            int nd = 6;
+            while (nd > 1 && dig[nd - 1] == '0') nd--;                      // significant digits left after dropping trailing zeros
+            char* p = dst;
+            if (std::signbit(v)) *p++ = '-';
+            if (X >= 0) {
+                for (int i = 0; i <= X; i++) *p++ = dig[i];                 // (zeros inside the integer part are digits, not trailing zeros)
+                if (nd > X + 1) { *p++ = '.'; for (int i = X + 1; i < nd; i++) *p++ = dig[i]; }
+            } else {
+                *p++ = '0'; *p++ = '.';
+                for (int i = -1; i > X; i--) *p++ = '0';
+                for (int i = 0; i < nd; i++) *p++ = dig[i];
+            }
+            return (int)(p - dst);
+        }
+    }
+    if (!std::isfinite(v)) return snprintf(dst, 32, "%g", (double)v);
+    return (int)(std::to_chars(dst, dst + 32, (double)v, std::chars_format::general, 6).ptr - dst);
+}
+
 
 } // namespace blamm

@@ -60,6 +60,10 @@ int  blamm_fasta_counts(const blamm_fasta* f, uint64_t counts[4]);
 int  blamm_pack_ascii(const char* chars, uint64_t n, int fold_lower, uint32_t* codes2, uint32_t* zero_mask);
 int  blamm_fasta_pack(blamm_fasta* f, int fold_lower, uint32_t* codes2, uint32_t* zero_mask);
 
+/* Score column of the occurrence file: the text `ostream << float` produces in the reference's writer (pwmscan.cpp:94),
+ * i.e. "%g" with 6 significant digits.  dst needs 32 bytes; returns the length (no terminator is written). */
+int  blamm_format_score(float score, char* dst);
+
 #ifdef __cplusplus
 }
 #endif

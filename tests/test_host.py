@@ -258,6 +258,41 @@ def test_fasta_stream_packs_its_chunks(tmp_path, threads):
     assert n_chunks == 3
 
 
+def test_format_score_matches_printf():
+    """blamm_format_score (fast "%g" of the occurrence writer, pwmscan.cpp:94) == C printf("%g") on random bit patterns of
+    every magnitude, on scores as a scan produces them, and on the edges of its fast path (ties, carries into the next
+    decade, the switch to exponent notation).  tools/format_check.cpp runs the same comparison over every float in
+    [1e-5, 1e7]."""
+    L = capi.host_lib()
+    buf = ctypes.create_string_buffer(40)
+
+    def fmt(v):
+        n = L.blamm_format_score(ctypes.c_float(float(v)), buf)
+        return buf.raw[:n].decode()
+
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2 ** 32, size=60_000, dtype=np.uint64).astype(np.uint32)
+    vals = bits.view(np.float32)
+    vals = vals[~np.isnan(vals)]                                  # (printf prints the sign of a NaN, Python does not)
+    scores = rng.uniform(-40, 40, size=60_000).astype(np.float32)
+    small = (rng.uniform(-1, 1, size=20_000) * 10.0 ** rng.integers(-6, 8, size=20_000)).astype(np.float32)
+    edges = np.array([0.0, -0.0, 1.0, 9.999995, 9.9999949, 99999.95, 999999.4, 999999.5, 999999.94, 1e6, 100000.5, 100001.5, 1e-4,
+                      9.9999e-5, 0.00099999994, 0.001, 0.01, 0.1, 0.5, 123456.7, 2.5e-4, 1.0000005, 7.25, -12.0625, 3.4e38, 1e-45,
+                      np.inf, -np.inf], dtype=np.float32)
+    for v in np.concatenate([vals, scores, small, edges]):
+        assert fmt(v) == "%g" % float(v), (float(v), fmt(v))
+
+
+@pytest.mark.parametrize("n_hits,threads", [(0, 2), (100, 3), (5000, 1), (300_000, 4), (1_000_000, 7)])
+def test_occurrence_writer_selftest(n_hits, threads):
+    """`blamm-b200 selftest-writer` (no GPU): the CLI's occurrence writer -- range partition, radix sort by (position, column),
+    line formatting, writer thread -- for 16-byte and 12-byte hit records against a plain std::sort + snprintf restatement of
+    the reference's line format (pwmscan.cpp:88-95), compiled into the same binary."""
+    r = subprocess.run([CLI, "selftest-writer", str(n_hits), str(threads)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("identical") == 2 and "DIFFERENT" not in r.stdout
+
+
 def test_fasta_rejects_headerless_input(tmp_path):
     p = tmp_path / "bad.fa"
     p.write_text("ACGT\n>late\nACGT\n")
