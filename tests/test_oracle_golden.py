@@ -108,3 +108,41 @@ def test_empirical_histograms_match_reference(golden, case, exact):
                 assert np.array_equal(ref, cnt[c]), (sp.name, m.name)
             else:
                 assert int(np.abs(ref.astype(np.int64) - cnt[c].astype(np.int64)).sum()) <= 1e-4 * int(ref.sum()) + 4
+
+
+REF_BIN = os.path.join(util.ROOT, "oracle", "_ref", "blamm")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/blamm (the compiled reference) has not been built")
+@pytest.mark.parametrize("seed,flags,mode", [(77, ["-rc", "-pt", "0.001"], ("pt", 0.001, True)), (78, ["-rc"], ("rt", 0.95, True)),
+                                             (79, ["-at", "7.5"], ("at", 7.5, False))])
+def test_oracle_matches_live_reference_binary(tmp_path, seed, flags, mode):
+    """Beyond the committed fixtures: the oracle's whole-`scan` restatement against the UNMODIFIED reference binary run here on
+    fresh seeded inputs -- two manifest groups with distinct backgrounds, N runs, lower-case stretches, records shorter than a
+    motif.  Motifs are at most 14 long, where the reference's sgemm sums in position order, so the sorted
+    occurrence text must be identical byte for byte."""
+    import subprocess
+    from blamm_b200 import synth
+    rng = np.random.default_rng(seed)
+    synth.make_jaspar_like(str(tmp_path / "motifs.jaspar"), 30, seed, uniform_len=(5, 14))
+    manifest = []
+    for g, gc in enumerate((0.38, 0.5)):
+        probs = ((1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2)
+        seq = synth.random_acgt(260_000, seed * 10 + g, probs)
+        for _ in range(5):
+            a = int(rng.integers(0, len(seq) - 3000)); seq[a:a + int(rng.integers(1, 2000))] = ord("N")
+            b = int(rng.integers(0, len(seq) - 3000)); seq[b:b + int(rng.integers(1, 2500))] |= 0x20
+        recs = [("g%dchr1" % g, seq[:120_000]), ("g%dtiny" % g, seq[120_000:120_009]), ("g%dchr2 note" % g, seq[120_009:])]
+        synth.write_fasta(str(tmp_path / ("g%d.fa" % g)), recs)
+        manifest.append("grp%d\tg%d.fa\n" % (g, g))
+    open(tmp_path / "seq.mf", "w").write("".join(manifest))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    ob = os.path.join(util.ROOT, "oracle", "_ref", "openblas_dir.txt")
+    if os.path.exists(ob):
+        env["LD_LIBRARY_PATH"] = open(ob).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
+    for args in (["dict", "seq.mf"], ["hist", "motifs.jaspar", "seq.mf"], ["scan", "-t", "2"] + flags + ["motifs.jaspar", "seq.mf"]):
+        r = subprocess.run([REF_BIN] + args, cwd=tmp_path, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    want = sorted(open(tmp_path / "occurrences.txt").read().splitlines(True))
+    lines, det = O.scan("motifs.jaspar", "seq.mf", mode[0], mode[1], mode[2], histdir=".", base_dir=str(tmp_path))
+    assert len(want) > 200 and sorted(lines) == want
