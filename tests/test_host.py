@@ -318,6 +318,47 @@ def test_cli_dict_and_hist_are_byte_identical_to_reference(golden, tmp_path):
             assert (work / f).read_bytes() == open(os.path.join(src, f), "rb").read(), f
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "blamm")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/blamm (the compiled reference) has not been built")
+def test_cli_dict_and_hist_match_live_reference_binary(tmp_path):
+    """blamm-b200 dict / hist next to the unmodified reference binary on fresh seeded inputs (120 motifs of 5..35 positions, three
+    groups, several files per group, N runs, lower case, CRLF-free 60-column FASTA): `.dict`, every `hist_*.dat` / `.gnu` and
+    the nucleotide report byte-identical; with 8 parser threads as well."""
+    synth.make_jaspar_like(str(tmp_path / "motifs.jaspar"), 120, 404)
+    rng = np.random.default_rng(404)
+    manifest = []
+    for g, gc in enumerate((0.36, 0.44, 0.55)):
+        probs = ((1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2)
+        for f in range(1 + g % 2):
+            seq = synth.random_acgt(300_000 + 7_001 * g, 900 + 10 * g + f, probs)
+            for _ in range(6):
+                a = int(rng.integers(0, len(seq) - 4000)); seq[a:a + int(rng.integers(1, 3000))] = ord("N")
+                b = int(rng.integers(0, len(seq) - 4000)); seq[b:b + int(rng.integers(1, 3000))] |= 0x20
+            synth.write_fasta(str(tmp_path / ("g%d_%d.fa" % (g, f))), [("g%d_%d_a" % (g, f), seq[:100_000]), ("g%d_%d_b x" % (g, f), seq[100_000:])])
+            manifest.append("grp%d\tg%d_%d.fa\n" % (g, g, f))
+    open(tmp_path / "seq.mf", "w").write("".join(manifest))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    ob = os.path.join(ROOT, "oracle", "_ref", "openblas_dir.txt")
+    if os.path.exists(ob):
+        env["LD_LIBRARY_PATH"] = open(ob).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
+    outs = {}
+    for who, exe, extra in (("ref", REF_BIN, {}), ("b200", CLI, {"BLAMM_B200_INGEST_THREADS": "8"})):
+        d = tmp_path / who
+        os.makedirs(d)
+        for f in os.listdir(tmp_path):
+            if os.path.isfile(tmp_path / f):
+                shutil.copy(tmp_path / f, d / f)
+        for args in (["dict", "seq.mf"], ["hist", "motifs.jaspar", "seq.mf"]):
+            r = subprocess.run([exe] + args, cwd=d, env=dict(env, **extra), capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr
+        outs[who] = {f: (d / f).read_bytes() for f in os.listdir(d) if f.endswith(".dict") or f.startswith("hist_")}
+    assert len(outs["ref"]) == 1 + 2 * 3 * 120 and sorted(outs["ref"]) == sorted(outs["b200"])
+    for f, data in outs["ref"].items():
+        assert outs["b200"][f] == data, f
+
+
 def test_cli_error_behaviour(golden, tmp_path):
     work = tmp_path / "ex"
     shutil.copytree(os.path.join(golden, "example"), work)
