@@ -14,6 +14,7 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <future>
 #include <iostream>
 #include <mutex>
@@ -128,6 +129,7 @@ int runHist(int argc, char** argv)
 {
     if (argc < 4) { histUsage(); return EXIT_FAILURE; }
     uint64_t maxLength = 10000000; size_t numBins = 250; bool empirical = false; string histdir;
+    size_t numThreads = thread::hardware_concurrency();
     for (int i = 2; i < argc - 2; i++) {
         string arg(argv[i]);
         const bool hasVal = i + 1 < argc - 2;
@@ -135,10 +137,25 @@ int runHist(int argc, char** argv)
         else if ((arg == "-l" || arg == "--length") && hasVal) maxLength = atoll(argv[++i]);
         else if ((arg == "-b" || arg == "--numbins") && hasVal) { numBins = atoll(argv[++i]); if (numBins < 2) numBins = 2; }
         else if (arg == "-e" || arg == "--empirical") empirical = true;
-        else if ((arg == "-t" || arg == "--numthreads") && hasVal) ++i;
+        else if ((arg == "-t" || arg == "--numthreads") && hasVal) numThreads = (size_t)max(1, atoi(argv[++i]));
         else if ((arg == "-H" || arg == "--histdir") && hasVal) { histdir = argv[++i]; if (histdir.back() != '/') histdir.push_back('/'); }
         else { histUsage(); return EXIT_FAILURE; }
     }
+    // one task per motif on -t threads: the spectrum DP and the two files of a motif are independent of every other motif
+    // (the reference computes and writes them one after the other, hist.cpp:162-175)
+    auto forEachMotif = [&](size_t n, const function<void(size_t)>& fn) {
+        const size_t T = max<size_t>(1, min<size_t>(min<size_t>(numThreads, 64), n));
+        atomic<size_t> next(0);
+        vector<string> err(T);
+        auto work = [&](size_t t) {
+            try { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); } catch (const exception& e) { err[t] = e.what(); next = n; }
+        };
+        vector<thread> pool;
+        for (size_t t = 1; t < T; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+        for (const auto& e : err) if (!e.empty()) throw runtime_error(e);
+    };
     cout << "Welcome to blamm -- histogram module" << endl;
     Settings settings;
     SpeciesSet sc;
@@ -167,7 +184,7 @@ int runHist(int argc, char** argv)
         vector<ScoreHistogram> hists;
         for (const auto& m : mc.motifs) hists.emplace_back(m.minScore(), m.maxScore(), numBins);
         if (!empirical) {
-            for (size_t i = 0; i < mc.motifs.size(); i++) MotifSet::theoreticalHistogram(mc.motifs[i], bg, numBins, maxLength, hists[i]);
+            forEachMotif(mc.motifs.size(), [&](size_t i) { MotifSet::theoreticalHistogram(mc.motifs[i], bg, numBins, maxLength, hists[i]); });
         } else {
             // reference: FastaBatch(filenames, maxLength) + histThread (hist.cpp:95-160)
             const auto len = mc.colLen();
@@ -188,8 +205,9 @@ int runHist(int argc, char** argv)
             for (size_t i = 0; i < hists.size(); i++)
                 for (size_t b = 0; b < numBins; b++) hists[i].counts[b] = counts[i * numBins + b];
         }
-        for (size_t i = 0; i < hists.size(); i++)
+        forEachMotif(hists.size(), [&](size_t i) {
             hists[i].writeGNUPlot(histdir, "hist_" + sp.name + "_" + mc.motifs[i].name, mc.motifs[i].name + " (" + sp.name + ")");
+        });
     }
     if (ctx) b200scan_destroy(ctx);
     return EXIT_SUCCESS;
