@@ -9,9 +9,10 @@ seeded Dirichlet-multinomial count matrices with CORE-like lengths, see blamm_b2
 A step = one pass of the hot path over the rank's 100 Mbp block.
   value : device-resident input (2-bit codes already in HBM), CUDA events around the scoring kernels
           (tensor-core filter + exact rescore), L2 flushed between steps, max over ranks.
-  e2e   : the same block from PINNED HOST memory through the C ABI (b200scan_submit_ascii + b200scan_collect, the two
-          slots alternating as in the CLI): H2D of the ASCII block, pack, score, rescore, D2H of the hit list every
-          step -- host clock over all steps, max over ranks.
+  e2e   : the same block from PINNED HOST memory through the C ABI (b200scan_submit_ascii + b200scan_collect12 -- 12-byte
+          hit records as in the CLI; --hits 16 for b200scan_collect -- the two slots alternating as in the CLI): H2D of
+          the ASCII block, pack, score, rescore, D2H of the hit list every step -- host clock over all steps, max over
+          ranks.
 --impl reference times the reference's own CPU implementation (oracle/_ref/blamm, built from the unmodified
 sources by oracle/build_ref.sh; falls back to the C oracle port if that binary is absent) on a bounded sample.
 """
