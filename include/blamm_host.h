@@ -6,8 +6,12 @@
  *                    (motif.cpp:323-338, 439-449, 542-564; pwmscan.cpp:599-616) and the theoretical
  *                    histogram writer of `blamm hist` (hist.cpp:162-175, motif.cpp:71-107, 151-192)
  *   blamm_fasta_*    FastaBatch::getNextOverlappingBlock with its SeqBlock markers (sequence.cpp:274-293)
+ *   blamm_pack_ascii / blamm_fasta_pack
+ *                    the operand fill of SeqMatrix::getNextSeqMatrix (sequence.cpp:299-340), as 2-bit codes + zero mask
+ *   blamm_format_score
+ *                    the score column of PWMScan::writeOccToDisk (pwmscan.cpp:88-95: ostream << float)
  *
- * All functions return 0 on success, -1 on error (text from blamm_host_last_error, thread local).
+ * Unless stated otherwise functions return 0 on success, -1 on error (text from blamm_host_last_error, thread local).
  */
 #ifndef BLAMM_HOST_H
 #define BLAMM_HOST_H
