@@ -6,7 +6,7 @@
  *
  * PARITY PIN: the reference ships no tests or golden vectors, so this oracle is
  * pinned against the reference ITSELF, compiled from /root/reference into oracle/_ref/ (build_ref.sh):
- * tests/test_oracle_vs_reference.py compares it hit-for-hit and bit-for-bit (scores, thresholds, P) with
+ * tests/test_oracle_golden.py compares it hit-for-hit and bit-for-bit (scores, thresholds, P) with
  * oracle/_ref/refdump on the example and on seeded synthetic inputs, and tests/golden/ holds fixtures
  * produced by oracle/_ref/blamm (tests/golden/make_golden.py).
  *
