@@ -40,6 +40,7 @@
 //                right after the load, candidate pushes land in slack instead of delaying the next MMAs.
 //   expand_kernel (rescore.cuh) later turns raw entries into (position, column) candidates for the exact rescorer.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace b200 {
@@ -71,6 +72,12 @@ namespace b200 {
 #ifndef TC_CTAS_PER_SM
 #define TC_CTAS_PER_SM 1
 #endif
+#ifndef TC_ISSUE_FAST
+#define TC_ISSUE_FAST 1       // 1: single-CTA instances issue whole E stages (4 tiles) from an unrolled loop with loop-invariant operands
+#endif
+#ifndef TC_EPI_FAST
+#define TC_EPI_FAST 1         // 1: 256-column tiles with packed accumulators take the specialised epilogue loop (one LDTM.x64 per warp at a precomputed
+#endif                        //    address, maximum pre-test, sign compaction only for the 16-word groups that hold a candidate)
 constexpr uint32_t kTcEpiWarps = TC_EPI_WARPS;                 // per TMEM lane quarter: kTcEpiWarps / 4
 constexpr uint32_t kTcCtasPerSm = TC_CTAS_PER_SM;             // co-resident CTAs share the SM's 512 TMEM columns
 constexpr uint32_t kTcProducers = TC_PRODUCERS;                         // warps filling the E ring, 32 entries of every stage each
@@ -186,6 +193,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
     if (mbar_try(bar, parity)) return;
     mbar_wait_slow(bar, parity, error_flag);
 }
+// The same wait without a function call: the slow path above is a CALL, and across a call ptxas gives up everything it holds in
+// uniform registers (descriptors, TMEM and barrier addresses are then re-derived and moved with R2UR after every wake-up -- on
+// the issuing lane that is the critical path of every tile).  Bounded by a spin count instead of the clock (every failed
+// mbarrier.try_wait already suspends the thread for a hardware time slice, so 2^26 of them are far beyond any legal wait).
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, unsigned int* error_flag) {
+    uint32_t spins = 0;
+#pragma unroll 1
+    while (!mbar_try(bar, parity)) {
+        if (++spins > (1u << 26)) { atomicExch(error_flag, 0xDEAD0000u | (bar & 0xFFFFu)); __trap(); }
+    }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -245,6 +263,13 @@ __device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[3
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
                    "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+// 64 registers in one instruction (LDTM.x64): with .pack::16b that is 128 TMEM columns = half of a 256-column tile per warp
+__device__ __forceinline__ void tmem_ld64_pack16(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
                  : "r"(taddr) : "memory");
 }
 template <bool ACC16> __device__ __forceinline__ void tmem_ld_words(uint32_t taddr_buf, uint32_t word, uint32_t (&v)[32]) {
@@ -329,20 +354,36 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {  
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-template <bool ACC16> __device__ __forceinline__ void sign_words(const uint32_t (&v)[32], uint32_t& x0, uint32_t& x1) {
+template <bool ACC16, int OFF, int N> __device__ __forceinline__ uint32_t sign_word16(const uint32_t (&v)[N]) {   // one sign word from the 16 TMEM words v[OFF .. OFF + 15]
     constexpr uint32_t sel = ACC16 ? 0xFDB9u : 0xFBFBu;          // sign(byte 1, 3, 5, 7)  /  sign(byte 3, 7, 3, 7)
-    uint32_t x[2];
+    uint32_t ea = prmt(v[OFF], v[OFF + 1], sel), eb = 0u;         // two independent chains
 #pragma unroll
-    for (int w = 0; w < 2; w++) {
-        uint32_t ea = prmt(v[16 * w], v[16 * w + 1], sel), eb = 0u;           // two independent chains
-#pragma unroll
-        for (int t = 1; t < 8; t += 2) {
-            eb = imad(prmt(v[16 * w + 2 * t], v[16 * w + 2 * t + 1], sel), 1u << t, eb);
-            if (t + 1 < 8) ea = imad(prmt(v[16 * w + 2 * t + 2], v[16 * w + 2 * t + 3], sel), 1u << (t + 1), ea);
-        }
-        x[w] = ea + eb;
+    for (int t = 1; t < 8; t += 2) {
+        eb = imad(prmt(v[OFF + 2 * t], v[OFF + 2 * t + 1], sel), 1u << t, eb);
+        if (t + 1 < 8) ea = imad(prmt(v[OFF + 2 * t + 2], v[OFF + 2 * t + 3], sel), 1u << (t + 1), ea);
     }
-    x0 = x[0]; x1 = x[1];
+    return ea + eb;
+}
+template <bool ACC16> __device__ __forceinline__ void sign_words(const uint32_t (&v)[32], uint32_t& x0, uint32_t& x1) {
+    x0 = sign_word16<ACC16, 0>(v); x1 = sign_word16<ACC16, 16>(v);
+}
+// Cheap pre-test of 16 TMEM words: the lane-wise maximum (VIMNMX3: three inputs per instruction, 8 instructions per 16 words, a
+// quarter of the sign compaction's 32).  "Some accumulator of the 16 words has its sign bit clear" <=> some 16-bit half (ACC16:
+// two S16 / FP16 accumulators per word) or the word itself (FP32 / S32) of the maximum is non-negative AS AN INTEGER -- a signed
+// integer maximum is negative iff every input is, whatever the bits below the sign mean, so this is the same predicate as
+// "sign word != kAllNegative" for all three accumulator types.
+template <bool ACC16> __device__ __forceinline__ uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) {
+    return ACC16 ? __vimax3_s16x2(a, b, c) : (uint32_t)__vimax3_s32((int)a, (int)b, (int)c);
+}
+template <bool ACC16, int OFF, int N> __device__ __forceinline__ uint32_t max16(const uint32_t (&v)[N]) {
+    const uint32_t a = vmax3<ACC16>(v[OFF], v[OFF + 1], v[OFF + 2]), b = vmax3<ACC16>(v[OFF + 3], v[OFF + 4], v[OFF + 5]),
+                   c = vmax3<ACC16>(v[OFF + 6], v[OFF + 7], v[OFF + 8]), d = vmax3<ACC16>(v[OFF + 9], v[OFF + 10], v[OFF + 11]),
+                   e = vmax3<ACC16>(v[OFF + 12], v[OFF + 13], v[OFF + 14]);
+    const uint32_t t1 = vmax3<ACC16>(a, b, c), t2 = vmax3<ACC16>(d, e, v[OFF + 15]);
+    return vmax3<ACC16>(t1, t2, t2);
+}
+template <bool ACC16> __device__ __forceinline__ bool any_nonneg(uint32_t m) {
+    return ACC16 ? ((m & 0x80008000u) != 0x80008000u) : ((int32_t)m >= 0);
 }
 
 // Per-epilogue-warp cursor into the raw-entry blocks.  next/left/blk are warp-uniform; `spare` (meaningful in lane 0) is
@@ -609,6 +650,81 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     }
                 }
             } else
+            if (TC_ISSUE_FAST && !PAIR && kBufs == 2 && kTcStageTiles == 4 && kTcStages == 4) {
+                // Lean issue loop.  Measured with the B200_TRACE build (tools/tc_trace.py, round 2): the issuing lane never actually
+                // waited for a TMEM buffer -- its own instruction stream (~70 SASS instructions per tile, each slowed by the four
+                // epilogue warps on the same scheduler) set the tile period, while the epilogue groups idled half of the time.  So:
+                // whole stages of four tiles from an unrolled body (tile-in-stage and buffer are static: A B A B), every MMA operand
+                // except the E address loop-invariant, waits as inline spins (no CALL: uniform registers survive), parities flipped
+                // in place, and nothing but the poll between a buffer's release and its next MMA.
+                if (elect_one()) {
+                    mbar_wait_spin(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
+                    const uint32_t b0 = kT & 1u;                         // buffer of the item's first tile
+                    const uint32_t dA = tmem_base + b0 * kBufCols, dB = tmem_base + (b0 ^ 1u) * kBufCols;
+                    const uint32_t teA = tEmpty + 8 * b0, teB = tEmpty + 8 * (b0 ^ 1u), tfA = tFull + 8 * b0, tfB = tFull + 8 * (b0 ^ 1u);
+                    uint32_t parA = ((kT >> 1) & 1u) ^ 1u, parB = (((kT + 1) >> 1) & 1u) ^ 1u;     // a buffer's parity flips with every use
+                    // NP = position steps per tile as a compile-time constant (1..4: the MMA chain is straight-line code), 0 = run-time loop
+                    auto run = [&](auto np_c) {
+                        constexpr uint32_t NP = decltype(np_c)::value;
+                        auto tileMma = [&](uint32_t d, uint32_t te, uint32_t par, uint32_t tf, uint32_t alo) {
+                            mbar_wait_spin(te, par, P.error_flag);
+                            tc_fence_after();
+                            uint32_t blo = bLo0;
+                            if (!(TC_KNOCKOUT & 2)) {
+                                if (ZMASK) {
+                                    umma_x<false, I8>(d, aLoOnes, aHi, blo, bHi, idesc, 0u);
+                                    blo += 16;
+                                    umma_x<false, I8>(d, alo, aHi, blo, bHi, idesc, 1u);
+                                } else {
+                                    umma_x<false, I8>(d, alo, aHi, blo, bHi, idesc, 0u);
+                                }
+                                if (NP) {
+#pragma unroll
+                                    for (uint32_t m = 1; m < NP; m++) umma_x<false, I8>(d, alo + m * kStepEnt, aHi, blo + 16 * m, bHi, idesc, 1u);
+                                } else {
+#pragma unroll 1
+                                    for (uint32_t m = 1; m < n_pos; m++) {
+                                        alo += kStepEnt; blo += 16;
+                                        umma_x<false, I8>(d, alo, aHi, blo, bHi, idesc, 1u);
+                                    }
+                                }
+                            }
+                            umma_commit(tf);
+                        };
+                        uint32_t kCur = kE;
+#pragma unroll 1
+                        for (uint32_t st = nT >> 2; st != 0; st--) {
+                            const uint32_t slot = kCur % kTcStages, nslot = (kCur + 1) % kTcStages;
+                            const uint32_t aS = aLo0 + slot * kTcStageEnt;                    // address fields are in 16-byte units = entries
+                            tileMma(dA, teA, parA, tfA, aS);        parA ^= 1u;
+                            tileMma(dB, teB, parB, tfB, aS + 128);  parB ^= 1u;
+                            tileMma(dA, teA, parA, tfA, aS + 256);  parA ^= 1u;
+                            mbar_wait_spin(eFull + 8 * nslot, ((kCur + 1) / kTcStages) & 1, P.error_flag);      // the last tile's halo lies in the next stage
+                            tileMma(dB, teB, parB, tfB, aS + 384);  parB ^= 1u;
+                            // MMAs complete in issue order: with the stage's last tile done, so is every reader of the stage
+                            umma_commit(eEmpty + 8 * slot);
+                            if (st == 1 && (nT & 3u) == 0) umma_commit(eEmpty + 8 * nslot);    // the item's last tile also frees its halo stage
+                            kCur++;
+                        }
+                        const uint32_t rem = nT & 3u;                        // the last span of a block: a partial stage (tiles + halo all inside it)
+                        if (rem) {
+                            const uint32_t slot = kCur % kTcStages;
+                            const uint32_t aS = aLo0 + slot * kTcStageEnt;
+                            tileMma(dA, teA, parA, tfA, aS);
+                            if (rem > 1) tileMma(dB, teB, parB, tfB, aS + 128);
+                            if (rem > 2) tileMma(dA, teA, parA ^ 1u, tfA, aS + 256);
+                            umma_commit(eEmpty + 8 * slot);
+                        }
+                    };
+                    switch (n_pos) {
+                        case 1: run(std::integral_constant<uint32_t, 1>{}); break;
+                        case 2: run(std::integral_constant<uint32_t, 2>{}); break;
+                        case 3: run(std::integral_constant<uint32_t, 3>{}); break;
+                        case 4: run(std::integral_constant<uint32_t, 4>{}); break;
+                        default: run(std::integral_constant<uint32_t, 0>{}); break;
+                    }
+                }
+            } else
             if (rank == 0 && elect_one()) {           // PAIR: the leader's lane issues for both CTAs
                 mbar_wait(eFull + 8 * (kE % kTcStages), (kE / kTcStages) & 1, P.error_flag);
                 // loop state is stepped incrementally (adds and masks only: every instruction of this lane is on the critical path)
@@ -618,19 +734,22 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 for (uint32_t left = nT; left != 0; left--) {
                     const uint32_t buf = kt % kBufs;
                     const bool lastOfStage = (j + 1 == kTcStageTiles), lastTile = (left == 1);
+                    // everything the MMAs need is computed BEFORE the wait for the TMEM buffer: what follows the wake-up is on the
+                    // critical path of the hand-back chain (release -> issue -> MMA -> tFull -> load -> release)
+                    const uint32_t d = tmem_base + buf * kBufCols;
+                    // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[entry0 + r + 2*kk]; one MMA = 4 entries = 64 B
+                    // B: [8-column group][chunk] blocks of 128 B: one MMA = 2 chunks = 256 B
+                    uint32_t alo = aLo0 + aOff, blo = bLo0;               // address fields are in 16-byte units = entries
+                    const uint32_t teBar = tEmpty + 8 * buf, tePar = ((kt / kBufs) & 1) ^ 1, tfBar = tFull + 8 * buf;
                     PH_MARK();
                     if (lastOfStage)                                      // its halo lies in the next stage
                         mbar_wait(eFull + 8 * ((kCur + 1) % kTcStages), ((kCur + 1) / kTcStages) & 1, P.error_flag);
                     TC_TRACE(1, nT - left, 0);
                     PH_ACC(0);
-                    mbar_wait(tEmpty + 8 * buf, ((kt / kBufs) & 1) ^ 1, P.error_flag);
+                    mbar_wait(teBar, tePar, P.error_flag);
                     PH_ACC(1);
                     TC_TRACE(1, nT - left, 1);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + buf * kBufCols;
-                    // A: window rows straight out of E (Toeplitz): row r, chunk kk -> E[entry0 + r + 2*kk]; one MMA = 4 entries = 64 B
-                    // B: [8-column group][chunk] blocks of 128 B: one MMA = 2 chunks = 256 B
-                    uint32_t alo = aLo0 + aOff, blo = bLo0;               // address fields are in 16-byte units = entries
                     if (!(TC_KNOCKOUT & 2)) {
                         if (ZMASK) {                                      // step 0: D = bias (constant one-hot rows x chunk 0 of B)
                             umma_x<PAIR, I8>(d, aLoOnes, aHi, blo, bHi, idesc, 0u);
@@ -645,11 +764,12 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                             umma_x<PAIR, I8>(d, alo, aHi, blo, bHi, idesc, 1u);
                         }
                     }
-                    // MMAs complete in issue order: once the last tile of a stage is done, so is every reader of the stage
-                    // (its own tiles and the halo read of the stage before).  The item's last tile also frees its halo stage.
+                    // tFull first: the epilogue group waiting for it is the critical path.  MMAs complete in issue order: once the last
+                    // tile of a stage is done, so is every reader of the stage (its own tiles and the halo read of the stage before).
+                    // The item's last tile also frees its halo stage.
+                    commit_x<PAIR>(tfBar);
                     if (lastOfStage || lastTile) commit_x<PAIR>(eEmpty + 8 * (kCur % kTcStages));
                     if (lastOfStage && lastTile) commit_x<PAIR>(eEmpty + 8 * ((kCur + 1) % kTcStages));
-                    commit_x<PAIR>(tFull + 8 * buf);
                     PH_ACC(2); PH_COUNT();
                     TC_TRACE(1, nT - left, 2);
                     aOff = (aOff + 128) % (kTcStages * kTcStageEnt);
@@ -664,6 +784,46 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             // with two groups, group g takes the tiles whose running index is g mod 2 (= the tiles of TMEM buffer g)
             const uint32_t i0 = (kTcEpiGroups > 1) ? ((eGroup - kT) & (kTcEpiGroups - 1)) : 0u;
             uint32_t kt = kT + i0, win0 = w0 + 128 * i0 + 32 * eQ;    // running tile index; window of lane 0
+            constexpr bool kFastOk = TC_EPI_FAST && ACC16 && !PAIR && kTcEpiGroups == 2 && kBufs == 2 && kEpiPerQ == 2 && !(TC_KNOCKOUT & 1);
+            if (kFastOk && nWords == 128) {
+                // ---- full 256-column tile, packed accumulators: this warp owns 64 consecutive words (128 columns) of every tile of ITS
+                // buffer (group g <-> buffer g: the tiles with running index = g mod 2), so TMEM address and barriers are loop constants
+                // and nothing but the barrier poll stands between tFull and the load.
+                const uint32_t buf = kt & 1u;
+                const uint32_t fullBar = tFull + 8 * buf, emptyBar = tEmpty + 8 * buf;
+                const uint32_t taddr = eLaneAddr + buf * kBufCols + 4 * eWc0;           // eWc0 = 32 * sub: words 64 sub .. 64 sub + 63 = TMEM columns 128 sub ..
+                const uint32_t colA = tile.col0 + 4 * eWc0, colB = colA + 64;
+                uint32_t tph = (kt >> 1) & 1u, win = win0 + lane;
+                for (uint32_t i = i0; i < nT; i += 2, tph ^= 1u, win += 256) {
+                    PH_MARK();
+                    mbar_wait_spin(fullBar, tph, P.error_flag);
+                    PH_ACC(0);
+                    if (warp == kTcEpiWarp0) TC_TRACE(2, i, 0); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 0);
+                    tc_fence_after();
+                    uint32_t v[64];
+                    tmem_ld64_pack16(taddr, v);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(emptyBar);
+                    PH_ACC(1);
+                    if (warp == kTcEpiWarp0) TC_TRACE(2, i, 2); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 2);
+                    const uint32_t g0 = max16<true, 0>(v), g1 = max16<true, 16>(v), g2 = max16<true, 32>(v), g3 = max16<true, 48>(v);
+                    const uint32_t gm = vmax3<true>(g0, g1, vmax3<true>(g2, g3, g3));
+                    const bool c = win < blk.n_payload && any_nonneg<true>(gm);
+                    const unsigned t = (TC_KNOCKOUT & 8) ? 0u : __ballot_sync(0xffffffffu, c);
+                    if (t) {                                               // about every other pass: compact only the groups that hold a candidate
+                        uint32_t a0 = kAllNegative, a1 = kAllNegative, b0 = kAllNegative, b1 = kAllNegative;
+                        if (__any_sync(0xffffffffu, any_nonneg<true>(g0))) a0 = sign_word16<true, 0>(v);
+                        if (__any_sync(0xffffffffu, any_nonneg<true>(g1))) a1 = sign_word16<true, 16>(v);
+                        if (__any_sync(0xffffffffu, any_nonneg<true>(g2))) b0 = sign_word16<true, 32>(v);
+                        if (__any_sync(0xffffffffu, any_nonneg<true>(g3))) b1 = sign_word16<true, 48>(v);
+                        raw_push(rawc, P, t, c, win, colA, a0, a1, colB, b0, b1, lane);
+                    }
+                    PH_ACC(2); PH_COUNT();
+                    if (warp == kTcEpiWarp0) TC_TRACE(2, i, 3); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 3);
+                }
+            } else
             for (uint32_t i = i0; i < nT; i += kTcEpiGroups, kt += kTcEpiGroups, win0 += 128 * kTcEpiGroups) {
                 const uint32_t buf = kt % kBufs, tph = (kt / kBufs) & 1;
                 PH_MARK();
@@ -677,14 +837,17 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                 // time (both loads in flight).  As soon as its LAST loads have landed in registers the warp hands the
                 // TMEM buffer back, before looking at the data.
                 constexpr uint32_t step = 32 * kEpiPerQ;
+                // (instances that also carry the fast loop above take ONE chunk per iteration here: two 32-register loads next to the
+                // fast loop's 64-register one make ptxas spill; this loop then only sees narrow tiles)
+                constexpr uint32_t kPerIter = kFastOk ? 1u : 2u;
                 bool released = false;
-                for (uint32_t wc = eWc0; wc < ((TC_KNOCKOUT & 1) ? 0u : nWords); wc += 2 * step) {
-                    const bool has1 = wc + step < nWords;
+                for (uint32_t wc = eWc0; wc < ((TC_KNOCKOUT & 1) ? 0u : nWords); wc += kPerIter * step) {
+                    const bool has1 = kPerIter == 2 && wc + step < nWords;
                     uint32_t v0[32], v1[32];
                     tmem_ld_words<ACC16>(taddr, wc, v0);
-                    if (has1) tmem_ld_words<ACC16>(taddr, wc + step, v1);
+                    if (kPerIter == 2 && has1) tmem_ld_words<ACC16>(taddr, wc + step, v1);
                     tmem_ld_wait();
-                    if (wc + 2 * step >= nWords) {
+                    if (wc + kPerIter * step >= nWords) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { if (PAIR) mbar_arrive_cluster_cta(tEmptyL + 8 * buf); else mbar_arrive(tEmpty + 8 * buf); }
@@ -695,7 +858,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     // both compactions first (independent chains interleave in the issue slots), then ONE test and ONE vote
                     uint32_t a0, a1, b0 = kAllNegative, b1 = kAllNegative;
                     sign_words<ACC16>(v0, a0, a1);
-                    if (has1) sign_words<ACC16>(v1, b0, b1);
+                    if (kPerIter == 2 && has1) sign_words<ACC16>(v1, b0, b1);
                     const bool c = winOk && (((a0 ^ kAllNegative) | (a1 ^ kAllNegative) | (b0 ^ kAllNegative) | (b1 ^ kAllNegative)) != 0u);
                     const unsigned t = (TC_KNOCKOUT & 8) ? 0u : __ballot_sync(0xffffffffu, c);
                     if (t) raw_push(rawc, P, t, c, win0 + lane, (tile.col0 + wc * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), a0, a1,
