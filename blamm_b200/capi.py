@@ -15,17 +15,20 @@ from .build import lib_dir
 
 ENGINE_AUTO, ENGINE_GATHER, ENGINE_TENSOR = 0, 1, 2
 LOWER_ZERO, LOWER_FOLD = 0, 1
-NUM_SLOTS = 2
+NUM_SLOTS = 3
 
 HIT_DTYPE = np.dtype([("pos", "<u8"), ("col", "<u4"), ("score", "<f4")])
 HIT12_DTYPE = np.dtype([("pos", "<u4"), ("col", "<u4"), ("score", "<f4")])      # b200scan_hit12
-HITS_16, HITS_12 = 16, 12
+HIT8_DTYPE = np.dtype([("key", "<u4"), ("score", "<f4")])                      # b200scan_hit8: key = (pos & 255) << 24 | col
+HITS_16, HITS_12, HITS_8 = 16, 12, 8
+BUCKET_SHIFT = 8
 
 
 class Timing(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_float), ("pack_ms", ctypes.c_float), ("score_ms", ctypes.c_float),
                 ("rescore_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float), ("n_candidates", ctypes.c_uint64),
-                ("n_hits", ctypes.c_uint64), ("engine_used", ctypes.c_int32), ("kernel_launches", ctypes.c_int32)]
+                ("n_hits", ctypes.c_uint64), ("engine_used", ctypes.c_int32), ("kernel_launches", ctypes.c_int32),
+                ("order_ms", ctypes.c_float), ("reserved", ctypes.c_float)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -59,6 +62,7 @@ def scan_lib() -> ctypes.CDLL:
         L.b200scan_submit_packed.argtypes = [vp, ctypes.c_int, vp, vp, u64, u64, vp, u64]
         L.b200scan_collect.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), _u64p, ctypes.POINTER(Timing)]
         L.b200scan_collect12.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), _u64p, ctypes.POINTER(Timing)]
+        L.b200scan_collect8.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), _u64p, ctypes.POINTER(vp), _u64p, ctypes.POINTER(Timing)]
         L.b200scan_set_hit_format.argtypes = [vp, ctypes.c_int]
         L.b200scan_rerun_resident.argtypes = [vp, ctypes.c_int, ctypes.c_int, f32p, f32p, _u64p]
         L.b200scan_hist_begin.argtypes = [vp, vp, vp, ctypes.c_uint32]
@@ -144,7 +148,8 @@ class Scanner:
         self._chk(self._L.b200scan_set_tensor_accumulator(self._ctx, bits))
 
     def set_hit_format(self, fmt: int) -> None:
-        """HITS_16 (b200scan_hit, default) or HITS_12 (b200scan_hit12) for blocks submitted from now on."""
+        """HITS_16 (b200scan_hit, default), HITS_12 (b200scan_hit12) or HITS_8 (b200scan_hit8, ordered on the device) for
+        blocks submitted from now on."""
         self._chk(self._L.b200scan_set_hit_format(self._ctx, fmt))
         self._hit_format = fmt
 
@@ -195,6 +200,9 @@ class Scanner:
         (`fmt` overrides the choice of the collecting function: only the state tests do that)."""
         hp, n, t = ctypes.c_void_p(), ctypes.c_uint64(), Timing()
         fmt = self._slot_format.get(slot, self._hit_format) if fmt is None else fmt
+        if fmt == HITS_8:
+            h8, bstart, tm = self.collect8(slot, copy=copy)
+            return expand_hits8(h8, bstart), tm
         fn, dt = (self._L.b200scan_collect12, HIT12_DTYPE) if fmt == HITS_12 else (self._L.b200scan_collect, HIT_DTYPE)
         self._chk(fn(self._ctx, slot, ctypes.byref(hp), ctypes.byref(n), ctypes.byref(t)))
         self._keep.pop(slot, None)
@@ -203,6 +211,19 @@ class Scanner:
         raw = (ctypes.c_uint8 * (n.value * dt.itemsize)).from_address(hp.value)
         hits = np.frombuffer(raw, dtype=dt)
         return (hits.copy() if copy else hits), t.as_dict()
+
+    def collect8(self, slot: int, copy: bool = True) -> Tuple[np.ndarray, np.ndarray, dict]:
+        """b200scan_collect8: the block's hits as HIT8_DTYPE records in (position, column) order + bucket_start (one entry
+        per 256 window positions, plus the total)."""
+        hp, bp, n, nb, t = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_uint64(), Timing()
+        self._chk(self._L.b200scan_collect8(self._ctx, slot, ctypes.byref(hp), ctypes.byref(n), ctypes.byref(bp), ctypes.byref(nb),
+                                            ctypes.byref(t)))
+        self._keep.pop(slot, None)
+        hits = (np.frombuffer((ctypes.c_uint8 * (n.value * 8)).from_address(hp.value), dtype=HIT8_DTYPE) if n.value
+                else np.zeros(0, dtype=HIT8_DTYPE))
+        bstart = (np.frombuffer((ctypes.c_uint32 * (nb.value + 1)).from_address(bp.value), dtype=np.uint32) if bp.value
+                  else np.zeros(1, dtype=np.uint32))
+        return (hits.copy() if copy else hits), (bstart.copy() if copy else bstart), t.as_dict()
 
     def scan(self, block, frag_starts=None, n_payload=None, lower: int = LOWER_ZERO, slot: int = 0) -> Tuple[np.ndarray, dict]:
         self.submit_ascii(slot, block, n_payload=n_payload, frag_starts=frag_starts, lower=lower)
@@ -237,6 +258,18 @@ class Scanner:
         a, b, c, d, e = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_uint64()
         self._chk(self._L.b200scan_describe(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d), ctypes.byref(e)))
         return dict(n_cols=a.value, max_len=b.value, n_tiles=c.value, sm_count=d.value, sum_len=e.value)
+
+
+def expand_hits8(hits8: np.ndarray, bucket_start: np.ndarray) -> np.ndarray:
+    """Ordered b200scan_hit8 records + bucket index -> HIT12_DTYPE records with full block positions (same order)."""
+    out = np.zeros(len(hits8), dtype=HIT12_DTYPE)
+    if len(hits8):
+        per_bucket = np.diff(bucket_start.astype(np.int64))
+        bucket = np.repeat(np.arange(len(per_bucket), dtype=np.uint32), per_bucket)
+        out["pos"] = (bucket << np.uint32(BUCKET_SHIFT)) + (hits8["key"] >> np.uint32(24))
+        out["col"] = hits8["key"] & np.uint32(0xFFFFFF)
+        out["score"] = hits8["score"]
+    return out
 
 
 class HostError(RuntimeError):

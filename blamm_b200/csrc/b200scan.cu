@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "filter_tc.cuh"
 #include "gather.cuh"
+#include "order.cuh"
 #include "pack.cuh"
 #include "rescore.cuh"
 
@@ -24,17 +25,17 @@ using namespace b200;
 namespace {
 
 thread_local std::string g_create_error;
-double g_margin16_scale = 1.0;        // debug knob (env B200SCAN_MARGIN16_SCALE): scales the FP16-accumulation error bound
-double g_i8_max_overshoot = 16.0;     // INT8 operands for a tile iff every column's WORST-CASE overshoot (L / scale, score units) stays below (env B200SCAN_I8_MAX_OVERSHOOT; 0 = never).  Measured on the bench set the mean overshoot is far below the bound: 1.20 candidates per hit with every tile on INT8, against 1.44 for FP16 accumulators
 
 constexpr uint32_t kPadBytes = 16384;             // slack behind every device sequence buffer (window / span over-reads)
 constexpr size_t   kGatherSmemW = 64 * 1024;      // FP32 weights per gather column tile
 
 struct Slot {
-    // host staging (pinned)
-    uint8_t*  h_ascii = nullptr;
+    // host staging (pinned).  Everything but the counters is allocated at the slot's first use (a caller that alternates two of
+    // the three slots pays for two; the ASCII staging buffers exist only for callers that submit characters).
+    uint8_t*  h_ascii = nullptr;                  // pageable b200scan_submit_ascii sources are staged here
     uint32_t* h_frag = nullptr;  size_t frag_cap = 0;
-    b200scan_hit* h_hits = nullptr;
+    void*     h_hits = nullptr;  size_t h_hit_bytes = 0;      // sized from the blocks actually collected (grows by 1/4 steps)
+    uint32_t* h_bucket = nullptr;  size_t h_bucket_cap = 0;   // B200SCAN_HITS_8: host copy of bucket_start
     unsigned long long* h_counters = nullptr;     // [0] n_cand, [1] n_hits, [2] has_zero|error (as 2 x u32)
     // device
     uint8_t*  d_ascii = nullptr;
@@ -42,14 +43,15 @@ struct Slot {
     uint32_t* d_zmask = nullptr;
     uint32_t* d_frag = nullptr;
     b200scan_hit* d_hits = nullptr;  unsigned long long hit_cap = 0;
+    uint32_t* d_bucket_start = nullptr;  size_t bucket_cap = 0;      // B200SCAN_HITS_8: bucket_start of the block in flight
     unsigned long long* d_counters = nullptr;     // [0] n_cand, [1] n_hits, [2] {has_zero, error_flag}, [3] {work_counter, -}
     // state
     bool in_flight = false, resident = false;
     uint64_t n_total = 0, n_payload = 0, n_frag = 0;
     bool packed_zero_known = false;               // submit_packed: has_zero decided on the host
     int  hit_bytes = B200SCAN_HITS_16;            // record format of the block in flight / resident (b200scan_set_hit_format)
-    cudaEvent_t ev[9] = {};                       // upload stream: 0 start, 1 after h2d, 2 after pack; compute stream: 8 scoring starts,
-                                                  // 3 after score, 4 after rescore, 5 after counters d2h; copy stream: 6/7 hit d2h
+    cudaEvent_t ev[10] = {};                      // upload stream: 0 start, 1 after h2d, 2 after pack; compute stream: 8 scoring starts,
+                                                  // 3 after score, 4 after rescore, 9 after ordering, 5 after counters d2h; copy stream: 6/7 hit d2h
     b200scan_timing timing = {};
 };
 
@@ -62,6 +64,9 @@ struct b200scan_ctx {
     cudaStream_t copy_stream = nullptr;      // hit downloads: overlap the next block's kernels
     cudaStream_t up_stream = nullptr;        // block uploads + packing: overlap the previous block's kernels
     uint64_t max_block = 0;
+    unsigned long long max_hits = 0;         // initial per-slot hit capacity (b200scan_create)
+    double margin16_scale = 1.0;             // debug knob (env B200SCAN_MARGIN16_SCALE): scales the FP16-accumulation error bound
+    double i8_max_overshoot = 16.0;          // INT8 operands for a tile iff every column's WORST-CASE overshoot (L / scale, score units) stays below (env B200SCAN_I8_MAX_OVERSHOOT; 0 = never).  Measured on the bench set the mean overshoot is far below the bound: 1.20 candidates per hit with every tile on INT8, against 1.44 for FP16 accumulators
     int engine = B200SCAN_ENGINE_AUTO;
     int hit_format = B200SCAN_HITS_16;
     std::string err;
@@ -86,6 +91,10 @@ struct b200scan_ctx {
     double cand_inflation = 0;    // mean margin over columns (diagnostic)
     uint8_t* d_flush = nullptr;
     unsigned long long* d_trace = nullptr;   // B200_TRACE builds only
+    // B200SCAN_HITS_8 (order.cuh): per-bucket counters / cursors and the bucket-contiguous scratch list, shared by the slots
+    // (the ordering kernels of a block run back to back on the compute stream)
+    uint32_t *d_bucket_cnt = nullptr, *d_bucket_cursor = nullptr;  size_t bucket_cap = 0;
+    Hit12* d_sort_tmp = nullptr;  unsigned long long sort_cap = 0;
     // empirical histograms
     uint32_t hist_bins = 0;  unsigned long long* d_hist = nullptr;  float *d_hmin = nullptr, *d_hwid = nullptr;
     GatherTile* d_htiles = nullptr;  std::vector<GatherTile> htiles;  size_t hist_smem = 0;
@@ -246,7 +255,7 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                 sum += Bprev + Ak; tot_abs += Ak;
             }
             if (tot_abs > 30000.0) { f.always = true; return f; }
-            const double need = 1e-3 + e1 + g_margin16_scale * std::ldexp(4.0 * sum, -10);
+            const double need = 1e-3 + e1 + ctx->margin16_scale * std::ldexp(4.0 * sum, -10);
             if (need <= margin) { f.margin = margin; return f; }
             margin = need * 1.02;
         }
@@ -307,7 +316,7 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                 const double hi = b + pre[k - 1], lo = std::max(-suf[k - 1], b + pmin[k - 1]);
                 sum += std::max(std::fabs(hi), std::fabs(lo)) + Ak;
             }
-            const double need = 1e-3 + e1 + g_margin16_scale * std::ldexp(4.0 * sum, -10);
+            const double need = 1e-3 + e1 + ctx->margin16_scale * std::ldexp(4.0 * sum, -10);
             if (need <= margin) return f;
             margin = need * 1.02;
         }
@@ -369,11 +378,11 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     // Accumulator type PER TILE: FP16 accumulators (half the epilogue work) where every column of the tile keeps its margin
     // <= 2 score units, FP32 otherwise -- a few long or extreme motifs then cost their own tile, not the whole set.
     // Operand type PER TILE as well: INT8 operands (half the MMAs) where the worst-case overshoot of every column of the tile
-    // stays <= g_i8_max_overshoot score units (the bound is pessimistic, see its definition; it guards the exact rescorer
+    // stays <= ctx->i8_max_overshoot score units (the bound is pessimistic, see its definition; it guards the exact rescorer
     // against columns whose threshold lies far below their best score); the FP16-operand kinds otherwise.  acc_pref 8 forces
     // INT8 everywhere, 16 / 32 exclude it.
     const bool try16 = ctx->acc_pref != 32 && max_len <= (uint32_t)kMaxLen;
-    const bool try8 = (ctx->acc_pref == 0 || ctx->acc_pref == 8) && max_len <= (uint32_t)kMaxLen && g_i8_max_overshoot > 0;
+    const bool try8 = (ctx->acc_pref == 0 || ctx->acc_pref == 8) && max_len <= (uint32_t)kMaxLen && ctx->i8_max_overshoot > 0;
     std::vector<std::pair<uint32_t, uint32_t>> cuts;
     plan_tc_tiles(len, try16, try8 ? 8u : 4u, cuts);
     bool tc_ok = true;
@@ -389,7 +398,7 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                 bool ok8 = true;
                 for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second && ok8; sc++) {
                     f8.push_back(fold_i8(sc, zmode));
-                    if (ctx->acc_pref != 8 && !f8.back().never && f8.back().margin > g_i8_max_overshoot) ok8 = false;     // (a non-finite column has margin 0: 'always' under every kind)
+                    if (ctx->acc_pref != 8 && !f8.back().never && f8.back().margin > ctx->i8_max_overshoot) ok8 = false;     // (a non-finite column has margin 0: 'always' under every kind)
                 }
                 if (ok8) {
                     for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++) folded[sc] = std::move(f8[sc - cuts[ti].first]);
@@ -528,11 +537,20 @@ BlockDev block_dev(const Slot& s)
 
 // Launch the scoring kernels for the block resident in `s` (counters must already be reset).
 // Returns the number of kernels launched; records ev[3] after the dominant kernel(s) and ev[4] after the rescorer.
-int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaEvent_t ev_after_rescore, int* launches)
+int ensure_order(b200scan_ctx* ctx, Slot& s);
+
+int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaEvent_t ev_after_rescore, int* launches, cudaEvent_t ev_after_order = nullptr)
 {
     const MotifDev md = motif_dev(ctx);
     const BlockDev blk = block_dev(s);
-    HitSink sink{s.d_hits, s.d_counters + 1, s.hit_cap, s.hit_bytes == B200SCAN_HITS_12 ? 1u : 0u};
+    const bool ordered = s.hit_bytes == B200SCAN_HITS_8;
+    const uint32_t n_buckets = (uint32_t)((s.n_payload + kBucketSize - 1) >> kBucketShift);
+    if (ordered) {                                   // per-bucket counters of this block (rescore / gather count into them)
+        int rc = ensure_order(ctx, s);
+        if (rc) return rc;
+        if (n_buckets) CU(cudaMemsetAsync(ctx->d_bucket_cnt, 0, (size_t)n_buckets * 4, ctx->stream));
+    }
+    HitSink sink{s.d_hits, s.d_counters + 1, s.hit_cap, s.hit_bytes == B200SCAN_HITS_16 ? 0u : 1u, ordered ? ctx->d_bucket_cnt : nullptr};
     unsigned int* err = reinterpret_cast<unsigned int*>(s.d_counters + 2) + 1;
     unsigned int* work = reinterpret_cast<unsigned int*>(s.d_counters + 3);
     unsigned int* work2 = reinterpret_cast<unsigned int*>(s.d_counters + 4);      // work counter of the FP32-accumulator instance
@@ -540,6 +558,8 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     if (s.n_payload == 0) {                          // nothing to score (empty block): keep the event protocol intact
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
         if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
+        if (ordered) CU(cudaMemsetAsync(s.d_bucket_start, 0, 4, ctx->stream));
+        if (ev_after_order) CU(cudaEventRecord(ev_after_order, ctx->stream));
         return B200SCAN_OK;
     }
     const bool want_tc = (ctx->engine != B200SCAN_ENGINE_GATHER) && ctx->tc_usable;
@@ -611,8 +631,74 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
         if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
     }
+    if (ordered) {
+        // (position, column) order on the device: scan of the per-bucket counts, scatter into bucket-contiguous order, order
+        // inside every bucket; the final 8-byte records overwrite the slot's (now dead) unordered list.
+        bucket_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_buckets, s.d_bucket_start, ctx->d_bucket_cursor);
+        bucket_scatter_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const Hit12*>(s.d_hits), s.d_counters + 1, s.hit_cap,
+                                                                         ctx->d_bucket_cursor, ctx->d_sort_tmp);
+        bucket_order_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_sort_tmp, s.d_bucket_start, n_buckets, reinterpret_cast<uint2*>(s.d_hits));
+        n += 3;
+    }
+    if (ev_after_order) CU(cudaEventRecord(ev_after_order, ctx->stream));
     CU(cudaGetLastError());
     if (launches) *launches += n;
+    return B200SCAN_OK;
+}
+
+// ---- lazily allocated buffers ----------------------------------------------------------------------------
+// device block buffers + hit list of a slot (first submit on the slot)
+int ensure_slot(b200scan_ctx* ctx, Slot& s)
+{
+    if (s.d_codes) return B200SCAN_OK;
+    const size_t nb = (size_t)ctx->max_block;
+    CU(cudaMalloc(&s.d_codes, nb / 4 + kPadBytes));
+    CU(cudaMalloc(&s.d_zmask, nb / 8 + kPadBytes));
+    CU(cudaMemsetAsync(s.d_codes, 0, nb / 4 + kPadBytes, ctx->up_stream));
+    CU(cudaMemsetAsync(s.d_zmask, 0, nb / 8 + kPadBytes, ctx->up_stream));
+    CU(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * ctx->max_hits));
+    s.hit_cap = ctx->max_hits;
+    return B200SCAN_OK;
+}
+// character staging (b200scan_submit_ascii / b200scan_hist_block_ascii only)
+int ensure_ascii(b200scan_ctx* ctx, Slot& s, bool need_host)
+{
+    const size_t nb = (size_t)ctx->max_block;
+    if (!s.d_ascii) CU(cudaMalloc(&s.d_ascii, nb + kPadBytes));
+    if (need_host && !s.h_ascii) CU(cudaMallocHost(&s.h_ascii, nb + 64));
+    return B200SCAN_OK;
+}
+// B200SCAN_HITS_8: bucket arrays for max_block characters, scratch list for the slot's hit capacity
+int ensure_order(b200scan_ctx* ctx, Slot& s)
+{
+    const size_t want = (size_t)(ctx->max_block >> kBucketShift) + 2;
+    if (ctx->bucket_cap < want) {
+        dfree(ctx->d_bucket_cnt); dfree(ctx->d_bucket_cursor);
+        CU(cudaMalloc(&ctx->d_bucket_cnt, want * 4)); CU(cudaMalloc(&ctx->d_bucket_cursor, want * 4));
+        ctx->bucket_cap = want;
+    }
+    if (s.bucket_cap < want) {
+        dfree(s.d_bucket_start);
+        CU(cudaMalloc(&s.d_bucket_start, want * 4));
+        s.bucket_cap = want;
+    }
+    if (ctx->sort_cap < s.hit_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));          // a previous block's ordering kernels may still read the old scratch list
+        dfree(ctx->d_sort_tmp);
+        CU(cudaMalloc(&ctx->d_sort_tmp, sizeof(Hit12) * s.hit_cap));
+        ctx->sort_cap = s.hit_cap;
+    }
+    return B200SCAN_OK;
+}
+// pinned host copy of a collected hit list: sized from the lists themselves
+int ensure_host_hits(b200scan_ctx* ctx, Slot& s, size_t bytes)
+{
+    if (bytes <= s.h_hit_bytes) return B200SCAN_OK;
+    hfree(s.h_hits);
+    s.h_hit_bytes = 0;
+    const size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    CU(cudaMallocHost(&s.h_hits, want));
+    s.h_hit_bytes = want;
     return B200SCAN_OK;
 }
 
@@ -659,12 +745,11 @@ int stage_frags(b200scan_ctx* ctx, Slot& s, const uint64_t* frag, uint64_t n_fra
 int finish_submit(b200scan_ctx* ctx, Slot& s)
 {
     s.timing.kernel_launches = 0;
-    s.hit_bytes = ctx->hit_format;
     int launches = 0;
     // the block was uploaded and packed on the upload stream (behind the kernels of the other slot's block)
     CU(cudaStreamWaitEvent(ctx->stream, s.ev[2], 0));
     CU(cudaEventRecord(s.ev[8], ctx->stream));
-    int rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
+    int rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches, s.ev[9]);
     if (rc) return rc;
     s.timing.kernel_launches += launches;
     CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -747,32 +832,25 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     if (const char* e = getenv("B200SCAN_PAIR")) c->pair_mode = atoi(e) != 0;
-    if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) g_margin16_scale = atof(e);
-    if (const char* e = getenv("B200SCAN_I8_MAX_OVERSHOOT")) g_i8_max_overshoot = atof(e);
+    if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) c->margin16_scale = atof(e);
+    if (const char* e = getenv("B200SCAN_I8_MAX_OVERSHOOT")) c->i8_max_overshoot = atof(e);
     CUB(cudaFuncSetAttribute(filter_tc_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     lap("streams + kernel attributes");
     if (max_hits == 0) max_hits = 1 << 20;
-    const size_t nb = (size_t)max_block_nt;
+    c->max_hits = max_hits;
+    // Per slot only the counters and events exist from the start; block buffers, hit lists and pinned staging memory are
+    // allocated at the slot's first use (ensure_slot / ensure_ascii / ensure_host_hits): a short run does not pay ~0.5 s for
+    // pinning memory it never touches.
     for (auto& s : c->slot) {
-        CUB(cudaMallocHost(&s.h_ascii, nb + 64));
-        CUB(cudaMallocHost(&s.h_hits, sizeof(b200scan_hit) * max_hits));
-        CUB(cudaMallocHost(&s.h_counters, 32));
-        lap("pinned buffers of a slot");
-        CUB(cudaMalloc(&s.d_ascii, nb + kPadBytes));
-        CUB(cudaMalloc(&s.d_codes, nb / 4 + kPadBytes));
-        CUB(cudaMalloc(&s.d_zmask, nb / 8 + kPadBytes));
-        CUB(cudaMemset(s.d_codes, 0, nb / 4 + kPadBytes));
-        CUB(cudaMemset(s.d_zmask, 0, nb / 8 + kPadBytes));
-        CUB(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * max_hits));
-        s.hit_cap = max_hits;
+        CUB(cudaMallocHost(&s.h_counters, 64));
         CUB(cudaMalloc(&s.d_counters, 64));
-        CUB(cudaMemset(s.d_counters, 0, 32));
+        CUB(cudaMemset(s.d_counters, 0, 64));
         for (auto& e : s.ev) CUB(cudaEventCreate(&e));
-        lap("device buffers of a slot");
     }
+    lap("counters + events of the slots");
 #if defined(B200_TRACE) || defined(B200_PHASE)
     CUB(cudaMalloc(&c->d_trace, 4 * kTraceTiles * 4 * 8));
     CUB(cudaMemset(c->d_trace, 0, 4 * kTraceTiles * 4 * 8));
@@ -794,11 +872,12 @@ void b200scan_destroy(b200scan_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& s : c->slot) {
-        hfree(s.h_ascii); hfree(s.h_frag); hfree(s.h_hits); hfree(s.h_counters);
-        dfree(s.d_ascii); dfree(s.d_codes); dfree(s.d_zmask); dfree(s.d_frag); dfree(s.d_hits); dfree(s.d_counters);
+        hfree(s.h_ascii); hfree(s.h_frag); hfree(s.h_hits); hfree(s.h_counters); hfree(s.h_bucket);
+        dfree(s.d_ascii); dfree(s.d_codes); dfree(s.d_zmask); dfree(s.d_frag); dfree(s.d_hits); dfree(s.d_counters); dfree(s.d_bucket_start);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     }
     dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_flush);
+    dfree(c->d_bucket_cnt); dfree(c->d_bucket_cursor); dfree(c->d_sort_tmp);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg); dfree(c->d_ttiles_z); dfree(c->d_bimg_z);
     dfree(c->d_hist); dfree(c->d_hmin); dfree(c->d_hwid); dfree(c->d_htiles);
@@ -834,6 +913,8 @@ int b200scan_set_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t 
         if (col_len[c] > B200SCAN_MAX_MOTIF_LEN) return fail(ctx, B200SCAN_ELIMIT, "column %d has length %d > %d", c, col_len[c], B200SCAN_MAX_MOTIF_LEN);
         if (4 * col_len[c] > ldp) return fail(ctx, B200SCAN_EINVAL, "ldp %d < 4*len of column %d", ldp, c);
     }
+    if (ctx->hit_format == B200SCAN_HITS_8 && (uint32_t)n_cols > (1u << 24))
+        return fail(ctx, B200SCAN_ELIMIT, "B200SCAN_HITS_8 records hold 24-bit column indices (%d columns)", n_cols);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     return build_motifs(ctx, P, ldp, n_cols, col_len, thr);
@@ -850,12 +931,17 @@ int b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64
     Slot& s = ctx->slot[slot];
     s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag;
     s.timing = b200scan_timing{};
-    CU(cudaEventRecord(s.ev[0], ctx->up_stream));
+    s.hit_bytes = ctx->hit_format;
     // pinned caller memory goes straight to the device; pageable memory is staged through the slot's pinned buffer
     const void* src = block;
     cudaPointerAttributes pa;
-    if (cudaPointerGetAttributes(&pa, block) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
-        cudaGetLastError();
+    const bool pageable = n_total && (cudaPointerGetAttributes(&pa, block) != cudaSuccess || pa.type != cudaMemoryTypeHost);
+    cudaGetLastError();
+    rc = ensure_slot(ctx, s);
+    if (rc == B200SCAN_OK) rc = ensure_ascii(ctx, s, pageable);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.ev[0], ctx->up_stream));
+    if (pageable) {
         std::memcpy(s.h_ascii, block, n_total);
         src = s.h_ascii;
     }
@@ -887,6 +973,9 @@ int b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2, 
     Slot& s = ctx->slot[slot];
     s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag;
     s.timing = b200scan_timing{};
+    s.hit_bytes = ctx->hit_format;
+    rc = ensure_slot(ctx, s);
+    if (rc) return rc;
     CU(cudaEventRecord(s.ev[0], ctx->up_stream));
     const size_t cw = (n_total + 15) / 16, zw = (n_total + 31) / 32;
     // pageable sources: cudaMemcpyAsync stages them itself and returns once the source may be reused
@@ -965,6 +1054,10 @@ int b200scan_hist_block_ascii(b200scan_ctx* ctx, const char* block, uint64_t n_t
     CU(cudaStreamSynchronize(ctx->stream));                 // the previous block still reads the staging buffers
     s.n_total = n_total; s.n_payload = n_payload; s.n_frag = n_frag; s.resident = false;
     if (n_total == 0 || n_payload == 0) return B200SCAN_OK;
+    rc = ensure_slot(ctx, s);
+    if (rc == B200SCAN_OK) rc = ensure_ascii(ctx, s, true);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->up_stream));              // (ensure_slot clears fresh buffers on the upload stream)
     std::memcpy(s.h_ascii, block, n_total);
     CU(cudaMemcpyAsync(s.d_ascii, s.h_ascii, n_total, cudaMemcpyHostToDevice, ctx->stream));
     rc = stage_frags(ctx, s, frag_starts, n_frag, ctx->stream);
@@ -995,7 +1088,8 @@ int b200scan_hist_read(b200scan_ctx* ctx, uint64_t* counts, uint64_t n_counts)
     return B200SCAN_OK;
 }
 
-static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void** hits, uint64_t* n_hits, b200scan_timing* timing)
+static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void** hits, uint64_t* n_hits, b200scan_timing* timing,
+                        const uint32_t** bucket_start = nullptr, uint64_t* n_buckets = nullptr)
 {
     if (!ctx) return B200SCAN_EINVAL;
     if (slot < 0 || slot >= B200SCAN_NUM_SLOTS) return fail(ctx, B200SCAN_EINVAL, "slot %d out of range", slot);
@@ -1003,7 +1097,7 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
     if (!s.in_flight) return fail(ctx, B200SCAN_ESTATE, "slot %d has nothing to collect", slot);
     if (s.hit_bytes != want_bytes)
         return fail(ctx, B200SCAN_ESTATE, "slot %d was submitted with %d-byte hit records: collect it with %s", slot, s.hit_bytes,
-                    s.hit_bytes == B200SCAN_HITS_12 ? "b200scan_collect12" : "b200scan_collect");
+                    s.hit_bytes == B200SCAN_HITS_12 ? "b200scan_collect12" : (s.hit_bytes == B200SCAN_HITS_8 ? "b200scan_collect8" : "b200scan_collect"));
     CU(cudaSetDevice(ctx->device));
     s.in_flight = false;
     for (int attempt = 0;; attempt++) {
@@ -1042,26 +1136,37 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
         if (hit_over || cand_over) {
             unsigned long long want = std::max<unsigned long long>(nh + nh / 8 + 1024, s.hit_cap);
             if (want > s.hit_cap) {
-                dfree(s.d_hits); hfree(s.h_hits);
+                dfree(s.d_hits);
                 CU(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * want));
-                CU(cudaMallocHost(&s.h_hits, sizeof(b200scan_hit) * want));
                 s.hit_cap = want;
             }
         }
         int rc = reset_counters(ctx, s, true, ctx->stream);
         if (rc) return rc;
         int launches = 0;
-        rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches);
+        rc = launch_scoring(ctx, s, s.ev[3], s.ev[4], &launches, s.ev[9]);
         if (rc) return rc;
         s.timing.kernel_launches += launches;
         CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(s.ev[5], ctx->stream));
     }
     const unsigned long long nh = s.h_counters[1];
+    {
+        const int rc = ensure_host_hits(ctx, s, (size_t)s.hit_bytes * nh);
+        if (rc) return rc;
+    }
+    const uint64_t nbk = (s.n_payload + kBucketSize - 1) >> kBucketShift;
+    if (s.hit_bytes == B200SCAN_HITS_8 && s.h_bucket_cap < nbk + 1) {
+        hfree(s.h_bucket);
+        s.h_bucket_cap = 0;
+        CU(cudaMallocHost(&s.h_bucket, (nbk + 1 + nbk / 4) * 4));
+        s.h_bucket_cap = nbk + 1 + nbk / 4;
+    }
     // the scan of this slot is complete (ev[5] was waited for): download its hits on the copy stream, so that the
     // kernels of a block already submitted on the other slot keep the compute stream busy meanwhile
     CU(cudaEventRecord(s.ev[6], ctx->copy_stream));
     if (nh) CU(cudaMemcpyAsync(s.h_hits, s.d_hits, (size_t)s.hit_bytes * nh, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (s.hit_bytes == B200SCAN_HITS_8) CU(cudaMemcpyAsync(s.h_bucket, s.d_bucket_start, (nbk + 1) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
     CU(cudaEventRecord(s.ev[7], ctx->copy_stream));
     CU(cudaEventSynchronize(s.ev[7]));
     cudaEventElapsedTime(&s.timing.h2d_ms, s.ev[0], s.ev[1]);
@@ -1069,6 +1174,9 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
     cudaEventElapsedTime(&s.timing.score_ms, s.ev[8], s.ev[3]);
     cudaEventElapsedTime(&s.timing.rescore_ms, s.ev[3], s.ev[4]);
     cudaEventElapsedTime(&s.timing.d2h_ms, s.ev[6], s.ev[7]);
+    cudaEventElapsedTime(&s.timing.order_ms, s.ev[4], s.ev[9]);
+    if (bucket_start) *bucket_start = s.h_bucket;
+    if (n_buckets) *n_buckets = nbk;
     if (hits) *hits = s.h_hits;
     if (n_hits) *n_hits = nh;
     if (timing) *timing = s.timing;
@@ -1091,10 +1199,22 @@ int b200scan_collect12(b200scan_ctx* ctx, int slot, const b200scan_hit12** hits,
     return rc;
 }
 
+int b200scan_collect8(b200scan_ctx* ctx, int slot, const b200scan_hit8** hits, uint64_t* n_hits, const uint32_t** bucket_start,
+                      uint64_t* n_buckets, b200scan_timing* timing)
+{
+    const void* p = nullptr;
+    const int rc = collect_impl(ctx, slot, B200SCAN_HITS_8, &p, n_hits, timing, bucket_start, n_buckets);
+    if (rc == B200SCAN_OK && hits) *hits = static_cast<const b200scan_hit8*>(p);
+    return rc;
+}
+
 int b200scan_set_hit_format(b200scan_ctx* ctx, int format)
 {
     if (!ctx) return B200SCAN_EINVAL;
-    if (format != B200SCAN_HITS_16 && format != B200SCAN_HITS_12) return fail(ctx, B200SCAN_EINVAL, "hit format must be B200SCAN_HITS_16 or B200SCAN_HITS_12");
+    if (format != B200SCAN_HITS_16 && format != B200SCAN_HITS_12 && format != B200SCAN_HITS_8)
+        return fail(ctx, B200SCAN_EINVAL, "hit format must be B200SCAN_HITS_16, B200SCAN_HITS_12 or B200SCAN_HITS_8");
+    if (format == B200SCAN_HITS_8 && ctx->have_motifs && ctx->n_cols > (1u << 24))
+        return fail(ctx, B200SCAN_ELIMIT, "B200SCAN_HITS_8 records hold 24-bit column indices (%u columns loaded)", ctx->n_cols);
     for (auto& s : ctx->slot) if (s.in_flight) return fail(ctx, B200SCAN_ESTATE, "set_hit_format while a block is in flight");
     ctx->hit_format = format;
     return B200SCAN_OK;
@@ -1114,7 +1234,7 @@ int b200scan_rerun_resident(b200scan_ctx* ctx, int slot, int iters, float* total
         rc = reset_counters(ctx, s, true, ctx->stream);
         if (rc) break;
         CU(cudaEventRecord(ev[3 * i], ctx->stream));
-        rc = launch_scoring(ctx, s, ev[3 * i + 1], ev[3 * i + 2], nullptr);
+        rc = launch_scoring(ctx, s, ev[3 * i + 1], nullptr, nullptr, ev[3 * i + 2]);      // [.. + 2]: after rescoring and, for B200SCAN_HITS_8, the ordering kernels
     }
     if (rc == B200SCAN_OK) {
         CU(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));

@@ -38,6 +38,7 @@ struct HitSink {
     unsigned long long*  n_hits;   // keeps counting past `cap` so the host can size a retry exactly
     unsigned long long   cap;
     uint32_t             compact;  // 1: the list holds 12-byte b200scan_hit12 records
+    uint32_t*            bucket_cnt; // B200SCAN_HITS_8 (order.cuh): hits per bucket of 2^B200SCAN_BUCKET_SHIFT positions, else nullptr
 };
 // record `idx` of the hit list in the sink's format
 __device__ __forceinline__ void store_hit(const HitSink& sink, unsigned long long idx, const b200scan_hit& h)
@@ -88,6 +89,7 @@ __device__ __forceinline__ void emit_hits_warp(bool pred, uint32_t pos, uint32_t
         if (idx < sink.cap) {
             b200scan_hit h; h.pos = pos; h.col = col; h.score = score;
             store_hit(sink, idx, h);
+            if (sink.bucket_cnt) atomicAdd(sink.bucket_cnt + (pos >> B200SCAN_BUCKET_SHIFT), 1u);
         }
     }
 }

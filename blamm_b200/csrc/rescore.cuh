@@ -110,7 +110,10 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
         if (lane == 0) o = atomicAdd(sink.n_hits, (unsigned long long)n_st);
         o = __shfl_sync(0xffffffffu, o, 0);
         for (uint32_t k = lane; k < n_st; k += 32)
-            if (o + k < sink.cap) store_hit(sink, o + k, st[k]);
+            if (o + k < sink.cap) {
+                store_hit(sink, o + k, st[k]);
+                if (sink.bucket_cnt) atomicAdd(sink.bucket_cnt + (uint32_t)(st[k].pos >> B200SCAN_BUCKET_SHIFT), 1u);
+            }
         __syncwarp();
         n_st = 0; round = 0;
     };

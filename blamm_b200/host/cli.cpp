@@ -17,6 +17,7 @@
 #include <functional>
 #include <future>
 #include <iostream>
+#include <map>
 #include <mutex>
 #include <random>
 #include <sstream>
@@ -251,6 +252,7 @@ struct Job {
     vector<uint64_t> fragStarts;
     vector<Fragment> frags;
     uint64_t nTotal = 0, nPayload = 0;
+    uint64_t seq = 0;                              // index of the chunk in the group's stream: the writer emits chunks in this order
 };
 
 struct ScanShared {
@@ -264,9 +266,12 @@ struct ScanShared {
     mutex qMutex; condition_variable qCv;
     deque<unique_ptr<Job>> queue; bool done = false; size_t maxQueue = 2;
     // output queue (producers = the GPU threads, consumer = one writer thread): the file write of block k overlaps the
-    // formatting of block k+1 (the reference formats outside and writes inside its output mutex, pwmscan.cpp:88-101)
+    // formatting of block k+1 (the reference formats outside and writes inside its output mutex, pwmscan.cpp:88-101).
+    // The writer emits the chunks in STREAM order whatever GPU scored them (Job::seq): the per-GPU hit lists are merged in the
+    // order of the input, so the file does not depend on -g.  A producer whose chunk lies more than maxOut chunks ahead of the
+    // one the writer waits for blocks; the chunk the writer waits for never does.
     mutex oMutex; condition_variable oCv;
-    deque<vector<string>> outQueue; bool outDone = false; size_t maxOut = 4;
+    map<uint64_t, vector<string>> outQueue; uint64_t nextOut = 0; bool outDone = false; size_t maxOut = 4;
     string error; atomic<bool> failed{false};
 };
 
@@ -334,6 +339,18 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, std
     text.resize((size_t)(p - base));
 }
 
+// formatted text of one chunk -> the writer's reorder window
+void pushText(ScanShared& sh, const Job& job, vector<string>&& text, uint64_t n)
+{
+    const double t0 = now();
+    unique_lock<mutex> lock(sh.oMutex);
+    sh.oCv.wait(lock, [&] { return job.seq < sh.nextOut + sh.maxOut || sh.failed; });
+    sh.totMatches += n;
+    sh.outQueue.emplace(job.seq, std::move(text));
+    sh.oCv.notify_all();
+    gTimer.add("wait for writer (wall)", now() - t0);
+}
+
 template <class H>
 void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n)
 {
@@ -372,13 +389,59 @@ void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n)
     for (size_t t = 1; t < T; t++) pool.emplace_back(formatRange<H>, cref(sh), cref(job), ref(part[t]), ref(text[t]));
     formatRange(sh, job, part[0], text[0]);
     for (auto& th : pool) th.join();
-    gTimer.add("sort + format (wall)", now() - t0); t0 = now();
-    unique_lock<mutex> lock(sh.oMutex);
-    sh.oCv.wait(lock, [&] { return sh.outQueue.size() < sh.maxOut || sh.failed; });
-    sh.totMatches += n;
-    sh.outQueue.push_back(std::move(text));
-    sh.oCv.notify_all();
-    gTimer.add("wait for writer (wall)", now() - t0);
+    gTimer.add("sort + format (wall)", now() - t0);
+    pushText(sh, job, std::move(text), n);
+}
+
+// Ordered 8-byte records (B200SCAN_HITS_8): the device has already put the block's hits in (position, column) order and
+// grouped them in buckets of 256 positions, so the host neither partitions nor sorts: every formatting thread takes a run of
+// buckets holding about n / T hits.
+void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hits, const uint32_t* bucketStart, uint64_t b0, uint64_t b1,
+                   std::string& text)
+{
+    const uint64_t n = bucketStart[b1] - bucketStart[b0];
+    text.resize(n * (sh.maxNameLen + 96) + 64);
+    char* const base = &text[0];
+    char* p = base;
+    size_t f = 0;
+    for (uint64_t b = b0; b < b1; b++) {
+        for (uint32_t i = bucketStart[b]; i < bucketStart[b + 1]; i++) {
+            const uint64_t pos = (b << B200SCAN_BUCKET_SHIFT) + (hits[i].key >> 24);
+            const uint32_t col = hits[i].key & 0xFFFFFFu;
+            while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= pos) f++;
+            const Fragment& fr = job.frags[f];
+            const uint64_t seqPos = fr.seqPos + (pos - fr.streamPos);
+            const Motif& m = sh.motifs->motifs[col];
+            const string& sn = sh.species->seqNames.at(fr.seqIdx);
+            memcpy(p, sn.data(), sn.size()); p += sn.size();
+            memcpy(p, "\tblamm\t", 7); p += 7;
+            memcpy(p, m.name.data(), m.name.size()); p += m.name.size();
+            *p++ = '\t';
+            p = to_chars(p, p + 24, (unsigned long long)seqPos).ptr; *p++ = '\t';
+            p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size())).ptr; *p++ = '\t';
+            p += formatScore(p, hits[i].score);
+            *p++ = '\t'; *p++ = m.revComp ? '-' : '+';
+            memcpy(p, "\t.\t.\n", 5); p += 5;
+        }
+    }
+    text.resize((size_t)(p - base));
+}
+
+void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets)
+{
+    const double t0 = now();
+    const size_t T = std::max<size_t>(1, std::min<size_t>(sh.formatThreads, n / 50000 + 1));
+    vector<uint64_t> cut(T + 1, nBuckets);
+    cut[0] = 0;
+    for (size_t t = 1; t < T; t++)                   // first bucket whose start reaches t/T of the hits
+        cut[t] = (uint64_t)(std::lower_bound(bucketStart, bucketStart + nBuckets, (uint32_t)(n * t / T)) - bucketStart);
+    vector<string> text(T);
+    vector<thread> pool;
+    for (size_t t = 1; t < T; t++) pool.emplace_back(formatBuckets, cref(sh), cref(job), hits, bucketStart, cut[t], cut[t + 1], ref(text[t]));
+    formatBuckets(sh, job, hits, bucketStart, cut[0], cut[1], text[0]);
+    for (auto& th : pool) th.join();
+    gTimer.add("format ordered hits (wall)", now() - t0);
+    pushText(sh, job, std::move(text), n);
 }
 
 void writerThread(ScanShared& sh)
@@ -387,9 +450,11 @@ void writerThread(ScanShared& sh)
         vector<string> text;
         {
             unique_lock<mutex> l(sh.oMutex);
-            sh.oCv.wait(l, [&] { return !sh.outQueue.empty() || sh.outDone; });
+            sh.oCv.wait(l, [&] { return (!sh.outQueue.empty() && sh.outQueue.begin()->first == sh.nextOut) || sh.outDone; });
             if (sh.outQueue.empty()) return;
-            text = std::move(sh.outQueue.front()); sh.outQueue.pop_front();
+            // (after outDone only a failed run can have left a gap: write what there is, in order)
+            text = std::move(sh.outQueue.begin()->second); sh.outQueue.erase(sh.outQueue.begin());
+            sh.nextOut++;
             sh.oCv.notify_all();
         }
         const double t0 = now();
@@ -417,45 +482,64 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
     }
     const auto len = sh.motifs->colLen();
     const auto thr = sh.motifs->colThr();
-    if (b200scan_set_engine(ctx, engine) != B200SCAN_OK || b200scan_set_hit_format(ctx, B200SCAN_HITS_12) != B200SCAN_OK ||
+    const char* hitEnv = getenv("BLAMM_B200_HITS");
+    const int hitFormat = (hitEnv && atoi(hitEnv) == 12) || len.size() > (1u << 24) ? B200SCAN_HITS_12 : B200SCAN_HITS_8;
+    if (b200scan_set_engine(ctx, engine) != B200SCAN_OK || b200scan_set_hit_format(ctx, hitFormat) != B200SCAN_OK ||
         b200scan_set_motifs(ctx, sh.motifs->P().data(), sh.motifs->ldp(), (int32_t)len.size(), len.data(), thr.data()) != B200SCAN_OK) {
         die(string("CUDA error: ") + b200scan_last_error(ctx)); return;
     }
+    // Three slots: while the hits of chunk k-1 come down and are formatted, chunk k is being scored and chunk k+1 goes up.
+    // BLAMM_B200_HITS=12 keeps the unordered 12-byte records and the host sort (diagnostic / comparison).
     unique_ptr<Job> inFlight[B200SCAN_NUM_SLOTS];
-    int slot = 0;
-    auto collect = [&](int s) -> bool {
-        const b200scan_hit12* hits = nullptr; uint64_t n = 0;
+    int head = 0, tail = 0, nFlight = 0;               // slots tail .. head-1 (mod 3) hold chunks, oldest first
+    auto collectOldest = [&]() -> bool {
+        const int s = tail;
         const double tc = now();
-        if (b200scan_collect12(ctx, s, &hits, &n, nullptr) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
-        gTimer.add("b200scan_collect (wait GPU)", now() - tc);
-        writeHits(sh, *inFlight[s], hits, n);
+        if (hitFormat == B200SCAN_HITS_8) {
+            const b200scan_hit8* hits = nullptr; const uint32_t* bucketStart = nullptr; uint64_t n = 0, nb = 0;
+            if (b200scan_collect8(ctx, s, &hits, &n, &bucketStart, &nb, nullptr) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
+            gTimer.add("b200scan_collect (wait GPU)", now() - tc);
+            writeHits8(sh, *inFlight[s], hits, n, bucketStart, nb);
+        } else {
+            const b200scan_hit12* hits = nullptr; uint64_t n = 0;
+            if (b200scan_collect12(ctx, s, &hits, &n, nullptr) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
+            gTimer.add("b200scan_collect (wait GPU)", now() - tc);
+            writeHits(sh, *inFlight[s], hits, n);
+        }
         inFlight[s].reset();
+        tail = (tail + 1) % B200SCAN_NUM_SLOTS; nFlight--;
         return true;
     };
     while (!sh.failed) {
         unique_ptr<Job> job;
+        bool drainOne = false;
         {
             unique_lock<mutex> l(sh.qMutex);
-            sh.qCv.wait(l, [&] { return !sh.queue.empty() || sh.done || sh.failed; });
-            if (sh.failed) break;
-            if (sh.queue.empty()) break;                 // done
-            job = std::move(sh.queue.front()); sh.queue.pop_front();
-            sh.qCv.notify_all();
+            // with chunks in flight and nothing to submit, use the time to collect the oldest one instead of waiting
+            if (sh.queue.empty() && !sh.done && !sh.failed && nFlight > 0) drainOne = true;
+            else {
+                sh.qCv.wait(l, [&] { return !sh.queue.empty() || sh.done || sh.failed; });
+                if (sh.failed) break;
+                if (sh.queue.empty()) break;                 // done
+                job = std::move(sh.queue.front()); sh.queue.pop_front();
+                sh.qCv.notify_all();
+            }
         }
-        if (inFlight[slot] && !collect(slot)) break;
+        if (drainOne) { if (!collectOldest()) break; continue; }
+        if (nFlight == B200SCAN_NUM_SLOTS && !collectOldest()) break;
         const int rc = job->codes
-            ? b200scan_submit_packed(ctx, slot, job->codes.get(), job->hasZero ? job->zmask.get() : nullptr, job->nTotal, job->nPayload,
+            ? b200scan_submit_packed(ctx, head, job->codes.get(), job->hasZero ? job->zmask.get() : nullptr, job->nTotal, job->nPayload,
                                      job->fragStarts.data(), job->fragStarts.size())
-            : b200scan_submit_ascii(ctx, slot, job->chars.get(), job->nTotal, job->nPayload, job->fragStarts.data(),
+            : b200scan_submit_ascii(ctx, head, job->chars.get(), job->nTotal, job->nPayload, job->fragStarts.data(),
                                     job->fragStarts.size(), foldLower ? B200SCAN_LOWER_FOLD : B200SCAN_LOWER_ZERO);
         if (rc != B200SCAN_OK) {
             die(string("CUDA error: ") + b200scan_last_error(ctx)); break;
         }
-        inFlight[slot] = std::move(job);
-        slot ^= 1;
-        if (inFlight[slot] && !collect(slot)) break;     // overlap: format block k-1 while the GPU scores block k
+        inFlight[head] = std::move(job);
+        head = (head + 1) % B200SCAN_NUM_SLOTS; nFlight++;
+        if (nFlight == B200SCAN_NUM_SLOTS && !collectOldest()) break;     // overlap: format chunk k-2 while k-1 is scored and k goes up
     }
-    for (int s = 0; s < B200SCAN_NUM_SLOTS && !sh.failed; s++) { if (inFlight[slot]) collect(slot); slot ^= 1; }
+    while (nFlight > 0 && !sh.failed) if (!collectOldest()) break;
 }
 
 // `blamm-b200 selftest-writer [hits] [threads]` (no GPU): the occurrence writer -- partition, radix sort, formatting, writer
@@ -516,8 +600,36 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
     ifstream is(path, ios::binary);
     const string got((istreambuf_iterator<char>(is)), istreambuf_iterator<char>());
     remove(path.c_str());
-    const bool ok = got == want;
+    bool ok = got == want;
     cout << label << ": " << hits.size() << " hits, " << threads << " threads, " << got.size() << " bytes: " << (ok ? "identical" : "DIFFERENT") << "\n";
+    if (sizeof(H) == sizeof(b200scan_hit12)) {
+        // the same list as the device hands it over under B200SCAN_HITS_8: ordered 8-byte records + bucket index
+        const uint64_t nb = (job.nPayload + (1u << B200SCAN_BUCKET_SHIFT) - 1) >> B200SCAN_BUCKET_SHIFT;
+        vector<b200scan_hit8> h8(inOrder.size());
+        vector<uint32_t> bs(nb + 1, 0);
+        for (size_t i = 0; i < inOrder.size(); i++) {
+            h8[i].key = (uint32_t)((inOrder[i].pos & 255u) << 24) | inOrder[i].col; h8[i].score = inOrder[i].score;
+            bs[(inOrder[i].pos >> B200SCAN_BUCKET_SHIFT) + 1]++;
+        }
+        for (uint64_t b = 0; b < nb; b++) bs[b + 1] += bs[b];
+        {
+            ofstream os(path, ios::binary);
+            ScanShared sh;
+            sh.motifs = &ms; sh.species = &sp; sh.os = &os; sh.formatThreads = threads;
+            sh.maxNameLen = 23 + 8;
+            thread writer(writerThread, ref(sh));
+            writeHits8(sh, job, h8.data(), h8.size(), bs.data(), nb);
+            { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; }
+            sh.oCv.notify_all();
+            writer.join();
+        }
+        ifstream is8(path, ios::binary);
+        const string got8((istreambuf_iterator<char>(is8)), istreambuf_iterator<char>());
+        remove(path.c_str());
+        const bool ok8 = got8 == want;
+        cout << "b200scan_hit8 : " << h8.size() << " hits, " << threads << " threads, " << got8.size() << " bytes: " << (ok8 ? "identical" : "DIFFERENT") << "\n";
+        ok = ok && ok8;
+    }
     return ok;
 }
 
@@ -676,6 +788,7 @@ int runScan(int argc, char** argv)
         ScanShared sh;
         sh.motifs = &mc; sh.species = &sp; sh.os = &os;
         sh.formatThreads = std::max<size_t>(1, numThreads / (size_t)nDev);
+        sh.maxOut = 2 * (size_t)nDev + 2;
         size_t sl = 0, ml = 0;
         for (const auto& n : sp.seqNames) sl = max(sl, n.size());
         for (const auto& m : mc.motifs) ml = max(ml, m.name.size());
@@ -690,6 +803,7 @@ int runScan(int argc, char** argv)
             const char* asciiEnv = getenv("BLAMM_B200_ASCII");
             const bool sendAscii = asciiEnv && *asciiEnv && *asciiEnv != '0';
             FastaStream::Chunk c;
+            uint64_t nJobs = 0;
             for (;;) {
                 double tr = now();
                 if (sh.failed || !fs.next(maxBlock - halo - 64, halo, c)) break;
@@ -704,6 +818,7 @@ int runScan(int argc, char** argv)
                 }
                 job->fragStarts = c.fragStarts; job->frags = c.frags;
                 job->nTotal = c.nTotal; job->nPayload = c.nPayload;
+                job->seq = nJobs++;
                 gTimer.add("FASTA read + filter (reader)", now() - tr);
                 unique_lock<mutex> l(sh.qMutex);
                 sh.qCv.wait(l, [&] { return sh.queue.size() < sh.maxQueue || sh.failed; });

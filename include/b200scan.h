@@ -17,6 +17,8 @@
  *   b200scan_submit_packed         same, for callers that already hold the 2-bit packed stream
  *   b200scan_collect               cublasGetVector(d_nOcc / occIdx / occScore) + the boundary filter of
  *                                  PWMScan::extractOccurrences2                      pwmscan.cpp:393-406, 135-163
+ *   b200scan_collect8              same, with the block's occurrences already in (position, column) order -- what the
+ *                                  reference leaves to the order of its R sweep      pwmscan.cpp:108-131 (README.md:165)
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * B200SCAN_E* code (no exception crosses the ABI); b200scan_last_error() gives the text.  The context owns
@@ -43,7 +45,7 @@
 extern "C" {
 #endif
 
-#define B200SCAN_ABI_VERSION 1
+#define B200SCAN_ABI_VERSION 2   /* 2: three slots, B200SCAN_HITS_8 / b200scan_collect8, order_ms in b200scan_timing, lazy buffers */
 
 /* error codes */
 #define B200SCAN_OK            0
@@ -55,7 +57,10 @@ extern "C" {
 #define B200SCAN_ELIMIT       -6   /* motif longer than B200SCAN_MAX_MOTIF_LEN, block larger than max_block_nt */
 
 #define B200SCAN_MAX_MOTIF_LEN 64
-#define B200SCAN_NUM_SLOTS      2  /* submit/collect double buffering */
+#define B200SCAN_NUM_SLOTS      3  /* blocks in flight per context: one uploading, one being scored, one whose hits are downloading.
+                                    * A slot's device buffers are allocated at its first submit, so a caller that alternates two
+                                    * slots (the CLI) pays for two. */
+#define B200SCAN_BUCKET_SHIFT   8  /* B200SCAN_HITS_8: hits are grouped in buckets of 2^8 = 256 window positions */
 
 /* scoring engines (b200scan_set_engine) */
 #define B200SCAN_ENGINE_AUTO    0  /* tensor-core filter + exact rescore (gather-add only if the motif set is unusable for it) */
@@ -88,6 +93,18 @@ typedef struct b200scan_hit12 {
 } b200scan_hit12;
 #define B200SCAN_HITS_16 16   /* b200scan_hit records, b200scan_collect (default) */
 #define B200SCAN_HITS_12 12   /* b200scan_hit12 records, b200scan_collect12        */
+#define B200SCAN_HITS_8   8   /* b200scan_hit8 records IN (position, column) ORDER, b200scan_collect8 */
+
+/* The same occurrence as an 8-byte record of an ORDERED list (B200SCAN_HITS_8): the device sorts the block's hits by
+ * (position, column) (csrc/order.cuh) and groups them in buckets of 256 window positions; b200scan_collect8 returns the
+ * records together with bucket_start[0 .. n_buckets], n_buckets = ceil(n_payload / 256): the hits of bucket b are records
+ * bucket_start[b] .. bucket_start[b + 1] - 1 and record i of them lies at block position 256 b + (key >> 24); its column is
+ * key & 0xFFFFFF.  A third less device->host traffic than b200scan_hit12 (plus 4 bytes per 256 positions), and the host no
+ * longer sorts.  Column indices must fit 24 bits (n_cols <= 2^24: b200scan_set_hit_format checks at the next set_motifs). */
+typedef struct b200scan_hit8 {
+    uint32_t key;      /* (pos & 255) << 24 | col */
+    float    score;
+} b200scan_hit8;
 
 /* timings of the last launch on a slot, CUDA events on the context's stream (milliseconds) */
 typedef struct b200scan_timing {
@@ -100,6 +117,8 @@ typedef struct b200scan_timing {
     uint64_t n_hits;
     int32_t  engine_used;    /* B200SCAN_ENGINE_GATHER or _TENSOR */
     int32_t  kernel_launches;/* kernels launched for this block */
+    float order_ms;      /* B200SCAN_HITS_8: bucket scan + scatter + order kernels (0 otherwise)   */
+    float reserved;
 } b200scan_timing;
 
 int  b200scan_abi_version(void);
@@ -108,7 +127,13 @@ int  b200scan_abi_version(void);
 int  b200scan_device_count(void);
 
 /* Create a context on CUDA device `device`.  max_block_nt: largest n_total a submit may carry.
- * max_hits: capacity of the per-slot device hit buffer (a block producing more is rescanned in halves). */
+ * max_hits: initial capacity (records) of the per-slot hit buffers.  A block that produces more hits (or more filter
+ * candidates) than the buffers hold is NOT lost: every counter keeps counting past its capacity, b200scan_collect then
+ * frees the buffers, allocates them at the counted size (+ 1/8) and scores the whole block again -- at the price of that
+ * second pass and of device memory of about 100 bytes per hit of the densest block (B200SCAN_ENOMEM if that fails: the
+ * caller should then submit smaller blocks; the CLI sizes its chunks from the expected hit rate, cli.cpp: hitBudget).
+ * Device and pinned buffers of a slot are allocated at the slot's first use; the pinned hit buffer is sized from the
+ * blocks actually collected. */
 int  b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint64_t max_hits);
 void b200scan_destroy(b200scan_ctx* ctx);
 const char* b200scan_last_error(const b200scan_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
@@ -147,7 +172,9 @@ int  b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint6
 
 /* Same for a pre-packed block: codes2 holds 2 bits per character (A=0,C=1,G=2,T=3; character i in bits
  * 2*(i%16) of 32-bit word i/16); zero_mask (may be NULL) holds 1 bit per character (bit i%32 of word i/32),
- * set = the character contributes 0. */
+ * set = the character contributes 0.  Lifetime of the sources: the copy engine reads codes2 / zero_mask asynchronously when
+ * they lie in page-locked memory (b200scan_host_alloc) -- such buffers must stay unchanged until the block has been
+ * collected, exactly as for b200scan_submit_ascii; pageable sources are staged by the CUDA runtime before the call returns. */
 int  b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2, const uint32_t* zero_mask,
                             uint64_t n_total, uint64_t n_payload, const uint64_t* frag_starts,
                             uint64_t n_frag);
@@ -156,11 +183,15 @@ int  b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2,
  * the slot).  timing may be NULL. */
 int  b200scan_collect(b200scan_ctx* ctx, int slot, const b200scan_hit** hits, uint64_t* n_hits,
                       b200scan_timing* timing);
-/* Record format of the hit lists (B200SCAN_HITS_16 | B200SCAN_HITS_12) for blocks submitted from now on; no block may be
+/* Record format of the hit lists (B200SCAN_HITS_16 | B200SCAN_HITS_12 | B200SCAN_HITS_8) for blocks submitted from now on; no block may be
  * in flight.  A block must be collected with the function of the format it was submitted under (else B200SCAN_ESTATE). */
 int  b200scan_set_hit_format(b200scan_ctx* ctx, int format);
 int  b200scan_collect12(b200scan_ctx* ctx, int slot, const b200scan_hit12** hits, uint64_t* n_hits,
                         b200scan_timing* timing);
+/* B200SCAN_HITS_8: ordered records + bucket index (see b200scan_hit8); *n_buckets = ceil(n_payload / 256), bucket_start has
+ * *n_buckets + 1 entries.  Both arrays are owned by ctx until the next submit on the slot. */
+int  b200scan_collect8(b200scan_ctx* ctx, int slot, const b200scan_hit8** hits, uint64_t* n_hits,
+                       const uint32_t** bucket_start, uint64_t* n_buckets, b200scan_timing* timing);
 
 /* Empirical score histograms (`blamm hist -e`, reference Histogram::histThread + extractObsScore, hist.cpp:70-140):
  * same scoring as the scan, but instead of thresholding every window that lies inside one fragment adds 1 to bin

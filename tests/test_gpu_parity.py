@@ -398,6 +398,59 @@ def test_compact_hit_records(engine):
         s.close()
 
 
+@pytest.mark.parametrize("engine", [capi.ENGINE_GATHER, capi.ENGINE_TENSOR])
+def test_ordered_hit_records(engine):
+    """B200SCAN_HITS_8 / b200scan_collect8 (csrc/order.cuh): the device returns the block's occurrences already in
+    (position, column) order as 8-byte records + a bucket index -- compared RECORD BY RECORD, without sorting, with the
+    oracle's list (which is in that order); through the regrow path (max_hits = 1024), with all three slots in flight, for
+    an empty block, for a block whose last bucket is partial, and the state errors of mixing the formats."""
+    s = capi.Scanner(0, max_block_nt=1 << 20, max_hits=1024)
+    try:
+        case = util.random_case(73, n_motifs=12, n_nt=150_001, lower=True)
+        s.set_engine(engine)
+        s.set_motifs(case["P"], case["col_len"], case["thr"])
+        want = _oracle_hits(case)
+        s.set_hit_format(capi.HITS_8)
+        s.submit_ascii(0, case["chars"], frag_starts=case["frag_start"][1:])
+        h8, bstart, t = s.collect8(0)
+        assert h8.dtype.itemsize == 8 and len(h8) == len(want[0]) > 1024 and t["order_ms"] > 0
+        assert len(bstart) == (150_001 + 255) // 256 + 1 and bstart[0] == 0 and bstart[-1] == len(h8)
+        assert np.all(np.diff(bstart.astype(np.int64)) >= 0)
+        h = capi.expand_hits8(h8, bstart)
+        assert np.array_equal(h["pos"], want[0]) and np.array_equal(h["col"], want[1])          # in order: no sort here
+        assert np.array_equal(h["score"].view(np.uint32), want[2].view(np.uint32))
+        # three blocks in flight, of different sizes (the ordering scratch buffers are shared by the slots)
+        fs = case["frag_start"][1:]
+        s.submit_ascii(0, case["chars"], frag_starts=fs)
+        s.submit_ascii(1, case["chars"][:70_029], n_payload=70_000, frag_starts=fs[fs < 70_029])
+        s.submit_ascii(2, case["chars"][:300], n_payload=256, frag_starts=fs[fs < 300])
+        with pytest.raises(capi.ScanError):
+            s.set_hit_format(capi.HITS_12)                   # blocks in flight
+        with pytest.raises(capi.ScanError):
+            s.collect(0, fmt=capi.HITS_12)                   # submitted under the 8-byte format
+        for slot, lim in ((2, 256), (0, 1 << 30), (1, 70_000)):
+            got, _ = s.collect(slot)                         # Scanner.collect expands ordered records itself
+            k = want[0] < lim
+            assert np.array_equal(got["pos"], want[0][k]) and np.array_equal(got["col"], want[1][k])
+            assert np.array_equal(got["score"].view(np.uint32), want[2][k].view(np.uint32))
+        # empty block, then a dense one: every window of 4 columns is an occurrence (many hits per position and bucket)
+        s.submit_ascii(0, np.zeros(0, np.uint8))
+        h8, bstart, _ = s.collect8(0)
+        assert len(h8) == 0 and len(bstart) == 1 and bstart[0] == 0
+        dense = util.random_case(51, n_motifs=4, n_nt=40_000, len_range=(5, 9))
+        thr = np.full(len(dense["thr"]), -1000.0, dtype=np.float32)
+        s.set_motifs(dense["P"], dense["col_len"], thr)
+        got, _ = s.scan(dense["chars"], dense["frag_start"][1:])
+        wd = _oracle_hits(dict(dense, thr=thr))
+        assert len(got) > 100_000 and np.array_equal(got["pos"], wd[0]) and np.array_equal(got["col"], wd[1])
+        assert np.array_equal(got["score"].view(np.uint32), wd[2].view(np.uint32))
+        s.set_hit_format(capi.HITS_16)
+        h16, _ = s.scan(dense["chars"], dense["frag_start"][1:])
+        _assert_same(h16, *wd)
+    finally:
+        s.close()
+
+
 def test_double_buffered_slots_and_state_errors(scanner):
     a, b = util.random_case(61, n_motifs=8, n_nt=80_000), util.random_case(62, n_motifs=8, n_nt=70_000)
     scanner.set_engine(capi.ENGINE_AUTO)

@@ -31,7 +31,7 @@ def test_scan_library_exports_every_declared_symbol():
     assert len(names) >= 14
     for n in names:
         assert hasattr(L, n), n
-    assert L.b200scan_abi_version() == 1
+    assert L.b200scan_abi_version() == 2 and "b200scan_collect8" in names
 
 
 def test_host_library_exports_every_declared_symbol():
@@ -297,11 +297,12 @@ def test_format_score_sweep_against_printf(tmp_path):
 @pytest.mark.parametrize("n_hits,threads", [(0, 2), (100, 3), (5000, 1), (300_000, 4), (1_000_000, 7)])
 def test_occurrence_writer_selftest(n_hits, threads):
     """`blamm-b200 selftest-writer` (no GPU): the CLI's occurrence writer -- range partition, radix sort by (position, column),
-    line formatting, writer thread -- for 16-byte and 12-byte hit records against a plain std::sort + snprintf restatement of
+    line formatting, in-order writer thread -- for 16-byte and 12-byte hit records, and for the ordered 8-byte records + bucket
+    index the device hands over under B200SCAN_HITS_8 (no host sort), against a plain std::sort + snprintf restatement of
     the reference's line format (pwmscan.cpp:88-95), compiled into the same binary."""
     r = subprocess.run([CLI, "selftest-writer", str(n_hits), str(threads)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("identical") == 2 and "DIFFERENT" not in r.stdout
+    assert r.stdout.count("identical") == 3 and "DIFFERENT" not in r.stdout
 
 
 def test_fasta_rejects_headerless_input(tmp_path):
