@@ -10,7 +10,7 @@ CSRC     := $(wildcard blamm_b200/csrc/*.cu blamm_b200/csrc/*.cuh) include/b200s
 HSRC     := blamm_b200/host/motifs.cpp blamm_b200/host/sequence.cpp
 HHDR     := blamm_b200/host/host.h include/blamm_host.h include/b200scan.h
 
-all: $(LIBDIR)/libb200scan.so $(LIBDIR)/libblammhost.so $(LIBDIR)/blamm-b200
+all: $(LIBDIR)/libb200scan.so $(LIBDIR)/libblammhost.so $(LIBDIR)/blamm-b200 $(LIBDIR)/i8_peak
 
 $(LIBDIR)/libb200scan.so: $(CSRC)
 	@mkdir -p $(LIBDIR)
@@ -32,6 +32,11 @@ $(LIBDIR)/libblammhost.so: $(HSRC) blamm_b200/host/host_abi.cpp $(HHDR)
 
 $(LIBDIR)/blamm-b200: $(HSRC) blamm_b200/host/cli.cpp $(HHDR) $(LIBDIR)/libb200scan.so
 	$(CXX) $(CXXFLAGS) $(HSRC) blamm_b200/host/cli.cpp -o $@ -L$(LIBDIR) -lb200scan -Wl,-rpath,'$$ORIGIN' -lpthread
+
+# dense tcgen05.mma peak of the INT8 / FP16 tensor pipe: the measured denominator of bench.py's roofline
+$(LIBDIR)/i8_peak: tools/micro/i8_peak.cu blamm_b200/csrc/filter_tc.cuh blamm_b200/csrc/common.cuh
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) tools/micro/i8_peak.cu -o $@
 
 oracle:
 	$(MAKE) -C oracle

@@ -69,6 +69,7 @@ def scan_lib() -> ctypes.CDLL:
         L.b200scan_hist_block_ascii.argtypes = [vp, vp, u64, u64, vp, u64, ctypes.c_int]
         L.b200scan_hist_read.argtypes = [vp, vp, u64]
         L.b200scan_flush_l2.argtypes = [vp]
+        L.b200scan_tensor_work.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.b200scan_describe.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), _u64p]
         _scan = L
     return _scan
@@ -195,6 +196,15 @@ class Scanner:
                                                  n_total, n_payload, fs.ctypes.data if len(fs) else None, len(fs)))
         self._slot_format[slot] = self._hit_format
 
+    def submit_packed_ptr(self, slot: int, codes_ptr: int, zmask_ptr: Optional[int], n_total: int, n_payload: int,
+                          frag_starts: Optional[np.ndarray] = None) -> None:
+        """b200scan_submit_packed on raw addresses (page-locked buffers of b200scan_host_alloc: they must stay unchanged until
+        the block has been collected)."""
+        fs = np.ascontiguousarray(frag_starts if frag_starts is not None else [], dtype=np.uint64)
+        self._chk(self._L.b200scan_submit_packed(self._ctx, slot, codes_ptr, zmask_ptr, n_total, n_payload,
+                                                 fs.ctypes.data if len(fs) else None, len(fs)))
+        self._slot_format[slot] = self._hit_format
+
     def collect(self, slot: int, copy: bool = True, fmt: Optional[int] = None) -> Tuple[np.ndarray, dict]:
         """Hits of the block on `slot`, as HIT_DTYPE or HIT12_DTYPE records -- the format the block was submitted under
         (`fmt` overrides the choice of the collecting function: only the state tests do that)."""
@@ -250,6 +260,12 @@ class Scanner:
         out = np.zeros(self._hist_shape, dtype=np.uint64)
         self._chk(self._L.b200scan_hist_read(self._ctx, out.ctypes.data, out.size))
         return out
+
+    def tensor_work(self) -> dict:
+        """Tensor-core operations per window: as issued (padded tiles) and algorithmic (8 x sum L)."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._chk(self._L.b200scan_tensor_work(self._ctx, ctypes.byref(a), ctypes.byref(b)))
+        return dict(mma_ops_per_window=a.value, algorithmic_ops_per_window=b.value)
 
     def flush_l2(self) -> None:
         self._chk(self._L.b200scan_flush_l2(self._ctx))

@@ -1287,6 +1287,19 @@ int b200scan_tensor_info(const b200scan_ctx* ctx, int32_t* accumulator_bits, dou
     return B200SCAN_OK;
 }
 
+int b200scan_tensor_work(const b200scan_ctx* ctx, double* mma_ops_per_window, double* algorithmic_ops_per_window)
+{
+    if (!ctx) return B200SCAN_EINVAL;
+    // one MMA of tile t covers N = n_pad columns and K = 32 (INT8) or 16 (FP16 operands) one-hot rows of one window: 2 N K
+    // operations; n_k of them per window (the bias step of masked blocks is not counted)
+    double ops = 0;
+    for (size_t t = 0; t < ctx->ttiles.size(); t++)
+        ops += 2.0 * ctx->ttiles[t].n_pad * ctx->ttiles[t].n_k * (t < ctx->n_tiles8 ? 32.0 : 16.0);
+    if (mma_ops_per_window) *mma_ops_per_window = ctx->tc_usable ? ops : 0.0;
+    if (algorithmic_ops_per_window) *algorithmic_ops_per_window = 8.0 * (double)ctx->sum_len;
+    return B200SCAN_OK;
+}
+
 int b200scan_describe(const b200scan_ctx* ctx, int32_t* n_cols, int32_t* max_len, int32_t* n_tiles, int32_t* sm_count, uint64_t* sum_len)
 {
     if (!ctx) return B200SCAN_EINVAL;

@@ -33,7 +33,7 @@ namespace blamm {
 // precision 6 is specified to give exactly that conversion (checked against snprintf on 4e7 floats) at a fifth of the cost.
 namespace {
 struct PhaseTimer {            // BLAMM_B200_TIMING=1: wall-clock seconds per phase on stderr (sums over threads where noted)
-    bool on = getenv("BLAMM_B200_TIMING") != nullptr;
+    bool on = getenv("BLAMM_B200_TIMING") != nullptr, quiet = false;
     std::mutex m; std::vector<std::pair<std::string, double>> acc;
     void add(const char* what, double s) {
         if (!on) return;
@@ -41,9 +41,22 @@ struct PhaseTimer {            // BLAMM_B200_TIMING=1: wall-clock seconds per ph
         for (auto& a : acc) if (a.first == what) { a.second += s; return; }
         acc.emplace_back(what, s);
     }
-    void report() { if (on) for (auto& a : acc) fprintf(stderr, "[timing] %-28s %8.3f s\n", a.first.c_str(), a.second); }
+    void report() { if (on && !quiet) for (auto& a : acc) fprintf(stderr, "[timing] %-28s %8.3f s\n", a.first.c_str(), a.second); }
 } gTimer;
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// `scan --stats FILE`: machine-readable account of the run (phases of gTimer + per-GPU sums of the b200scan_timing records)
+struct DeviceStats { uint64_t chunks = 0, chars = 0, hits = 0, candidates = 0; double h2d = 0, pack = 0, score = 0, rescore = 0, order = 0, d2h = 0; };
+struct RunStats {
+    std::string file; std::mutex m; std::vector<DeviceStats> dev;
+    void add(size_t d, const b200scan_timing& t, uint64_t chars) {
+        std::lock_guard<std::mutex> l(m);
+        if (dev.size() <= d) dev.resize(d + 1);
+        DeviceStats& s = dev[d];
+        s.chunks++; s.chars += chars; s.hits += t.n_hits; s.candidates += t.n_candidates;
+        s.h2d += t.h2d_ms; s.pack += t.pack_ms; s.score += t.score_ms; s.rescore += t.rescore_ms; s.order += t.order_ms; s.d2h += t.d2h_ms;
+    }
+} gStats;
+uint64_t gStatsColumns = 0, gStatsMatches = 0;
 // FASTA parser threads: -t where the module has it, else the host's cores; BLAMM_B200_INGEST_THREADS overrides (1 = serial)
 unsigned ingestThreads(size_t wanted = 0)
 {
@@ -121,7 +134,9 @@ static void histUsage()
             " [options arg]\n"
             "  -l\t--length\tmaximum sequence length to analyze (default = 10000000)\n"
             "  -b\t--numbins\tnumber of bins per histogram (default = 250)\n"
-            "  -t\t--numthreads\tset the number of parallel threads [default = #cores]\n\n"
+            "  -t\t--numthreads\tset the number of parallel threads [default = #cores]\n"
+            "  -e\t--empirical\tscore the sequences themselves (on the GPUs) instead of computing the theoretical spectrum\n"
+            "  -g\t--gpus\t\tnumber of GPUs for -e [default = all]\n\n"
             " [file_options]\n  -H\t--histdir\toutput directory for the histogram file(s) [default = .]\n\n"
             " Example:\n  blamm hist motifs.input sequences.input\n\n";
 }
@@ -131,6 +146,7 @@ int runHist(int argc, char** argv)
     if (argc < 4) { histUsage(); return EXIT_FAILURE; }
     uint64_t maxLength = 10000000; size_t numBins = 250; bool empirical = false; string histdir;
     size_t numThreads = thread::hardware_concurrency();
+    int gpusWanted = 0;
     for (int i = 2; i < argc - 2; i++) {
         string arg(argv[i]);
         const bool hasVal = i + 1 < argc - 2;
@@ -139,6 +155,7 @@ int runHist(int argc, char** argv)
         else if ((arg == "-b" || arg == "--numbins") && hasVal) { numBins = atoll(argv[++i]); if (numBins < 2) numBins = 2; }
         else if (arg == "-e" || arg == "--empirical") empirical = true;
         else if ((arg == "-t" || arg == "--numthreads") && hasVal) numThreads = (size_t)max(1, atoi(argv[++i]));
+        else if ((arg == "-g" || arg == "--gpus") && hasVal) gpusWanted = atoi(argv[++i]);
         else if ((arg == "-H" || arg == "--histdir") && hasVal) { histdir = argv[++i]; if (histdir.back() != '/') histdir.push_back('/'); }
         else { histUsage(); return EXIT_FAILURE; }
     }
@@ -166,17 +183,29 @@ int runHist(int argc, char** argv)
     cout << "Loaded " << mc.motifs.size() << " motifs from disk";
     cout << "\nMaximum motif size: " << mc.maxLen() << endl;
     if (mc.motifs.empty()) throw runtime_error("No motifs found in " + string(argv[argc - 2]));
-    b200scan_ctx* ctx = nullptr;
+    // `hist -e`: one context per GPU (-g, default all); the chunks of a group are dealt to the devices, every device keeps its own
+    // 64-bit bin counters, the host adds them up (integer sums: the result does not depend on the deal).  The reference runs
+    // histThread on -t host threads over 250,000-character blocks (hist.cpp:95-160).
+    vector<b200scan_ctx*> ctxs;
     const uint64_t halo = mc.maxLen() - 1;
     const uint64_t chunk = std::min<uint64_t>(maxLength, 32ull << 20);
+    auto destroyAll = [&] { for (auto c : ctxs) if (c) b200scan_destroy(c); ctxs.clear(); };
     if (empirical) {
         if (mc.maxLen() > B200SCAN_MAX_MOTIF_LEN)
             throw runtime_error("Motifs longer than " + to_string(B200SCAN_MAX_MOTIF_LEN) + " positions are not supported by this build");
-        if (b200scan_device_count() == 0) throw runtime_error("CUDA error: no sm_100 devices found. Aborting...");
-        if (b200scan_create(&ctx, 0, chunk + halo + 64, 1024) != B200SCAN_OK)
-            throw runtime_error(string("CUDA error: ") + b200scan_last_error(nullptr));
+        int nDev = b200scan_device_count();
+        if (nDev == 0) throw runtime_error("CUDA error: no sm_100 devices found. Aborting...");
+        if (gpusWanted > 0) nDev = min(nDev, gpusWanted);
+        ctxs.assign((size_t)nDev, nullptr);
+        vector<future<string>> made;
+        for (int d = 0; d < nDev; d++)
+            made.push_back(async(launch::async, [&ctxs, d, chunk, halo]() -> string {
+                return b200scan_create(&ctxs[(size_t)d], d, chunk + halo + 64, 1024) == B200SCAN_OK ? string() : string(b200scan_last_error(nullptr));
+            }));
+        string err;
+        for (auto& m : made) { const string e = m.get(); if (!e.empty() && err.empty()) err = e; }
+        if (!err.empty()) { destroyAll(); throw runtime_error("CUDA error: " + err); }
     }
-    auto check = [&](int rc) { if (rc != B200SCAN_OK) { string e = b200scan_last_error(ctx); b200scan_destroy(ctx); throw runtime_error("CUDA error: " + e); } };
     for (const auto& sp : sc.species) {
         cout << "Generating histograms for species: " << sp.name;
         sp.printNuclProb(settings.pseudocount);
@@ -191,26 +220,68 @@ int runHist(int argc, char** argv)
             const auto len = mc.colLen();
             vector<float> thr(len.size(), 0.0f), mn, mx;
             for (const auto& h : hists) { mn.push_back(h.minScore); mx.push_back(h.maxScore); }
-            check(b200scan_set_motifs(ctx, mc.P().data(), mc.ldp(), (int32_t)len.size(), len.data(), thr.data()));
-            check(b200scan_hist_begin(ctx, mn.data(), mx.data(), (uint32_t)numBins));
-            FastaStream fs(sp.files, maxLength);
-            fs.setParallel(ingestThreads());
-            FastaStream::Chunk c;
-            while (fs.next(chunk, halo, c)) {
-                check(b200scan_hist_block_ascii(ctx, c.chars, c.nTotal, c.nPayload, c.fragStarts.data(), c.fragStarts.size(), B200SCAN_LOWER_ZERO));
-                cout << "."; cout.flush();
+            struct HistJob { unique_ptr<char[]> chars; vector<uint64_t> fragStarts; uint64_t nTotal = 0, nPayload = 0; };
+            mutex qm; condition_variable qcv; deque<unique_ptr<HistJob>> q; bool done = false; string failure;
+            auto worker = [&](b200scan_ctx* ctx) {
+                auto fail = [&](const string& e) { lock_guard<mutex> l(qm); if (failure.empty()) failure = e; qcv.notify_all(); };
+                if (b200scan_set_motifs(ctx, mc.P().data(), mc.ldp(), (int32_t)len.size(), len.data(), thr.data()) != B200SCAN_OK ||
+                    b200scan_hist_begin(ctx, mn.data(), mx.data(), (uint32_t)numBins) != B200SCAN_OK) { fail(b200scan_last_error(ctx)); return; }
+                for (;;) {
+                    unique_ptr<HistJob> job;
+                    {
+                        unique_lock<mutex> l(qm);
+                        qcv.wait(l, [&] { return !q.empty() || done || !failure.empty(); });
+                        if (!failure.empty() || q.empty()) return;
+                        job = std::move(q.front()); q.pop_front();
+                        qcv.notify_all();
+                    }
+                    if (b200scan_hist_block_ascii(ctx, job->chars.get(), job->nTotal, job->nPayload, job->fragStarts.data(), job->fragStarts.size(),
+                                                  B200SCAN_LOWER_ZERO) != B200SCAN_OK) { fail(b200scan_last_error(ctx)); return; }
+                }
+            };
+            vector<thread> workers;
+            for (auto c : ctxs) workers.emplace_back(worker, c);
+            try {
+                FastaStream fs(sp.files, maxLength);
+                fs.setParallel(ingestThreads(numThreads));
+                FastaStream::Chunk c;
+                while (fs.next(chunk, halo, c)) {
+                    unique_ptr<HistJob> job(new HistJob);
+                    job->chars.reset(new char[c.nTotal]);
+                    fs.copyChunk(c, job->chars.get());
+                    job->fragStarts = c.fragStarts; job->nTotal = c.nTotal; job->nPayload = c.nPayload;
+                    unique_lock<mutex> l(qm);
+                    qcv.wait(l, [&] { return q.size() < ctxs.size() + 1 || !failure.empty(); });
+                    if (!failure.empty()) break;
+                    q.push_back(std::move(job));
+                    qcv.notify_all();
+                    cout << "."; cout.flush();
+                }
+            } catch (...) {
+                { lock_guard<mutex> l(qm); done = true; if (failure.empty()) failure = "input error"; }
+                qcv.notify_all();
+                for (auto& w : workers) w.join();
+                destroyAll();
+                throw;
             }
+            { lock_guard<mutex> l(qm); done = true; }
+            qcv.notify_all();
+            for (auto& w : workers) w.join();
             cout << endl;
-            vector<uint64_t> counts(len.size() * numBins);
-            check(b200scan_hist_read(ctx, counts.data(), counts.size()));
+            if (!failure.empty()) { destroyAll(); throw runtime_error("CUDA error: " + failure); }
+            vector<uint64_t> counts(len.size() * numBins), total(len.size() * numBins, 0);
+            for (auto c : ctxs) {
+                if (b200scan_hist_read(c, counts.data(), counts.size()) != B200SCAN_OK) { const string e = b200scan_last_error(c); destroyAll(); throw runtime_error("CUDA error: " + e); }
+                for (size_t i = 0; i < counts.size(); i++) total[i] += counts[i];
+            }
             for (size_t i = 0; i < hists.size(); i++)
-                for (size_t b = 0; b < numBins; b++) hists[i].counts[b] = counts[i * numBins + b];
+                for (size_t b = 0; b < numBins; b++) hists[i].counts[b] = total[i * numBins + b];
         }
         forEachMotif(hists.size(), [&](size_t i) {
             hists[i].writeGNUPlot(histdir, "hist_" + sp.name + "_" + mc.motifs[i].name, mc.motifs[i].name + " (" + sp.name + ")");
         });
     }
-    if (ctx) b200scan_destroy(ctx);
+    destroyAll();
     return EXIT_SUCCESS;
 }
 
@@ -235,7 +306,8 @@ static void scanUsage()
             "  -e\t--engine\tauto | tensor | gather [default = auto]\n\n"
             " [file_options]\n"
             "  -H\t--histdir\tdirectory where the histogram file(s) are stored [default = .]\n"
-            "  -o\t--output\tfilename for the motif occurrences [default = occurences.txt]\n\n"
+            "  -o\t--output\tfilename for the motif occurrences [default = occurences.txt]\n"
+            "  \t--stats\tfilename for a JSON account of the run (phases, per-GPU kernel and transfer times)\n\n"
             " File \"motifs.input\" should contain the motifs in Jaspar format\n"
             " File \"sequences.input\" should contain a list of input fasta files (see blamm dict)\n\n"
             " Example:\n  blamm scan -o occurences.txt motifs.input sequences.input\n\n";
@@ -466,7 +538,7 @@ void writerThread(ScanShared& sh)
 // `ctxSlot` persists across the species groups of a run: the context (CUDA initialisation, pinned and device buffers,
 // ~0.7 s) is created once, on its own thread, while the host still loads histograms and parses the first chunk (`ready`
 // carries the error text of a failed creation); every group only re-loads it with its motifs.
-void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctxSlot, shared_future<string> ready)
+void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctxSlot, shared_future<string> ready, size_t devIndex)
 {
     b200scan_ctx*& ctx = *ctxSlot;
     auto die = [&](const string& what) {
@@ -495,17 +567,19 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
     auto collectOldest = [&]() -> bool {
         const int s = tail;
         const double tc = now();
+        b200scan_timing tm{};
         if (hitFormat == B200SCAN_HITS_8) {
             const b200scan_hit8* hits = nullptr; const uint32_t* bucketStart = nullptr; uint64_t n = 0, nb = 0;
-            if (b200scan_collect8(ctx, s, &hits, &n, &bucketStart, &nb, nullptr) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
+            if (b200scan_collect8(ctx, s, &hits, &n, &bucketStart, &nb, &tm) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
             gTimer.add("b200scan_collect (wait GPU)", now() - tc);
             writeHits8(sh, *inFlight[s], hits, n, bucketStart, nb);
         } else {
             const b200scan_hit12* hits = nullptr; uint64_t n = 0;
-            if (b200scan_collect12(ctx, s, &hits, &n, nullptr) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
+            if (b200scan_collect12(ctx, s, &hits, &n, &tm) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
             gTimer.add("b200scan_collect (wait GPU)", now() - tc);
             writeHits(sh, *inFlight[s], hits, n);
         }
+        gStats.add(devIndex, tm, inFlight[s]->nPayload);
         inFlight[s].reset();
         tail = (tail + 1) % B200SCAN_NUM_SLOTS; nFlight--;
         return true;
@@ -644,6 +718,23 @@ int runWriterSelfTest(int argc, char** argv)
 
 } // namespace
 
+void writeStats()
+{
+    if (gStats.file.empty()) return;
+    ofstream js(gStats.file);
+    js.precision(9);
+    js << "{\"phases_s\": {";
+    for (size_t i = 0; i < gTimer.acc.size(); i++) js << (i ? ", " : "") << "\"" << gTimer.acc[i].first << "\": " << gTimer.acc[i].second;
+    js << "}, \"devices\": [";
+    for (size_t d = 0; d < gStats.dev.size(); d++) {
+        const DeviceStats& s = gStats.dev[d];
+        js << (d ? ", " : "") << "{\"device\": " << d << ", \"chunks\": " << s.chunks << ", \"characters\": " << s.chars << ", \"hits\": " << s.hits
+           << ", \"candidates\": " << s.candidates << ", \"h2d_ms\": " << s.h2d << ", \"pack_ms\": " << s.pack << ", \"score_ms\": " << s.score
+           << ", \"rescore_ms\": " << s.rescore << ", \"order_ms\": " << s.order << ", \"d2h_ms\": " << s.d2h << "}";
+    }
+    js << "], \"columns\": " << gStatsColumns << ", \"matches\": " << gStatsMatches << "}\n";
+}
+
 int runScan(int argc, char** argv)
 {
     bool foldLower = false, revCompl = false;
@@ -678,6 +769,7 @@ int runScan(int argc, char** argv)
             else if (e == "gather") engine = B200SCAN_ENGINE_GATHER; else throw runtime_error("Unknown engine: " + e);
         } else if ((arg == "-H" || arg == "--histdir") && hasVal) { histdir = argv[++i]; if (histdir.back() != '/') histdir.push_back('/'); }
         else if ((arg == "-o" || arg == "--output") && hasVal) outputFilename = argv[++i];
+        else if (arg == "--stats" && hasVal) { gStats.file = argv[++i]; gTimer.on = true; gTimer.quiet = getenv("BLAMM_B200_TIMING") == nullptr; }
         else { scanUsage(); return EXIT_FAILURE; }
     }
     if (!(absSpec || relSpec || pSpec)) relSpec = true;
@@ -796,7 +888,7 @@ int runScan(int argc, char** argv)
         thread writer(writerThread, ref(sh));
         auto stopWriter = [&] { { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; } sh.oCv.notify_all(); writer.join(); };
         vector<thread> workers;
-        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), engine, foldLower, &pool.ctx[(size_t)d], pool.ready[(size_t)d]);
+        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), engine, foldLower, &pool.ctx[(size_t)d], pool.ready[(size_t)d], (size_t)d);
         try {
             FastaStream fs(sp.files, sp.totSeqLen);
             fs.setParallel(ingestThreads(numThreads));
@@ -845,6 +937,7 @@ int runScan(int argc, char** argv)
     os.close();
     ofsCutoff.close();
     cout << "\nWrote " << totMatches << " matches to " << outputFilename << ".\n";
+    gStatsColumns = mc.motifs.size(); gStatsMatches = totMatches;
     gTimer.add("scan module before teardown", now() - tStart);
     return EXIT_SUCCESS;
 }
@@ -876,6 +969,7 @@ int main(int argc, char** argv)
             int rc = blamm::runScan(argc, argv);
             blamm::gTimer.add("scan module incl. teardown", blamm::now() - t0);
             blamm::gTimer.report();
+            blamm::writeStats();
             if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl;
             return rc;
         }

@@ -217,6 +217,12 @@ int  b200scan_flush_l2(b200scan_ctx* ctx);
 int  b200scan_describe(const b200scan_ctx* ctx, int32_t* n_cols, int32_t* max_len, int32_t* n_tiles,
                        int32_t* sm_count, uint64_t* sum_len);
 
+/* Roofline bookkeeping: tensor-core operations per WINDOW of the loaded motif set -- as issued by the filter
+ * (every column tile padded to its N and to whole K steps: 2 N K n_k per tile; 0 if the set runs on the gather engine) and
+ * as the algorithm needs (8 x sum of the column lengths, un-padded).  What the reference spends per window is the same
+ * 8 sum L inside sgemm (matrix.h:295-304). */
+int  b200scan_tensor_work(const b200scan_ctx* ctx, double* mma_ops_per_window, double* algorithmic_ops_per_window);
+
 #ifdef __cplusplus
 }
 #endif

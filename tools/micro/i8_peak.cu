@@ -89,7 +89,7 @@ template <bool I8> static int run(const char* name, int sms, int chains, double*
 
 int main(int argc, char** argv)
 {
-    int dev = 0; cudaSetDevice(dev);
+    int dev = argc > 2 ? atoi(argv[2]) : 0; cudaSetDevice(dev);
     cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
     const int sms = p.multiProcessorCount;
     const int chains = argc > 1 ? atoi(argv[1]) : 4000;      // 4000 chains x 8 MMAs x 128 cycles = 4.1 M cycles ~ 2 ms per launch
