@@ -217,6 +217,20 @@ def make_motifs(workdir: str, config: str) -> str:
     return mfile
 
 
+def build_inputs(workdir: str, n_nt: int, k: int = 0):
+    """c2: motif set, P, thresholds (`-rc -pt 1e-4` from theoretical histograms, host C++ model) and chunk k of the stream -- the
+    inputs run_blocks() scans; tests/test_gpu_parity.py checks the full-size workload through this function."""
+    from blamm_b200 import capi, synth
+    ms = capi.MotifSet(make_motifs(workdir, "c2"), revcompl=True)
+    seq = chunk_chars(k, n_nt, (0.25, 0.25, 0.25, 0.25))
+    first = seq[: min(n_nt, 4_000_000)]
+    bg = [int(round(c * (n_nt / len(first)))) for c in synth.counts_of(first)]
+    ms.write_histograms(bg, SPECIES, workdir)
+    P, col_len, _ = ms.generate_matrix(bg)
+    thr = ms.thresholds("pt", 1e-4, SPECIES, workdir)
+    return ms, P, col_len, thr, seq, bg
+
+
 def chunk_chars(k: int, n_nt: int, probs, softmask: float = 0.0) -> np.ndarray:
     """Chunk k of the synthetic stream (every chunk has its own seed, so a rank generates only what it scans)."""
     from blamm_b200 import synth
@@ -335,7 +349,7 @@ def run_reference(args, rank: int, world: int) -> None:
         shutil.rmtree(work, ignore_errors=True)
 
 
-def cpu_baseline(work: str, seq: np.ndarray, n_cols: int, sample_nt: int, scan_args) -> dict:
+def cpu_baseline(work: str, seq: np.ndarray, n_cols: int, sample_nt: int, scan_args, device=None) -> dict:
     """Reference binary on a bounded sample of the same workload (rank 0, N = 1 only; ~20 s of wall clock on 16 cores)."""
     cores = os.cpu_count() or 1
     sub = os.path.join(work, "cpu")
@@ -351,9 +365,25 @@ def cpu_baseline(work: str, seq: np.ndarray, n_cols: int, sample_nt: int, scan_a
         if "-pt" in scan_args:
             ref_run(["hist", "motifs.jaspar", "sequences.mf"], sub, env)
         dt = ref_run(["scan"] + scan_args + ["-t", str(cores), "motifs.jaspar", "sequences.mf"], sub, env)
-        return {"value": n * n_cols / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": "first %.1f Mbp of the workload (%d reference blocks) x %d columns, `blamm scan %s -t %d` (OpenBLAS threads=1), %.1f s wall" % (
-                    n / 1e6, n // 250000, n_cols, " ".join(scan_args), cores, dt)}
+        out = {"value": n * n_cols / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": "first %.1f Mbp of the workload (%d reference blocks) x %d columns, `blamm scan %s -t %d` (OpenBLAS threads=1), %.1f s wall" % (
+                   n / 1e6, n // 250000, n_cols, " ".join(scan_args), cores, dt)}
+        # the reference's OWN GPU path on this B200 (`scan -c`: cuBLAS sgemm per offset + filterScore, pwmscan.cpp:297-437, kernel.cu),
+        # compiled for sm_100 by oracle/build_ref.sh: the existing GPU implementation next to the B200-native one
+        ref_cuda = os.path.join(ROOT, "oracle", "_ref", "blamm_cuda")
+        if os.path.exists(ref_cuda) and device is not None:
+            try:
+                env1 = dict(env, CUDA_VISIBLE_DEVICES=str(device))
+                t0 = time.perf_counter()
+                subprocess.run([ref_cuda, "scan", "-c"] + scan_args + ["-t", str(cores), "-o", "occ_cuda.txt", "motifs.jaspar", "sequences.mf"],
+                               cwd=sub, env=env1, check=True, stdout=subprocess.DEVNULL, timeout=600)
+                dtc = time.perf_counter() - t0
+                same = subprocess.run("cmp -s <(LC_ALL=C sort occurrences.txt) <(LC_ALL=C sort occ_cuda.txt)", shell=True, executable="/bin/bash", cwd=sub).returncode == 0
+                out["gpu_reference"] = {"value": n * n_cols / dtc, "unit": UNIT, "how": "reference `blamm scan -c` (cuBLAS sgemm + filterScore, unmodified sources compiled "
+                                        "for sm_100) on 1 B200, same %.1f Mbp sample, %.1f s wall; sorted output identical to its CPU path: %s" % (n / 1e6, dtc, same)}
+            except Exception as e:
+                out["gpu_reference"] = {"value": None, "how": "reference `scan -c` failed: %s" % e}
+        return out
     except Exception as e:                                        # reference binary unusable: time the C oracle port instead
         from blamm_b200 import capi, synth
         from oracle import oracle as O
@@ -521,8 +551,8 @@ def run_blocks(args, rank: int, local_rank: int, world: int) -> None:
             for k, (s, ptr) in enumerate(blocks):
                 if not args.ascii:
                     has_zero[k] = packer.pack(ptr, s.n_total, code_bufs[0][0], code_bufs[0][1])
-                submit(0, k, code_bufs[0])
-                n_hits[k], _, t_last, _ = collect(0)
+                submit(w % capi.NUM_SLOTS, k, code_bufs[0])             # every slot allocates its buffers at its first use: outside the timed region
+                n_hits[k], _, t_last, _ = collect(w % capi.NUM_SLOTS)
 
         sampler = ClockSampler(local_rank, bus)
         # ---- timed: device-resident steps (CUDA events on the scan stream), L2 flushed between launches ----
@@ -632,7 +662,7 @@ def run_blocks(args, rank: int, local_rank: int, world: int) -> None:
                              "note": "achieved / frac = ALGORITHMIC operations (8 x sum L per window, integer multiply-adds counted like flops) per measured kernel time"},
             }
             if world == 1 and not args.no_cpu_baseline and seq0 is not None:
-                line["cpu_baseline"] = cpu_baseline(work, seq0, n_cols, min(args.cpu_sample_nt if not c4 else 4_000_000, len(seq0)), scan_args)
+                line["cpu_baseline"] = cpu_baseline(work, seq0, n_cols, min(args.cpu_sample_nt if not c4 else 4_000_000, len(seq0)), scan_args, local_rank)
             print(json.dumps(line), flush=True)
         sc.close()
         for _, ptr in blocks:
@@ -775,7 +805,7 @@ def main() -> None:
     ap.add_argument("--workdir", default="", help="c3 / c5: directory for the FASTA set and the outputs (default: /dev/shm if roomy, else the temp dir)")
     ap.add_argument("--keep", action="store_true", help="c3 / c5: keep the work directory")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if (args.impl == "b200" and args.config in ("c2", "c4")) else args.warmup
+    args.warmup = max(args.warmup, 3) if (args.impl == "b200" and args.config in ("c2", "c4")) else args.warmup     # >= 3: one per slot
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

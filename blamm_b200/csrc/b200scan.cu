@@ -93,7 +93,7 @@ struct b200scan_ctx {
     unsigned long long* d_trace = nullptr;   // B200_TRACE builds only
     // B200SCAN_HITS_8 (order.cuh): per-bucket counters / cursors and the bucket-contiguous scratch list, shared by the slots
     // (the ordering kernels of a block run back to back on the compute stream)
-    uint32_t *d_bucket_cnt = nullptr, *d_bucket_cursor = nullptr;  size_t bucket_cap = 0;
+    uint32_t *d_bucket_cnt = nullptr, *d_bucket_cursor = nullptr, *d_coarse_start = nullptr;  size_t bucket_cap = 0;     // per coarse bucket
     Hit12* d_sort_tmp = nullptr;  unsigned long long sort_cap = 0;
     // empirical histograms
     uint32_t hist_bins = 0;  unsigned long long* d_hist = nullptr;  float *d_hmin = nullptr, *d_hwid = nullptr;
@@ -544,11 +544,12 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     const MotifDev md = motif_dev(ctx);
     const BlockDev blk = block_dev(s);
     const bool ordered = s.hit_bytes == B200SCAN_HITS_8;
-    const uint32_t n_buckets = (uint32_t)((s.n_payload + kBucketSize - 1) >> kBucketShift);
-    if (ordered) {                                   // per-bucket counters of this block (rescore / gather count into them)
+    const uint32_t n_fine = (uint32_t)((s.n_payload + kBucketSize - 1) >> kBucketShift);
+    const uint32_t n_coarse = (uint32_t)((s.n_payload + kCoarseSize - 1) >> kCoarseShift);
+    if (ordered) {                                   // per-coarse-bucket counters of this block (rescore / gather count into them)
         int rc = ensure_order(ctx, s);
         if (rc) return rc;
-        if (n_buckets) CU(cudaMemsetAsync(ctx->d_bucket_cnt, 0, (size_t)n_buckets * 4, ctx->stream));
+        if (n_coarse) CU(cudaMemsetAsync(ctx->d_bucket_cnt, 0, (size_t)n_coarse * 4, ctx->stream));
     }
     HitSink sink{s.d_hits, s.d_counters + 1, s.hit_cap, s.hit_bytes == B200SCAN_HITS_16 ? 0u : 1u, ordered ? ctx->d_bucket_cnt : nullptr};
     unsigned int* err = reinterpret_cast<unsigned int*>(s.d_counters + 2) + 1;
@@ -634,10 +635,11 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     if (ordered) {
         // (position, column) order on the device: scan of the per-bucket counts, scatter into bucket-contiguous order, order
         // inside every bucket; the final 8-byte records overwrite the slot's (now dead) unordered list.
-        bucket_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_buckets, s.d_bucket_start, ctx->d_bucket_cursor);
+        bucket_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_coarse, ctx->d_coarse_start, ctx->d_bucket_cursor);
         bucket_scatter_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const Hit12*>(s.d_hits), s.d_counters + 1, s.hit_cap,
                                                                          ctx->d_bucket_cursor, ctx->d_sort_tmp);
-        bucket_order_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_sort_tmp, s.d_bucket_start, n_buckets, reinterpret_cast<uint2*>(s.d_hits));
+        bucket_order_kernel<<<ctx->sm_count * 8, kOrderThreads, 0, ctx->stream>>>(ctx->d_sort_tmp, ctx->d_coarse_start, n_coarse, n_fine, s.d_bucket_start,
+                                                                                 reinterpret_cast<uint2*>(s.d_hits));
         n += 3;
     }
     if (ev_after_order) CU(cudaEventRecord(ev_after_order, ctx->stream));
@@ -671,11 +673,11 @@ int ensure_ascii(b200scan_ctx* ctx, Slot& s, bool need_host)
 // B200SCAN_HITS_8: bucket arrays for max_block characters, scratch list for the slot's hit capacity
 int ensure_order(b200scan_ctx* ctx, Slot& s)
 {
-    const size_t want = (size_t)(ctx->max_block >> kBucketShift) + 2;
-    if (ctx->bucket_cap < want) {
-        dfree(ctx->d_bucket_cnt); dfree(ctx->d_bucket_cursor);
-        CU(cudaMalloc(&ctx->d_bucket_cnt, want * 4)); CU(cudaMalloc(&ctx->d_bucket_cursor, want * 4));
-        ctx->bucket_cap = want;
+    const size_t want = (size_t)(ctx->max_block >> kBucketShift) + 2, want_c = (size_t)(ctx->max_block >> kCoarseShift) + 2;
+    if (ctx->bucket_cap < want_c) {
+        dfree(ctx->d_bucket_cnt); dfree(ctx->d_bucket_cursor); dfree(ctx->d_coarse_start);
+        CU(cudaMalloc(&ctx->d_bucket_cnt, want_c * 4)); CU(cudaMalloc(&ctx->d_bucket_cursor, want_c * 4)); CU(cudaMalloc(&ctx->d_coarse_start, want_c * 4));
+        ctx->bucket_cap = want_c;
     }
     if (s.bucket_cap < want) {
         dfree(s.d_bucket_start);
@@ -877,7 +879,7 @@ void b200scan_destroy(b200scan_ctx* c)
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     }
     dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_flush);
-    dfree(c->d_bucket_cnt); dfree(c->d_bucket_cursor); dfree(c->d_sort_tmp);
+    dfree(c->d_bucket_cnt); dfree(c->d_bucket_cursor); dfree(c->d_coarse_start); dfree(c->d_sort_tmp);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg); dfree(c->d_ttiles_z); dfree(c->d_bimg_z);
     dfree(c->d_hist); dfree(c->d_hmin); dfree(c->d_hwid); dfree(c->d_htiles);

@@ -38,8 +38,17 @@ struct HitSink {
     unsigned long long*  n_hits;   // keeps counting past `cap` so the host can size a retry exactly
     unsigned long long   cap;
     uint32_t             compact;  // 1: the list holds 12-byte b200scan_hit12 records
-    uint32_t*            bucket_cnt; // B200SCAN_HITS_8 (order.cuh): hits per bucket of 2^B200SCAN_BUCKET_SHIFT positions, else nullptr
+    uint32_t*            bucket_cnt; // B200SCAN_HITS_8 (order.cuh): hits per COARSE bucket of 2^kCoarseShift positions, else nullptr
 };
+constexpr uint32_t kCoarseShift = 12;   // order.cuh: the device orders the hits of 4096 window positions per CTA
+// One more hit at block position `pos` for the ordering pass: lanes of the calling warp that share a coarse bucket add up first
+// (hits of one warp come from neighbouring windows).  Every lane named in `mask` must call this.
+__device__ __forceinline__ void count_hit_bucket(const HitSink& sink, uint32_t mask, uint32_t pos)
+{
+    const uint32_t bucket = pos >> kCoarseShift;
+    const uint32_t peers = __match_any_sync(mask, bucket);
+    if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(sink.bucket_cnt + bucket, (uint32_t)__popc(peers));
+}
 // record `idx` of the hit list in the sink's format
 __device__ __forceinline__ void store_hit(const HitSink& sink, unsigned long long idx, const b200scan_hit& h)
 {
@@ -84,13 +93,15 @@ __device__ __forceinline__ void emit_hits_warp(bool pred, uint32_t pos, uint32_t
     unsigned long long base = 0;
     if (lane == leader) base = atomicAdd(sink.n_hits, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) {
-        unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
-        if (idx < sink.cap) {
-            b200scan_hit h; h.pos = pos; h.col = col; h.score = score;
-            store_hit(sink, idx, h);
-            if (sink.bucket_cnt) atomicAdd(sink.bucket_cnt + (pos >> B200SCAN_BUCKET_SHIFT), 1u);
-        }
+    const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+    const bool stored = pred && idx < sink.cap;
+    if (stored) {
+        b200scan_hit h; h.pos = pos; h.col = col; h.score = score;
+        store_hit(sink, idx, h);
+    }
+    if (sink.bucket_cnt) {
+        const uint32_t sm = __ballot_sync(0xffffffffu, stored);
+        if (stored) count_hit_bucket(sink, sm, pos);
     }
 }
 

@@ -109,11 +109,15 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
         unsigned long long o = 0;
         if (lane == 0) o = atomicAdd(sink.n_hits, (unsigned long long)n_st);
         o = __shfl_sync(0xffffffffu, o, 0);
-        for (uint32_t k = lane; k < n_st; k += 32)
-            if (o + k < sink.cap) {
-                store_hit(sink, o + k, st[k]);
-                if (sink.bucket_cnt) atomicAdd(sink.bucket_cnt + (uint32_t)(st[k].pos >> B200SCAN_BUCKET_SHIFT), 1u);
+        for (uint32_t k0 = 0; k0 < n_st; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const bool stored = k < n_st && o + k < sink.cap;
+            if (stored) store_hit(sink, o + k, st[k]);
+            if (sink.bucket_cnt) {
+                const uint32_t sm = __ballot_sync(0xffffffffu, stored);
+                if (stored) count_hit_bucket(sink, sm, (uint32_t)st[k].pos);
             }
+        }
         __syncwarp();
         n_st = 0; round = 0;
     };

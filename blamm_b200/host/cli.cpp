@@ -779,13 +779,27 @@ int runScan(int argc, char** argv)
 
     cout << "Welcome to blamm -- PWM scan module" << endl;
     const double tStart = now();
-    // CUDA start-up (driver initialisation grows with the number of GPUs in the box) overlaps the loading of the inputs
-    future<int> devCount = async(launch::async, [] { return b200scan_device_count(); });
     Settings settings;
     settings.print();
 
     SpeciesSet sc;
     sc.loadDict(string(argv[argc - 1]) + ".dict");
+    uint64_t chunk = 32ull << 20;
+    if (const char* e = getenv("BLAMM_B200_CHUNK")) chunk = max<uint64_t>(strtoull(e, nullptr, 10), 1024);
+    // CUDA start-up overlaps the loading of the inputs.  Driver initialisation grows with the number of GPUs it has to bring up, so
+    // a run that cannot keep more than k devices busy (k = chunks of the largest group, or -g) only shows the first k to the
+    // driver -- unless the user has chosen the devices (CUDA_VISIBLE_DEVICES).
+    {
+        uint64_t maxChunks = 1;
+        for (const auto& sp : sc.species) maxChunks = max<uint64_t>(maxChunks, (sp.totSeqLen + chunk - 1) / chunk);
+        const uint64_t useful = gpusWanted > 0 ? min<uint64_t>((uint64_t)gpusWanted, maxChunks) : maxChunks;
+        if (!getenv("CUDA_VISIBLE_DEVICES") && useful < 16) {
+            string vis;
+            for (uint64_t d = 0; d < useful; d++) vis += (d ? "," : "") + to_string(d);
+            setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+        }
+    }
+    future<int> devCount = async(launch::async, [] { return b200scan_device_count(); });
     MotifSet mc;
     mc.load(argv[argc - 2], true);
     cout << "Loaded " << mc.motifs.size() << " motifs from disk\n";
@@ -800,7 +814,10 @@ int runScan(int argc, char** argv)
     else if (relSpec) cout << "Relative motif score threshold set to: " << relThr << endl;
     else cout << "P-value motif score threshold set to: " << pvalue << endl;
 
+    gTimer.add("setup: settings, dict, motifs", now() - tStart);
+    const double tDev = now();
     int nDev = devCount.get();
+    gTimer.add("setup: wait for the CUDA driver (device count)", now() - tDev);
     if (nDev == 0) throw runtime_error("CUDA error: no sm_100 devices found. Aborting...");
     if (gpusWanted > 0) nDev = min(nDev, gpusWanted);
     cout << "Using " << nDev << " GPU devices" << endl;
@@ -809,8 +826,6 @@ int runScan(int argc, char** argv)
     ofstream os(outputFilename);
     if (!os) throw runtime_error("Cannot write to file: " + outputFilename);
 
-    uint64_t chunk = 32ull << 20;
-    if (const char* e = getenv("BLAMM_B200_CHUNK")) chunk = max<uint64_t>(strtoull(e, nullptr, 10), 1024);
     const uint64_t halo = mc.maxLen() - 1;
     uint64_t totMatches = 0;
     // one context per device for the whole run, sized for the largest group
@@ -843,7 +858,7 @@ int runScan(int argc, char** argv)
             return string();
         }).share());
 
-    double tSetup = tStart;
+    double tSetup = now();
     for (const auto& sp : sc.species) {
         cout << "Scanning species: " << sp.name;
         sp.printNuclProb(settings.pseudocount);
@@ -876,7 +891,7 @@ int runScan(int argc, char** argv)
             ofsCutoff << sp.name << "\t" << m.name << "\t" << m.minScore() << "\t" << m.threshold << "\t" << m.maxScore() << endl;
         }
 
-        gTimer.add("setup: dict, motifs, thresholds", now() - tSetup);
+        gTimer.add("setup: matrix P, histograms, thresholds (per group)", now() - tSetup);
         ScanShared sh;
         sh.motifs = &mc; sh.species = &sp; sh.os = &os;
         sh.formatThreads = std::max<size_t>(1, numThreads / (size_t)nDev);
@@ -971,7 +986,9 @@ int main(int argc, char** argv)
             blamm::gTimer.report();
             blamm::writeStats();
             if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl;
-            return rc;
+            // every output file is closed and the contexts are destroyed: skip the CUDA runtime's own at-exit teardown (~0.1 s)
+            cout.flush(); cerr.flush(); fflush(nullptr);
+            _exit(rc);
         }
     } catch (const exception& e) {
         cerr << e.what() << endl;

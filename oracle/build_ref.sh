@@ -7,6 +7,9 @@
 #   * BLAS = OpenBLAS 0.3.15 that ships inside the opencv wheel of this image (exports plain sgemm_)
 # Outputs:  oracle/_ref/blamm          the reference CLI (CPU BLAS path + naive path)
 #           oracle/_ref/refdump        float-level harness linking the reference's own classes (refdump.cpp)
+#           oracle/_ref/blamm_cuda     the reference CLI with its own GPU path (`scan -c`: cuBLAS sgemm + kernel.cu's filterScore,
+#                                      pwmscan.cpp:297-437) compiled for sm_100 -- the "existing GPU implementation" bench.py times
+#                                      beside the B200-native path; only built where nvcc exists
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${BLAMM_REFERENCE:-/root/reference}"
@@ -23,5 +26,13 @@ CXXFLAGS="-O3 -std=c++11 -DNDEBUG -DHAVE_CONFIG_H -DBLAMM_MAJOR_VERSION=1 -DBLAM
 LDFLAGS="-L$OB -l:$OBLIB -Wl,--disable-new-dtags -Wl,-rpath,$OB -lpthread"
 /usr/bin/g++ $CXXFLAGS "$REF"/src/*.cpp -o "$OUT/blamm" $LDFLAGS
 /usr/bin/g++ $CXXFLAGS -I"$REF/src" "$HERE/refdump.cpp" "$REF"/src/{motif,sequence,species,settings,matrix}.cpp -o "$OUT/refdump" $LDFLAGS
+if command -v nvcc > /dev/null 2>&1; then
+  CUDA="$(dirname "$(dirname "$(command -v nvcc)")")"
+  [ -d "$CUDA/include" ] || CUDA=/usr/local/cuda
+  nvcc -O3 -gencode arch=compute_100,code=sm_100 -c "$REF/src/kernel.cu" -o "$OUT/cfg/kernel.o"
+  /usr/bin/g++ $CXXFLAGS -DHAVE_CUDA -I"$CUDA/include" "$REF"/src/*.cpp "$OUT/cfg/kernel.o" -o "$OUT/blamm_cuda" $LDFLAGS \
+      -L"$CUDA/lib64" -Wl,-rpath,"$CUDA/lib64" -lcublas -lcudart
+  echo "build_ref: built $OUT/blamm_cuda (reference GPU path, sm_100)"
+fi
 echo "$OB" > "$OUT/openblas_dir.txt"
 echo "build_ref: built $OUT/blamm and $OUT/refdump"

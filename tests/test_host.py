@@ -6,6 +6,7 @@ import os
 import re
 import shutil
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -402,3 +403,36 @@ def test_synthetic_generators_are_seeded(tmp_path):
     assert [len(x) for x in p1][:3] == [35, 30, 5]
     motifs = O.load_jaspar(str(tmp_path / "a.jaspar"))
     assert sorted(len(m) for m in motifs) == sorted(len(x) for x in p2)
+
+
+def test_parity_lister_lists_only_near_threshold_differences(tmp_path, golden):
+    """tools/parity_list.py (north_star's correctness clause): identical files pass; a missing occurrence FAR from its threshold
+    fails; an occurrence present on one side only whose score lies within 1e-4 of its threshold is listed and tolerated; a score
+    that differs by more than the tolerance fails."""
+    d = os.path.join(golden, "example")
+    ref = open(os.path.join(d, "occ_pt_rc.txt")).read().splitlines(True)
+    ms = capi.MotifSet(os.path.join(d, "motifs.jaspar"), revcompl=True)
+    sp = O.load_dict(os.path.join(d, "sequences.mf.dict"))[0]
+    P, col_len, is_rc = ms.generate_matrix(sp.counts)
+    thr = ms.thresholds("pt", 1e-4, sp.name, d)
+
+    def run(ours_lines, ref_lines):
+        a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+        a.write_text("".join(ours_lines)); b.write_text("".join(ref_lines))
+        return subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parity_list.py"), "--ours", str(a), "--ref", str(b),
+                               "--motifs", os.path.join(d, "motifs.jaspar"), "--manifest", os.path.join(d, "sequences.mf"), "--pt", "0.0001",
+                               "--rc", "--out", str(tmp_path / "list.txt")], capture_output=True, text=True)
+    shuffled = ref[::-1]
+    r = run(shuffled, ref)
+    assert r.returncode == 0 and "identical occurrence sets" in r.stdout, r.stdout + r.stderr
+    r = run(ref[1:], ref)                                             # 10.8353 is not within 1e-4 of its threshold
+    assert r.returncode == 1 and "only-ref" in r.stdout and "FAILED" in r.stdout
+    # a made-up occurrence 4e-5 above its threshold, on the reference side only: listed, tolerated
+    c = 0
+    near = "%s\tblamm\t%s\t7\t%d\t%s\t%s\t.\t.\n" % (sp.seq_names[0], ms.names[c], 7 + int(col_len[c]), O.fmt_g(np.float32(thr[c] + 4e-5)),
+                                                    "-" if is_rc[c] else "+")
+    r = run(ref, ref + [near])
+    assert r.returncode == 0 and "within the tolerance" in r.stdout and "only-ref" in open(tmp_path / "list.txt").read()
+    bent = ref[0].split("\t"); bent[5] = O.fmt_g(np.float32(float(bent[5]) + 0.01))
+    r = run(["\t".join(bent)] + ref[1:], ref)
+    assert r.returncode == 1 and "differences above the tolerance (+ print resolution): 1" in r.stdout
