@@ -638,7 +638,7 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
         bucket_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_bucket_cnt, n_coarse, ctx->d_coarse_start, ctx->d_bucket_cursor);
         bucket_scatter_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const Hit12*>(s.d_hits), s.d_counters + 1, s.hit_cap,
                                                                          ctx->d_bucket_cursor, ctx->d_sort_tmp);
-        bucket_order_kernel<<<ctx->sm_count * 8, kOrderThreads, 0, ctx->stream>>>(ctx->d_sort_tmp, ctx->d_coarse_start, n_coarse, n_fine, s.d_bucket_start,
+        bucket_order_kernel<<<ctx->sm_count * 4, kOrderThreads, 0, ctx->stream>>>(ctx->d_sort_tmp, ctx->d_coarse_start, n_coarse, n_fine, s.d_bucket_start,
                                                                                  reinterpret_cast<uint2*>(s.d_hits));
         n += 3;
     }

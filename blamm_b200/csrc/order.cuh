@@ -98,15 +98,23 @@ bucket_scatter_kernel(const Hit12* __restrict__ in, const unsigned long long* __
 }
 
 // One CTA per coarse bucket (grid-stride).  Pass 1 counts the bucket's hits per position (4096 shared-memory bins), a block scan
-// turns the bins into offsets (and yields bucket_start of the 16 fine buckets), pass 2 places every hit at start + offset[position]++
-// as an 8-byte record; the positions that hold several hits (a few per cent at the usual densities) are collected in a list and
-// put in column order, one thread per position (selection sort in place: the runs are tiny; a run longer than the list can take
-// is handled by its owner thread directly).
+// turns the bins into offsets (and yields bucket_start of the 16 fine buckets), pass 2 places every hit at offset[position]++ as
+// an 8-byte record; the positions that hold several hits (a few per cent at the usual densities) are collected in a list and put
+// in column order, one thread per position (selection sort in place: the runs are tiny).
+// Usual case (<= kStageHits hits in the bucket, about 1000 at -pt 1e-4 x 1800 columns): every thread loads its <= 8 hits ONCE, all
+// loads in flight together (the list was just written by the scatter pass and mostly lies in DRAM: one latency instead of eight),
+// keeps them in registers across the two passes, the records are placed and tie-ordered in shared memory and leave with coalesced
+// stores.  Denser buckets take the same steps out of global memory.
 constexpr uint32_t kOrderThreads = 256;
 constexpr uint32_t kBinsPerThread = kCoarseSize / kOrderThreads;  // 16
-constexpr uint32_t kMultiCap = 1024;
+constexpr uint32_t kHitsPerThread = 8;
+constexpr uint32_t kStageHits = kOrderThreads * kHitsPerThread;   // 2048 records = 16 KB of shared memory
+constexpr uint32_t kMultiCap = 512;
 
-__device__ __forceinline__ void order_run(uint2* r, uint32_t m)
+// bin of position p: the scan reads bins 16 t .. 16 t + 15 from thread t -- XOR with the thread's low bits spreads them over the banks
+__device__ __forceinline__ uint32_t bin_at(uint32_t p) { return p ^ ((p >> 4) & 15u); }
+
+template <class T> __device__ __forceinline__ void order_run(T* r, uint32_t m)
 {
     for (uint32_t a = 0; a + 1 < m; a++) {                           // keys of one position differ only in the column bits
         uint32_t best = a; uint2 vb = r[a];
@@ -120,8 +128,9 @@ bucket_order_kernel(const Hit12* __restrict__ in, const uint32_t* __restrict__ c
                     uint32_t* __restrict__ bucket_start, uint2* __restrict__ out)
 {
     __shared__ uint32_t s_bins[kCoarseSize];
+    __shared__ uint2    s_rec[kStageHits];
     __shared__ uint32_t s_warp[kOrderThreads / 32];
-    __shared__ uint32_t s_multi[kMultiCap];                          // (first slot relative to lo) of positions with several hits
+    __shared__ uint32_t s_multi[kMultiCap];                          // first slot (relative to the bucket) of positions with several hits
     __shared__ uint32_t s_mlen[kMultiCap];
     __shared__ uint32_t s_nmulti;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -134,16 +143,31 @@ bucket_order_kernel(const Hit12* __restrict__ in, const uint32_t* __restrict__ c
             }
             continue;
         }
+        const bool staged = hi - lo <= kStageHits;
+        Hit12 h[kHitsPerThread];
+        if (staged) {
+#pragma unroll
+            for (uint32_t r = 0; r < kHitsPerThread; r++) {
+                const uint32_t i = lo + tid + kOrderThreads * r;
+                if (i < hi) h[r] = in[i];
+            }
+        }
 #pragma unroll
         for (uint32_t k = 0; k < kBinsPerThread; k++) s_bins[tid + kOrderThreads * k] = 0u;
         if (tid == 0) s_nmulti = 0;
         __syncthreads();
-        for (uint32_t i = lo + tid; i < hi; i += kOrderThreads) atomicAdd(s_bins + (in[i].pos & (kCoarseSize - 1)), 1u);
+        if (staged) {
+#pragma unroll
+            for (uint32_t r = 0; r < kHitsPerThread; r++)
+                if (lo + tid + kOrderThreads * r < hi) atomicAdd(s_bins + bin_at(h[r].pos & (kCoarseSize - 1)), 1u);
+        } else {
+            for (uint32_t i = lo + tid; i < hi; i += kOrderThreads) atomicAdd(s_bins + bin_at(in[i].pos & (kCoarseSize - 1)), 1u);
+        }
         __syncthreads();
-        // exclusive scan over the 4096 bins: thread t owns bins 16 t .. 16 t + 15 (= one fine bucket per thread)
+        // exclusive scan over the 4096 bins: thread t owns the positions 16 t .. 16 t + 15
         uint32_t c[kBinsPerThread], sum = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < kBinsPerThread; k++) { c[k] = s_bins[kBinsPerThread * tid + k]; sum += c[k]; }
+        for (uint32_t k = 0; k < kBinsPerThread; k++) { c[k] = s_bins[bin_at(kBinsPerThread * tid + k)]; sum += c[k]; }
         uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += u; }
@@ -151,15 +175,16 @@ bucket_order_kernel(const Hit12* __restrict__ in, const uint32_t* __restrict__ c
         __syncthreads();
         uint32_t run = incl - sum;
         for (uint32_t w = 0; w < wib; w++) run += s_warp[w];
-        // thread t's bins are the positions 16 t .. 16 t + 15: fine bucket t / 16 starts at thread 16 j's offset
+        // fine bucket j of this coarse bucket starts at the offset of thread 16 j
         if ((tid & (kFinePerCoarse - 1)) == 0) {
             const uint32_t f = b * kFinePerCoarse + tid / kFinePerCoarse;
             if (f < n_fine) bucket_start[f] = lo + run;
         }
         if (b == n_coarse - 1 && tid == 0) bucket_start[n_fine] = hi;
+        const uint32_t first = run;
 #pragma unroll
         for (uint32_t k = 0; k < kBinsPerThread; k++) {
-            s_bins[kBinsPerThread * tid + k] = run;
+            s_bins[bin_at(kBinsPerThread * tid + k)] = run;
             if (c[k] >= 2) {
                 const uint32_t slot = atomicAdd(&s_nmulti, 1u);
                 if (slot < kMultiCap) { s_multi[slot] = run; s_mlen[slot] = c[k]; }
@@ -167,22 +192,37 @@ bucket_order_kernel(const Hit12* __restrict__ in, const uint32_t* __restrict__ c
             run += c[k];
         }
         __syncthreads();
-        for (uint32_t i = lo + tid; i < hi; i += kOrderThreads) {
-            const Hit12 h = in[i];
-            const uint32_t p = h.pos & (kCoarseSize - 1);
-            const uint32_t slot = atomicAdd(s_bins + p, 1u);
-            out[lo + slot] = make_uint2(((p & (kBucketSize - 1)) << 24) | h.col, h.score);
+        if (staged) {
+#pragma unroll
+            for (uint32_t r = 0; r < kHitsPerThread; r++)
+                if (lo + tid + kOrderThreads * r < hi) {
+                    const uint32_t p = h[r].pos & (kCoarseSize - 1);
+                    s_rec[atomicAdd(s_bins + bin_at(p), 1u)] = make_uint2(((p & (kBucketSize - 1)) << 24) | h[r].col, h[r].score);
+                }
+        } else {
+            for (uint32_t i = lo + tid; i < hi; i += kOrderThreads) {
+                const Hit12 g = in[i];
+                const uint32_t p = g.pos & (kCoarseSize - 1);
+                out[lo + atomicAdd(s_bins + bin_at(p), 1u)] = make_uint2(((p & (kBucketSize - 1)) << 24) | g.col, g.score);
+            }
         }
         __syncthreads();                                             // the records of this bucket are visible to the whole CTA
         const uint32_t nm = s_nmulti;
         if (nm <= kMultiCap) {
-            for (uint32_t j = tid; j < nm; j += kOrderThreads) order_run(out + lo + s_multi[j], s_mlen[j]);
-        } else {                                                     // dense block: every thread orders the runs of its own bins
-            uint32_t first = s_bins[kBinsPerThread * tid] - c[0];    // (bins now hold the END of every run)
+            for (uint32_t j = tid; j < nm; j += kOrderThreads) { if (staged) order_run(s_rec + s_multi[j], s_mlen[j]); else order_run(out + lo + s_multi[j], s_mlen[j]); }
+        } else {                                                     // many ties: every thread orders the runs of its own positions
+            uint32_t at = first;
 #pragma unroll
-            for (uint32_t k = 0; k < kBinsPerThread; k++) { if (c[k] >= 2) order_run(out + lo + first, c[k]); first += c[k]; }
+            for (uint32_t k = 0; k < kBinsPerThread; k++) {
+                if (c[k] >= 2) { if (staged) order_run(s_rec + at, c[k]); else order_run(out + lo + at, c[k]); }
+                at += c[k];
+            }
         }
-        __syncthreads();                                             // s_bins / s_nmulti are reused by the next bucket
+        __syncthreads();
+        if (staged) {
+            for (uint32_t i = tid; i < hi - lo; i += kOrderThreads) out[lo + i] = s_rec[i];
+            __syncthreads();                                         // s_rec / s_bins / s_nmulti are reused by the next bucket
+        }
     }
 }
 

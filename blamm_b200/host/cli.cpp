@@ -23,6 +23,7 @@
 #include <sstream>
 #include <thread>
 #include <unordered_map>
+#include <fcntl.h>
 #include <unistd.h>
 
 using namespace std;
@@ -315,6 +316,61 @@ static void scanUsage()
 
 namespace {
 
+// A pool of host threads shared by everything that works on hit lists (formatting, file writes): however many GPUs feed the
+// run, the occurrence writer uses all -t threads.  parallel(n, fn) runs fn(0 .. n-1) on the pool AND on the calling thread and
+// returns when all are done; calls from several threads queue up behind one another.
+class WorkPool {
+public:
+    explicit WorkPool(size_t threads) { for (size_t t = 0; t + 1 < threads; t++) workers.emplace_back([this] { loop(); }); }
+    ~WorkPool() { { lock_guard<mutex> l(m); stop = true; } cv.notify_all(); for (auto& t : workers) t.join(); }
+    void parallel(size_t n, const function<void(size_t)>& fn)
+    {
+        if (n == 0) return;
+        if (n == 1 || workers.empty()) { for (size_t i = 0; i < n; i++) fn(i); return; }
+        auto t = make_shared<Task>();
+        t->fn = &fn; t->n = n;
+        { lock_guard<mutex> l(m); q.push_back(t); }
+        cv.notify_all();
+        for (size_t i; (i = t->next.fetch_add(1)) < n;) { fn(i); t->done.fetch_add(1); }
+        unique_lock<mutex> l(m);
+        cvDone.wait(l, [&] { return t->done.load() == n; });
+        for (auto it = q.begin(); it != q.end(); ++it) if (*it == t) { q.erase(it); break; }
+    }
+private:
+    struct Task { const function<void(size_t)>* fn = nullptr; size_t n = 0; atomic<size_t> next{0}, done{0}; };
+    void loop()
+    {
+        for (;;) {
+            shared_ptr<Task> t;
+            {
+                unique_lock<mutex> l(m);
+                cv.wait(l, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                t = q.front();
+            }
+            const size_t i = t->next.fetch_add(1);
+            if (i >= t->n) {                                   // exhausted: drop it from the queue (its owner may have done so already)
+                lock_guard<mutex> l(m);
+                if (!q.empty() && q.front() == t) q.pop_front();
+                continue;
+            }
+            (*t->fn)(i);
+            if (t->done.fetch_add(1) + 1 == t->n) { lock_guard<mutex> l(m); cvDone.notify_all(); }
+        }
+    }
+    vector<thread> workers; mutex m; condition_variable cv, cvDone; deque<shared_ptr<Task>> q; bool stop = false;
+};
+
+// What a device needs to score the chunks of ONE manifest group (its own background -> its own P and thresholds,
+// pwmscan.cpp:594-616).  Jobs carry a pointer to it, so the reader can already parse group g+1 while the GPUs and the
+// formatting threads still work on group g: the run is one pipeline, not one per group.
+struct GroupParams {
+    const Species* species = nullptr;
+    uint64_t id = 0;
+    vector<float> P; int ldp = 0; vector<int32_t> len; vector<float> thr;
+    size_t maxNameLen = 0;                         // longest "<sequence>\tblamm\t<motif>" prefix, for sizing the text buffers
+};
+
 struct Job {
     unique_ptr<char[]> chars;                      // not a vector: no zero fill before the parallel copy
     // packed hand-over (default): 2 bits per character + the zero mask, produced by the parser threads (FastaStream::packChunk);
@@ -324,27 +380,35 @@ struct Job {
     vector<uint64_t> fragStarts;
     vector<Fragment> frags;
     uint64_t nTotal = 0, nPayload = 0;
-    uint64_t seq = 0;                              // index of the chunk in the group's stream: the writer emits chunks in this order
+    uint64_t seq = 0;                              // index of the chunk in the run's stream: the file holds the chunks in this order
+    shared_ptr<const GroupParams> group;
 };
 
+struct MotifText { string name; uint64_t size = 0; bool revComp = false; };      // what a line needs of a column (same for every group)
+
 struct ScanShared {
-    const MotifSet* motifs = nullptr;
-    const Species* species = nullptr;
-    ofstream* os = nullptr;
-    uint64_t totMatches = 0;
-    size_t formatThreads = 1;
-    size_t maxNameLen = 0;                      // longest "<sequence>\tblamm\t<motif>" prefix, for sizing the text buffers
+    vector<MotifText> mtext;
+    int fd = -1;                                   // occurrence file (pwrite at offsets handed out in chunk order)
+    WorkPool* pool = nullptr;
+    atomic<uint64_t> totMatches{0};
     // job queue (producer = FASTA reader, consumers = one thread per GPU)
     mutex qMutex; condition_variable qCv;
     deque<unique_ptr<Job>> queue; bool done = false; size_t maxQueue = 2;
-    // output queue (producers = the GPU threads, consumer = one writer thread): the file write of block k overlaps the
-    // formatting of block k+1 (the reference formats outside and writes inside its output mutex, pwmscan.cpp:88-101).
-    // The writer emits the chunks in STREAM order whatever GPU scored them (Job::seq): the per-GPU hit lists are merged in the
-    // order of the input, so the file does not depend on -g.  A producer whose chunk lies more than maxOut chunks ahead of the
-    // one the writer waits for blocks; the chunk the writer waits for never does.
+    // Output: the chunks land in the file in STREAM order whatever GPU scored them (Job::seq) -- the per-GPU hit lists are merged
+    // in the order of the input, so the file does not depend on -g.  There is no writer thread and no reorder buffer: when a
+    // chunk's text is ready its owner waits for its turn (all earlier chunks have taken their place), takes the next
+    // `bytes` of the file, and the pieces are written in parallel with pwrite (the reference formats outside and writes inside
+    // its output mutex, pwmscan.cpp:88-101).
     mutex oMutex; condition_variable oCv;
-    map<uint64_t, vector<string>> outQueue; uint64_t nextOut = 0; bool outDone = false; size_t maxOut = 4;
+    uint64_t nextOut = 0, fileOffset = 0;
     string error; atomic<bool> failed{false};
+    void fail(const string& what)
+    {
+        { lock_guard<mutex> l(qMutex); if (!failed.exchange(true)) error = what; }
+        qCv.notify_all();
+        { lock_guard<mutex> l(oMutex); }
+        oCv.notify_all();
+    }
 };
 
 // hits of one block -> text lines (reference format: pwmscan.cpp:88-95), in (position, column) order.
@@ -388,7 +452,7 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, std
 {
     sortHits(hits);
     // worst-case line: names + 2 positions of <= 20 digits + score (<= 16) + 5 tabs + strand + "\t.\t.\n"
-    text.resize(hits.size() * (sh.maxNameLen + 96) + 64);
+    text.resize(hits.size() * (job.group->maxNameLen + 96) + 64);
     char* const base = &text[0];
     char* p = base;
     size_t f = 0;
@@ -396,14 +460,14 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, std
         while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= h.pos) f++;
         const Fragment& fr = job.frags[f];
         const uint64_t seqPos = fr.seqPos + (h.pos - fr.streamPos);
-        const Motif& m = sh.motifs->motifs[h.col];
-        const string& sn = sh.species->seqNames.at(fr.seqIdx);
+        const MotifText& m = sh.mtext[h.col];
+        const string& sn = job.group->species->seqNames.at(fr.seqIdx);
         memcpy(p, sn.data(), sn.size()); p += sn.size();
         memcpy(p, "\tblamm\t", 7); p += 7;
         memcpy(p, m.name.data(), m.name.size()); p += m.name.size();
         *p++ = '\t';
         p = to_chars(p, p + 24, (unsigned long long)seqPos).ptr; *p++ = '\t';
-        p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size())).ptr; *p++ = '\t';
+        p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size)).ptr; *p++ = '\t';
         p += formatScore(p, h.score);
         *p++ = '\t'; *p++ = m.revComp ? '-' : '+';
         memcpy(p, "\t.\t.\n", 5); p += 5;
@@ -411,23 +475,49 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, std
     text.resize((size_t)(p - base));
 }
 
-// formatted text of one chunk -> the writer's reorder window
-void pushText(ScanShared& sh, const Job& job, vector<string>&& text, uint64_t n)
+// formatted text of one chunk -> its place in the file: wait for the chunk's turn, take the byte range, write the pieces in parallel
+void emitText(ScanShared& sh, const Job& job, vector<string>& text, uint64_t n)
 {
-    const double t0 = now();
-    unique_lock<mutex> lock(sh.oMutex);
-    sh.oCv.wait(lock, [&] { return job.seq < sh.nextOut + sh.maxOut || sh.failed; });
-    sh.totMatches += n;
-    sh.outQueue.emplace(job.seq, std::move(text));
+    double t0 = now();
+    uint64_t bytes = 0;
+    for (const auto& t : text) bytes += t.size();
+    uint64_t at;
+    {
+        unique_lock<mutex> lock(sh.oMutex);
+        sh.oCv.wait(lock, [&] { return job.seq == sh.nextOut || sh.failed; });
+        if (sh.failed) return;
+        at = sh.fileOffset;
+        sh.fileOffset += bytes;
+        sh.nextOut++;
+    }
     sh.oCv.notify_all();
-    gTimer.add("wait for writer (wall)", now() - t0);
+    sh.totMatches += n;
+    gTimer.add("wait for the chunk's turn in the file (wall)", now() - t0); t0 = now();
+    vector<uint64_t> off(text.size());
+    for (size_t i = 0; i < text.size(); i++) { off[i] = at; at += text[i].size(); }
+    // pieces of at most 64 MiB, one pwrite loop each
+    struct Piece { const char* p; size_t n; uint64_t at; };
+    vector<Piece> pieces;
+    for (size_t i = 0; i < text.size(); i++)
+        for (size_t o = 0; o < text[i].size(); o += (64u << 20)) pieces.push_back({text[i].data() + o, min<size_t>(64u << 20, text[i].size() - o), off[i] + o});
+    atomic<bool> bad{false};
+    sh.pool->parallel(pieces.size(), [&](size_t i) {
+        const char* p = pieces[i].p; size_t left = pieces[i].n; uint64_t o = pieces[i].at;
+        while (left) {
+            const ssize_t w = pwrite(sh.fd, p, left, (off_t)o);
+            if (w <= 0) { if (w < 0 && errno == EINTR) continue; bad = true; return; }
+            p += w; left -= (size_t)w; o += (uint64_t)w;
+        }
+    });
+    if (bad) sh.fail("Cannot write to the occurrence file");
+    gTimer.add("file write (pwrite, wall)", now() - t0);
 }
 
 template <class H>
-void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n)
+void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n, size_t threads)
 {
     double t0 = now();
-    const size_t T = std::max<size_t>(1, std::min<size_t>(sh.formatThreads, n / 50000 + 1));
+    const size_t T = std::max<size_t>(1, std::min<size_t>(threads, n / 50000 + 1));
     vector<vector<H>> part(T);
     if (T == 1) part[0].assign(hits, hits + n);
     else {
@@ -435,34 +525,23 @@ void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n)
         // the device is arbitrary, so every thread scans its slice of the list and appends to per-(thread, range) bins)
         const uint64_t span = job.nPayload / T + 1;
         vector<vector<vector<H>>> bins(T, vector<vector<H>>(T));
-        vector<thread> pool;
-        auto scatter = [&](size_t t) {
+        sh.pool->parallel(T, [&](size_t t) {
             const uint64_t lo = n * t / T, hi = n * (t + 1) / T;
             for (auto& b : bins[t]) b.reserve((hi - lo) / T + (hi - lo) / (4 * T) + 16);
             for (uint64_t i = lo; i < hi; i++) bins[t][hits[i].pos / span].push_back(hits[i]);
-        };
-        for (size_t t = 1; t < T; t++) pool.emplace_back(scatter, t);
-        scatter(0);
-        for (auto& th : pool) th.join();
-        pool.clear();
-        auto gather = [&](size_t r) {
+        });
+        sh.pool->parallel(T, [&](size_t r) {
             size_t c = 0;
             for (size_t t = 0; t < T; t++) c += bins[t][r].size();
             part[r].reserve(c);
             for (size_t t = 0; t < T; t++) part[r].insert(part[r].end(), bins[t][r].begin(), bins[t][r].end());
-        };
-        for (size_t r = 1; r < T; r++) pool.emplace_back(gather, r);
-        gather(0);
-        for (auto& th : pool) th.join();
+        });
     }
     gTimer.add("partition hits (wall)", now() - t0); t0 = now();
     vector<string> text(T);
-    vector<thread> pool;
-    for (size_t t = 1; t < T; t++) pool.emplace_back(formatRange<H>, cref(sh), cref(job), ref(part[t]), ref(text[t]));
-    formatRange(sh, job, part[0], text[0]);
-    for (auto& th : pool) th.join();
+    sh.pool->parallel(T, [&](size_t t) { formatRange<H>(sh, job, part[t], text[t]); });
     gTimer.add("sort + format (wall)", now() - t0);
-    pushText(sh, job, std::move(text), n);
+    emitText(sh, job, text, n);
 }
 
 // Ordered 8-byte records (B200SCAN_HITS_8): the device has already put the block's hits in (position, column) order and
@@ -472,7 +551,7 @@ void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hi
                    std::string& text)
 {
     const uint64_t n = bucketStart[b1] - bucketStart[b0];
-    text.resize(n * (sh.maxNameLen + 96) + 64);
+    text.resize(n * (job.group->maxNameLen + 96) + 64);
     char* const base = &text[0];
     char* p = base;
     size_t f = 0;
@@ -483,14 +562,14 @@ void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hi
             while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= pos) f++;
             const Fragment& fr = job.frags[f];
             const uint64_t seqPos = fr.seqPos + (pos - fr.streamPos);
-            const Motif& m = sh.motifs->motifs[col];
-            const string& sn = sh.species->seqNames.at(fr.seqIdx);
+            const MotifText& m = sh.mtext[col];
+            const string& sn = job.group->species->seqNames.at(fr.seqIdx);
             memcpy(p, sn.data(), sn.size()); p += sn.size();
             memcpy(p, "\tblamm\t", 7); p += 7;
             memcpy(p, m.name.data(), m.name.size()); p += m.name.size();
             *p++ = '\t';
             p = to_chars(p, p + 24, (unsigned long long)seqPos).ptr; *p++ = '\t';
-            p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size())).ptr; *p++ = '\t';
+            p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size)).ptr; *p++ = '\t';
             p += formatScore(p, hits[i].score);
             *p++ = '\t'; *p++ = m.revComp ? '-' : '+';
             memcpy(p, "\t.\t.\n", 5); p += 5;
@@ -499,67 +578,40 @@ void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hi
     text.resize((size_t)(p - base));
 }
 
-void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets)
+void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets, size_t threads)
 {
     const double t0 = now();
-    const size_t T = std::max<size_t>(1, std::min<size_t>(sh.formatThreads, n / 50000 + 1));
+    // a few pieces per thread: the pool is shared by all the GPUs' chunks, short pieces even out the load
+    const size_t T = std::max<size_t>(1, std::min<size_t>(2 * threads, n / 50000 + 1));
     vector<uint64_t> cut(T + 1, nBuckets);
     cut[0] = 0;
     for (size_t t = 1; t < T; t++)                   // first bucket whose start reaches t/T of the hits
         cut[t] = (uint64_t)(std::lower_bound(bucketStart, bucketStart + nBuckets, (uint32_t)(n * t / T)) - bucketStart);
     vector<string> text(T);
-    vector<thread> pool;
-    for (size_t t = 1; t < T; t++) pool.emplace_back(formatBuckets, cref(sh), cref(job), hits, bucketStart, cut[t], cut[t + 1], ref(text[t]));
-    formatBuckets(sh, job, hits, bucketStart, cut[0], cut[1], text[0]);
-    for (auto& th : pool) th.join();
+    sh.pool->parallel(T, [&](size_t t) { formatBuckets(sh, job, hits, bucketStart, cut[t], cut[t + 1], text[t]); });
     gTimer.add("format ordered hits (wall)", now() - t0);
-    pushText(sh, job, std::move(text), n);
+    emitText(sh, job, text, n);
 }
 
-void writerThread(ScanShared& sh)
-{
-    for (;;) {
-        vector<string> text;
-        {
-            unique_lock<mutex> l(sh.oMutex);
-            sh.oCv.wait(l, [&] { return (!sh.outQueue.empty() && sh.outQueue.begin()->first == sh.nextOut) || sh.outDone; });
-            if (sh.outQueue.empty()) return;
-            // (after outDone only a failed run can have left a gap: write what there is, in order)
-            text = std::move(sh.outQueue.begin()->second); sh.outQueue.erase(sh.outQueue.begin());
-            sh.nextOut++;
-            sh.oCv.notify_all();
-        }
-        const double t0 = now();
-        for (const auto& t : text) sh.os->write(t.data(), (streamsize)t.size());
-        gTimer.add("file write (writer thread)", now() - t0);
-    }
-}
-
-// `ctxSlot` persists across the species groups of a run: the context (CUDA initialisation, pinned and device buffers,
-// ~0.7 s) is created once, on its own thread, while the host still loads histograms and parses the first chunk (`ready`
-// carries the error text of a failed creation); every group only re-loads it with its motifs.
-void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctxSlot, shared_future<string> ready, size_t devIndex)
+// One thread per GPU for the whole run.  The context (CUDA initialisation ~0.5-1.5 s) is created on its own thread while the host
+// still loads the inputs (`ready` carries the error text of a failed creation); a job of another manifest group than the one loaded
+// makes the worker drain its chunks in flight and load that group's P and thresholds (b200scan_set_motifs).
+void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctxSlot, shared_future<string> ready, size_t devIndex, size_t threads)
 {
     b200scan_ctx*& ctx = *ctxSlot;
-    auto die = [&](const string& what) {
-        lock_guard<mutex> l(sh.qMutex);
-        if (!sh.failed.exchange(true)) sh.error = what;
-        sh.qCv.notify_all();
-    };
+    auto die = [&](const string& what) { sh.fail(what); };
     {   // the context is being created since the start of the run (runScan: CtxPool), normally it is ready by now
         const double t0 = now();
         const string err = ready.get();
         gTimer.add("wait for b200scan_create", now() - t0);
         if (!err.empty() || !ctx) { die(err.empty() ? "CUDA error: no context" : err); return; }
     }
-    const auto len = sh.motifs->colLen();
-    const auto thr = sh.motifs->colThr();
     const char* hitEnv = getenv("BLAMM_B200_HITS");
-    const int hitFormat = (hitEnv && atoi(hitEnv) == 12) || len.size() > (1u << 24) ? B200SCAN_HITS_12 : B200SCAN_HITS_8;
-    if (b200scan_set_engine(ctx, engine) != B200SCAN_OK || b200scan_set_hit_format(ctx, hitFormat) != B200SCAN_OK ||
-        b200scan_set_motifs(ctx, sh.motifs->P().data(), sh.motifs->ldp(), (int32_t)len.size(), len.data(), thr.data()) != B200SCAN_OK) {
+    const int hitFormat = (hitEnv && atoi(hitEnv) == 12) || sh.mtext.size() > (1u << 24) ? B200SCAN_HITS_12 : B200SCAN_HITS_8;
+    if (b200scan_set_engine(ctx, engine) != B200SCAN_OK || b200scan_set_hit_format(ctx, hitFormat) != B200SCAN_OK) {
         die(string("CUDA error: ") + b200scan_last_error(ctx)); return;
     }
+    shared_ptr<const GroupParams> loaded;
     // Three slots: while the hits of chunk k-1 come down and are formatted, chunk k is being scored and chunk k+1 goes up.
     // BLAMM_B200_HITS=12 keeps the unordered 12-byte records and the host sort (diagnostic / comparison).
     unique_ptr<Job> inFlight[B200SCAN_NUM_SLOTS];
@@ -572,17 +624,17 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
             const b200scan_hit8* hits = nullptr; const uint32_t* bucketStart = nullptr; uint64_t n = 0, nb = 0;
             if (b200scan_collect8(ctx, s, &hits, &n, &bucketStart, &nb, &tm) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
             gTimer.add("b200scan_collect (wait GPU)", now() - tc);
-            writeHits8(sh, *inFlight[s], hits, n, bucketStart, nb);
+            writeHits8(sh, *inFlight[s], hits, n, bucketStart, nb, threads);
         } else {
             const b200scan_hit12* hits = nullptr; uint64_t n = 0;
             if (b200scan_collect12(ctx, s, &hits, &n, &tm) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
             gTimer.add("b200scan_collect (wait GPU)", now() - tc);
-            writeHits(sh, *inFlight[s], hits, n);
+            writeHits(sh, *inFlight[s], hits, n, threads);
         }
         gStats.add(devIndex, tm, inFlight[s]->nPayload);
         inFlight[s].reset();
         tail = (tail + 1) % B200SCAN_NUM_SLOTS; nFlight--;
-        return true;
+        return !sh.failed;
     };
     while (!sh.failed) {
         unique_ptr<Job> job;
@@ -600,6 +652,16 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
             }
         }
         if (drainOne) { if (!collectOldest()) break; continue; }
+        if (job->group != loaded) {                          // next manifest group: its own P and thresholds
+            bool ok = true;
+            while (nFlight > 0 && ok) ok = collectOldest();
+            if (!ok) break;
+            const GroupParams& g = *job->group;
+            if (b200scan_set_motifs(ctx, g.P.data(), g.ldp, (int32_t)g.len.size(), g.len.data(), g.thr.data()) != B200SCAN_OK) {
+                die(string("CUDA error: ") + b200scan_last_error(ctx)); break;
+            }
+            loaded = job->group;
+        }
         if (nFlight == B200SCAN_NUM_SLOTS && !collectOldest()) break;
         const int rc = job->codes
             ? b200scan_submit_packed(ctx, head, job->codes.get(), job->hasZero ? job->zmask.get() : nullptr, job->nTotal, job->nPayload,
@@ -630,7 +692,16 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
     }
     Species sp; sp.name = "syn";
     sp.seqNames = {"chr1", "chr2_with_a_longer_name", "s3"};
+    auto group = make_shared<GroupParams>();
+    group->species = &sp; group->maxNameLen = 23 + 8;
+    WorkPool workPool(threads);
+    auto openOut = [](const string& path) { return open(path.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644); };
+    auto fillShared = [&](ScanShared& sh, int fd) {
+        for (const auto& m : ms.motifs) sh.mtext.push_back({m.name, (uint64_t)m.size(), m.revComp});
+        sh.fd = fd; sh.pool = &workPool;
+    };
     Job job;
+    job.group = group;
     job.nPayload = 3000000; job.nTotal = job.nPayload + 40;
     job.frags = {{0, 0, 1234567890123ull}, {700001, 0, 1234567990123ull}, {1500000, 1, 0}, {1500007, 1, 19}, {2999990, 2, 5}};
     // distinct (position, column) pairs, shuffled
@@ -660,16 +731,12 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
     }
     const string path = "/tmp/blamm_b200_selftest_" + to_string((long)getpid()) + ".txt";
     {
-        ofstream os(path, ios::binary);
+        const int fd = openOut(path);
         ScanShared sh;
-        sh.motifs = &ms; sh.species = &sp; sh.os = &os; sh.formatThreads = threads;
-        sh.maxNameLen = 23 + 8;
-        thread writer(writerThread, ref(sh));
-        writeHits(sh, job, hits.data(), hits.size());
-        { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; }
-        sh.oCv.notify_all();
-        writer.join();
-        if (sh.totMatches != hits.size()) { cerr << label << ": match count differs\n"; return false; }
+        fillShared(sh, fd);
+        writeHits(sh, job, hits.data(), hits.size(), threads);
+        close(fd);
+        if (sh.totMatches != hits.size() || sh.failed) { cerr << label << ": match count differs\n"; return false; }
     }
     ifstream is(path, ios::binary);
     const string got((istreambuf_iterator<char>(is)), istreambuf_iterator<char>());
@@ -687,15 +754,11 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
         }
         for (uint64_t b = 0; b < nb; b++) bs[b + 1] += bs[b];
         {
-            ofstream os(path, ios::binary);
+            const int fd = openOut(path);
             ScanShared sh;
-            sh.motifs = &ms; sh.species = &sp; sh.os = &os; sh.formatThreads = threads;
-            sh.maxNameLen = 23 + 8;
-            thread writer(writerThread, ref(sh));
-            writeHits8(sh, job, h8.data(), h8.size(), bs.data(), nb);
-            { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; }
-            sh.oCv.notify_all();
-            writer.join();
+            fillShared(sh, fd);
+            writeHits8(sh, job, h8.data(), h8.size(), bs.data(), nb, threads);
+            close(fd);
         }
         ifstream is8(path, ios::binary);
         const string got8((istreambuf_iterator<char>(is8)), istreambuf_iterator<char>());
@@ -823,8 +886,9 @@ int runScan(int argc, char** argv)
     cout << "Using " << nDev << " GPU devices" << endl;
 
     ofstream ofsCutoff("PWMthresholds.txt");
-    ofstream os(outputFilename);
-    if (!os) throw runtime_error("Cannot write to file: " + outputFilename);
+    const int outFd = open(outputFilename.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (outFd < 0) throw runtime_error("Cannot write to file: " + outputFilename);
+    struct FdCloser { int fd; ~FdCloser() { if (fd >= 0) close(fd); } } outCloser{outFd};
 
     const uint64_t halo = mc.maxLen() - 1;
     uint64_t totMatches = 0;
@@ -858,59 +922,64 @@ int runScan(int argc, char** argv)
             return string();
         }).share());
 
+    // One pipeline for the whole run: this thread plans the groups (P, thresholds) and reads + packs their FASTA files, one worker
+    // per GPU scores the chunks, the shared pool formats and writes.  Nothing drains at a group boundary except a GPU's own
+    // chunks in flight when it loads the next group's motifs.
+    WorkPool workPool(numThreads);
+    ScanShared sh;
+    for (const auto& m : mc.motifs) sh.mtext.push_back({m.name, (uint64_t)m.size(), m.revComp});
+    sh.fd = outFd; sh.pool = &workPool;
+    sh.maxQueue = (size_t)nDev + 1;
+    vector<thread> workers;
+    for (int d = 0; d < nDev; d++)
+        workers.emplace_back(deviceWorker, ref(sh), engine, foldLower, &pool.ctx[(size_t)d], pool.ready[(size_t)d], (size_t)d, numThreads);
+    auto finish = [&](bool failed) {
+        { lock_guard<mutex> l(sh.qMutex); sh.done = true; }
+        if (failed) sh.fail("input error"); else sh.qCv.notify_all();
+        for (auto& w : workers) w.join();
+    };
+    uint64_t nJobs = 0, groupId = 0;
     double tSetup = now();
-    for (const auto& sp : sc.species) {
-        cout << "Scanning species: " << sp.name;
-        sp.printNuclProb(settings.pseudocount);
-        mc.generateMatrix(sp.nuclCounts, settings.pseudocount);
-        if (pSpec) {
-            // a reverse complement and the permutations of a motif read the histogram of their base name (motif.h:256-267,
-            // pwmscan.cpp:607-611): every file is parsed once, on -t threads; the first missing file is reported as before
-            vector<string> base; unordered_map<string, size_t> slotOf;
-            for (const auto& m : mc.motifs) if (slotOf.emplace(m.baseName(), base.size()).second) base.push_back(m.baseName());
-            vector<float> cutoff(base.size()); vector<string> err(base.size());
-            atomic<size_t> nextBase(0);
-            auto load = [&] {
-                for (size_t i; (i = nextBase.fetch_add(1)) < base.size();) {
+    try {
+        for (const auto& sp : sc.species) {
+            if (sh.failed) break;
+            cout << "Scanning species: " << sp.name;
+            sp.printNuclProb(settings.pseudocount);
+            mc.generateMatrix(sp.nuclCounts, settings.pseudocount);
+            if (pSpec) {
+                // a reverse complement and the permutations of a motif read the histogram of their base name (motif.h:256-267,
+                // pwmscan.cpp:607-611): every file is parsed once, on -t threads; the first missing file is reported as before
+                vector<string> base; unordered_map<string, size_t> slotOf;
+                for (const auto& m : mc.motifs) if (slotOf.emplace(m.baseName(), base.size()).second) base.push_back(m.baseName());
+                vector<float> cutoff(base.size()); vector<string> err(base.size());
+                workPool.parallel(base.size(), [&](size_t i) {
                     try { ScoreHistogram h; h.load(histdir, "hist_" + sp.name + "_" + base[i]); cutoff[i] = h.scoreCutoff(pvalue); }
                     catch (const exception& e) { err[i] = e.what(); }
-                }
-            };
-            vector<thread> loaders;
-            for (size_t t = 1; t < min<size_t>(numThreads, 16); t++) loaders.emplace_back(load);
-            load();
-            for (auto& t : loaders) t.join();
-            for (const auto& e : err) if (!e.empty()) throw runtime_error(e);
-            for (auto& m : mc.motifs) m.threshold = cutoff[slotOf[m.baseName()]];
-        } else for (auto& m : mc.motifs) {
-            if (absSpec) m.threshold = absThr;
-            else { const float mx = m.maxScore(), mn = m.minScore(); m.threshold = relThr * (mx - mn) + mn; }
-        }
-        for (const auto& m : mc.motifs) {
-            if (m.size() > 15) continue;                 // the reference lists only short motifs (pwmscan.cpp:620)
-            ofsCutoff << sp.name << "\t" << m.name << "\t" << m.minScore() << "\t" << m.threshold << "\t" << m.maxScore() << endl;
-        }
+                });
+                for (const auto& e : err) if (!e.empty()) throw runtime_error(e);
+                for (auto& m : mc.motifs) m.threshold = cutoff[slotOf[m.baseName()]];
+            } else for (auto& m : mc.motifs) {
+                if (absSpec) m.threshold = absThr;
+                else { const float mx = m.maxScore(), mn = m.minScore(); m.threshold = relThr * (mx - mn) + mn; }
+            }
+            for (const auto& m : mc.motifs) {
+                if (m.size() > 15) continue;                 // the reference lists only short motifs (pwmscan.cpp:620)
+                ofsCutoff << sp.name << "\t" << m.name << "\t" << m.minScore() << "\t" << m.threshold << "\t" << m.maxScore() << "\n";
+            }
+            auto group = make_shared<GroupParams>();
+            group->species = &sp; group->id = groupId++;
+            group->P = mc.P(); group->ldp = mc.ldp(); group->len = mc.colLen(); group->thr = mc.colThr();
+            size_t sl = 0, ml = 0;
+            for (const auto& n : sp.seqNames) sl = max(sl, n.size());
+            for (const auto& m : mc.motifs) ml = max(ml, m.name.size());
+            group->maxNameLen = sl + ml;
+            gTimer.add("setup: matrix P, histograms, thresholds (per group)", now() - tSetup);
 
-        gTimer.add("setup: matrix P, histograms, thresholds (per group)", now() - tSetup);
-        ScanShared sh;
-        sh.motifs = &mc; sh.species = &sp; sh.os = &os;
-        sh.formatThreads = std::max<size_t>(1, numThreads / (size_t)nDev);
-        sh.maxOut = 2 * (size_t)nDev + 2;
-        size_t sl = 0, ml = 0;
-        for (const auto& n : sp.seqNames) sl = max(sl, n.size());
-        for (const auto& m : mc.motifs) ml = max(ml, m.name.size());
-        sh.maxNameLen = sl + ml;
-        thread writer(writerThread, ref(sh));
-        auto stopWriter = [&] { { lock_guard<mutex> l(sh.oMutex); sh.outDone = true; } sh.oCv.notify_all(); writer.join(); };
-        vector<thread> workers;
-        for (int d = 0; d < nDev; d++) workers.emplace_back(deviceWorker, ref(sh), engine, foldLower, &pool.ctx[(size_t)d], pool.ready[(size_t)d], (size_t)d);
-        try {
             FastaStream fs(sp.files, sp.totSeqLen);
             fs.setParallel(ingestThreads(numThreads));
             const char* asciiEnv = getenv("BLAMM_B200_ASCII");
             const bool sendAscii = asciiEnv && *asciiEnv && *asciiEnv != '0';
             FastaStream::Chunk c;
-            uint64_t nJobs = 0;
             for (;;) {
                 double tr = now();
                 if (sh.failed || !fs.next(maxBlock - halo - 64, halo, c)) break;
@@ -926,30 +995,31 @@ int runScan(int argc, char** argv)
                 job->fragStarts = c.fragStarts; job->frags = c.frags;
                 job->nTotal = c.nTotal; job->nPayload = c.nPayload;
                 job->seq = nJobs++;
+                job->group = group;
                 gTimer.add("FASTA read + filter (reader)", now() - tr);
+                tr = now();
                 unique_lock<mutex> l(sh.qMutex);
                 sh.qCv.wait(l, [&] { return sh.queue.size() < sh.maxQueue || sh.failed; });
                 sh.queue.push_back(std::move(job));
                 sh.qCv.notify_all();
+                l.unlock();
+                gTimer.add("reader waits for a free queue slot", now() - tr);
                 if (sp.totSeqLen) { cout << "Progress... " << (100 * min(fs.filteredLength(), sp.totSeqLen)) / sp.totSeqLen << "%\r"; cout.flush(); }
             }
-        } catch (...) {
-            { lock_guard<mutex> l(sh.qMutex); sh.done = true; sh.failed = true; }
-            sh.qCv.notify_all();
-            for (auto& w : workers) w.join();
-            stopWriter();
-            throw;
+            cout << "Progress... 100%  " << endl;          // (of the reading: scoring and writing of the group's last chunks go on)
+            tSetup = now();
         }
-        { lock_guard<mutex> l(sh.qMutex); sh.done = true; }
-        sh.qCv.notify_all();
-        for (auto& w : workers) w.join();
-        stopWriter();
-        if (sh.failed) throw runtime_error(sh.error.empty() ? "scan failed" : sh.error);
-        cout << "Progress... 100%  " << endl;
-        totMatches += sh.totMatches;
-        tSetup = now();
+    } catch (...) {
+        finish(true);
+        throw;
     }
-    os.close();
+    {
+        const double t0 = now();
+        finish(false);
+        gTimer.add("wait for the last chunks (workers join)", now() - t0);
+    }
+    if (sh.failed) throw runtime_error(sh.error.empty() ? "scan failed" : sh.error);
+    totMatches = sh.totMatches;
     ofsCutoff.close();
     cout << "\nWrote " << totMatches << " matches to " << outputFilename << ".\n";
     gStatsColumns = mc.motifs.size(); gStatsMatches = totMatches;
