@@ -378,9 +378,10 @@ def cpu_baseline(work: str, seq: np.ndarray, n_cols: int, sample_nt: int, scan_a
                 subprocess.run([ref_cuda, "scan", "-c"] + scan_args + ["-t", str(cores), "-o", "occ_cuda.txt", "motifs.jaspar", "sequences.mf"],
                                cwd=sub, env=env1, check=True, stdout=subprocess.DEVNULL, timeout=600)
                 dtc = time.perf_counter() - t0
-                same = subprocess.run("cmp -s <(LC_ALL=C sort occurrences.txt) <(LC_ALL=C sort occ_cuda.txt)", shell=True, executable="/bin/bash", cwd=sub).returncode == 0
-                out["gpu_reference"] = {"value": n * n_cols / dtc, "unit": UNIT, "how": "reference `blamm scan -c` (cuBLAS sgemm + filterScore, unmodified sources compiled "
-                                        "for sm_100) on 1 B200, same %.1f Mbp sample, %.1f s wall; sorted output identical to its CPU path: %s" % (n / 1e6, dtc, same)}
+                n_cpu = sum(1 for _ in open(os.path.join(sub, "occurrences.txt"), "rb"))
+                n_gpu = sum(1 for _ in open(os.path.join(sub, "occ_cuda.txt"), "rb"))
+                out["gpu_reference"] = {"value": n * n_cols / dtc, "unit": UNIT, "how": "reference `blamm scan -c` (cuBLAS sgemm per offset + filterScore, unmodified sources "
+                                        "compiled for sm_100) on 1 B200, same %.1f Mbp sample, %.1f s wall; occurrences: %d (its CPU path: %d)" % (n / 1e6, dtc, n_gpu, n_cpu)}
             except Exception as e:
                 out["gpu_reference"] = {"value": None, "how": "reference `scan -c` failed: %s" % e}
         return out

@@ -24,6 +24,7 @@
 #include <thread>
 #include <unordered_map>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <unistd.h>
 
 using namespace std;
@@ -388,7 +389,9 @@ struct MotifText { string name; uint64_t size = 0; bool revComp = false; };     
 
 struct ScanShared {
     vector<MotifText> mtext;
-    int fd = -1;                                   // occurrence file (pwrite at offsets handed out in chunk order)
+    int fd = -1;                                   // occurrence file (byte ranges handed out in chunk order)
+    // write through shared mappings (falls back to pwrite where the file cannot be mapped; BLAMM_B200_WRITER=pwrite forces that)
+    atomic<bool> useMmap{!(getenv("BLAMM_B200_WRITER") && string(getenv("BLAMM_B200_WRITER")) == "pwrite")};
     WorkPool* pool = nullptr;
     atomic<uint64_t> totMatches{0};
     // job queue (producer = FASTA reader, consumers = one thread per GPU)
@@ -482,26 +485,39 @@ void emitText(ScanShared& sh, const Job& job, vector<string>& text, uint64_t n)
     uint64_t bytes = 0;
     for (const auto& t : text) bytes += t.size();
     uint64_t at;
+    bool mapped = sh.useMmap;
     {
         unique_lock<mutex> lock(sh.oMutex);
         sh.oCv.wait(lock, [&] { return job.seq == sh.nextOut || sh.failed; });
         if (sh.failed) return;
         at = sh.fileOffset;
         sh.fileOffset += bytes;
+        // (the file grows here, in chunk order, so that every chunk can map its own byte range)
+        if (mapped && bytes && ftruncate(sh.fd, (off_t)sh.fileOffset) != 0) mapped = sh.useMmap = false;
         sh.nextOut++;
     }
     sh.oCv.notify_all();
     sh.totMatches += n;
     gTimer.add("wait for the chunk's turn in the file (wall)", now() - t0); t0 = now();
+    if (!bytes) return;
     vector<uint64_t> off(text.size());
-    for (size_t i = 0; i < text.size(); i++) { off[i] = at; at += text[i].size(); }
-    // pieces of at most 64 MiB, one pwrite loop each
+    { uint64_t o = at; for (size_t i = 0; i < text.size(); i++) { off[i] = o; o += text[i].size(); } }
+    // pieces of at most 16 MiB.  Writes through a shared mapping of the chunk's byte range: buffered write() calls on one file
+    // serialise on the inode lock (measured: 16 threads of pwrite = one thread's 3.7 GB/s), page faults of a mapping do not.
     struct Piece { const char* p; size_t n; uint64_t at; };
     vector<Piece> pieces;
     for (size_t i = 0; i < text.size(); i++)
-        for (size_t o = 0; o < text[i].size(); o += (64u << 20)) pieces.push_back({text[i].data() + o, min<size_t>(64u << 20, text[i].size() - o), off[i] + o});
+        for (size_t o = 0; o < text[i].size(); o += (16u << 20)) pieces.push_back({text[i].data() + o, min<size_t>(16u << 20, text[i].size() - o), off[i] + o});
     atomic<bool> bad{false};
+    char* base = nullptr; uint64_t mapAt = 0; size_t mapLen = 0;
+    if (mapped) {
+        const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+        mapAt = at / page * page; mapLen = (size_t)(at + bytes - mapAt);
+        void* m = mmap(nullptr, mapLen, PROT_READ | PROT_WRITE, MAP_SHARED, sh.fd, (off_t)mapAt);
+        if (m == MAP_FAILED) { mapped = false; sh.useMmap = false; } else base = static_cast<char*>(m);
+    }
     sh.pool->parallel(pieces.size(), [&](size_t i) {
+        if (mapped) { memcpy(base + (pieces[i].at - mapAt), pieces[i].p, pieces[i].n); return; }
         const char* p = pieces[i].p; size_t left = pieces[i].n; uint64_t o = pieces[i].at;
         while (left) {
             const ssize_t w = pwrite(sh.fd, p, left, (off_t)o);
@@ -509,8 +525,9 @@ void emitText(ScanShared& sh, const Job& job, vector<string>& text, uint64_t n)
             p += w; left -= (size_t)w; o += (uint64_t)w;
         }
     });
+    if (base) munmap(base, mapLen);
     if (bad) sh.fail("Cannot write to the occurrence file");
-    gTimer.add("file write (pwrite, wall)", now() - t0);
+    gTimer.add("file write (wall)", now() - t0);
 }
 
 template <class H>
@@ -695,7 +712,7 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
     auto group = make_shared<GroupParams>();
     group->species = &sp; group->maxNameLen = 23 + 8;
     WorkPool workPool(threads);
-    auto openOut = [](const string& path) { return open(path.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644); };
+    auto openOut = [](const string& path) { return open(path.c_str(), O_CREAT | O_TRUNC | O_RDWR, 0644); };
     auto fillShared = [&](ScanShared& sh, int fd) {
         for (const auto& m : ms.motifs) sh.mtext.push_back({m.name, (uint64_t)m.size(), m.revComp});
         sh.fd = fd; sh.pool = &workPool;
@@ -886,7 +903,7 @@ int runScan(int argc, char** argv)
     cout << "Using " << nDev << " GPU devices" << endl;
 
     ofstream ofsCutoff("PWMthresholds.txt");
-    const int outFd = open(outputFilename.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    const int outFd = open(outputFilename.c_str(), O_CREAT | O_TRUNC | O_RDWR, 0644);
     if (outFd < 0) throw runtime_error("Cannot write to file: " + outputFilename);
     struct FdCloser { int fd; ~FdCloser() { if (fd >= 0) close(fd); } } outCloser{outFd};
 
