@@ -433,8 +433,8 @@ class HostPacker:
 
 def workload_c4(n_gpus: int, mbp: float) -> dict:
     return {"workload": "configs[3]: 10,000 synthetic PWMs of length 6-30 x2 strands (20,000 columns) x %.0f Mbp synthetic uniform ACGT, -rc -at 12, "
-                        "100 Mbp blocks dealt to %d GPU(s)" % (mbp, n_gpus),
-            "l2": "GPU arm: every timed launch reads a different 100 Mbp block's codes (25 MB) and a 5 MB weight image; hit lists of 0.3-0.5 GB per block exceed L2"}
+                        "16 blocks dealt to %d GPU(s)" % (mbp, n_gpus),
+            "l2": "GPU arm: every timed launch reads a different block's codes (16 MB at 1 Gbp) and a 5 MB weight image; the hit lists of a block (0.2-0.3 GB) exceed L2"}
 
 
 def workload_c3(n_gpus: int, gbp: float) -> dict:
@@ -471,8 +471,9 @@ def run_blocks(args, rank: int, local_rank: int, world: int) -> None:
         torch.cuda.synchronize()
 
     c4 = args.config == "c4"
-    block_nt = 100_000_000 if c4 else int((args.mbp or 100.0) * 1e6)
-    n_blocks_total = max(1, int(round((args.mbp or 1000.0) * 1e6 / block_nt))) if c4 else world
+    # c4: the stream is always cut into 16 blocks (62.5 Mbp at the nominal 1 Gbp), so that 1, 2, 4 and 8 ranks get equal shares
+    block_nt = int((args.mbp or 1000.0) * 1e6 / 16) if c4 else int((args.mbp or 100.0) * 1e6)
+    n_blocks_total = 16 if c4 else world
     probs = HUMAN_LIKE if args.bias else (0.25, 0.25, 0.25, 0.25)
     work = tempfile.mkdtemp(prefix="bench_b200_")
     packer = None
@@ -692,7 +693,11 @@ def run_cli(args, rank: int, local_rank: int, world: int) -> None:
     n_groups = 24
     per_group = int(args.gbp * 1e9 / n_groups)
     box = [None]
-    if rank == 0:
+    reuse = bool(args.reuse) and os.path.exists(os.path.join(args.reuse, "sequences.mf"))
+    if rank == 0 and args.reuse:
+        os.makedirs(args.reuse, exist_ok=True)
+        box[0] = args.reuse
+    elif rank == 0:
         base = args.workdir
         if not base:
             try:
@@ -706,7 +711,7 @@ def run_cli(args, rank: int, local_rank: int, world: int) -> None:
     work = box[0]
     try:
         t_gen = time.perf_counter()
-        for g in range(rank, n_groups, world):
+        for g in ([] if reuse else range(rank, n_groups, world)):
             gc = 0.36 + 0.12 * g / (n_groups - 1)
             seq = synth.random_acgt(per_group, 500 + g, (0.5 - gc / 2, gc / 2, gc / 2, 0.5 - gc / 2))
             rng = np.random.default_rng(900 + g)
@@ -777,7 +782,7 @@ def run_cli(args, rank: int, local_rank: int, world: int) -> None:
         if world > 1:
             dist.barrier()
     finally:
-        if rank == 0 and not args.keep:
+        if rank == 0 and not args.keep and not args.reuse:
             shutil.rmtree(work, ignore_errors=True)
         if world > 1:
             dist.destroy_process_group()
@@ -805,6 +810,7 @@ def main() -> None:
     ap.add_argument("--ref-budget", type=float, default=200.0, help="reference arm: seconds available for the timed passes")
     ap.add_argument("--workdir", default="", help="c3 / c5: directory for the FASTA set and the outputs (default: /dev/shm if roomy, else the temp dir)")
     ap.add_argument("--keep", action="store_true", help="c3 / c5: keep the work directory")
+    ap.add_argument("--reuse", default="", help="c3 / c5: directory whose FASTA set is generated once and kept for later runs (e.g. the same input at -g 8 and -g 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if (args.impl == "b200" and args.config in ("c2", "c4")) else args.warmup     # >= 3: one per slot
 

@@ -19,6 +19,9 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>      // the AVX2 / BMI2 packer is compiled with a target attribute and chosen at run time
+#endif
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -506,6 +509,7 @@ inline uint32_t interleave16(uint32_t lo, uint32_t hi)         // bit i of lo ->
     x = (x | (x << 1)) & 0x5555555555555555ULL;
     return (uint32_t)x | ((uint32_t)(x >> 32) << 1);
 }
+#if defined(__SSE2__)
 // 16 characters -> their code word; `zero` receives the 16 "contributes zero" bits
 inline uint32_t pack16(const char* p, bool foldLower, uint32_t& zero)
 {
@@ -522,11 +526,57 @@ inline uint32_t pack16(const char* p, bool foldLower, uint32_t& zero)
     if (!foldLower) zero |= (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(x, 2));                                      // bit 5: lower case
     return interleave16(lo, hi);
 }
+#else
+// portable twin of the SSE2 routine (hosts without it, e.g. aarch64): the same rule, one character at a time
+inline uint32_t pack16(const char* p, bool foldLower, uint32_t& zero)
+{
+    uint32_t code = 0; zero = 0;
+    for (int i = 0; i < 16; i++) {
+        const unsigned char x = (unsigned char)p[i], u = x & 0xDF;
+        const bool valid = u == 0x41 || u == 0x43 || u == 0x47 || u == 0x54;
+        if (valid) code |= (uint32_t)((((u >> 2) & 1u) << 1) | (((u >> 1) ^ (u >> 2)) & 1u)) << (2 * i);
+        if (!valid || (!foldLower && (x & 0x20))) zero |= 1u << i;
+    }
+    return code;
+}
+#endif
+#if defined(__x86_64__) && defined(__GNUC__)
+// AVX2 + BMI2 twin (run-time dispatch): 32 characters per step, PDEP interleaves the two bit planes; twice the SSE2 rate
+__attribute__((target("avx2,bmi2")))
+uint64_t packWordsAvx2(const char* chars, uint64_t base, uint64_t i1, bool foldLower, uint32_t* codes2, uint32_t* zmask, bool& anyZero)
+{
+    const __m256i mDF = _mm256_set1_epi8((char)0xDF), cA = _mm256_set1_epi8(0x41), cC = _mm256_set1_epi8(0x43), cG = _mm256_set1_epi8(0x47),
+                  cT = _mm256_set1_epi8(0x54);
+    uint32_t any = 0;
+    for (; base + 32 <= i1; base += 32) {
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(chars + base));
+        const __m256i u = _mm256_and_si256(x, mDF);
+        const __m256i v = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
+                                          _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
+        const uint32_t valid = (uint32_t)_mm256_movemask_epi8(v);
+        const uint32_t hi = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(u, 5)) & valid;
+        const uint32_t lo = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(_mm256_xor_si256(u, _mm256_srli_epi16(u, 1)), 6)) & valid;
+        uint32_t zero = ~valid;
+        if (!foldLower) zero |= (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 2));
+        const uint64_t code = _pdep_u64(lo, 0x5555555555555555ULL) | _pdep_u64(hi, 0xAAAAAAAAAAAAAAAAULL);
+        codes2[base / 16] = (uint32_t)code;
+        codes2[base / 16 + 1] = (uint32_t)(code >> 32);
+        zmask[base / 32] = zero;
+        any |= zero;
+    }
+    anyZero |= any != 0;
+    return base;
+}
+const bool kHaveAvx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && !getenv("BLAMM_B200_NO_AVX2");
+#endif
 // characters [i0, i1) of `chars` (i0 a multiple of 32) -> their code and mask words; true if a live character contributes 0
 bool packRange(const char* chars, uint64_t i0, uint64_t i1, bool foldLower, uint32_t* codes2, uint32_t* zmask)
 {
     bool anyZero = false;
     uint64_t base = i0;
+#if defined(__x86_64__) && defined(__GNUC__)
+    if (kHaveAvx2) base = packWordsAvx2(chars, base, i1, foldLower, codes2, zmask, anyZero);
+#endif
     for (; base + 32 <= i1; base += 32) {
         uint32_t z0, z1;
         codes2[base / 16] = pack16(chars + base, foldLower, z0);

@@ -719,3 +719,47 @@ def test_cli_empirical_histograms_example(golden, tmp_path):
     assert len(files) == 4
     for f in files:
         assert (out / f).read_bytes() == open(os.path.join(ref, f), "rb").read(), f
+
+
+def test_block_offsets_beyond_2_to_31():
+    """One block of 2.2e9 characters (the ABI takes up to 2^32 - 2^28): window positions, code-word offsets and bucket indices
+    pass 2^31.  The block is a 1,000,003-character segment repeated 2200 times, so the exact answer is periodic: the oracle scans
+    two periods once, and every period of the block -- in particular those that lie beyond position 2^31 -- must return exactly
+    its hits (position + k * period), in order, through the host packer, b200scan_submit_packed and the ordered 8-byte records."""
+    period, reps = 1_000_003, 2200
+    case = util.random_case(91, n_motifs=6, n_nt=period, len_range=(8, 20), with_gaps=False)
+    thr = (case["thr"] + np.float32(3.0)).astype(np.float32)                 # a few hundred hits per period
+    seg = case["chars"]
+    two = np.concatenate([seg, seg])
+    pos, col, sc = O.scan_stream(bytes(two), np.zeros(1, np.uint64), case["P"], case["col_len"], thr)
+    k = pos < period
+    pos, col, sc = pos[k], col[k], sc[k]
+    assert 50 < len(pos) < 20000
+    block = np.tile(seg, reps)
+    n = len(block)
+    assert n > (1 << 31) + (1 << 26)
+    codes, zm, has_zero = capi.pack_ascii(block)
+    del block
+    assert not has_zero
+    s = capi.Scanner(0, max_block_nt=n + 64, max_hits=1 << 22)
+    try:
+        s.set_engine(capi.ENGINE_AUTO)
+        s.set_hit_format(capi.HITS_8)
+        s.set_motifs(case["P"], case["col_len"], thr)
+        s.submit_packed(0, codes, None, n, n)
+        h8, bstart, t = s.collect8(0)
+        assert t["engine_used"] == capi.ENGINE_TENSOR
+        h = capi.expand_hits8(h8, bstart)
+        # the last period has no successor to wrap into: count what the oracle finds in a lone period for it
+        p1, c1, s1 = O.scan_stream(bytes(seg), np.zeros(1, np.uint64), case["P"], case["col_len"], thr)
+        assert len(h) == (reps - 1) * len(pos) + len(p1)
+        hp = h["pos"].astype(np.int64)
+        assert np.all(np.diff(hp) >= 0)
+        for rep in (0, 1073, 2147, 2148, reps - 2):                          # 2147 / 2148: the periods around position 2^31
+            m = (hp >= rep * period) & (hp < (rep + 1) * period)
+            assert np.array_equal(hp[m] - rep * period, pos.astype(np.int64)) and np.array_equal(h["col"][m], col)
+            assert np.array_equal(h["score"][m].view(np.uint32), sc.view(np.uint32))
+        m = hp >= (reps - 1) * period
+        assert np.array_equal(hp[m] - (reps - 1) * period, p1.astype(np.int64)) and np.array_equal(h["col"][m], c1)
+    finally:
+        s.close()

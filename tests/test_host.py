@@ -436,3 +436,28 @@ def test_parity_lister_lists_only_near_threshold_differences(tmp_path, golden):
     bent = ref[0].split("\t"); bent[5] = O.fmt_g(np.float32(float(bent[5]) + 0.01))
     r = run(["\t".join(bent)] + ref[1:], ref)
     assert r.returncode == 1 and "differences above the tolerance (+ print resolution): 1" in r.stdout
+
+
+def test_packer_sse2_and_avx2_paths_agree(tmp_path):
+    """The host 2-bit packer picks its AVX2 + BMI2 routine at run time (BLAMM_B200_NO_AVX2=1 keeps the SSE2 one): both must give
+    the same code and mask words on every byte value, both lower-case rules, lengths around the 32-character step."""
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from blamm_b200 import capi\n"
+        "rng = np.random.default_rng(5)\n"
+        "out = []\n"
+        "for n in (0, 1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 1000, 4099, 1 << 20):\n"
+        "    a = rng.integers(0, 256, size=n, dtype=np.uint8)\n"
+        "    b = np.frombuffer(b'ACGTacgtNn', dtype=np.uint8)[rng.integers(0, 10, size=n)]\n"
+        "    for block in (a, b):\n"
+        "        for lower in (capi.LOWER_ZERO, capi.LOWER_FOLD):\n"
+        "            c, z, h = capi.pack_ascii(block, lower)\n"
+        "            out += [c, z, np.array([h], dtype=np.uint32)]\n"
+        "np.save(sys.argv[1], np.concatenate([o.astype(np.uint32) for o in out]))\n" % ROOT)
+    res = []
+    for k, env in enumerate(({}, {"BLAMM_B200_NO_AVX2": "1"})):
+        f = str(tmp_path / ("p%d.npy" % k))
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, **env))
+        res.append(np.load(f))
+    assert len(res[0]) > 100000 and np.array_equal(res[0], res[1])
