@@ -65,6 +65,7 @@ struct b200scan_ctx {
     cudaStream_t up_stream = nullptr;        // block uploads + packing: overlap the previous block's kernels
     uint64_t max_block = 0;
     unsigned long long max_hits = 0;         // initial per-slot hit capacity (b200scan_create)
+    unsigned long long hit_budget = 0;       // largest hit / candidate capacity a regrow may reach (b200scan_create: from the free device memory)
     double margin16_scale = 1.0;             // debug knob (env B200SCAN_MARGIN16_SCALE): scales the FP16-accumulation error bound
     double i8_max_overshoot = 16.0;          // INT8 operands for a tile iff every column's WORST-CASE overshoot (L / scale, score units) stays below (env B200SCAN_I8_MAX_OVERSHOOT; 0 = never).  Measured on the bench set the mean overshoot is far below the bound: 1.20 candidates per hit with every tile on INT8, against 1.44 for FP16 accumulators
     int engine = B200SCAN_ENGINE_AUTO;
@@ -687,6 +688,7 @@ int ensure_order(b200scan_ctx* ctx, Slot& s)
     if (ctx->sort_cap < s.hit_cap) {
         CU(cudaStreamSynchronize(ctx->stream));          // a previous block's ordering kernels may still read the old scratch list
         dfree(ctx->d_sort_tmp);
+        ctx->sort_cap = 0;
         CU(cudaMalloc(&ctx->d_sort_tmp, sizeof(Hit12) * s.hit_cap));
         ctx->sort_cap = s.hit_cap;
     }
@@ -842,6 +844,17 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     CUB(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
     lap("streams + kernel attributes");
     if (max_hits == 0) max_hits = 1 << 20;
+    {
+        // Budget for the buffers that grow with the hit density: about 136 bytes of device memory per hit record of the densest
+        // block (three slots x 16 B hit list, 12 B ordering scratch, 16 B candidates + 64 B raw entries for ~1.2 candidates per hit)
+        // may take 60 % of what is free now.  A block that needs more is refused with B200SCAN_ENOMEM (the caller submits it in
+        // smaller pieces: the CLI halves it, cli.cpp: scanSplit); B200SCAN_HIT_BUDGET=<records> overrides the figure.
+        size_t free_b = 0, total_b = 0;
+        CUB(cudaMemGetInfo(&free_b, &total_b));
+        c->hit_budget = std::max<unsigned long long>((unsigned long long)(0.6 * (double)free_b / 136.0), 1 << 16);
+        if (const char* e = getenv("B200SCAN_HIT_BUDGET")) c->hit_budget = std::max<unsigned long long>(strtoull(e, nullptr, 10), 1024);
+        max_hits = std::min<unsigned long long>(max_hits, c->hit_budget);
+    }
     c->max_hits = max_hits;
     // Per slot only the counters and events exist from the start; block buffers, hit lists and pinned staging memory are
     // allocated at the slot's first use (ensure_slot / ensure_ascii / ensure_host_hits): a short run does not pay ~0.5 s for
@@ -1122,26 +1135,53 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
         if (attempt >= 4) return fail(ctx, B200SCAN_ECUDA, "hit buffers still too small after regrowing");
         // the counters kept counting, so they say exactly how much room a re-run needs
         CU(cudaStreamSynchronize(ctx->stream));
-        if (raw_over) {
-            dfree(ctx->d_raw); dfree(ctx->d_blk_count);
-            ctx->blk_cap = n_blocks + n_blocks / 8 + 1024;
-            CU(cudaMalloc(&ctx->d_raw, ((size_t)ctx->blk_cap + 1) * kRawBlock * kRawWords * 4));
-            CU(cudaMalloc(&ctx->d_blk_count, (size_t)ctx->blk_cap * 4));
-            // every raw entry holds at least one candidate and at most 64; size the candidate list for the typical ~1.5
-            const unsigned long long want = (unsigned long long)ctx->blk_cap * kRawBlock * 2;
-            if (want > ctx->cand_cap) { dfree(ctx->d_cand); ctx->cand_cap = want; CU(cudaMalloc(&ctx->d_cand, sizeof(Cand) * ctx->cand_cap)); }
-        } else if (n_cand > ctx->cand_cap) {
-            dfree(ctx->d_cand);
-            ctx->cand_cap = n_cand + n_cand / 8 + 1024;
-            CU(cudaMalloc(&ctx->d_cand, sizeof(Cand) * ctx->cand_cap));
+        {
+            const unsigned long long need_hits = hit_over ? nh + nh / 8 + 1024 : s.hit_cap;
+            const unsigned long long need_cand = raw_over ? ((unsigned long long)n_blocks + n_blocks / 8 + 1024) * kRawBlock * 2
+                                                          : (n_cand > ctx->cand_cap ? n_cand + n_cand / 8 + 1024 : ctx->cand_cap);
+            if (need_hits > ctx->hit_budget || need_cand > 4 * ctx->hit_budget) {
+                s.resident = false;
+                return fail(ctx, B200SCAN_ENOMEM, "block too dense for the device buffers: %llu hits, %llu candidates against a budget of %llu hit records "
+                            "-- submit it in smaller blocks", nh, n_cand, ctx->hit_budget);
+            }
         }
-        if (hit_over || cand_over) {
+        // grow with a way back: if the larger allocation fails the old size is restored, the block is dropped and the caller told
+        auto regrow = [&](void** ptr, size_t old_bytes, size_t new_bytes) -> bool {
+            cudaFree(*ptr); *ptr = nullptr;
+            if (cudaMalloc(ptr, new_bytes) == cudaSuccess) return true;
+            cudaGetLastError();
+            *ptr = nullptr;
+            if (cudaMalloc(ptr, old_bytes) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; }
+            return false;
+        };
+        bool ok = true;
+        if (raw_over) {
+            const uint32_t new_cap = n_blocks + n_blocks / 8 + 1024;
+            const size_t raw_old = ((size_t)ctx->blk_cap + 1) * kRawBlock * kRawWords * 4, raw_new = ((size_t)new_cap + 1) * kRawBlock * kRawWords * 4;
+            if (regrow(reinterpret_cast<void**>(&ctx->d_raw), raw_old, raw_new) &&
+                regrow(reinterpret_cast<void**>(&ctx->d_blk_count), (size_t)ctx->blk_cap * 4, (size_t)new_cap * 4)) {
+                ctx->blk_cap = new_cap;
+                // every raw entry holds at least one candidate and at most 64; size the candidate list for the typical ~1.5
+                const unsigned long long want = (unsigned long long)ctx->blk_cap * kRawBlock * 2;
+                if (want > ctx->cand_cap) {
+                    if (regrow(reinterpret_cast<void**>(&ctx->d_cand), sizeof(Cand) * ctx->cand_cap, sizeof(Cand) * want)) ctx->cand_cap = want; else ok = false;
+                }
+            } else ok = false;
+        } else if (n_cand > ctx->cand_cap) {
+            const unsigned long long want = n_cand + n_cand / 8 + 1024;
+            if (regrow(reinterpret_cast<void**>(&ctx->d_cand), sizeof(Cand) * ctx->cand_cap, sizeof(Cand) * want)) ctx->cand_cap = want; else ok = false;
+        }
+        if (ok && (hit_over || cand_over)) {
             unsigned long long want = std::max<unsigned long long>(nh + nh / 8 + 1024, s.hit_cap);
             if (want > s.hit_cap) {
-                dfree(s.d_hits);
-                CU(cudaMalloc(&s.d_hits, sizeof(b200scan_hit) * want));
-                s.hit_cap = want;
+                if (regrow(reinterpret_cast<void**>(&s.d_hits), sizeof(b200scan_hit) * s.hit_cap, sizeof(b200scan_hit) * want)) s.hit_cap = want; else ok = false;
             }
+        }
+        if (!ok) {
+            s.resident = false;
+            if (!ctx->d_raw || !ctx->d_blk_count || !ctx->d_cand || !s.d_hits)
+                return fail(ctx, B200SCAN_ECUDA, "out of device memory while regrowing the hit buffers, and the previous size could not be restored");
+            return fail(ctx, B200SCAN_ENOMEM, "out of device memory for a block with %llu hits and %llu candidates -- submit it in smaller blocks", nh, n_cand);
         }
         int rc = reset_counters(ctx, s, true, ctx->stream);
         if (rc) return rc;

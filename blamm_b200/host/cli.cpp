@@ -565,7 +565,7 @@ void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n, size_t
 // grouped them in buckets of 256 positions, so the host neither partitions nor sorts: every formatting thread takes a run of
 // buckets holding about n / T hits.
 void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hits, const uint32_t* bucketStart, uint64_t b0, uint64_t b1,
-                   std::string& text)
+                   std::string& text, uint64_t posOffset = 0)
 {
     const uint64_t n = bucketStart[b1] - bucketStart[b0];
     text.resize(n * (job.group->maxNameLen + 96) + 64);
@@ -574,7 +574,7 @@ void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hi
     size_t f = 0;
     for (uint64_t b = b0; b < b1; b++) {
         for (uint32_t i = bucketStart[b]; i < bucketStart[b + 1]; i++) {
-            const uint64_t pos = (b << B200SCAN_BUCKET_SHIFT) + (hits[i].key >> 24);
+            const uint64_t pos = posOffset + (b << B200SCAN_BUCKET_SHIFT) + (hits[i].key >> 24);
             const uint32_t col = hits[i].key & 0xFFFFFFu;
             while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= pos) f++;
             const Fragment& fr = job.frags[f];
@@ -595,7 +595,9 @@ void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hi
     text.resize((size_t)(p - base));
 }
 
-void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets, size_t threads)
+// format the ordered hit list of (a piece of) a chunk: appends the text pieces to `text`
+void formatHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets, size_t threads,
+                 vector<string>& text, uint64_t posOffset = 0)
 {
     const double t0 = now();
     // a few pieces per thread: the pool is shared by all the GPUs' chunks, short pieces even out the load
@@ -604,16 +606,53 @@ void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint6
     cut[0] = 0;
     for (size_t t = 1; t < T; t++)                   // first bucket whose start reaches t/T of the hits
         cut[t] = (uint64_t)(std::lower_bound(bucketStart, bucketStart + nBuckets, (uint32_t)(n * t / T)) - bucketStart);
-    vector<string> text(T);
-    sh.pool->parallel(T, [&](size_t t) { formatBuckets(sh, job, hits, bucketStart, cut[t], cut[t + 1], text[t]); });
+    const size_t first = text.size();
+    text.resize(first + T);
+    sh.pool->parallel(T, [&](size_t t) { formatBuckets(sh, job, hits, bucketStart, cut[t], cut[t + 1], text[first + t], posOffset); });
     gTimer.add("format ordered hits (wall)", now() - t0);
+}
+
+void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets, size_t threads)
+{
+    vector<string> text;
+    formatHits8(sh, job, hits, n, bucketStart, nBuckets, threads, text);
     emitText(sh, job, text, n);
+}
+
+// A chunk whose hits do not fit the device buffers (b200scan_collect8 -> B200SCAN_ENOMEM: thresholds so low that a large part of
+// all windows are occurrences): the payload range [lo, hi) is scored again in two halves, recursively, each half a block of its
+// own with the halo behind it; the text comes out in position order.  The reference streams any hit density to disk block by
+// block (250,000 characters, pwmscan.cpp:258); here only such dense chunks fall back to smaller blocks.
+bool scanSplit(ScanShared& sh, b200scan_ctx* ctx, const Job& job, uint64_t lo, uint64_t hi, uint64_t halo, bool foldLower, size_t threads,
+               vector<string>& text, uint64_t& nHits, string& err, size_t devIndex)
+{
+    const uint64_t nTotal = std::min<uint64_t>(job.nTotal - lo, hi - lo + halo);
+    vector<uint64_t> frag;
+    for (uint64_t f : job.fragStarts) if (f > lo && f < lo + nTotal) frag.push_back(f - lo);
+    const int rc = job.codes
+        ? b200scan_submit_packed(ctx, 0, job.codes.get() + lo / 16, job.hasZero ? job.zmask.get() + lo / 32 : nullptr, nTotal, hi - lo, frag.data(), frag.size())
+        : b200scan_submit_ascii(ctx, 0, job.chars.get() + lo, nTotal, hi - lo, frag.data(), frag.size(), foldLower ? B200SCAN_LOWER_FOLD : B200SCAN_LOWER_ZERO);
+    if (rc != B200SCAN_OK) { err = b200scan_last_error(ctx); return false; }
+    const b200scan_hit8* hits = nullptr; const uint32_t* bucketStart = nullptr; uint64_t n = 0, nb = 0;
+    b200scan_timing tm{};
+    const int rc2 = b200scan_collect8(ctx, 0, &hits, &n, &bucketStart, &nb, &tm);
+    if (rc2 == B200SCAN_OK) {
+        gStats.add(devIndex, tm, hi - lo);
+        formatHits8(sh, job, hits, n, bucketStart, nb, threads, text, lo);
+        nHits += n;
+        return true;
+    }
+    if (rc2 != B200SCAN_ENOMEM || hi - lo < 2048) { err = b200scan_last_error(ctx); return false; }
+    const uint64_t mid = lo + ((hi - lo) / 2 + 31) / 32 * 32;           // code and mask words start at multiples of 32 characters
+    return scanSplit(sh, ctx, job, lo, mid, halo, foldLower, threads, text, nHits, err, devIndex) &&
+           scanSplit(sh, ctx, job, mid, hi, halo, foldLower, threads, text, nHits, err, devIndex);
 }
 
 // One thread per GPU for the whole run.  The context (CUDA initialisation ~0.5-1.5 s) is created on its own thread while the host
 // still loads the inputs (`ready` carries the error text of a failed creation); a job of another manifest group than the one loaded
 // makes the worker drain its chunks in flight and load that group's P and thresholds (b200scan_set_motifs).
-void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctxSlot, shared_future<string> ready, size_t devIndex, size_t threads)
+void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctxSlot, shared_future<string> ready, size_t devIndex, size_t threads,
+                  uint64_t halo)
 {
     b200scan_ctx*& ctx = *ctxSlot;
     auto die = [&](const string& what) { sh.fail(what); };
@@ -633,14 +672,32 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
     // BLAMM_B200_HITS=12 keeps the unordered 12-byte records and the host sort (diagnostic / comparison).
     unique_ptr<Job> inFlight[B200SCAN_NUM_SLOTS];
     int head = 0, tail = 0, nFlight = 0;               // slots tail .. head-1 (mod 3) hold chunks, oldest first
+    // dense chunks (B200SCAN_ENOMEM at collect) waiting to be scored in halves, and the chunks collected behind them
+    struct Held { unique_ptr<Job> job; vector<b200scan_hit8> hits; vector<uint32_t> buckets; };
+    vector<unique_ptr<Job>> pendingSplit; vector<Held> held;
     auto collectOldest = [&]() -> bool {
         const int s = tail;
         const double tc = now();
         b200scan_timing tm{};
         if (hitFormat == B200SCAN_HITS_8) {
             const b200scan_hit8* hits = nullptr; const uint32_t* bucketStart = nullptr; uint64_t n = 0, nb = 0;
-            if (b200scan_collect8(ctx, s, &hits, &n, &bucketStart, &nb, &tm) != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
+            const int rc = b200scan_collect8(ctx, s, &hits, &n, &bucketStart, &nb, &tm);
+            if (rc == B200SCAN_ENOMEM) {
+                // too dense for the device buffers: finish the younger chunks in flight (they may be as dense: same treatment, in
+                // order), then score this one in halves.  All slots are free while a chunk is split.
+                pendingSplit.push_back(std::move(inFlight[s]));
+                tail = (tail + 1) % B200SCAN_NUM_SLOTS; nFlight--;
+                return !sh.failed;
+            }
+            if (rc != B200SCAN_OK) { die(string("CUDA error: ") + b200scan_last_error(ctx)); return false; }
             gTimer.add("b200scan_collect (wait GPU)", now() - tc);
+            if (!pendingSplit.empty()) {                      // keep the stream order: a younger chunk waits behind the split ones (rare path: copy its hits)
+                Held h; h.job = std::move(inFlight[s]); h.hits.assign(hits, hits + n); h.buckets.assign(bucketStart, bucketStart + nb + 1);
+                held.push_back(std::move(h));
+                gStats.add(devIndex, tm, held.back().job->nPayload);
+                tail = (tail + 1) % B200SCAN_NUM_SLOTS; nFlight--;
+                return !sh.failed;
+            }
             writeHits8(sh, *inFlight[s], hits, n, bucketStart, nb, threads);
         } else {
             const b200scan_hit12* hits = nullptr; uint64_t n = 0;
@@ -653,7 +710,36 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
         tail = (tail + 1) % B200SCAN_NUM_SLOTS; nFlight--;
         return !sh.failed;
     };
+    // dense chunks: drain what is in flight, score them in halves (slot 0, synchronously), then release the chunks held behind them.
+    // Everything this worker holds is emitted in increasing chunk order, so nobody waits for a chunk that cannot come.
+    auto resolveSplits = [&]() -> bool {
+        while (nFlight > 0) if (!collectOldest()) return false;
+        struct Item { uint64_t seq; int kind; size_t idx; };
+        vector<Item> order;
+        for (size_t i = 0; i < pendingSplit.size(); i++) order.push_back({pendingSplit[i]->seq, 0, i});
+        for (size_t i = 0; i < held.size(); i++) order.push_back({held[i].job->seq, 1, i});
+        sort(order.begin(), order.end(), [](const Item& a, const Item& b) { return a.seq < b.seq; });
+        for (const auto& it : order) {
+            if (it.kind == 0) {
+                const Job& job = *pendingSplit[it.idx];
+                vector<string> text; uint64_t n = 0; string err;
+                const uint64_t mid = (job.nPayload / 2 + 31) / 32 * 32;
+                const bool ok = job.nPayload < 4096 ? false
+                              : scanSplit(sh, ctx, job, 0, mid, halo, foldLower, threads, text, n, err, devIndex) &&
+                                scanSplit(sh, ctx, job, mid, job.nPayload, halo, foldLower, threads, text, n, err, devIndex);
+                if (!ok) { die("CUDA error: " + (err.empty() ? string("chunk too dense for the device buffers") : err)); return false; }
+                emitText(sh, job, text, n);
+            } else {
+                const Held& h = held[it.idx];
+                writeHits8(sh, *h.job, h.hits.data(), h.hits.size(), h.buckets.data(), h.buckets.size() - 1, threads);
+            }
+            if (sh.failed) return false;
+        }
+        pendingSplit.clear(); held.clear();
+        return true;
+    };
     while (!sh.failed) {
+        if (!pendingSplit.empty() && !resolveSplits()) break;
         unique_ptr<Job> job;
         bool drainOne = false;
         {
@@ -672,6 +758,7 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
         if (job->group != loaded) {                          // next manifest group: its own P and thresholds
             bool ok = true;
             while (nFlight > 0 && ok) ok = collectOldest();
+            if (ok && !pendingSplit.empty()) ok = resolveSplits();       // (dense chunks of the old group are re-scored with ITS motifs)
             if (!ok) break;
             const GroupParams& g = *job->group;
             if (b200scan_set_motifs(ctx, g.P.data(), g.ldp, (int32_t)g.len.size(), g.len.data(), g.thr.data()) != B200SCAN_OK) {
@@ -693,6 +780,7 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
         if (nFlight == B200SCAN_NUM_SLOTS && !collectOldest()) break;     // overlap: format chunk k-2 while k-1 is scored and k goes up
     }
     while (nFlight > 0 && !sh.failed) if (!collectOldest()) break;
+    if (!pendingSplit.empty() && !sh.failed) resolveSplits();
 }
 
 // `blamm-b200 selftest-writer [hits] [threads]` (no GPU): the occurrence writer -- partition, radix sort, formatting, writer
@@ -912,9 +1000,13 @@ int runScan(int argc, char** argv)
     // one context per device for the whole run, sized for the largest group
     uint64_t maxTot = 1024;
     for (const auto& sp : sc.species) maxTot = max<uint64_t>(maxTot, sp.totSeqLen);
-    const uint64_t maxBlock = min<uint64_t>(chunk, maxTot) + halo + 64;
-    // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block)
+    // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block); where the rate is
+    // known to be high (-pt) the chunks shrink so that a chunk's hits stay within ~4e8 records (device memory: ~136 B per hit).
+    // Chunks that turn out denser than the device can hold are scored in halves (deviceWorker: scanSplit).
     const double rate = pSpec ? std::min(1.0, 3.0 * pvalue) : 2e-4;
+    if (rate * (double)mc.motifs.size() * (double)chunk > 4e8)
+        chunk = max<uint64_t>(1 << 20, (uint64_t)(4e8 / (rate * (double)mc.motifs.size())) / 32 * 32);
+    const uint64_t maxBlock = min<uint64_t>(chunk, maxTot) + halo + 64;
     const uint64_t maxHits = std::max<uint64_t>(1 << 20, (uint64_t)(rate * (double)maxBlock * (double)mc.motifs.size()));
     struct CtxPool {
         vector<b200scan_ctx*> ctx;
@@ -949,7 +1041,7 @@ int runScan(int argc, char** argv)
     sh.maxQueue = (size_t)nDev + 1;
     vector<thread> workers;
     for (int d = 0; d < nDev; d++)
-        workers.emplace_back(deviceWorker, ref(sh), engine, foldLower, &pool.ctx[(size_t)d], pool.ready[(size_t)d], (size_t)d, numThreads);
+        workers.emplace_back(deviceWorker, ref(sh), engine, foldLower, &pool.ctx[(size_t)d], pool.ready[(size_t)d], (size_t)d, numThreads, halo);
     auto finish = [&](bool failed) {
         { lock_guard<mutex> l(sh.qMutex); sh.done = true; }
         if (failed) sh.fail("input error"); else sh.qCv.notify_all();

@@ -722,11 +722,11 @@ def test_cli_empirical_histograms_example(golden, tmp_path):
 
 
 def test_block_offsets_beyond_2_to_31():
-    """One block of 2.2e9 characters (the ABI takes up to 2^32 - 2^28): window positions, code-word offsets and bucket indices
-    pass 2^31.  The block is a 1,000,003-character segment repeated 2200 times, so the exact answer is periodic: the oracle scans
+    """One block of 2.3e9 characters (the ABI takes up to 2^32 - 2^28): window positions, code-word offsets and bucket indices
+    pass 2^31.  The block is a 1,000,003-character segment repeated 2300 times, so the exact answer is periodic: the oracle scans
     two periods once, and every period of the block -- in particular those that lie beyond position 2^31 -- must return exactly
     its hits (position + k * period), in order, through the host packer, b200scan_submit_packed and the ordered 8-byte records."""
-    period, reps = 1_000_003, 2200
+    period, reps = 1_000_003, 2300
     case = util.random_case(91, n_motifs=6, n_nt=period, len_range=(8, 20), with_gaps=False)
     thr = (case["thr"] + np.float32(3.0)).astype(np.float32)                 # a few hundred hits per period
     seg = case["chars"]
@@ -763,3 +763,34 @@ def test_block_offsets_beyond_2_to_31():
         assert np.array_equal(hp[m] - (reps - 1) * period, p1.astype(np.int64)) and np.array_equal(h["col"][m], c1)
     finally:
         s.close()
+
+
+def test_cli_splits_chunks_too_dense_for_the_device_buffers(tmp_path):
+    """Thresholds so low that a third of all windows are occurrences, and a device budget of 30,000 hit records
+    (B200SCAN_HIT_BUDGET): b200scan_collect8 refuses the chunks with B200SCAN_ENOMEM and the CLI scores them in halves,
+    recursively (cli.cpp: scanSplit), still writing every chunk in stream order.  The occurrence file must equal the oracle's
+    whole-scan restatement, line for line after sorting -- and, per sequence, already be in position order."""
+    cli = os.path.join(lib_dir(), "blamm-b200")
+    work = str(tmp_path)
+    rng = np.random.default_rng(3)
+    synth.make_jaspar_like(os.path.join(work, "motifs.jaspar"), 6, 11, uniform_len=(6, 10))
+    seq = synth.random_acgt(300_000, 12)
+    seq[100_000:100_050] = ord("N")
+    synth.write_fasta(os.path.join(work, "a.fa"), [("s1", seq[:180_000]), ("s2", seq[180_000:])])
+    open(os.path.join(work, "sequences.mf"), "w").write("g\ta.fa\n")
+    subprocess.run([cli, "dict", "sequences.mf"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+    env = dict(os.environ, B200SCAN_HIT_BUDGET="30000", BLAMM_B200_CHUNK="70000")
+    r = subprocess.run([cli, "scan", "-rc", "-at", "-6", "-t", "4", "motifs.jaspar", "sequences.mf"], cwd=work, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = open(os.path.join(work, "occurrences.txt")).read().splitlines(True)
+    want, _ = O.scan("motifs.jaspar", "sequences.mf", mode="at", value=-6.0, revcompl=True, base_dir=work)
+    assert len(got) == len(want) > 300_000
+    assert sorted(got) == sorted(want)
+    starts = {}
+    for l in got:
+        c = l.split("\t")
+        assert int(c[3]) >= starts.get(c[0], 0)
+        starts[c[0]] = int(c[3])
+    # without the budget the same run takes the normal path and writes the same file
+    r = subprocess.run([cli, "scan", "-rc", "-at", "-6", "-t", "4", "-o", "plain.txt", "motifs.jaspar", "sequences.mf"], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0 and open(os.path.join(work, "plain.txt")).read().splitlines(True) == got
