@@ -532,9 +532,9 @@ def run_blocks(args, rank: int, local_rank: int, world: int) -> None:
         total_scores_per_step = stream_len * n_cols
         ordered = args.hits == capi.HITS_8
 
-        def submit(slot, k, buf):
+        def submit(slot, k, buf, ascii_mode=None):
             s, ptr = blocks[k]
-            if args.ascii:
+            if args.ascii if ascii_mode is None else ascii_mode:
                 sc.submit_ascii(slot, ptr, n_total=s.n_total, n_payload=s.n_payload)
             else:
                 sc.submit_packed_ptr(slot, buf[0], buf[1] if has_zero[k] else None, s.n_total, s.n_payload)
@@ -575,34 +575,58 @@ def run_blocks(args, rank: int, local_rank: int, world: int) -> None:
         barrier()
         # ---- timed: end to end from characters in pinned host memory, the way the CLI drives the library: pack on the host
         #      threads, three slots in flight (chunk j+1 uploads and chunk j scores while the hits of chunk j-1 come down) ----
-        seq_of_blocks = [k for _ in range(args.steps) for k in range(len(blocks))]
         nS = capi.NUM_SLOTS
+
+        def e2e_pass(n_steps, ascii_mode):
+            """n_steps passes over the rank's chunks, pipelined; returns (seconds, h2d bytes, d2h bytes, host pack ms, hits, last timing)."""
+            order = [k for _ in range(n_steps) for k in range(len(blocks))]
+            t_start = time.perf_counter()
+            d2h_b = h2d_b = 0
+            p_ms = 0.0
+            hits_seen = 0
+            t_last = None
+            fut = None if ascii_mode else packer.pack_async(blocks[order[0]][1], blocks[order[0]][0].n_total, code_bufs[0][0], code_bufs[0][1])
+            for j, k in enumerate(order):
+                buf = code_bufs[j % n_code_bufs]
+                if fut is not None:
+                    fut.result(); p_ms += packer.last_ms
+                if not ascii_mode and j + 1 < len(order):            # buffer (j+1) % 4 was last read by chunk j-3, collected in iteration j-1
+                    k2 = order[j + 1]; b2 = code_bufs[(j + 1) % n_code_bufs]
+                    fut = packer.pack_async(blocks[k2][1], blocks[k2][0].n_total, b2[0], b2[1])
+                else:
+                    fut = None
+                submit(j % nS, k, buf, ascii_mode)
+                s = blocks[k][0]
+                h2d_b += s.n_total if ascii_mode else ((s.n_total + 15) // 16) * 4 + (((s.n_total + 31) // 32) * 4 if has_zero[k] else 0)
+                if j >= nS - 1:
+                    nh, nbytes, t_last, _ = collect((j - (nS - 1)) % nS)
+                    d2h_b += nbytes; hits_seen += nh
+            for j in range(max(0, len(order) - (nS - 1)), len(order)):
+                nh, nbytes, t_last, _ = collect(j % nS)
+                d2h_b += nbytes; hits_seen += nh
+            torch.cuda.synchronize()
+            return time.perf_counter() - t_start, h2d_b, d2h_b, p_ms, hits_seen, t_last
+
+        # Hand-over: the ABI takes a block as characters (device packer: 1 B per character over PCIe, no host work) or as host-packed
+        # 2-bit codes (0.25 B per character, but the host cores must keep up: N ranks share them).  Unless one is forced, both are
+        # tried for a few untimed steps and the faster one (max over ranks) is used -- the choice a caller of the ABI would make.
+        calib = None
+        ascii_mode = args.ascii
+        if not args.ascii and not args.packed:
+            cal = []
+            for mode in (False, True):
+                e2e_pass(1, mode)                                     # first use of this hand-over's buffers
+                barrier()
+                cal.append(e2e_pass(max(4 // len(blocks), 1), mode)[0])
+                barrier()
+            ct = torch.tensor(cal, dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+            cal = ct.tolist()
+            ascii_mode = cal[1] < 0.95 * cal[0]
+            calib = {"packed_s": cal[0], "characters_s": cal[1], "steps": max(4 // len(blocks), 1)}
         barrier()
-        t0 = time.perf_counter()
-        d2h = h2d = 0
-        pack_ms = 0.0
-        checksum = 0
-        fut = None if args.ascii else packer.pack_async(blocks[seq_of_blocks[0]][1], blocks[seq_of_blocks[0]][0].n_total, code_bufs[0][0], code_bufs[0][1])
-        for j, k in enumerate(seq_of_blocks):
-            buf = code_bufs[j % n_code_bufs]
-            if fut is not None:
-                fut.result(); pack_ms += packer.last_ms
-            if not args.ascii and j + 1 < len(seq_of_blocks):         # buffer (j+1) % 4 was last read by chunk j-3, collected in iteration j-1
-                k2 = seq_of_blocks[j + 1]; b2 = code_bufs[(j + 1) % n_code_bufs]
-                fut = packer.pack_async(blocks[k2][1], blocks[k2][0].n_total, b2[0], b2[1])
-            else:
-                fut = None
-            submit(j % nS, k, buf)
-            s = blocks[k][0]
-            h2d += s.n_total if args.ascii else ((s.n_total + 15) // 16) * 4 + (((s.n_total + 31) // 32) * 4 if has_zero[k] else 0)
-            if j >= nS - 1:
-                nh, nbytes, t_e2e, _ = collect((j - (nS - 1)) % nS)
-                d2h += nbytes; checksum += nh
-        for j in range(max(0, len(seq_of_blocks) - (nS - 1)), len(seq_of_blocks)):
-            nh, nbytes, t_e2e, last = collect(j % nS)
-            d2h += nbytes; checksum += nh
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+        e2e_s, h2d, d2h, pack_ms, checksum, t_e2e = e2e_pass(args.steps, ascii_mode)
         barrier()
         clocks = sampler.stop()
         assert checksum == sum(n_hits) * args.steps or os.environ.get("B200_BENCH_DIAG"), "e2e passes changed the hit count"
@@ -644,10 +668,11 @@ def run_blocks(args, rank: int, local_rank: int, world: int) -> None:
                          "parallelism": "one stream of %d chunk(s) dealt to %d rank(s) (chunk k -> rank k mod N, halo %d), no data-path collective; "
                                         "merge = chunk-ordered concatenation of per-chunk (position, column)-ordered hit lists, ranks exchange hit counts only" % (len(plan), world, halo),
                          "host_binding": numa, "hits_per_step": hits_total, "hit_record_bytes": args.hits,
-                         "candidates_last_block": int(t_e2e["n_candidates"]), "hand_over": "characters (b200scan_submit_ascii)" if args.ascii else
+                         "candidates_last_block": int(t_e2e["n_candidates"]), "hand_over": "characters in pinned host memory (b200scan_submit_ascii: 1 B per character up, packed on the device)" if ascii_mode else
                          "host 2-bit packer on %d threads (blamm_pack_ascii) + b200scan_submit_packed" % packer.threads,
+                         "hand_over_calibration": calib,
                          "slots_in_flight": nS},
-                "gpu_launches": int(launches_per_pass * launches * 2),
+                "gpu_launches": int(launches * (2 * launches_per_pass - (1 if ascii_mode else 0))),     # (the character hand-over adds the pack kernel to the e2e passes)
                 "clocks": clocks,
                 "e2e": {"value": total_scores_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d // args.steps),
                         "d2h_bytes_per_step": int(d2h // args.steps), "ms_per_step": e2e_ms / args.steps,
@@ -802,7 +827,8 @@ def main() -> None:
     ap.add_argument("--acc", type=int, default=0, choices=[0, 8, 16, 32], help="tensor filter operand/accumulator kind: 0 = automatic (diagnostic)")
     ap.add_argument("--softmask", type=float, default=0.0, help="diagnostic: fraction of the sequence turned lower case (runs of 1..3000), scored with BLAS-path semantics")
     ap.add_argument("--hits", type=int, default=8, choices=[8, 12, 16], help="hit record format (b200scan_set_hit_format): 8 = ordered b200scan_hit8, what the CLI uses")
-    ap.add_argument("--ascii", action="store_true", help="diagnostic: hand characters over (b200scan_submit_ascii, device packer) instead of host-packed codes")
+    ap.add_argument("--ascii", action="store_true", help="force the character hand-over (b200scan_submit_ascii, device packer)")
+    ap.add_argument("--packed", action="store_true", help="force the host-packed hand-over (blamm_pack_ascii + b200scan_submit_packed); default: the faster of the two")
     ap.add_argument("--pack-threads", type=int, default=0, help="host packer threads per rank (default: cores / ranks, at most 16)")
     ap.add_argument("--cpu-sample-nt", type=int, default=32_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

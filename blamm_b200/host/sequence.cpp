@@ -568,6 +568,32 @@ uint64_t packWordsAvx2(const char* chars, uint64_t base, uint64_t i1, bool foldL
     return base;
 }
 const bool kHaveAvx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && !getenv("BLAMM_B200_NO_AVX2");
+// AVX-512BW twin: 64 characters per step, the byte tests deliver the bit planes directly as mask registers (no shift + MOVMSK)
+__attribute__((target("avx512f,avx512bw,bmi2")))
+uint64_t packWordsAvx512(const char* chars, uint64_t base, uint64_t i1, bool foldLower, uint32_t* codes2, uint32_t* zmask, bool& anyZero)
+{
+    const __m512i mDF = _mm512_set1_epi8((char)0xDF), cA = _mm512_set1_epi8(0x41), cC = _mm512_set1_epi8(0x43), cG = _mm512_set1_epi8(0x47),
+                  cT = _mm512_set1_epi8(0x54), b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04), b5 = _mm512_set1_epi8(0x20);
+    uint64_t any = 0;
+    for (; base + 64 <= i1; base += 64) {
+        const __m512i x = _mm512_loadu_si512(reinterpret_cast<const void*>(chars + base));
+        const __m512i u = _mm512_and_si512(x, mDF);
+        const uint64_t valid = _mm512_cmpeq_epi8_mask(u, cA) | _mm512_cmpeq_epi8_mask(u, cC) | _mm512_cmpeq_epi8_mask(u, cG) | _mm512_cmpeq_epi8_mask(u, cT);
+        const uint64_t hi = _mm512_test_epi8_mask(u, b2) & valid;                                                   // bit 2
+        const uint64_t lo = _mm512_test_epi8_mask(_mm512_xor_si512(u, _mm512_srli_epi16(u, 1)), b1) & valid;        // bit 1 ^ bit 2
+        uint64_t zero = ~valid;
+        if (!foldLower) zero |= _mm512_test_epi8_mask(x, b5);                                                       // bit 5: lower case
+        const uint64_t c0 = _pdep_u64(lo & 0xFFFFFFFFu, 0x5555555555555555ULL) | _pdep_u64(hi & 0xFFFFFFFFu, 0xAAAAAAAAAAAAAAAAULL);
+        const uint64_t c1 = _pdep_u64(lo >> 32, 0x5555555555555555ULL) | _pdep_u64(hi >> 32, 0xAAAAAAAAAAAAAAAAULL);
+        codes2[base / 16] = (uint32_t)c0; codes2[base / 16 + 1] = (uint32_t)(c0 >> 32);
+        codes2[base / 16 + 2] = (uint32_t)c1; codes2[base / 16 + 3] = (uint32_t)(c1 >> 32);
+        zmask[base / 32] = (uint32_t)zero; zmask[base / 32 + 1] = (uint32_t)(zero >> 32);
+        any |= zero;
+    }
+    anyZero |= any != 0;
+    return base;
+}
+const bool kHaveAvx512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("bmi2") && !getenv("BLAMM_B200_NO_AVX512") && !getenv("BLAMM_B200_NO_AVX2");
 #endif
 // characters [i0, i1) of `chars` (i0 a multiple of 32) -> their code and mask words; true if a live character contributes 0
 bool packRange(const char* chars, uint64_t i0, uint64_t i1, bool foldLower, uint32_t* codes2, uint32_t* zmask)
@@ -575,6 +601,7 @@ bool packRange(const char* chars, uint64_t i0, uint64_t i1, bool foldLower, uint
     bool anyZero = false;
     uint64_t base = i0;
 #if defined(__x86_64__) && defined(__GNUC__)
+    if (kHaveAvx512) base = packWordsAvx512(chars, base, i1, foldLower, codes2, zmask, anyZero);
     if (kHaveAvx2) base = packWordsAvx2(chars, base, i1, foldLower, codes2, zmask, anyZero);
 #endif
     for (; base + 32 <= i1; base += 32) {

@@ -439,7 +439,8 @@ def test_parity_lister_lists_only_near_threshold_differences(tmp_path, golden):
 
 
 def test_packer_sse2_and_avx2_paths_agree(tmp_path):
-    """The host 2-bit packer picks its AVX2 + BMI2 routine at run time (BLAMM_B200_NO_AVX2=1 keeps the SSE2 one): both must give
+    """The host 2-bit packer picks its AVX-512BW or AVX2 (+ BMI2) routine at run time (BLAMM_B200_NO_AVX512=1 / BLAMM_B200_NO_AVX2=1
+    step down to AVX2 / SSE2): all must give
     the same code and mask words on every byte value, both lower-case rules, lengths around the 32-character step."""
     code = (
         "import sys, numpy as np\n"
@@ -456,8 +457,8 @@ def test_packer_sse2_and_avx2_paths_agree(tmp_path):
         "            out += [c, z, np.array([h], dtype=np.uint32)]\n"
         "np.save(sys.argv[1], np.concatenate([o.astype(np.uint32) for o in out]))\n" % ROOT)
     res = []
-    for k, env in enumerate(({}, {"BLAMM_B200_NO_AVX2": "1"})):
+    for k, env in enumerate(({}, {"BLAMM_B200_NO_AVX512": "1"}, {"BLAMM_B200_NO_AVX2": "1"})):
         f = str(tmp_path / ("p%d.npy" % k))
         subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, **env))
         res.append(np.load(f))
-    assert len(res[0]) > 100000 and np.array_equal(res[0], res[1])
+    assert len(res[0]) > 100000 and np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
