@@ -75,7 +75,9 @@ struct b200scan_ctx {
     // candidates are shared by the slots (stream order serialises filter -> rescore per block)
     Cand* d_cand = nullptr;  unsigned long long cand_cap = 0;
     // raw entries of the tensor filter (blocks of kRawBlock entries of kRawWords words), also shared by the slots
-    uint32_t* d_raw = nullptr;  uint32_t* d_blk_count = nullptr;  uint32_t blk_cap = 0;
+    uint32_t* d_raw = nullptr;  uint32_t* d_blk_count = nullptr;  uint32_t* d_blk_tag = nullptr;  uint32_t blk_cap = 0;
+    bool fused = true;            // rescore_tile_kernel (expand + rescore fused, tile by tile); B200SCAN_RESCORE=list keeps the round-1 chain
+    uint32_t fuse_max_w = 0;      // shared-memory weight positions of the fused kernel for the loaded motif set
     // motifs
     bool have_motifs = false;
     uint32_t n_cols = 0, max_len = 0;  uint64_t sum_len = 0;
@@ -516,6 +518,25 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     CU(cudaMemcpy(ctx->d_ttiles_z, tt_z.data(), sizeof(TcTile) * tt_z.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_bimg_z, bimg_z.data(), bimg_z.size(), cudaMemcpyHostToDevice));
     ctx->gtiles = gt; ctx->ttiles = tt;
+    {   // fused rescorer: shared memory for the largest tile's FP32 weights (both tilings), capped; room for the partial raw
+        // blocks the filter's warps close at every change of column tile
+        uint32_t mw = 1;
+        for (const auto* tv : {&tt, &tt_z})
+            for (const TcTile& t : *tv) {
+                uint32_t nw = 0;
+                for (uint32_t c = t.col0; c < t.col0 + t.n_cols; c++) nw += len[c];
+                mw = std::max(mw, nw);
+            }
+        ctx->fuse_max_w = std::min(mw, kFuseMaxW);
+        const unsigned long long want = ctx->cand_cap / kRawBlock + 4096 + (unsigned long long)ctx->sm_count * kTcEpiWarps * (tt.size() + 2);
+        if (want > ctx->blk_cap) {
+            dfree(ctx->d_raw); dfree(ctx->d_blk_count); dfree(ctx->d_blk_tag);
+            ctx->blk_cap = (uint32_t)want;
+            CU(cudaMalloc(&ctx->d_raw, ((size_t)ctx->blk_cap + 1) * kRawBlock * kRawWords * 4));
+            CU(cudaMalloc(&ctx->d_blk_count, (size_t)ctx->blk_cap * 4));
+            CU(cudaMalloc(&ctx->d_blk_tag, (size_t)ctx->blk_cap * 4));
+        }
+    }
     ctx->h_len_sorted = len; ctx->h_woff_sorted = woff; ctx->h_orig_sorted = orig;
     ctx->hist_bins = 0;
     ctx->n_cols = (uint32_t)n_cols; ctx->max_len = max_len; ctx->sum_len = sum_len;
@@ -568,7 +589,7 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
     const dim3 ggrid((unsigned)((s.n_payload + kGatherSpan - 1) / kGatherSpan), (unsigned)ctx->gtiles.size());
     if (want_tc) {
         TcParams tp;
-        tp.work_counter = work; tp.raw = ctx->d_raw; tp.blk_count = ctx->d_blk_count; tp.n_blocks = work + 1; tp.blk_cap = ctx->blk_cap;
+        tp.work_counter = work; tp.raw = ctx->d_raw; tp.blk_count = ctx->d_blk_count; tp.blk_tag = ctx->d_blk_tag; tp.n_blocks = work + 1; tp.blk_cap = ctx->blk_cap;
         tp.error_flag = err;
         tp.trace = ctx->d_trace;
         // One instance per accumulator type over its share of the tiles (FP16 tiles are stored first), and that for both
@@ -621,10 +642,22 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
             }
         }
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
-        expand_kernel<<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
-        n++;
-        rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(md, blk, ctx->d_cand, s.d_counters, ctx->cand_cap, sink);
-        n++;
+        if (ctx->fused) {
+            // expand + exact rescoring in one kernel, a column tile's weights at a time in shared memory (the instance that does not
+            // match the block's has_zero flag returns at once)
+            unsigned int* fwork = reinterpret_cast<unsigned int*>(s.d_counters + 5);
+            const size_t fsm = fuse_smem_bytes(ctx->fuse_max_w);
+            rescore_tile_kernel<false><<<ctx->sm_count, kFuseThreads, fsm, ctx->stream>>>(md, blk, ctx->d_raw, ctx->d_blk_count, ctx->d_blk_tag, work + 1, ctx->blk_cap,
+                                                                                        fwork, s.d_counters, ctx->fuse_max_w, sink);
+            rescore_tile_kernel<true><<<ctx->sm_count, kFuseThreads, fsm, ctx->stream>>>(md, blk, ctx->d_raw, ctx->d_blk_count, ctx->d_blk_tag, work + 1, ctx->blk_cap,
+                                                                                       fwork, s.d_counters, ctx->fuse_max_w, sink);
+            n += 2;
+        } else {
+            expand_kernel<<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
+            n++;
+            rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(md, blk, ctx->d_cand, s.d_counters, ctx->cand_cap, sink);
+            n++;
+        }
         if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
     } else {
         gather_scan_kernel<false><<<ggrid, kGatherThreads, ctx->gather_smem, ctx->stream>>>(md, blk, ctx->d_gtiles, sink, 0);
@@ -713,7 +746,7 @@ int reset_counters(b200scan_ctx* ctx, Slot& s, bool keep_has_zero, cudaStream_t 
     CU(cudaMemsetAsync(s.d_counters, 0, 16, st));
     if (keep_has_zero) CU(cudaMemsetAsync(reinterpret_cast<uint32_t*>(s.d_counters + 2) + 1, 0, 4, st));
     else CU(cudaMemsetAsync(s.d_counters + 2, 0, 8, st));
-    CU(cudaMemsetAsync(s.d_counters + 3, 0, 16, st));               // both work counters and the block counter
+    CU(cudaMemsetAsync(s.d_counters + 3, 0, 24, st));               // the work counters (filter instances, fused rescorer) and the block counter
     return B200SCAN_OK;
 }
 
@@ -870,11 +903,15 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     CUB(cudaMalloc(&c->d_trace, 4 * kTraceTiles * 4 * 8));
     CUB(cudaMemset(c->d_trace, 0, 4 * kTraceTiles * 4 * 8));
 #endif
+    if (const char* e = getenv("B200SCAN_RESCORE")) c->fused = std::string(e) != "list";
     c->cand_cap = std::max<unsigned long long>(2 * max_hits, 1 << 20);
-    CUB(cudaMalloc(&c->d_cand, sizeof(Cand) * c->cand_cap));
+    if (!c->fused) CUB(cudaMalloc(&c->d_cand, sizeof(Cand) * c->cand_cap));
     c->blk_cap = (uint32_t)std::max<unsigned long long>(c->cand_cap / kRawBlock + 4096, 8192);
+    CUB(cudaFuncSetAttribute(rescore_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem_bytes(kFuseMaxW)));
+    CUB(cudaFuncSetAttribute(rescore_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem_bytes(kFuseMaxW)));
     CUB(cudaMalloc(&c->d_raw, ((size_t)c->blk_cap + 1) * kRawBlock * kRawWords * 4));     // + the sacrificial overflow block
     CUB(cudaMalloc(&c->d_blk_count, (size_t)c->blk_cap * 4));
+    CUB(cudaMalloc(&c->d_blk_tag, (size_t)c->blk_cap * 4));
     lap("candidate / raw buffers");
 #undef CUB
     *out = c;
@@ -891,7 +928,7 @@ void b200scan_destroy(b200scan_ctx* c)
         dfree(s.d_ascii); dfree(s.d_codes); dfree(s.d_zmask); dfree(s.d_frag); dfree(s.d_hits); dfree(s.d_counters); dfree(s.d_bucket_start);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     }
-    dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_flush);
+    dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_blk_tag); dfree(c->d_flush);
     dfree(c->d_bucket_cnt); dfree(c->d_bucket_cursor); dfree(c->d_coarse_start); dfree(c->d_sort_tmp);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg); dfree(c->d_ttiles_z); dfree(c->d_bimg_z);
@@ -1125,7 +1162,7 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
             return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR unavailable for this motif set");
         const uint32_t n_blocks = (uint32_t)(s.h_counters[3] >> 32);
         const bool raw_over = n_blocks > ctx->blk_cap;
-        const bool cand_over = raw_over || n_cand > ctx->cand_cap, hit_over = nh > s.hit_cap;
+        const bool cand_over = raw_over || (!ctx->fused && n_cand > ctx->cand_cap), hit_over = nh > s.hit_cap;
         if (!cand_over && !hit_over) {
             s.timing.n_candidates = n_cand; s.timing.n_hits = nh;
             s.timing.engine_used = (ctx->engine == B200SCAN_ENGINE_GATHER || !ctx->tc_usable) ? B200SCAN_ENGINE_GATHER : B200SCAN_ENGINE_TENSOR;
@@ -1138,7 +1175,7 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
         {
             const unsigned long long need_hits = hit_over ? nh + nh / 8 + 1024 : s.hit_cap;
             const unsigned long long need_cand = raw_over ? ((unsigned long long)n_blocks + n_blocks / 8 + 1024) * kRawBlock * 2
-                                                          : (n_cand > ctx->cand_cap ? n_cand + n_cand / 8 + 1024 : ctx->cand_cap);
+                                                          : (!ctx->fused && n_cand > ctx->cand_cap ? n_cand + n_cand / 8 + 1024 : ctx->cand_cap);
             if (need_hits > ctx->hit_budget || need_cand > 4 * ctx->hit_budget) {
                 s.resident = false;
                 return fail(ctx, B200SCAN_ENOMEM, "block too dense for the device buffers: %llu hits, %llu candidates against a budget of %llu hit records "
@@ -1159,15 +1196,17 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
             const uint32_t new_cap = n_blocks + n_blocks / 8 + 1024;
             const size_t raw_old = ((size_t)ctx->blk_cap + 1) * kRawBlock * kRawWords * 4, raw_new = ((size_t)new_cap + 1) * kRawBlock * kRawWords * 4;
             if (regrow(reinterpret_cast<void**>(&ctx->d_raw), raw_old, raw_new) &&
-                regrow(reinterpret_cast<void**>(&ctx->d_blk_count), (size_t)ctx->blk_cap * 4, (size_t)new_cap * 4)) {
+                regrow(reinterpret_cast<void**>(&ctx->d_blk_count), (size_t)ctx->blk_cap * 4, (size_t)new_cap * 4) &&
+                regrow(reinterpret_cast<void**>(&ctx->d_blk_tag), (size_t)ctx->blk_cap * 4, (size_t)new_cap * 4)) {
                 ctx->blk_cap = new_cap;
                 // every raw entry holds at least one candidate and at most 64; size the candidate list for the typical ~1.5
                 const unsigned long long want = (unsigned long long)ctx->blk_cap * kRawBlock * 2;
                 if (want > ctx->cand_cap) {
-                    if (regrow(reinterpret_cast<void**>(&ctx->d_cand), sizeof(Cand) * ctx->cand_cap, sizeof(Cand) * want)) ctx->cand_cap = want; else ok = false;
+                    if (ctx->fused) ctx->cand_cap = want;
+                    else if (regrow(reinterpret_cast<void**>(&ctx->d_cand), sizeof(Cand) * ctx->cand_cap, sizeof(Cand) * want)) ctx->cand_cap = want; else ok = false;
                 }
             } else ok = false;
-        } else if (n_cand > ctx->cand_cap) {
+        } else if (!ctx->fused && n_cand > ctx->cand_cap) {
             const unsigned long long want = n_cand + n_cand / 8 + 1024;
             if (regrow(reinterpret_cast<void**>(&ctx->d_cand), sizeof(Cand) * ctx->cand_cap, sizeof(Cand) * want)) ctx->cand_cap = want; else ok = false;
         }
@@ -1179,7 +1218,7 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
         }
         if (!ok) {
             s.resident = false;
-            if (!ctx->d_raw || !ctx->d_blk_count || !ctx->d_cand || !s.d_hits)
+            if (!ctx->d_raw || !ctx->d_blk_count || !ctx->d_blk_tag || (!ctx->fused && !ctx->d_cand) || !s.d_hits)
                 return fail(ctx, B200SCAN_ECUDA, "out of device memory while regrowing the hit buffers, and the previous size could not be restored");
             return fail(ctx, B200SCAN_ENOMEM, "out of device memory for a block with %llu hits and %llu candidates -- submit it in smaller blocks", nh, n_cand);
         }

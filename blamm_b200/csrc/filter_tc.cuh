@@ -120,6 +120,7 @@ struct TcParams {
     unsigned int*  work_counter;
     uint32_t*      raw;            // raw entries: block b, entry e at raw[(b * kRawBlock + e) * kRawWords]
     uint32_t*      blk_count;      // entries used in block b
+    uint32_t*      blk_tag;        // column tile of block b: first sorted column << 9 | real columns (rescore.cuh: rescore_tile_kernel)
     unsigned int*  n_blocks;       // blocks reserved so far (keeps counting past blk_cap so the host can size a retry)
     uint32_t       blk_cap;
     unsigned int*  error_flag;
@@ -393,10 +394,11 @@ template <bool ACC16> __device__ __forceinline__ bool any_nonneg(uint32_t m) {
 struct RawCursor { uint32_t* next; uint32_t left; uint32_t blk; uint32_t spare; };
 // Open the pre-reserved block and reserve the one after it.  When the buffer is full the cursor points at the
 // sacrificial block behind blk_cap, whose contents are never read: the host sees n_blocks > blk_cap and re-runs.
-__device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, uint32_t lane) {      // (inlined: a call would spill the cursor to local memory)
+__device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, uint32_t lane, uint32_t tag) {      // (inlined: a call would spill the cursor to local memory)
     const uint32_t nb = __shfl_sync(0xffffffffu, rc.spare, 0);
     if (lane == 0) {
         if (rc.blk < P.blk_cap) P.blk_count[rc.blk] = kRawBlock - rc.left;          // close the old block
+        if (nb < P.blk_cap) P.blk_tag[nb] = tag;                                    // a block holds entries of ONE column tile
         rc.spare = atomicAdd(P.n_blocks, 1u);
     }
     rc.blk = nb;
@@ -408,9 +410,9 @@ __device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, 
 // one cursor update and one predicated, fire-and-forget 256-bit store (~2e-4 of the accumulators are candidates, so this
 // runs for about every other tile of every warp).
 __device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, unsigned t, bool c, uint32_t win, uint32_t col0, uint32_t a0, uint32_t a1,
-                                         uint32_t col1, uint32_t b0, uint32_t b1, uint32_t lane) {
+                                         uint32_t col1, uint32_t b0, uint32_t b1, uint32_t lane, uint32_t tag) {
     const uint32_t n = __popc(t);
-    if (n > rc.left) raw_new_block(rc, P, lane);            // n <= 32 <= kRawBlock
+    if (n > rc.left) raw_new_block(rc, P, lane, tag);       // n <= 32 <= kRawBlock
     uint32_t* d = rc.next + __popc(t & ((1u << lane) - 1u)) * kRawWords;
     if (!(TC_KNOCKOUT & 16))
         asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %8, 0;\n@q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %7};\n}"
@@ -781,6 +783,11 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
             const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
+            const uint32_t tileTag = (tile.col0 << 9) | tile.n_cols;
+            if (newTile && rawc.blk != 0xffffffffu) {                 // another column tile: close the open block (a block holds ONE tile's entries)
+                if (lane == 0 && rawc.blk < P.blk_cap) P.blk_count[rawc.blk] = kRawBlock - rawc.left;
+                rawc.blk = 0xffffffffu; rawc.left = 0;
+            }
             // with two groups, group g takes the tiles whose running index is g mod 2 (= the tiles of TMEM buffer g)
             const uint32_t i0 = (kTcEpiGroups > 1) ? ((eGroup - kT) & (kTcEpiGroups - 1)) : 0u;
             uint32_t kt = kT + i0, win0 = w0 + 128 * i0 + 32 * eQ;    // running tile index; window of lane 0
@@ -818,7 +825,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         if (__any_sync(0xffffffffu, any_nonneg<true>(g1))) a1 = sign_word16<true, 16>(v);
                         if (__any_sync(0xffffffffu, any_nonneg<true>(g2))) b0 = sign_word16<true, 32>(v);
                         if (__any_sync(0xffffffffu, any_nonneg<true>(g3))) b1 = sign_word16<true, 48>(v);
-                        raw_push(rawc, P, t, c, win, colA, a0, a1, colB, b0, b1, lane);
+                        raw_push(rawc, P, t, c, win, colA, a0, a1, colB, b0, b1, lane, tileTag);
                     }
                     PH_ACC(2); PH_COUNT();
                     if (warp == kTcEpiWarp0) TC_TRACE(2, i, 3); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 3);
@@ -862,7 +869,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     const bool c = winOk && (((a0 ^ kAllNegative) | (a1 ^ kAllNegative) | (b0 ^ kAllNegative) | (b1 ^ kAllNegative)) != 0u);
                     const unsigned t = (TC_KNOCKOUT & 8) ? 0u : __ballot_sync(0xffffffffu, c);
                     if (t) raw_push(rawc, P, t, c, win0 + lane, (tile.col0 + wc * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), a0, a1,
-                                    (tile.col0 + (wc + step) * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), b0, b1, lane);
+                                    (tile.col0 + (wc + step) * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), b0, b1, lane, tileTag);
                 }
                 if (!released) {                                      // this warp owns no chunk of such a narrow tile
                     tc_fence_before();

@@ -165,4 +165,172 @@ rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
     if (n_st) flush();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused expand + rescore, column tile by column tile (round 2).
+//
+// rescore_kernel above is L1/TEX bound (ncu: l1tex throughput 90 %, 16 sectors per candidate): the lanes of a warp hold
+// candidates of different columns, so every weight load of a warp touches up to 32 sectors of the 360 KB FP32 table.  Here
+// the raw blocks carry the TAG of the column tile that produced them (filter_tc.cuh: an epilogue warp closes its block when its
+// CTA moves to another tile), a CTA takes a batch of consecutive blocks -- in allocation order they are almost always of one
+// tile, because all CTAs of the filter work through the items tile by tile -- loads THAT tile's FP32 weights and column records
+// into shared memory once, and scores the batch's raw entries straight from them: one thread per entry, the window's codes
+// loaded once per entry, every weight read an LDS.  The candidate list and expand_kernel disappear.
+// The sum is the same in-order FP32 sum as in rescore_kernel (bit-identical scores); hits leave through the same warp staging.
+// Tiles whose weights exceed the shared-memory budget (256 columns of > 36 positions) are scored from global memory.
+// ---------------------------------------------------------------------------------------------------------
+// FP32 score of one window against one column: the weights of the window's letters added strictly in position order (16 at a time:
+// all loads first, then the additions); masked positions add nothing (the reference's BLAS-path semantics of lower case)
+template <bool MASKED>
+__device__ __forceinline__ float score_in_order(const float* wp, uint32_t L, const uint32_t (&codes)[4], const uint32_t (&zm)[2])
+{
+    float s = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        if ((uint32_t)(16 * g) < L) {
+            const uint32_t rr = codes[g], n = min(16u, L - 16u * g);
+            float wv[16];
+#pragma unroll
+            for (uint32_t t = 0; t < 16; t++) wv[t] = (t < n) ? wp[4 * (16 * g + t) + ((rr >> (2 * t)) & 3u)] : 0.0f;
+#pragma unroll
+            for (uint32_t t = 0; t < 16; t++)
+                if (t < n && !(MASKED && ((zm[g >> 1] >> (16 * (g & 1) + t)) & 1u))) s += wv[t];
+        }
+    }
+    return s;
+}
+
+constexpr uint32_t kFuseThreads = 512;
+constexpr uint32_t kFuseBatch   = 256;                 // raw blocks per work item (16,384 entry slots)
+constexpr uint32_t kFuseRounds  = 4;                   // warp rounds of hits staged per global atomic
+constexpr uint32_t kFuseMaxW    = 9728;                // positions of weights a tile may hold in shared memory (152 KB)
+__host__ __device__ constexpr size_t fuse_smem_bytes(uint32_t max_w) { return (size_t)max_w * 16 + 256 * 16 + (size_t)(kFuseThreads / 32) * 32 * kFuseRounds * 16; }
+struct ColRec { uint32_t woff; uint32_t len; float thr; uint32_t orig; };
+
+template <bool MASKED>
+__global__ void __launch_bounds__(kFuseThreads)
+rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count,
+                    const uint32_t* __restrict__ blk_tag, const unsigned int* __restrict__ n_blocks_ptr, uint32_t blk_cap,
+                    unsigned int* work_counter, unsigned long long* n_cand, uint32_t max_w, HitSink sink)
+{
+    if ((__ldg(blk.has_zero) != 0) != MASKED) return;
+    extern __shared__ __align__(16) uint8_t fuse_smem[];
+    float4* s_w = reinterpret_cast<float4*>(fuse_smem);                                       // weights of the tile: max_w positions
+    ColRec* s_col = reinterpret_cast<ColRec*>(fuse_smem + (size_t)max_w * 16);                 // its <= 256 column records
+    constexpr uint32_t kRounds = kFuseRounds;
+    b200scan_hit* s_hits = reinterpret_cast<b200scan_hit*>(s_col + 256);                      // [warp][32 * kRounds]
+    __shared__ uint32_t s_item, s_next_tag;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    b200scan_hit* st = s_hits + wib * 32 * kRounds;
+    uint32_t n_st = 0, round = 0;
+    unsigned long long my_cand = 0;
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long o = 0;
+        if (lane == 0) o = atomicAdd(sink.n_hits, (unsigned long long)n_st);
+        o = __shfl_sync(0xffffffffu, o, 0);
+        for (uint32_t k0 = 0; k0 < n_st; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const bool stored = k < n_st && o + k < sink.cap;
+            if (stored) store_hit(sink, o + k, st[k]);
+            if (sink.bucket_cnt) {
+                const uint32_t sm = __ballot_sync(0xffffffffu, stored);
+                if (stored) count_hit_bucket(sink, sm, (uint32_t)st[k].pos);
+            }
+        }
+        __syncwarp();
+        n_st = 0; round = 0;
+    };
+    const uint32_t nb = min(*n_blocks_ptr, blk_cap);
+    const uint4* ent = reinterpret_cast<const uint4*>(raw);
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t b0 = s_item * kFuseBatch;
+        if (b0 >= nb) break;
+        const uint32_t b1 = min(nb, b0 + kFuseBatch);
+        // the batch's tiles, one after the other in increasing tag order (almost always one tile; two or three where the filter's
+        // CTAs changed tile) -- every tile exactly once, however many there are
+        uint32_t last_tag = 0;                                // tags are >= 1 (n_cols >= 1)
+        for (;;) {
+            if (threadIdx.x == 0) s_next_tag = 0xffffffffu;
+            __syncthreads();
+            for (uint32_t b = b0 + threadIdx.x; b < b1; b += kFuseThreads) {
+                if (__ldg(blk_count + b) == 0) continue;      // spare / unused reservations carry no tag
+                const uint32_t t = __ldg(blk_tag + b);
+                if (t > last_tag) atomicMin(&s_next_tag, t);
+            }
+            __syncthreads();
+            const uint32_t tag = s_next_tag;
+            if (tag == 0xffffffffu) break;
+            const uint32_t col0 = tag >> 9, ncol = tag & 511u;
+            const uint32_t wbase = __ldg(md.woff + col0);
+            const uint32_t nW = __ldg(md.woff + col0 + ncol - 1) + __ldg(md.len + col0 + ncol - 1) - wbase;
+            const bool in_smem = nW <= max_w;
+            __syncthreads();                                  // (everybody has read s_next_tag and is done with the previous tile's tables)
+            if (in_smem) for (uint32_t i = threadIdx.x; i < nW; i += kFuseThreads) s_w[i] = __ldg(md.w + wbase + i);
+            for (uint32_t c = threadIdx.x; c < ncol; c += kFuseThreads) {
+                ColRec r; r.woff = __ldg(md.woff + col0 + c) - wbase; r.len = __ldg(md.len + col0 + c); r.thr = __ldg(md.thr + col0 + c); r.orig = __ldg(md.orig + col0 + c);
+                s_col[c] = r;
+            }
+            __syncthreads();
+            const float* wsm = reinterpret_cast<const float*>(s_w);
+            const float* wgl = reinterpret_cast<const float*>(md.w + wbase);
+            // one warp per 32 entry slots of a block of this tile
+            for (uint32_t sidx = wib * 32; sidx < (b1 - b0) * kRawBlock; sidx += kFuseThreads) {
+                const uint32_t b = b0 + sidx / kRawBlock, e = sidx % kRawBlock + lane;           // kRawBlock % 32 == 0: same block
+                if (__ldg(blk_tag + b) != tag) continue;                                        // (warp-uniform)
+                const uint32_t cnt = __ldg(blk_count + b);
+                if (sidx % kRawBlock >= cnt) continue;
+                const bool live = e < cnt;
+                uint4 x = make_uint4(0u, 0u, kAllNegative, kAllNegative), y = make_uint4(0u, kAllNegative, kAllNegative, 0u);
+                if (live) { x = __ldg(ent + 2 * ((size_t)b * kRawBlock + e)); y = __ldg(ent + 2 * ((size_t)b * kRawBlock + e) + 1); }
+                const bool acc16 = !(x.y & kRawFp32Flag);
+                uint32_t z[4] = {~decode_sign_word(acc16, x.z), ~decode_sign_word(acc16, x.w), ~decode_sign_word(acc16, y.y), ~decode_sign_word(acc16, y.z)};
+                const uint32_t first[2] = {(x.y & ~kRawFp32Flag) - col0, (y.x & ~kRawFp32Flag) - col0};        // columns relative to the tile
+                const uint32_t pos = x.x;
+                uint32_t codes[4] = {0u, 0u, 0u, 0u}, zm[2] = {0u, 0u};
+                const bool any = (z[0] | z[1] | z[2] | z[3]) != 0u;
+                if (any) {
+                    load_window_codes(blk.codes, pos, codes);
+                    if (MASKED) load_window_zmask(blk.zmask, pos, zm);
+                }
+                my_cand += __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
+                uint32_t q = 0;
+                // rounds: every lane scores its next candidate; the warp votes once per round
+                while (__any_sync(0xffffffffu, (z[0] | z[1] | z[2] | z[3]) != 0u)) {
+                    bool hit = false; uint32_t colo = 0; float s = 0.0f;
+                    while (q < 4 && z[q] == 0u) q++;
+                    if (q < 4) {
+                        const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1;
+                        const uint32_t w = q & 1u;
+                        const uint32_t c = acc16 ? first[q >> 1] + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first[q >> 1] + 16 * w + 2 * (bit & 7u) + (bit >> 3);
+                        if (c < ncol) {                                  // (a padding column can never be a candidate; belt and braces)
+                            const ColRec r = s_col[c];
+                            const uint32_t L = r.len;
+                            s = in_smem ? score_in_order<MASKED>(wsm + 4 * r.woff, L, codes, zm) : score_in_order<MASKED>(wgl + 4 * r.woff, L, codes, zm);
+                            hit = (pos < blk.n_payload) && !(s < r.thr);
+                            if (hit) hit = window_in_fragment(blk, pos, L);
+                            colo = r.orig;
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        b200scan_hit h; h.pos = pos; h.col = colo; h.score = s;
+                        st[n_st + __popc(m & ((1u << lane) - 1u))] = h;
+                    }
+                    n_st += __popc(m);
+                    if (++round == kRounds) flush();
+                }
+            }
+            last_tag = tag;
+        }
+        __syncthreads();
+    }
+    if (n_st) flush();
+    // candidates seen (b200scan_timing.n_candidates): one atomic per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_cand += __shfl_xor_sync(0xffffffffu, my_cand, d);
+    if (lane == 0 && my_cand) atomicAdd(n_cand, my_cand);
+}
+
 } // namespace b200
