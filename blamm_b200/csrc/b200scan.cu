@@ -78,6 +78,7 @@ struct b200scan_ctx {
     uint32_t* d_raw = nullptr;  uint32_t* d_blk_count = nullptr;  uint32_t* d_blk_tag = nullptr;  uint32_t blk_cap = 0;
     bool fused = true;            // rescore_tile_kernel (expand + rescore fused, tile by tile); B200SCAN_RESCORE=list keeps the round-1 chain
     uint32_t fuse_max_w = 0;      // shared-memory weight positions of the fused kernel for the loaded motif set
+    int fuse_ctas_per_sm = 1;     // its CTAs that fit an SM with that much shared memory
     // motifs
     bool have_motifs = false;
     uint32_t n_cols = 0, max_len = 0;  uint64_t sum_len = 0;
@@ -520,14 +521,22 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     ctx->gtiles = gt; ctx->ttiles = tt;
     {   // fused rescorer: shared memory for the largest tile's FP32 weights (both tilings), capped; room for the partial raw
         // blocks the filter's warps close at every change of column tile
+        // (tiles of 256 padded columns with packed accumulators tag their raw blocks per 128-column half, filter_tc.cuh: halfTags)
         uint32_t mw = 1;
         for (const auto* tv : {&tt, &tt_z})
             for (const TcTile& t : *tv) {
-                uint32_t nw = 0;
-                for (uint32_t c = t.col0; c < t.col0 + t.n_cols; c++) nw += len[c];
-                mw = std::max(mw, nw);
+                const bool halves = t.acc16 && t.n_pad == 256;
+                uint32_t nw = 0, nw_half = 0;
+                for (uint32_t c = t.col0; c < t.col0 + t.n_cols; c++) {
+                    nw += len[c];
+                    if (c - t.col0 == 127) { nw_half = nw; nw = halves ? 0 : nw; }
+                }
+                mw = std::max(mw, std::max(nw, halves ? nw_half : 0u));
             }
         ctx->fuse_max_w = std::min(mw, kFuseMaxW);
+        int per_sm = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rescore_tile_kernel<false>, (int)kFuseThreads, fuse_smem_bytes(ctx->fuse_max_w)));
+        ctx->fuse_ctas_per_sm = std::max(1, std::min(per_sm, 4));
         const unsigned long long want = ctx->cand_cap / kRawBlock + 4096 + (unsigned long long)ctx->sm_count * kTcEpiWarps * (tt.size() + 2);
         if (want > ctx->blk_cap) {
             dfree(ctx->d_raw); dfree(ctx->d_blk_count); dfree(ctx->d_blk_tag);
@@ -647,9 +656,9 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
             // match the block's has_zero flag returns at once)
             unsigned int* fwork = reinterpret_cast<unsigned int*>(s.d_counters + 5);
             const size_t fsm = fuse_smem_bytes(ctx->fuse_max_w);
-            rescore_tile_kernel<false><<<ctx->sm_count, kFuseThreads, fsm, ctx->stream>>>(md, blk, ctx->d_raw, ctx->d_blk_count, ctx->d_blk_tag, work + 1, ctx->blk_cap,
+            rescore_tile_kernel<false><<<ctx->sm_count * ctx->fuse_ctas_per_sm, kFuseThreads, fsm, ctx->stream>>>(md, blk, ctx->d_raw, ctx->d_blk_count, ctx->d_blk_tag, work + 1, ctx->blk_cap,
                                                                                         fwork, s.d_counters, ctx->fuse_max_w, sink);
-            rescore_tile_kernel<true><<<ctx->sm_count, kFuseThreads, fsm, ctx->stream>>>(md, blk, ctx->d_raw, ctx->d_blk_count, ctx->d_blk_tag, work + 1, ctx->blk_cap,
+            rescore_tile_kernel<true><<<ctx->sm_count * ctx->fuse_ctas_per_sm, kFuseThreads, fsm, ctx->stream>>>(md, blk, ctx->d_raw, ctx->d_blk_count, ctx->d_blk_tag, work + 1, ctx->blk_cap,
                                                                                        fwork, s.d_counters, ctx->fuse_max_w, sink);
             n += 2;
         } else {

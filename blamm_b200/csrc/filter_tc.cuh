@@ -783,7 +783,11 @@ filter_tc_kernel(TcParams P, BlockDev blk)
         } else {
             // ===================== epilogue: TMEM -> sign test -> candidates =====================
             const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
-            const uint32_t tileTag = (tile.col0 << 9) | tile.n_cols;
+            // tag of the raw blocks this warp fills: the whole tile, or -- in the specialised loop below, where a warp owns one 128-column
+            // half of every tile -- that half (the fused rescorer then keeps only 128 columns' weights in shared memory)
+            const bool halfTags = TC_EPI_FAST && ACC16 && !PAIR && kTcEpiGroups == 2 && kBufs == 2 && kEpiPerQ == 2 && !(TC_KNOCKOUT & 1) && nWords == 128;
+            const uint32_t halfCol0 = 4 * eWc0, halfCols = tile.n_cols > halfCol0 ? min(128u, tile.n_cols - halfCol0) : 0u;
+            const uint32_t tileTag = halfTags ? (((tile.col0 + halfCol0) << 9) | halfCols) : ((tile.col0 << 9) | tile.n_cols);
             if (newTile && rawc.blk != 0xffffffffu) {                 // another column tile: close the open block (a block holds ONE tile's entries)
                 if (lane == 0 && rawc.blk < P.blk_cap) P.blk_count[rawc.blk] = kRawBlock - rawc.left;
                 rawc.blk = 0xffffffffu; rawc.left = 0;

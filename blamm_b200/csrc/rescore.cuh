@@ -275,51 +275,67 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
             __syncthreads();
             const float* wsm = reinterpret_cast<const float*>(s_w);
             const float* wgl = reinterpret_cast<const float*>(md.w + wbase);
-            // one warp per 32 entry slots of a block of this tile
-            for (uint32_t sidx = wib * 32; sidx < (b1 - b0) * kRawBlock; sidx += kFuseThreads) {
-                const uint32_t b = b0 + sidx / kRawBlock, e = sidx % kRawBlock + lane;           // kRawBlock % 32 == 0: same block
+            // one warp per raw block of this tile and pass; a lane takes the block's entries `lane` and `lane + 32`: both are loaded up
+            // front, then both windows' codes (the kernel is bound by memory latency: bytes in flight per thread are what count)
+            for (uint32_t b = b0 + wib; b < b1; b += kFuseThreads / 32) {
                 if (__ldg(blk_tag + b) != tag) continue;                                        // (warp-uniform)
                 const uint32_t cnt = __ldg(blk_count + b);
-                if (sidx % kRawBlock >= cnt) continue;
-                const bool live = e < cnt;
-                uint4 x = make_uint4(0u, 0u, kAllNegative, kAllNegative), y = make_uint4(0u, kAllNegative, kAllNegative, 0u);
-                if (live) { x = __ldg(ent + 2 * ((size_t)b * kRawBlock + e)); y = __ldg(ent + 2 * ((size_t)b * kRawBlock + e) + 1); }
-                const bool acc16 = !(x.y & kRawFp32Flag);
-                uint32_t z[4] = {~decode_sign_word(acc16, x.z), ~decode_sign_word(acc16, x.w), ~decode_sign_word(acc16, y.y), ~decode_sign_word(acc16, y.z)};
-                const uint32_t first[2] = {(x.y & ~kRawFp32Flag) - col0, (y.x & ~kRawFp32Flag) - col0};        // columns relative to the tile
-                const uint32_t pos = x.x;
-                uint32_t codes[4] = {0u, 0u, 0u, 0u}, zm[2] = {0u, 0u};
-                const bool any = (z[0] | z[1] | z[2] | z[3]) != 0u;
-                if (any) {
-                    load_window_codes(blk.codes, pos, codes);
-                    if (MASKED) load_window_zmask(blk.zmask, pos, zm);
+                if (cnt == 0) continue;
+                uint4 x[2], y[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    x[h] = make_uint4(0u, 0u, kAllNegative, kAllNegative); y[h] = make_uint4(0u, kAllNegative, kAllNegative, 0u);
+                    const uint32_t e = lane + 32 * h;
+                    if (e < cnt) { x[h] = __ldg(ent + 2 * ((size_t)b * kRawBlock + e)); y[h] = __ldg(ent + 2 * ((size_t)b * kRawBlock + e) + 1); }
                 }
-                my_cand += __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
-                uint32_t q = 0;
-                // rounds: every lane scores its next candidate; the warp votes once per round
-                while (__any_sync(0xffffffffu, (z[0] | z[1] | z[2] | z[3]) != 0u)) {
-                    bool hit = false; uint32_t colo = 0; float s = 0.0f;
-                    while (q < 4 && z[q] == 0u) q++;
-                    if (q < 4) {
-                        const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1;
-                        const uint32_t w = q & 1u;
-                        const uint32_t c = acc16 ? first[q >> 1] + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first[q >> 1] + 16 * w + 2 * (bit & 7u) + (bit >> 3);
-                        if (c < ncol) {                                  // (a padding column can never be a candidate; belt and braces)
-                            const ColRec r = s_col[c];
-                            const uint32_t L = r.len;
-                            s = in_smem ? score_in_order<MASKED>(wsm + 4 * r.woff, L, codes, zm) : score_in_order<MASKED>(wgl + 4 * r.woff, L, codes, zm);
-                            hit = (pos < blk.n_payload) && !(s < r.thr);
-                            if (hit) hit = window_in_fragment(blk, pos, L);
-                            colo = r.orig;
+                uint32_t zz[2][4], codes2[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, zm2[2][2] = {{0u, 0u}, {0u, 0u}};
+                bool acc16h[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    acc16h[h] = !(x[h].y & kRawFp32Flag);
+                    zz[h][0] = ~decode_sign_word(acc16h[h], x[h].z); zz[h][1] = ~decode_sign_word(acc16h[h], x[h].w);
+                    zz[h][2] = ~decode_sign_word(acc16h[h], y[h].y); zz[h][3] = ~decode_sign_word(acc16h[h], y[h].z);
+                    if ((zz[h][0] | zz[h][1] | zz[h][2] | zz[h][3]) != 0u) {
+                        load_window_codes(blk.codes, x[h].x, codes2[h]);
+                        if (MASKED) load_window_zmask(blk.zmask, x[h].x, zm2[h]);
+                    }
+                    my_cand += __popc(zz[h][0]) + __popc(zz[h][1]) + __popc(zz[h][2]) + __popc(zz[h][3]);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (h == 1 && cnt <= 32) break;
+                    const bool acc16 = acc16h[h];
+                    uint32_t (&z)[4] = zz[h];
+                    const uint32_t (&codes)[4] = codes2[h];
+                    const uint32_t (&zm)[2] = zm2[h];
+                    const uint32_t first[2] = {(x[h].y & ~kRawFp32Flag) - col0, (y[h].x & ~kRawFp32Flag) - col0};        // columns relative to the tile
+                    const uint32_t pos = x[h].x;
+                    uint32_t q = 0;
+                    // rounds: every lane scores its next candidate; the warp votes once per round
+                    while (__any_sync(0xffffffffu, (z[0] | z[1] | z[2] | z[3]) != 0u)) {
+                        bool hit = false; uint32_t colo = 0; float s = 0.0f;
+                        while (q < 4 && z[q] == 0u) q++;
+                        if (q < 4) {
+                            const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1;
+                            const uint32_t w = q & 1u;
+                            const uint32_t c = acc16 ? first[q >> 1] + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first[q >> 1] + 16 * w + 2 * (bit & 7u) + (bit >> 3);
+                            if (c < ncol) {                                  // (a padding column can never be a candidate; belt and braces)
+                                const ColRec r = s_col[c];
+                                const uint32_t L = r.len;
+                                s = in_smem ? score_in_order<MASKED>(wsm + 4 * r.woff, L, codes, zm) : score_in_order<MASKED>(wgl + 4 * r.woff, L, codes, zm);
+                                hit = (pos < blk.n_payload) && !(s < r.thr);
+                                if (hit) hit = window_in_fragment(blk, pos, L);
+                                colo = r.orig;
+                            }
                         }
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (hit) {
+                            b200scan_hit hh; hh.pos = pos; hh.col = colo; hh.score = s;
+                            st[n_st + __popc(m & ((1u << lane) - 1u))] = hh;
+                        }
+                        n_st += __popc(m);
+                        if (++round == kRounds) flush();
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (hit) {
-                        b200scan_hit h; h.pos = pos; h.col = colo; h.score = s;
-                        st[n_st + __popc(m & ((1u << lane) - 1u))] = h;
-                    }
-                    n_st += __popc(m);
-                    if (++round == kRounds) flush();
                 }
             }
             last_tag = tag;
