@@ -525,7 +525,7 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
         uint32_t mw = 1;
         for (const auto* tv : {&tt, &tt_z})
             for (const TcTile& t : *tv) {
-                const bool halves = t.acc16 && t.n_pad == 256;
+                const bool halves = TC_HALF_TAGS && t.acc16 && t.n_pad == 256;
                 uint32_t nw = 0, nw_half = 0;
                 for (uint32_t c = t.col0; c < t.col0 + t.n_cols; c++) {
                     nw += len[c];
@@ -534,6 +534,7 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                 mw = std::max(mw, std::max(nw, halves ? nw_half : 0u));
             }
         ctx->fuse_max_w = std::min(mw, kFuseMaxW);
+        if (const char* e = getenv("B200SCAN_FUSE_MAXW")) ctx->fuse_max_w = std::min<uint32_t>(ctx->fuse_max_w, (uint32_t)std::max(1, atoi(e)));     // experiment: smaller tables, more CTAs per SM
         int per_sm = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rescore_tile_kernel<false>, (int)kFuseThreads, fuse_smem_bytes(ctx->fuse_max_w)));
         ctx->fuse_ctas_per_sm = std::max(1, std::min(per_sm, 4));

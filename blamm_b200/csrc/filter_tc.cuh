@@ -75,6 +75,9 @@ namespace b200 {
 #ifndef TC_ISSUE_FAST
 #define TC_ISSUE_FAST 1       // 1: single-CTA instances issue whole E stages (4 tiles) from an unrolled loop with loop-invariant operands
 #endif
+#ifndef TC_HALF_TAGS
+#define TC_HALF_TAGS 0        // 1: the specialised epilogue tags its raw blocks per 128-column half (more, smaller weight tables for the fused rescorer)
+#endif
 #ifndef TC_EPI_FAST
 #define TC_EPI_FAST 1         // 1: 256-column tiles with packed accumulators take the specialised epilogue loop (one LDTM.x64 per warp at a precomputed
 #endif                        //    address, maximum pre-test, sign compaction only for the 16-word groups that hold a candidate)
@@ -785,7 +788,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
             const uint32_t nWords = tile.n_pad / kColsPerWord;        // 32-bit TMEM columns of a tile (multiple of 32)
             // tag of the raw blocks this warp fills: the whole tile, or -- in the specialised loop below, where a warp owns one 128-column
             // half of every tile -- that half (the fused rescorer then keeps only 128 columns' weights in shared memory)
-            const bool halfTags = TC_EPI_FAST && ACC16 && !PAIR && kTcEpiGroups == 2 && kBufs == 2 && kEpiPerQ == 2 && !(TC_KNOCKOUT & 1) && nWords == 128;
+            const bool halfTags = TC_HALF_TAGS && TC_EPI_FAST && ACC16 && !PAIR && kTcEpiGroups == 2 && kBufs == 2 && kEpiPerQ == 2 && !(TC_KNOCKOUT & 1) && nWords == 128;
             const uint32_t halfCol0 = 4 * eWc0, halfCols = tile.n_cols > halfCol0 ? min(128u, tile.n_cols - halfCol0) : 0u;
             const uint32_t tileTag = halfTags ? (((tile.col0 + halfCol0) << 9) | halfCols) : ((tile.col0 << 9) | tile.n_cols);
             if (newTile && rawc.blk != 0xffffffffu) {                 // another column tile: close the open block (a block holds ONE tile's entries)

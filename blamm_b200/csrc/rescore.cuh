@@ -221,6 +221,9 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
     __shared__ uint32_t s_item, s_next_tag;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     b200scan_hit* st = s_hits + wib * 32 * kRounds;
+    __shared__ uint2 s_queue[kFuseThreads / 32][64];               // per warp: (window, relative column) of the candidates beyond an entry's first
+    uint2* qbuf = s_queue[wib];
+    uint32_t qn = 0;
     uint32_t n_st = 0, round = 0;
     unsigned long long my_cand = 0;
     auto flush = [&]() {
@@ -275,6 +278,36 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
             __syncthreads();
             const float* wsm = reinterpret_cast<const float*>(s_w);
             const float* wgl = reinterpret_cast<const float*>(md.w + wbase);
+            // one round: every lane scores column c (relative to the tile; 0xffffffff = nothing) of the window at pos; hits are staged
+            auto score_round = [&](uint32_t c, uint32_t pos, const uint32_t (&codes)[4], const uint32_t (&zm)[2]) {
+                bool hit = false; uint32_t colo = 0; float sc = 0.0f;
+                if (c < ncol) {                                      // (a padding column can never be a candidate; belt and braces)
+                    const ColRec r = s_col[c];
+                    sc = in_smem ? score_in_order<MASKED>(wsm + 4 * r.woff, r.len, codes, zm) : score_in_order<MASKED>(wgl + 4 * r.woff, r.len, codes, zm);
+                    hit = (pos < blk.n_payload) && !(sc < r.thr);
+                    if (hit) hit = window_in_fragment(blk, pos, r.len);
+                    colo = r.orig;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    b200scan_hit hh; hh.pos = pos; hh.col = colo; hh.score = sc;
+                    st[n_st + __popc(m & ((1u << lane) - 1u))] = hh;
+                }
+                n_st += __popc(m);
+                if (++round == kRounds) flush();
+            };
+            // n queued candidates starting at qbuf[from]: one per lane, with their window's codes loaded again (L1 / L2 hits)
+            auto drain_queue = [&](uint32_t from, uint32_t n) {
+                uint32_t c = 0xffffffffu, pos = 0, codes[4] = {0u, 0u, 0u, 0u}, zm[2] = {0u, 0u};
+                if (lane < n) {
+                    const uint2 e = qbuf[from + lane];
+                    pos = e.x; c = e.y;
+                    load_window_codes(blk.codes, pos, codes);
+                    if (MASKED) load_window_zmask(blk.zmask, pos, zm);
+                }
+                __syncwarp();
+                score_round(c, pos, codes, zm);
+            };
             // one warp per raw block of this tile and pass; a lane takes the block's entries `lane` and `lane + 32`: both are loaded up
             // front, then both windows' codes (the kernel is bound by memory latency: bytes in flight per thread are what count)
             for (uint32_t b = b0 + wib; b < b1; b += kFuseThreads / 32) {
@@ -301,43 +334,36 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
                     }
                     my_cand += __popc(zz[h][0]) + __popc(zz[h][1]) + __popc(zz[h][2]) + __popc(zz[h][3]);
                 }
+                // Every lane scores the FIRST candidate of its entry at once (an entry has one candidate in 96 % of the cases); further
+                // candidates go to the warp's queue and are scored 32 at a time -- a second round for the whole warp because one or two
+                // lanes have a second candidate would double the work of the usual case.
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     if (h == 1 && cnt <= 32) break;
                     const bool acc16 = acc16h[h];
                     uint32_t (&z)[4] = zz[h];
-                    const uint32_t (&codes)[4] = codes2[h];
-                    const uint32_t (&zm)[2] = zm2[h];
                     const uint32_t first[2] = {(x[h].y & ~kRawFp32Flag) - col0, (y[h].x & ~kRawFp32Flag) - col0};        // columns relative to the tile
                     const uint32_t pos = x[h].x;
                     uint32_t q = 0;
-                    // rounds: every lane scores its next candidate; the warp votes once per round
-                    while (__any_sync(0xffffffffu, (z[0] | z[1] | z[2] | z[3]) != 0u)) {
-                        bool hit = false; uint32_t colo = 0; float s = 0.0f;
+                    auto next_col = [&]() -> uint32_t {              // pops the lane's next candidate column (0xffffffff: none)
                         while (q < 4 && z[q] == 0u) q++;
-                        if (q < 4) {
-                            const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1;
-                            const uint32_t w = q & 1u;
-                            const uint32_t c = acc16 ? first[q >> 1] + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first[q >> 1] + 16 * w + 2 * (bit & 7u) + (bit >> 3);
-                            if (c < ncol) {                                  // (a padding column can never be a candidate; belt and braces)
-                                const ColRec r = s_col[c];
-                                const uint32_t L = r.len;
-                                s = in_smem ? score_in_order<MASKED>(wsm + 4 * r.woff, L, codes, zm) : score_in_order<MASKED>(wgl + 4 * r.woff, L, codes, zm);
-                                hit = (pos < blk.n_payload) && !(s < r.thr);
-                                if (hit) hit = window_in_fragment(blk, pos, L);
-                                colo = r.orig;
-                            }
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, hit);
-                        if (hit) {
-                            b200scan_hit hh; hh.pos = pos; hh.col = colo; hh.score = s;
-                            st[n_st + __popc(m & ((1u << lane) - 1u))] = hh;
-                        }
-                        n_st += __popc(m);
-                        if (++round == kRounds) flush();
+                        if (q >= 4) return 0xffffffffu;
+                        const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1;
+                        const uint32_t w = q & 1u;
+                        return acc16 ? first[q >> 1] + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first[q >> 1] + 16 * w + 2 * (bit & 7u) + (bit >> 3);
+                    };
+                    score_round(next_col(), pos, codes2[h], zm2[h]);
+                    while (__any_sync(0xffffffffu, (z[0] | z[1] | z[2] | z[3]) != 0u)) {
+                        const uint32_t c = next_col();
+                        const unsigned m = __ballot_sync(0xffffffffu, c != 0xffffffffu);
+                        if (c != 0xffffffffu) qbuf[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2(pos, c);
+                        qn += __popc(m);
+                        __syncwarp();
+                        if (qn >= 32) { qn -= 32; drain_queue(qn, 32); }
                     }
                 }
             }
+            if (qn) { drain_queue(0, qn); qn = 0; }                  // the queued candidates belong to this tile's tables
             last_tag = tag;
         }
         __syncthreads();
