@@ -73,10 +73,9 @@ struct b200scan_ctx {
     std::string err;
     Slot slot[B200SCAN_NUM_SLOTS];
     // candidates are shared by the slots (stream order serialises filter -> rescore per block)
-    Cand* d_cand = nullptr;  unsigned long long cand_cap = 0;
+    unsigned long long cand_cap = 0;         // raw entries the filter may write (sizes d_raw: blk_cap blocks of kRawBlock entries)
     // raw entries of the tensor filter (blocks of kRawBlock entries of kRawWords words), also shared by the slots
     uint32_t* d_raw = nullptr;  uint32_t* d_blk_count = nullptr;  uint32_t* d_blk_tag = nullptr;  uint32_t blk_cap = 0;
-    bool fused = true;            // rescore_tile_kernel (expand + rescore fused, tile by tile); B200SCAN_RESCORE=list keeps the round-1 chain
     uint32_t fuse_max_w = 0;      // shared-memory weight positions of the fused kernel for the loaded motif set
     int fuse_ctas_per_sm = 1;     // its CTAs that fit an SM with that much shared memory
     // motifs
@@ -652,7 +651,7 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
             }
         }
         if (ev_after_score) CU(cudaEventRecord(ev_after_score, ctx->stream));
-        if (ctx->fused) {
+        {
             // expand + exact rescoring in one kernel, a column tile's weights at a time in shared memory (the instance that does not
             // match the block's has_zero flag returns at once)
             unsigned int* fwork = reinterpret_cast<unsigned int*>(s.d_counters + 5);
@@ -662,11 +661,6 @@ int launch_scoring(b200scan_ctx* ctx, Slot& s, cudaEvent_t ev_after_score, cudaE
             rescore_tile_kernel<true><<<ctx->sm_count * ctx->fuse_ctas_per_sm, kFuseThreads, fsm, ctx->stream>>>(md, blk, ctx->d_raw, ctx->d_blk_count, ctx->d_blk_tag, work + 1, ctx->blk_cap,
                                                                                        fwork, s.d_counters, ctx->fuse_max_w, sink);
             n += 2;
-        } else {
-            expand_kernel<<<ctx->sm_count * 32, 256, 0, ctx->stream>>>(ctx->d_raw, ctx->d_blk_count, work + 1, ctx->blk_cap, ctx->d_cand, s.d_counters, ctx->cand_cap, blk.has_zero);
-            n++;
-            rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(md, blk, ctx->d_cand, s.d_counters, ctx->cand_cap, sink);
-            n++;
         }
         if (ev_after_rescore) CU(cudaEventRecord(ev_after_rescore, ctx->stream));
     } else {
@@ -888,13 +882,13 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     lap("streams + kernel attributes");
     if (max_hits == 0) max_hits = 1 << 20;
     {
-        // Budget for the buffers that grow with the hit density: about 136 bytes of device memory per hit record of the densest
-        // block (three slots x 16 B hit list, 12 B ordering scratch, 16 B candidates + 64 B raw entries for ~1.2 candidates per hit)
+        // Budget for the buffers that grow with the hit density: about 96 bytes of device memory per hit record of the densest
+        // block (three slots x 16 B hit list, 12 B ordering scratch, 2 x 16 B raw entries for the ~1.2 candidates per hit)
         // may take 60 % of what is free now.  A block that needs more is refused with B200SCAN_ENOMEM (the caller submits it in
         // smaller pieces: the CLI halves it, cli.cpp: scanSplit); B200SCAN_HIT_BUDGET=<records> overrides the figure.
         size_t free_b = 0, total_b = 0;
         CUB(cudaMemGetInfo(&free_b, &total_b));
-        c->hit_budget = std::max<unsigned long long>((unsigned long long)(0.6 * (double)free_b / 136.0), 1 << 16);
+        c->hit_budget = std::max<unsigned long long>((unsigned long long)(0.6 * (double)free_b / 96.0), 1 << 16);
         if (const char* e = getenv("B200SCAN_HIT_BUDGET")) c->hit_budget = std::max<unsigned long long>(strtoull(e, nullptr, 10), 1024);
         max_hits = std::min<unsigned long long>(max_hits, c->hit_budget);
     }
@@ -913,9 +907,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     CUB(cudaMalloc(&c->d_trace, 4 * kTraceTiles * 4 * 8));
     CUB(cudaMemset(c->d_trace, 0, 4 * kTraceTiles * 4 * 8));
 #endif
-    if (const char* e = getenv("B200SCAN_RESCORE")) c->fused = std::string(e) != "list";
     c->cand_cap = std::max<unsigned long long>(2 * max_hits, 1 << 20);
-    if (!c->fused) CUB(cudaMalloc(&c->d_cand, sizeof(Cand) * c->cand_cap));
     c->blk_cap = (uint32_t)std::max<unsigned long long>(c->cand_cap / kRawBlock + 4096, 8192);
     CUB(cudaFuncSetAttribute(rescore_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem_bytes(kFuseMaxW)));
     CUB(cudaFuncSetAttribute(rescore_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem_bytes(kFuseMaxW)));
@@ -938,7 +930,7 @@ void b200scan_destroy(b200scan_ctx* c)
         dfree(s.d_ascii); dfree(s.d_codes); dfree(s.d_zmask); dfree(s.d_frag); dfree(s.d_hits); dfree(s.d_counters); dfree(s.d_bucket_start);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     }
-    dfree(c->d_cand); dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_blk_tag); dfree(c->d_flush);
+    dfree(c->d_raw); dfree(c->d_blk_count); dfree(c->d_blk_tag); dfree(c->d_flush);
     dfree(c->d_bucket_cnt); dfree(c->d_bucket_cursor); dfree(c->d_coarse_start); dfree(c->d_sort_tmp);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg); dfree(c->d_ttiles_z); dfree(c->d_bimg_z);
@@ -1172,7 +1164,7 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
             return fail(ctx, B200SCAN_ESTATE, "ENGINE_TENSOR unavailable for this motif set");
         const uint32_t n_blocks = (uint32_t)(s.h_counters[3] >> 32);
         const bool raw_over = n_blocks > ctx->blk_cap;
-        const bool cand_over = raw_over || (!ctx->fused && n_cand > ctx->cand_cap), hit_over = nh > s.hit_cap;
+        const bool cand_over = raw_over, hit_over = nh > s.hit_cap;
         if (!cand_over && !hit_over) {
             s.timing.n_candidates = n_cand; s.timing.n_hits = nh;
             s.timing.engine_used = (ctx->engine == B200SCAN_ENGINE_GATHER || !ctx->tc_usable) ? B200SCAN_ENGINE_GATHER : B200SCAN_ENGINE_TENSOR;
@@ -1184,8 +1176,7 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
         CU(cudaStreamSynchronize(ctx->stream));
         {
             const unsigned long long need_hits = hit_over ? nh + nh / 8 + 1024 : s.hit_cap;
-            const unsigned long long need_cand = raw_over ? ((unsigned long long)n_blocks + n_blocks / 8 + 1024) * kRawBlock * 2
-                                                          : (!ctx->fused && n_cand > ctx->cand_cap ? n_cand + n_cand / 8 + 1024 : ctx->cand_cap);
+            const unsigned long long need_cand = raw_over ? ((unsigned long long)n_blocks + n_blocks / 8 + 1024) * kRawBlock : ctx->cand_cap;
             if (need_hits > ctx->hit_budget || need_cand > 4 * ctx->hit_budget) {
                 s.resident = false;
                 return fail(ctx, B200SCAN_ENOMEM, "block too dense for the device buffers: %llu hits, %llu candidates against a budget of %llu hit records "
@@ -1209,16 +1200,8 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
                 regrow(reinterpret_cast<void**>(&ctx->d_blk_count), (size_t)ctx->blk_cap * 4, (size_t)new_cap * 4) &&
                 regrow(reinterpret_cast<void**>(&ctx->d_blk_tag), (size_t)ctx->blk_cap * 4, (size_t)new_cap * 4)) {
                 ctx->blk_cap = new_cap;
-                // every raw entry holds at least one candidate and at most 64; size the candidate list for the typical ~1.5
-                const unsigned long long want = (unsigned long long)ctx->blk_cap * kRawBlock * 2;
-                if (want > ctx->cand_cap) {
-                    if (ctx->fused) ctx->cand_cap = want;
-                    else if (regrow(reinterpret_cast<void**>(&ctx->d_cand), sizeof(Cand) * ctx->cand_cap, sizeof(Cand) * want)) ctx->cand_cap = want; else ok = false;
-                }
+                ctx->cand_cap = std::max<unsigned long long>(ctx->cand_cap, (unsigned long long)ctx->blk_cap * kRawBlock);
             } else ok = false;
-        } else if (!ctx->fused && n_cand > ctx->cand_cap) {
-            const unsigned long long want = n_cand + n_cand / 8 + 1024;
-            if (regrow(reinterpret_cast<void**>(&ctx->d_cand), sizeof(Cand) * ctx->cand_cap, sizeof(Cand) * want)) ctx->cand_cap = want; else ok = false;
         }
         if (ok && (hit_over || cand_over)) {
             unsigned long long want = std::max<unsigned long long>(nh + nh / 8 + 1024, s.hit_cap);
@@ -1228,7 +1211,7 @@ static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void*
         }
         if (!ok) {
             s.resident = false;
-            if (!ctx->d_raw || !ctx->d_blk_count || !ctx->d_blk_tag || (!ctx->fused && !ctx->d_cand) || !s.d_hits)
+            if (!ctx->d_raw || !ctx->d_blk_count || !ctx->d_blk_tag || !s.d_hits)
                 return fail(ctx, B200SCAN_ECUDA, "out of device memory while regrowing the hit buffers, and the previous size could not be restored");
             return fail(ctx, B200SCAN_ENOMEM, "out of device memory for a block with %llu hits and %llu candidates -- submit it in smaller blocks", nh, n_cand);
         }

@@ -8,9 +8,6 @@ namespace b200 {
 
 constexpr int kMaxLen = B200SCAN_MAX_MOTIF_LEN;   // 64 positions = 128 bits of 2-bit codes
 
-// A candidate handed from the tensor-core filter to the exact rescorer: block position + SORTED column.
-struct Cand { uint32_t pos; uint32_t col; };
-
 // Per-species motif data on the device.  Columns are sorted by length (stable); `orig` maps back to the
 // caller's column index (the reference's column order, motif.cpp:439-449).
 struct MotifDev {

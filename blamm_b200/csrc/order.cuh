@@ -149,6 +149,7 @@ bucket_order_kernel(const Hit12* __restrict__ in, const uint32_t* __restrict__ c
 #pragma unroll
             for (uint32_t r = 0; r < kHitsPerThread; r++) {
                 const uint32_t i = lo + tid + kOrderThreads * r;
+                if (lo + (tid & ~31u) + kOrderThreads * r >= hi) break;        // (warp-uniform: the usual bucket holds ~4 hits per thread, not 8)
                 if (i < hi) h[r] = in[i];
             }
         }
@@ -158,8 +159,10 @@ bucket_order_kernel(const Hit12* __restrict__ in, const uint32_t* __restrict__ c
         __syncthreads();
         if (staged) {
 #pragma unroll
-            for (uint32_t r = 0; r < kHitsPerThread; r++)
+            for (uint32_t r = 0; r < kHitsPerThread; r++) {
+                if (lo + (tid & ~31u) + kOrderThreads * r >= hi) break;
                 if (lo + tid + kOrderThreads * r < hi) atomicAdd(s_bins + bin_at(h[r].pos & (kCoarseSize - 1)), 1u);
+            }
         } else {
             for (uint32_t i = lo + tid; i < hi; i += kOrderThreads) atomicAdd(s_bins + bin_at(in[i].pos & (kCoarseSize - 1)), 1u);
         }
@@ -194,11 +197,13 @@ bucket_order_kernel(const Hit12* __restrict__ in, const uint32_t* __restrict__ c
         __syncthreads();
         if (staged) {
 #pragma unroll
-            for (uint32_t r = 0; r < kHitsPerThread; r++)
+            for (uint32_t r = 0; r < kHitsPerThread; r++) {
+                if (lo + (tid & ~31u) + kOrderThreads * r >= hi) break;
                 if (lo + tid + kOrderThreads * r < hi) {
                     const uint32_t p = h[r].pos & (kCoarseSize - 1);
                     s_rec[atomicAdd(s_bins + bin_at(p), 1u)] = make_uint2(((p & (kBucketSize - 1)) << 24) | h[r].col, h[r].score);
                 }
+            }
         } else {
             for (uint32_t i = lo + tid; i < hi; i += kOrderThreads) {
                 const Hit12 g = in[i];

@@ -1,17 +1,15 @@
-// Exact rescoring of the candidates that the tensor-core filter let through.  One thread per candidate:
-// the score is re-summed in FP32 in position order from the FP32 weights (bit-identical to the reference's
-// sgemm chain, see gather.cuh), compared with the exact threshold, checked against the fragment table and
-// the payload limit, and appended to the hit list.  Rare work (about 1e-4 of all scores), L2-resident.
+// Exact rescoring of the candidates that the tensor-core filter let through: the score is re-summed in FP32 in position order
+// from the FP32 weights (bit-identical to the in-order sum of the reference's naive path, motif.cpp:225-239; its BLAS path
+// re-associates the sums of longer motifs), compared with the exact threshold, checked against the fragment table and the payload
+// limit, and appended to the hit list.  Rare work (about 1.7e-4 of all scores).
 #pragma once
 #include "common.cuh"
 #include "filter_tc.cuh"
 
 namespace b200 {
 
-// Raw entries of the tensor-core filter -> (position, sorted column) candidates.  One thread per entry slot
-// {window, column of chunk 0, mask, mask, column of chunk 1, mask, mask, -}; sign words are decoded to masks whose zero bits are the
-// candidates (filter_tc.cuh: sign_words).  A warp's candidates are staged in shared memory and appended with one global atomic per
-// >= 256 of them.
+// Raw entries of the tensor-core filter {window, first column of the chunk, mask, mask}: sign words are decoded to masks whose zero
+// bits are the candidates (filter_tc.cuh: sign_words).
 // Inverse of filter_tc.cuh: sign_words().  X = sum_b 255 * M_b * 256^b (mod 2^32)  ->  M_0 | M_1 << 8 | M_2 << 16 | M_3 << 24
 // (bit 8b + t set <=> accumulator (t, b) negative).  255 M = 256 M - M, so X = -M_0 + (M_0 - M_1) 256 + (M_1 - M_2) 256^2 + ...
 // and the bytes peel off from the bottom.  FP32 accumulators only fill b < 2 (the upper bytes repeat them).
@@ -28,155 +26,22 @@ __device__ __forceinline__ uint32_t decode_sign_word(bool acc16, uint32_t x)
     return m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
 }
 
-__global__ void __launch_bounds__(256)
-expand_kernel(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ blk_count, const unsigned int* __restrict__ n_blocks_ptr,
-              uint32_t blk_cap, Cand* __restrict__ cand, unsigned long long* n_cand, unsigned long long cand_cap,
-              const uint32_t* __restrict__ has_zero)
-{
-    constexpr uint32_t kStage = 640;
-    __shared__ Cand s_stage[8][kStage];   // per-warp staging: one global atomic per >= 256 candidates
-    (void)has_zero;
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t nb = min(*n_blocks_ptr, blk_cap);
-    Cand* st = s_stage[wib];
-    uint32_t n = 0;
-    auto flush = [&]() {
-        __syncwarp();
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(n_cand, (unsigned long long)n);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (uint32_t s = lane; s < n; s += 32)
-            if (base + s < cand_cap) cand[base + s] = st[s];
-        __syncwarp();
-        n = 0;
-    };
-    auto column = [](bool acc16, uint32_t first, uint32_t w, uint32_t bit) {
-        return acc16 ? first + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first + 16 * w + 2 * (bit & 7u) + (bit >> 3);
-    };
-    const unsigned long long slots = (unsigned long long)nb * kRawBlock;
-    const uint4* ent = reinterpret_cast<const uint4*>(raw);
-    for (unsigned long long s0 = ((unsigned long long)blockIdx.x * 8 + wib) * 32; s0 < slots; s0 += (unsigned long long)gridDim.x * 8 * 32) {
-        const uint32_t b = (uint32_t)(s0 / kRawBlock), e = (uint32_t)(s0 % kRawBlock) + lane;     // kRawBlock % 32 == 0: same block
-        const bool live = e < __ldg(blk_count + b);
-        uint4 x = make_uint4(0u, 0u, kAllNegative, kAllNegative), y = make_uint4(0u, kAllNegative, kAllNegative, 0u);
-        if (live) { x = __ldg(ent + 2 * (s0 + lane)); y = __ldg(ent + 2 * (s0 + lane) + 1); }
-        const bool acc16 = !(x.y & kRawFp32Flag);                 // the tile's accumulator type travels in the column words
-        uint32_t z[4] = {~decode_sign_word(acc16, x.z), ~decode_sign_word(acc16, x.w), ~decode_sign_word(acc16, y.y), ~decode_sign_word(acc16, y.z)};
-        const uint32_t first[2] = {x.y & ~kRawFp32Flag, y.x & ~kRawFp32Flag};
-        const uint32_t c = __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
-        uint32_t incl = c;                                   // inclusive warp scan
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += u; }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        if (n + total > kStage) flush();
-        Cand cd; cd.pos = x.x;
-        if (total <= kStage) {
-            uint32_t o = n + incl - c;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(acc16, first[q >> 1], q & 1, bit); st[o++] = cd; }
-            n += total;
-            if (n > 256) flush();
-        } else {                                             // more than 20 candidates per entry on average: straight to global
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(n_cand, (unsigned long long)total);
-            unsigned long long o = __shfl_sync(0xffffffffu, base, 0) + incl - c;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                while (z[q]) { const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1; cd.col = column(acc16, first[q >> 1], q & 1, bit); if (o < cand_cap) cand[o] = cd; o++; }
-        }
-    }
-    if (n) flush();
-}
-
-__global__ void __launch_bounds__(256)
-rescore_kernel(MotifDev md, BlockDev blk, const Cand* __restrict__ cand,
-               const unsigned long long* __restrict__ n_cand_ptr, unsigned long long cand_cap, HitSink sink)
-{
-    const bool masked = __ldg(blk.has_zero) != 0;   // block with zero-contribution characters: such positions add exactly 0
-    unsigned long long n_cand = *n_cand_ptr;
-    if (n_cand > cand_cap) n_cand = cand_cap;       // overflow: the host re-runs with a larger buffer
-    // Hits of kRounds consecutive rounds are staged per warp in shared memory and appended with ONE global atomic
-    // (all hits of a block go through a single counter: one atomic per warp round made the atomic unit the bottleneck).
-    constexpr uint32_t kRounds = 4;
-    __shared__ b200scan_hit s_hits[8][32 * kRounds];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    b200scan_hit* st = s_hits[wib];
-    uint32_t n_st = 0, round = 0;
-    auto flush = [&]() {
-        __syncwarp();
-        unsigned long long o = 0;
-        if (lane == 0) o = atomicAdd(sink.n_hits, (unsigned long long)n_st);
-        o = __shfl_sync(0xffffffffu, o, 0);
-        for (uint32_t k0 = 0; k0 < n_st; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            const bool stored = k < n_st && o + k < sink.cap;
-            if (stored) store_hit(sink, o + k, st[k]);
-            if (sink.bucket_cnt) {
-                const uint32_t sm = __ballot_sync(0xffffffffu, stored);
-                if (stored) count_hit_bucket(sink, sm, (uint32_t)st[k].pos);
-            }
-        }
-        __syncwarp();
-        n_st = 0; round = 0;
-    };
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < n_cand; base += stride) {
-        unsigned long long i = base + threadIdx.x;
-        bool hit = false;
-        uint32_t pos = 0, col = 0;
-        float s = 0.0f;
-        if (i < n_cand && cand[i].col < md.n_cols) {      // (a candidate can never name a padding column; belt and braces)
-            Cand c = cand[i];
-            pos = c.pos; col = c.col;
-            const uint32_t L = __ldg(md.len + col);
-            const float* wp = reinterpret_cast<const float*>(md.w + __ldg(md.woff + col));
-            uint32_t codes[4], zm[2] = {0u, 0u};
-            load_window_codes(blk.codes, pos, codes);
-            if (masked) load_window_zmask(blk.zmask, pos, zm);
-            // 16 positions at a time: all (predicated) weight loads first -- independent, so one L2 round trip per group
-            // instead of one per position -- then the additions strictly in position order
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if ((uint32_t)(16 * q) < L) {
-                    const uint32_t r = codes[q], n = min(16u, L - 16u * q);
-                    float wv[16];
-#pragma unroll
-                    for (uint32_t t = 0; t < 16; t++)
-                        wv[t] = (t < n) ? __ldg(wp + 4 * (16 * q + t) + ((r >> (2 * t)) & 3u)) : 0.0f;
-#pragma unroll
-                    for (uint32_t t = 0; t < 16; t++)
-                        if (t < n && !((zm[q >> 1] >> (16 * (q & 1) + t)) & 1u)) s += wv[t];
-                }
-            }
-            hit = (pos < blk.n_payload) && !(s < __ldg(md.thr + col));
-            if (hit) hit = window_in_fragment(blk, pos, L);
-            col = __ldg(md.orig + col);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            b200scan_hit h; h.pos = pos; h.col = col; h.score = s;
-            st[n_st + __popc(m & ((1u << lane) - 1u))] = h;
-        }
-        n_st += __popc(m);
-        if (++round == kRounds) flush();
-    }
-    if (n_st) flush();
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Fused expand + rescore, column tile by column tile (round 2).
 //
-// rescore_kernel above is L1/TEX bound (ncu: l1tex throughput 90 %, 16 sectors per candidate): the lanes of a warp hold
-// candidates of different columns, so every weight load of a warp touches up to 32 sectors of the 360 KB FP32 table.  Here
-// the raw blocks carry the TAG of the column tile that produced them (filter_tc.cuh: an epilogue warp closes its block when its
-// CTA moves to another tile), a CTA takes a batch of consecutive blocks -- in allocation order they are almost always of one
-// tile, because all CTAs of the filter work through the items tile by tile -- loads THAT tile's FP32 weights and column records
-// into shared memory once, and scores the batch's raw entries straight from them: one thread per entry, the window's codes
-// loaded once per entry, every weight read an LDS.  The candidate list and expand_kernel disappear.
-// The sum is the same in-order FP32 sum as in rescore_kernel (bit-identical scores); hits leave through the same warp staging.
+// Round 1 expanded the raw entries into a (position, column) candidate list and rescored that with one thread per candidate; ncu
+// showed the rescorer L1/TEX bound (l1tex throughput 90 %, 16 sectors per candidate): the lanes of a warp hold candidates of
+// different columns, so every weight load of a warp touches up to 32 sectors of the 360 KB FP32 table.  Here the raw blocks
+// carry the TAG of the column tile that produced them (filter_tc.cuh: an epilogue warp closes its block when its CTA moves to
+// another tile); a CTA takes a batch of consecutive blocks -- in allocation order they are almost always of one tile, because all
+// CTAs of the filter work through the items tile by tile -- loads THAT tile's FP32 weights and column records into shared memory
+// once, and scores the batch's raw entries straight from them: a warp per block, two entries per lane in flight plus the next
+// block's, the window's codes loaded once per entry, every weight read an LDS.  Every lane scores its entry's first candidate in
+// the same round (96 % of the entries have one); further candidates go through a per-warp queue and are scored 32 at a time.
+// The candidate list and its two kernels are gone.  Scores are the same in-order FP32 sums, hits leave through warp staging.
 // Tiles whose weights exceed the shared-memory budget (256 columns of > 36 positions) are scored from global memory.
+// Measured (100 Mbp x 1800 columns, 3.0e7 candidates): 1.07 ms against 0.33 + 1.00 ms for expand + rescore; with half of the
+// sequence soft-masked (4.1e8 candidates) 12.4 against 12.9 ms.
 // ---------------------------------------------------------------------------------------------------------
 // FP32 score of one window against one column: the weights of the window's letters added strictly in position order (16 at a time:
 // all loads first, then the additions); masked positions add nothing (the reference's BLAS-path semantics of lower case)
@@ -201,7 +66,7 @@ __device__ __forceinline__ float score_in_order(const float* wp, uint32_t L, con
 
 constexpr uint32_t kFuseThreads = 512;
 constexpr uint32_t kFuseBatch   = 256;                 // raw blocks per work item (16,384 entry slots)
-constexpr uint32_t kFuseRounds  = 4;                   // warp rounds of hits staged per global atomic
+constexpr uint32_t kFuseRounds  = 2;                   // warp rounds of hits staged per global atomic
 constexpr uint32_t kFuseMaxW    = 9728;                // positions of weights a tile may hold in shared memory (152 KB)
 __host__ __device__ constexpr size_t fuse_smem_bytes(uint32_t max_w) { return (size_t)max_w * 16 + 256 * 16 + (size_t)(kFuseThreads / 32) * 32 * kFuseRounds * 16; }
 struct ColRec { uint32_t woff; uint32_t len; float thr; uint32_t orig; };
@@ -244,7 +109,7 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
         n_st = 0; round = 0;
     };
     const uint32_t nb = min(*n_blocks_ptr, blk_cap);
-    const uint4* ent = reinterpret_cast<const uint4*>(raw);
+    const uint4* ent = reinterpret_cast<const uint4*>(raw);                                  // one 16-byte entry each
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1u);
         __syncthreads();
@@ -309,30 +174,36 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
                 score_round(c, pos, codes, zm);
             };
             // one warp per raw block of this tile and pass; a lane takes the block's entries `lane` and `lane + 32`: both are loaded up
-            // front, then both windows' codes (the kernel is bound by memory latency: bytes in flight per thread are what count)
-            for (uint32_t b = b0 + wib; b < b1; b += kFuseThreads / 32) {
+            // front together with the NEXT block's (the kernel is bound by memory latency: bytes in flight per thread are what count),
+            // then both windows' codes
+            const uint32_t wstep = kFuseThreads / 32;
+            uint4 nx[2];
+            auto fetch = [&](uint32_t b, uint4 (&x)[2]) {
+                x[0] = x[1] = make_uint4(0u, 0u, kAllNegative, kAllNegative);
+                if (b < b1) {
+                    const uint32_t cnt = __ldg(blk_count + b);
+                    if (lane < cnt) x[0] = __ldg(ent + (size_t)b * kRawBlock + lane);
+                    if (lane + 32 < cnt) x[1] = __ldg(ent + (size_t)b * kRawBlock + lane + 32);
+                }
+            };
+            fetch(b0 + wib, nx);
+            for (uint32_t b = b0 + wib; b < b1; b += wstep) {
+                uint4 x[2] = {nx[0], nx[1]};
+                fetch(b + wstep, nx);
                 if (__ldg(blk_tag + b) != tag) continue;                                        // (warp-uniform)
                 const uint32_t cnt = __ldg(blk_count + b);
                 if (cnt == 0) continue;
-                uint4 x[2], y[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    x[h] = make_uint4(0u, 0u, kAllNegative, kAllNegative); y[h] = make_uint4(0u, kAllNegative, kAllNegative, 0u);
-                    const uint32_t e = lane + 32 * h;
-                    if (e < cnt) { x[h] = __ldg(ent + 2 * ((size_t)b * kRawBlock + e)); y[h] = __ldg(ent + 2 * ((size_t)b * kRawBlock + e) + 1); }
-                }
-                uint32_t zz[2][4], codes2[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, zm2[2][2] = {{0u, 0u}, {0u, 0u}};
+                uint32_t zz[2][2], codes2[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, zm2[2][2] = {{0u, 0u}, {0u, 0u}};
                 bool acc16h[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     acc16h[h] = !(x[h].y & kRawFp32Flag);
                     zz[h][0] = ~decode_sign_word(acc16h[h], x[h].z); zz[h][1] = ~decode_sign_word(acc16h[h], x[h].w);
-                    zz[h][2] = ~decode_sign_word(acc16h[h], y[h].y); zz[h][3] = ~decode_sign_word(acc16h[h], y[h].z);
-                    if ((zz[h][0] | zz[h][1] | zz[h][2] | zz[h][3]) != 0u) {
+                    if ((zz[h][0] | zz[h][1]) != 0u) {
                         load_window_codes(blk.codes, x[h].x, codes2[h]);
                         if (MASKED) load_window_zmask(blk.zmask, x[h].x, zm2[h]);
                     }
-                    my_cand += __popc(zz[h][0]) + __popc(zz[h][1]) + __popc(zz[h][2]) + __popc(zz[h][3]);
+                    my_cand += __popc(zz[h][0]) + __popc(zz[h][1]);
                 }
                 // Every lane scores the FIRST candidate of its entry at once (an entry has one candidate in 96 % of the cases); further
                 // candidates go to the warp's queue and are scored 32 at a time -- a second round for the whole warp because one or two
@@ -341,19 +212,17 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
                 for (int h = 0; h < 2; h++) {
                     if (h == 1 && cnt <= 32) break;
                     const bool acc16 = acc16h[h];
-                    uint32_t (&z)[4] = zz[h];
-                    const uint32_t first[2] = {(x[h].y & ~kRawFp32Flag) - col0, (y[h].x & ~kRawFp32Flag) - col0};        // columns relative to the tile
+                    uint32_t (&z)[2] = zz[h];
+                    const uint32_t first = (x[h].y & ~kRawFp32Flag) - col0;                       // chunk's first column relative to the tile
                     const uint32_t pos = x[h].x;
-                    uint32_t q = 0;
                     auto next_col = [&]() -> uint32_t {              // pops the lane's next candidate column (0xffffffff: none)
-                        while (q < 4 && z[q] == 0u) q++;
-                        if (q >= 4) return 0xffffffffu;
-                        const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1;
-                        const uint32_t w = q & 1u;
-                        return acc16 ? first[q >> 1] + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first[q >> 1] + 16 * w + 2 * (bit & 7u) + (bit >> 3);
+                        const uint32_t w = z[0] ? 0u : 1u;
+                        if (z[w] == 0u) return 0xffffffffu;
+                        const uint32_t bit = __ffs(z[w]) - 1; z[w] &= z[w] - 1;
+                        return acc16 ? first + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first + 16 * w + 2 * (bit & 7u) + (bit >> 3);
                     };
                     score_round(next_col(), pos, codes2[h], zm2[h]);
-                    while (__any_sync(0xffffffffu, (z[0] | z[1] | z[2] | z[3]) != 0u)) {
+                    while (__any_sync(0xffffffffu, (z[0] | z[1]) != 0u)) {
                         const uint32_t c = next_col();
                         const unsigned m = __ballot_sync(0xffffffffu, c != 0xffffffffu);
                         if (c != 0xffffffffu) qbuf[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2(pos, c);

@@ -1004,7 +1004,7 @@ int runScan(int argc, char** argv)
     uint64_t maxTot = 1024;
     for (const auto& sp : sc.species) maxTot = max<uint64_t>(maxTot, sp.totSeqLen);
     // size the hit buffers for the expected hit rate (they regrow on demand, at the price of re-scanning a block); where the rate is
-    // known to be high (-pt) the chunks shrink so that a chunk's hits stay within ~4e8 records (device memory: ~136 B per hit).
+    // known to be high (-pt) the chunks shrink so that a chunk's hits stay within ~4e8 records (device memory: ~96 B per hit).
     // Chunks that turn out denser than the device can hold are scored in halves (deviceWorker: scanSplit).
     const double rate = pSpec ? std::min(1.0, 3.0 * pvalue) : 2e-4;
     if (rate * (double)mc.motifs.size() * (double)chunk > 4e8)

@@ -130,7 +130,7 @@ int  b200scan_device_count(void);
  * max_hits: initial capacity (records) of the per-slot hit buffers.  A block that produces more hits (or more filter
  * candidates) than the buffers hold is NOT lost: every counter keeps counting past its capacity, b200scan_collect then
  * frees the buffers, allocates them at the counted size (+ 1/8) and scores the whole block again -- at the price of that
- * second pass and of device memory of about 100 bytes per hit of the densest block (B200SCAN_ENOMEM if that fails: the
+ * second pass and of device memory of about 96 bytes per hit of the densest block (B200SCAN_ENOMEM if that fails: the
  * caller should then submit smaller blocks; the CLI sizes its chunks from the expected hit rate, cli.cpp: hitBudget).
  * Device and pinned buffers of a slot are allocated at the slot's first use; the pinned hit buffer is sized from the
  * blocks actually collected. */
