@@ -35,7 +35,7 @@
 //                Within a group two warps share each TMEM lane quarter and split the tile's 32-word chunks:
 //                tcgen05.ld 32x32b.x32 into registers, RELEASE the TMEM buffer at once, compact the sign bits of the 32
 //                words into two sign words (PRMT on the ALU pipe + IMAD on the FMA pipe).  A lane that saw a non-negative
-//                accumulator stores {window, column, sign words} as one 16-byte raw entry in global memory (blocks of 64
+//                accumulator stores {window, column, sign words} as one 32-byte raw entry in global memory (blocks of 64
 //                entries reserved ahead of time, one predicated fire-and-forget store).  Because a buffer is released
 //                right after the load, candidate pushes land in slack instead of delaying the next MMAs.
 //   rescore_tile_kernel (rescore.cuh) later decodes the raw entries and recomputes those few scores exactly, a column tile at a time.
@@ -102,7 +102,7 @@ static_assert(TC_BUFS * TC_MAXN * TC_CTAS_PER_SM <= 512, "TMEM: buffers x N colu
 static_assert((4 * TC_STAGE_TILES) % TC_PRODUCERS == 0 && TC_STAGE_TILES >= 1 && TC_STAGE_TILES <= 8 && TC_EPI_WARPS % (4 * TC_EPI_GROUPS) == 0 && (TC_EPI_GROUPS & (TC_EPI_GROUPS - 1)) == 0 && TC_BUFS % TC_EPI_GROUPS == 0, "warp role split");
 constexpr uint32_t kTcEpiGroups = TC_EPI_GROUPS;
 constexpr uint32_t kRawBlock   = 64;         // raw entries per block (an epilogue warp reserves a block at a time)
-constexpr uint32_t kRawWords   = 4;          // {window, first column of a 64-column chunk (32 with FP32 accumulators), its 2 sign words} = 16 B per entry
+constexpr uint32_t kRawWords   = 8;          // {window, column of chunk 0, 2 sign words, column of chunk 1, 2 sign words, -} = 32 B per entry
 
 struct TcTile {
     uint32_t col0;      // first sorted column
@@ -408,18 +408,21 @@ __device__ __forceinline__ void raw_new_block(RawCursor& rc, const TcParams& P, 
     rc.next = P.raw + (size_t)min(rc.blk, P.blk_cap) * (kRawBlock * kRawWords);
     rc.left = kRawBlock;
 }
-// Lanes whose window has a candidate in a chunk append one entry {window, first column of the chunk, its two sign masks} to the warp's
-// current block.  `t` is the ballot of those lanes (non-zero): one cursor update and one predicated, fire-and-forget 128-bit store
-// (~2e-4 of the accumulators are candidates, so this runs for about every other tile of every warp).  Round 1 wrote 32-byte entries
-// holding two chunks, of which one was almost always empty: half of the 0.92 GB the filter wrote per launch was padding.
+// Lanes whose window has a candidate in either of the warp's two chunks append one entry {window, column of chunk 0, its two
+// sign masks, column of chunk 1, its two sign masks} to the warp's current block.  `t` is the ballot of those lanes (non-zero):
+// one cursor update and one predicated, fire-and-forget 256-bit store (~2e-4 of the accumulators are candidates, so this
+// runs for about every other tile of every warp).  One of the two chunks is almost always empty, but 16-byte entries of one chunk
+// each were measured and rejected in round 2: choosing the chunk per lane and voting once more for the rare lane with both costs
+// 0.4 ms of the 10.8 ms launch (two votes and two pushes: 1.0 ms) -- every instruction of this path competes with the issuing
+// lane -- against the 0.3 ms the rescorer gains from reading half the bytes.
 __device__ __forceinline__ void raw_push(RawCursor& rc, const TcParams& P, unsigned t, bool c, uint32_t win, uint32_t col0, uint32_t a0, uint32_t a1,
-                                         uint32_t lane, uint32_t tag) {
+                                         uint32_t col1, uint32_t b0, uint32_t b1, uint32_t lane, uint32_t tag) {
     const uint32_t n = __popc(t);
     if (n > rc.left) raw_new_block(rc, P, lane, tag);       // n <= 32 <= kRawBlock
     uint32_t* d = rc.next + __popc(t & ((1u << lane) - 1u)) * kRawWords;
     if (!(TC_KNOCKOUT & 16))
-        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %5, 0;\n@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n}"
-                     ::"l"(d), "r"(win), "r"(col0), "r"(a0), "r"(a1), "r"((uint32_t)c) : "memory");
+        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %8, 0;\n@q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %7};\n}"
+                     ::"l"(d), "r"(win), "r"(col0), "r"(a0), "r"(a1), "r"(col1), "r"(b0), "r"(b1), "r"((uint32_t)c) : "memory");
     rc.next += n * kRawWords;
     rc.left -= n;
 }
@@ -832,10 +835,7 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                         if (__any_sync(0xffffffffu, any_nonneg<true>(g1))) a1 = sign_word16<true, 16>(v);
                         if (__any_sync(0xffffffffu, any_nonneg<true>(g2))) b0 = sign_word16<true, 32>(v);
                         if (__any_sync(0xffffffffu, any_nonneg<true>(g3))) b1 = sign_word16<true, 48>(v);
-                        const bool cA = c && (((a0 ^ kAllNegative) | (a1 ^ kAllNegative)) != 0u), cB = c && (((b0 ^ kAllNegative) | (b1 ^ kAllNegative)) != 0u);
-                        const unsigned tA = __ballot_sync(0xffffffffu, cA), tB = __ballot_sync(0xffffffffu, cB);
-                        if (tA) raw_push(rawc, P, tA, cA, win, colA, a0, a1, lane, tileTag);
-                        if (tB) raw_push(rawc, P, tB, cB, win, colB, b0, b1, lane, tileTag);
+                        raw_push(rawc, P, t, c, win, colA, a0, a1, colB, b0, b1, lane, tileTag);
                     }
                     PH_ACC(2); PH_COUNT();
                     if (warp == kTcEpiWarp0) TC_TRACE(2, i, 3); else if (warp == kTcEpiWarp0 + 7) TC_TRACE(3, i, 3);
@@ -878,12 +878,8 @@ filter_tc_kernel(TcParams P, BlockDev blk)
                     if (kPerIter == 2 && has1) sign_words<ACC16>(v1, b0, b1);
                     const bool c = winOk && (((a0 ^ kAllNegative) | (a1 ^ kAllNegative) | (b0 ^ kAllNegative) | (b1 ^ kAllNegative)) != 0u);
                     const unsigned t = (TC_KNOCKOUT & 8) ? 0u : __ballot_sync(0xffffffffu, c);
-                    if (t) {
-                        const bool cA = c && (((a0 ^ kAllNegative) | (a1 ^ kAllNegative)) != 0u), cB = c && (((b0 ^ kAllNegative) | (b1 ^ kAllNegative)) != 0u);
-                        const unsigned tA = __ballot_sync(0xffffffffu, cA), tB = __ballot_sync(0xffffffffu, cB);
-                        if (tA) raw_push(rawc, P, tA, cA, win0 + lane, (tile.col0 + wc * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), a0, a1, lane, tileTag);
-                        if (tB) raw_push(rawc, P, tB, cB, win0 + lane, (tile.col0 + (wc + step) * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), b0, b1, lane, tileTag);
-                    }
+                    if (t) raw_push(rawc, P, t, c, win0 + lane, (tile.col0 + wc * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), a0, a1,
+                                    (tile.col0 + (wc + step) * kColsPerWord) | (ACC16 ? 0u : kRawFp32Flag), b0, b1, lane, tileTag);
                 }
                 if (!released) {                                      // this warp owns no chunk of such a narrow tile
                     tc_fence_before();

@@ -8,8 +8,8 @@
 
 namespace b200 {
 
-// Raw entries of the tensor-core filter {window, first column of the chunk, mask, mask}: sign words are decoded to masks whose zero
-// bits are the candidates (filter_tc.cuh: sign_words).
+// Raw entries of the tensor-core filter {window, column of chunk 0, mask, mask, column of chunk 1, mask, mask, -}: sign words are
+// decoded to masks whose zero bits are the candidates (filter_tc.cuh: sign_words).
 // Inverse of filter_tc.cuh: sign_words().  X = sum_b 255 * M_b * 256^b (mod 2^32)  ->  M_0 | M_1 << 8 | M_2 << 16 | M_3 << 24
 // (bit 8b + t set <=> accumulator (t, b) negative).  255 M = 256 M - M, so X = -M_0 + (M_0 - M_1) 256 + (M_1 - M_2) 256^2 + ...
 // and the bytes peel off from the bottom.  FP32 accumulators only fill b < 2 (the upper bytes repeat them).
@@ -35,8 +35,9 @@ __device__ __forceinline__ uint32_t decode_sign_word(bool acc16, uint32_t x)
 // carry the TAG of the column tile that produced them (filter_tc.cuh: an epilogue warp closes its block when its CTA moves to
 // another tile); a CTA takes a batch of consecutive blocks -- in allocation order they are almost always of one tile, because all
 // CTAs of the filter work through the items tile by tile -- loads THAT tile's FP32 weights and column records into shared memory
-// once, and scores the batch's raw entries straight from them: a warp per block, two entries per lane in flight plus the next
-// block's, the window's codes loaded once per entry, every weight read an LDS.  Every lane scores its entry's first candidate in
+// once, and scores the batch's raw entries straight from them: a warp per block, two entries per lane in flight (prefetching the
+// next block's as well spills at the 64 registers two CTAs per SM allow: 1.6 instead of 1.07 ms), the window's codes loaded once per
+// entry, every weight read an LDS.  Every lane scores its entry's first candidate in
 // the same round (96 % of the entries have one); further candidates go through a per-warp queue and are scored 32 at a time.
 // The candidate list and its two kernels are gone.  Scores are the same in-order FP32 sums, hits leave through warp staging.
 // Tiles whose weights exceed the shared-memory budget (256 columns of > 36 positions) are scored from global memory.
@@ -109,7 +110,7 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
         n_st = 0; round = 0;
     };
     const uint32_t nb = min(*n_blocks_ptr, blk_cap);
-    const uint4* ent = reinterpret_cast<const uint4*>(raw);                                  // one 16-byte entry each
+    const uint4* ent = reinterpret_cast<const uint4*>(raw);
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1u);
         __syncthreads();
@@ -174,36 +175,30 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
                 score_round(c, pos, codes, zm);
             };
             // one warp per raw block of this tile and pass; a lane takes the block's entries `lane` and `lane + 32`: both are loaded up
-            // front together with the NEXT block's (the kernel is bound by memory latency: bytes in flight per thread are what count),
-            // then both windows' codes
-            const uint32_t wstep = kFuseThreads / 32;
-            uint4 nx[2];
-            auto fetch = [&](uint32_t b, uint4 (&x)[2]) {
-                x[0] = x[1] = make_uint4(0u, 0u, kAllNegative, kAllNegative);
-                if (b < b1) {
-                    const uint32_t cnt = __ldg(blk_count + b);
-                    if (lane < cnt) x[0] = __ldg(ent + (size_t)b * kRawBlock + lane);
-                    if (lane + 32 < cnt) x[1] = __ldg(ent + (size_t)b * kRawBlock + lane + 32);
-                }
-            };
-            fetch(b0 + wib, nx);
-            for (uint32_t b = b0 + wib; b < b1; b += wstep) {
-                uint4 x[2] = {nx[0], nx[1]};
-                fetch(b + wstep, nx);
+            // front, then both windows' codes (the kernel is bound by memory latency: bytes in flight per thread are what count)
+            for (uint32_t b = b0 + wib; b < b1; b += kFuseThreads / 32) {
                 if (__ldg(blk_tag + b) != tag) continue;                                        // (warp-uniform)
                 const uint32_t cnt = __ldg(blk_count + b);
                 if (cnt == 0) continue;
-                uint32_t zz[2][2], codes2[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, zm2[2][2] = {{0u, 0u}, {0u, 0u}};
+                uint4 x[2], y[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    x[h] = make_uint4(0u, 0u, kAllNegative, kAllNegative); y[h] = make_uint4(0u, kAllNegative, kAllNegative, 0u);
+                    const uint32_t e = lane + 32 * h;
+                    if (e < cnt) { x[h] = __ldg(ent + 2 * ((size_t)b * kRawBlock + e)); y[h] = __ldg(ent + 2 * ((size_t)b * kRawBlock + e) + 1); }
+                }
+                uint32_t zz[2][4], codes2[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, zm2[2][2] = {{0u, 0u}, {0u, 0u}};
                 bool acc16h[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     acc16h[h] = !(x[h].y & kRawFp32Flag);
                     zz[h][0] = ~decode_sign_word(acc16h[h], x[h].z); zz[h][1] = ~decode_sign_word(acc16h[h], x[h].w);
-                    if ((zz[h][0] | zz[h][1]) != 0u) {
+                    zz[h][2] = ~decode_sign_word(acc16h[h], y[h].y); zz[h][3] = ~decode_sign_word(acc16h[h], y[h].z);
+                    if ((zz[h][0] | zz[h][1] | zz[h][2] | zz[h][3]) != 0u) {
                         load_window_codes(blk.codes, x[h].x, codes2[h]);
                         if (MASKED) load_window_zmask(blk.zmask, x[h].x, zm2[h]);
                     }
-                    my_cand += __popc(zz[h][0]) + __popc(zz[h][1]);
+                    my_cand += __popc(zz[h][0]) + __popc(zz[h][1]) + __popc(zz[h][2]) + __popc(zz[h][3]);
                 }
                 // Every lane scores the FIRST candidate of its entry at once (an entry has one candidate in 96 % of the cases); further
                 // candidates go to the warp's queue and are scored 32 at a time -- a second round for the whole warp because one or two
@@ -212,17 +207,19 @@ rescore_tile_kernel(MotifDev md, BlockDev blk, const uint32_t* __restrict__ raw,
                 for (int h = 0; h < 2; h++) {
                     if (h == 1 && cnt <= 32) break;
                     const bool acc16 = acc16h[h];
-                    uint32_t (&z)[2] = zz[h];
-                    const uint32_t first = (x[h].y & ~kRawFp32Flag) - col0;                       // chunk's first column relative to the tile
+                    uint32_t (&z)[4] = zz[h];
+                    const uint32_t first[2] = {(x[h].y & ~kRawFp32Flag) - col0, (y[h].x & ~kRawFp32Flag) - col0};        // columns relative to the tile
                     const uint32_t pos = x[h].x;
+                    uint32_t q = 0;
                     auto next_col = [&]() -> uint32_t {              // pops the lane's next candidate column (0xffffffff: none)
-                        const uint32_t w = z[0] ? 0u : 1u;
-                        if (z[w] == 0u) return 0xffffffffu;
-                        const uint32_t bit = __ffs(z[w]) - 1; z[w] &= z[w] - 1;
-                        return acc16 ? first + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first + 16 * w + 2 * (bit & 7u) + (bit >> 3);
+                        while (q < 4 && z[q] == 0u) q++;
+                        if (q >= 4) return 0xffffffffu;
+                        const uint32_t bit = __ffs(z[q]) - 1; z[q] &= z[q] - 1;
+                        const uint32_t w = q & 1u;
+                        return acc16 ? first[q >> 1] + 32 * w + 4 * (bit & 7u) + (bit >> 3) : first[q >> 1] + 16 * w + 2 * (bit & 7u) + (bit >> 3);
                     };
                     score_round(next_col(), pos, codes2[h], zm2[h]);
-                    while (__any_sync(0xffffffffu, (z[0] | z[1]) != 0u)) {
+                    while (__any_sync(0xffffffffu, (z[0] | z[1] | z[2] | z[3]) != 0u)) {
                         const uint32_t c = next_col();
                         const unsigned m = __ballot_sync(0xffffffffu, c != 0xffffffffu);
                         if (c != 0xffffffffu) qbuf[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2(pos, c);

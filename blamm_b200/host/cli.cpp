@@ -388,7 +388,47 @@ struct Job {
     shared_ptr<const GroupParams> group;
 };
 
-struct MotifText { string name; uint64_t size = 0; bool revComp = false; };      // what a line needs of a column (same for every group)
+struct MotifText { string name; uint64_t size = 0; bool revComp = false; };
+// Buffers for formatted text are recycled: a fresh multi-megabyte allocation is mapped and unmapped by malloc every time, and every
+// page of it faults (and is zeroed by the kernel) again -- as much memory traffic as the formatting itself.
+class TextPool {
+public:
+    char* get(size_t cap, size_t& got)
+    {
+        {
+            lock_guard<mutex> l(m);
+            auto it = pool.lower_bound(cap);
+            if (it != pool.end() && it->first <= 2 * cap + (1u << 20)) { char* p = it->second; got = it->first; held -= got; pool.erase(it); return p; }
+        }
+        got = cap;
+        return new char[cap];
+    }
+    void put(char* p, size_t cap)
+    {
+        {
+            lock_guard<mutex> l(m);
+            if (held + cap <= limit) { pool.emplace(cap, p); held += cap; return; }
+        }
+        delete[] p;
+    }
+    ~TextPool() { for (auto& kv : pool) delete[] kv.second; }
+private:
+    mutex m; multimap<size_t, char*> pool; size_t held = 0; const size_t limit = 48ull << 30;
+} gTextPool;
+// A piece of formatted occurrence text.  Not a std::string: resize() would zero-fill the worst-case capacity (three times the final
+// size) before the lines are written -- 113 GB of memset for configs[2]'s 756 M occurrences.
+struct Text {
+    char* p = nullptr; size_t cap = 0, n = 0;
+    Text() = default;
+    Text(const Text&) = delete; Text& operator=(const Text&) = delete;
+    Text(Text&& o) noexcept : p(o.p), cap(o.cap), n(o.n) { o.p = nullptr; o.cap = o.n = 0; }
+    Text& operator=(Text&& o) noexcept { if (this != &o) { release(); p = o.p; cap = o.cap; n = o.n; o.p = nullptr; o.cap = o.n = 0; } return *this; }
+    ~Text() { release(); }
+    void release() { if (p) gTextPool.put(p, cap); p = nullptr; cap = n = 0; }
+    char* alloc(size_t want) { release(); p = gTextPool.get(want, cap); n = 0; return p; }
+    const char* data() const { return p; }
+    size_t size() const { return n; }
+};
 
 struct ScanShared {
     vector<MotifText> mtext;
@@ -454,12 +494,11 @@ void sortHits(std::vector<H>& hits)
 }
 
 template <class H>
-void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, std::string& text)
+void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, Text& text)
 {
     sortHits(hits);
     // worst-case line: names + 2 positions of <= 20 digits + score (<= 16) + 5 tabs + strand + "\t.\t.\n"
-    text.resize(hits.size() * (job.group->maxNameLen + 96) + 64);
-    char* const base = &text[0];
+    char* const base = text.alloc(hits.size() * (job.group->maxNameLen + 96) + 64);
     char* p = base;
     size_t f = 0;
     for (const auto& h : hits) {
@@ -478,11 +517,11 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, std
         *p++ = '\t'; *p++ = m.revComp ? '-' : '+';
         memcpy(p, "\t.\t.\n", 5); p += 5;
     }
-    text.resize((size_t)(p - base));
+    text.n = (size_t)(p - base);
 }
 
 // formatted text of one chunk -> its place in the file: wait for the chunk's turn, take the byte range, write the pieces in parallel
-void emitText(ScanShared& sh, const Job& job, vector<string>& text, uint64_t n)
+void emitText(ScanShared& sh, const Job& job, vector<Text>& text, uint64_t n)
 {
     double t0 = now();
     uint64_t bytes = 0;
@@ -558,7 +597,7 @@ void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n, size_t
         });
     }
     gTimer.add("partition hits (wall)", now() - t0); t0 = now();
-    vector<string> text(T);
+    vector<Text> text(T);
     sh.pool->parallel(T, [&](size_t t) { formatRange<H>(sh, job, part[t], text[t]); });
     gTimer.add("sort + format (wall)", now() - t0);
     emitText(sh, job, text, n);
@@ -568,11 +607,10 @@ void writeHits(ScanShared& sh, const Job& job, const H* hits, uint64_t n, size_t
 // grouped them in buckets of 256 positions, so the host neither partitions nor sorts: every formatting thread takes a run of
 // buckets holding about n / T hits.
 void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hits, const uint32_t* bucketStart, uint64_t b0, uint64_t b1,
-                   std::string& text, uint64_t posOffset = 0)
+                   Text& text, uint64_t posOffset = 0)
 {
     const uint64_t n = bucketStart[b1] - bucketStart[b0];
-    text.resize(n * (job.group->maxNameLen + 96) + 64);
-    char* const base = &text[0];
+    char* const base = text.alloc(n * (job.group->maxNameLen + 96) + 64);
     char* p = base;
     size_t f = 0;
     for (uint64_t b = b0; b < b1; b++) {
@@ -595,12 +633,12 @@ void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hi
             memcpy(p, "\t.\t.\n", 5); p += 5;
         }
     }
-    text.resize((size_t)(p - base));
+    text.n = (size_t)(p - base);
 }
 
 // format the ordered hit list of (a piece of) a chunk: appends the text pieces to `text`
 void formatHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets, size_t threads,
-                 vector<string>& text, uint64_t posOffset = 0)
+                 vector<Text>& text, uint64_t posOffset = 0)
 {
     const double t0 = now();
     // a few pieces per thread: the pool is shared by all the GPUs' chunks, short pieces even out the load
@@ -617,7 +655,7 @@ void formatHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint
 
 void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint64_t n, const uint32_t* bucketStart, uint64_t nBuckets, size_t threads)
 {
-    vector<string> text;
+    vector<Text> text;
     formatHits8(sh, job, hits, n, bucketStart, nBuckets, threads, text);
     emitText(sh, job, text, n);
 }
@@ -627,7 +665,7 @@ void writeHits8(ScanShared& sh, const Job& job, const b200scan_hit8* hits, uint6
 // own with the halo behind it; the text comes out in position order.  The reference streams any hit density to disk block by
 // block (250,000 characters, pwmscan.cpp:258); here only such dense chunks fall back to smaller blocks.
 bool scanSplit(ScanShared& sh, b200scan_ctx* ctx, const Job& job, uint64_t lo, uint64_t hi, uint64_t halo, bool foldLower, size_t threads,
-               vector<string>& text, uint64_t& nHits, string& err, size_t devIndex)
+               vector<Text>& text, uint64_t& nHits, string& err, size_t devIndex)
 {
     const uint64_t nTotal = std::min<uint64_t>(job.nTotal - lo, hi - lo + halo);
     vector<uint64_t> frag;
@@ -725,7 +763,7 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
         for (const auto& it : order) {
             if (it.kind == 0) {
                 const Job& job = *pendingSplit[it.idx];
-                vector<string> text; uint64_t n = 0; string err;
+                vector<Text> text; uint64_t n = 0; string err;
                 const uint64_t mid = (job.nPayload / 2 + 31) / 32 * 32;
                 const bool ok = job.nPayload < 4096 ? false
                               : scanSplit(sh, ctx, job, 0, mid, halo, foldLower, threads, text, n, err, devIndex) &&

@@ -52,7 +52,7 @@ extern "C" {
 #define B200SCAN_EINVAL       -1   /* bad argument */
 #define B200SCAN_ECUDA        -2   /* CUDA runtime error (text in last_error) */
 #define B200SCAN_ENODEVICE    -3   /* no sm_100 device / device index out of range */
-#define B200SCAN_ENOMEM       -4   /* host or device allocation failed */
+#define B200SCAN_ENOMEM       -4   /* host or device allocation failed; from b200scan_collect*: block too dense for the hit budget (see b200scan_create) */
 #define B200SCAN_ESTATE       -5   /* call order violated (e.g. collect without submit) */
 #define B200SCAN_ELIMIT       -6   /* motif longer than B200SCAN_MAX_MOTIF_LEN, block larger than max_block_nt */
 
@@ -130,8 +130,11 @@ int  b200scan_device_count(void);
  * max_hits: initial capacity (records) of the per-slot hit buffers.  A block that produces more hits (or more filter
  * candidates) than the buffers hold is NOT lost: every counter keeps counting past its capacity, b200scan_collect then
  * frees the buffers, allocates them at the counted size (+ 1/8) and scores the whole block again -- at the price of that
- * second pass and of device memory of about 96 bytes per hit of the densest block (B200SCAN_ENOMEM if that fails: the
- * caller should then submit smaller blocks; the CLI sizes its chunks from the expected hit rate, cli.cpp: hitBudget).
+ * second pass and of device memory of about 96 bytes per hit of the densest block.  The growth has a ceiling: a budget of
+ * hit records derived from the free device memory at creation (60 % of it; B200SCAN_HIT_BUDGET=<records> overrides).  A block
+ * that needs more, or whose larger allocation fails (the previous size is then restored), makes b200scan_collect* return
+ * B200SCAN_ENOMEM: the slot is free again, nothing was returned for the block, and the caller submits it in smaller pieces --
+ * e.g. its two halves, each with the maxLen - 1 characters behind it as halo (what the CLI does, cli.cpp: scanSplit).
  * Device and pinned buffers of a slot are allocated at the slot's first use; the pinned hit buffer is sized from the
  * blocks actually collected. */
 int  b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint64_t max_hits);
