@@ -1,6 +1,8 @@
 // Gather-add scoring kernel: score(g, col) = sum_{j < L} W_col[j][code[g+j]], added in position order in FP32,
-// which is bit-identical to the reference's sgemm on a one-hot operand (one in-order FMA chain per output;
-// the zero products add exactly -- SURVEY.md 7.3 [probe]).  Replaces, for one block,
+// i.e. the naive in-order sum: bit-identical to the reference's naive path (Motif::getScore, motif.cpp:225-239) and to its sgemm
+// wherever the BLAS keeps one in-order FMA chain per output (the zero products add exactly -- SURVEY.md 7.3 [probe]); OpenBLAS
+// re-associates the sums of motifs longer than ~18 positions, and there the reference's BLAS path differs from its own naive path by
+// <= 3.8e-6.  Replaces, for one block,
 //   the w-iteration loop { Matrix::sgemm_batch ; extractOccurrences }           pwmscan.cpp:259-264, :104-133
 // without ever materialising the one-hot matrix S or the score matrix R.
 //
@@ -67,7 +69,7 @@ gather_scan_kernel(MotifDev md, BlockDev blk, const GatherTile* __restrict__ til
                     for (uint32_t t = 0; t < n; t++) {
                         float w = wq[4 * t + (r & 3u)];
                         if (ZMASK) { if (z & 1u) w = 0.0f; z >>= 1; }
-                        s += w;                       // in-order FP32 add == reference sgemm order
+                        s += w;                       // in-order FP32 add (the reference's naive path; its sgemm up to re-association)
                         r >>= 2;
                     }
                 }

@@ -75,7 +75,9 @@ typedef struct b200scan_ctx b200scan_ctx;
 
 /* One occurrence.  `pos` is the block position of the window start (0-based, < n_payload), `col` the motif
  * column as passed to b200scan_set_motifs, `score` the FP32 log-odds score summed in position order
- * (bit-identical to the in-order FMA chain of the reference's sgemm on a one-hot operand). */
+ * (the naive in-order sum: bit-identical to the reference's naive path, motif.cpp:225-239; its BLAS path re-associates the sums of
+ * longer motifs and differs from that by a few ulp -- an occurrence whose score lies that close to its threshold can differ between
+ * the two; north_star's tolerance for such cases is 1e-4, tools/parity_list.py lists them). */
 typedef struct b200scan_hit {
     uint64_t pos;
     uint32_t col;

@@ -14,5 +14,5 @@ cp_if $G/r2_cli_e2e.log $P/r02_cli_e2e.log; cp_if $G/r2_cli_startup.log $P/r02_c
 cp_if $G/r2_pytest_gpu.log $P/r02_pytest_gpu.log
 cat $G/r2_variants1.log $G/r2_variants_call3.log > $P/r02_variants.log 2>/dev/null || true
 # strip torchrun banners from the json files (keep the JSON line only)
-for f in $P/r02_*.json; do grep '^{' "$f" > "$f.tmp" 2>/dev/null && mv "$f.tmp" "$f" || rm -f "$f.tmp"; done
+for f in $P/r02_bench_*.json $P/r02_scale8_*.json $P/r02_two_*.json; do grep '^{"' "$f" > "$f.tmp" 2>/dev/null && mv "$f.tmp" "$f" || rm -f "$f.tmp"; done
 ls -la $P | grep r02

@@ -28,7 +28,7 @@ rows=list(csv.reader(sys.stdin))
 for h,u,v in zip(rows[0],rows[1],rows[2]):
     if h in ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active','sm__warps_active.avg.pct_of_peak_sustained_active','sm__throughput.avg.pct_of_peak_sustained_elapsed','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','launch__shared_mem_per_block_dynamic','launch__block_size','launch__grid_size','smsp__sass_inst_executed_op_tmem_ldt.sum'): print('%-80s %-12s %s'%(h,u,v))
 "
-echo; echo "## ordering kernels (bucket_scan, bucket_scatter, bucket_order), expand_kernel, rescore_kernel (ncu --set full, same workload)"
+echo; echo "## ordering kernels (bucket_scan, bucket_scatter, bucket_order) and the fused rescorer (rescore_tile_kernel) (ncu --set full, same workload)"
 ncu -i gpurun_out/prof_small.ncu-rep --page raw --csv 2>/dev/null | python3 -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin))
