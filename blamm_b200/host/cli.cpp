@@ -995,19 +995,9 @@ int runScan(int argc, char** argv)
     sc.loadDict(string(argv[argc - 1]) + ".dict");
     uint64_t chunk = 32ull << 20;
     if (const char* e = getenv("BLAMM_B200_CHUNK")) chunk = max<uint64_t>(strtoull(e, nullptr, 10), 1024);
-    // CUDA start-up overlaps the loading of the inputs.  Driver initialisation grows with the number of GPUs it has to bring up, so
-    // a run that cannot keep more than k devices busy (k = chunks of the largest group, or -g) only shows the first k to the
-    // driver -- unless the user has chosen the devices (CUDA_VISIBLE_DEVICES).
-    {
-        uint64_t maxChunks = 1;
-        for (const auto& sp : sc.species) maxChunks = max<uint64_t>(maxChunks, (sp.totSeqLen + chunk - 1) / chunk);
-        const uint64_t useful = gpusWanted > 0 ? min<uint64_t>((uint64_t)gpusWanted, maxChunks) : maxChunks;
-        if (!getenv("CUDA_VISIBLE_DEVICES") && useful < 16) {
-            string vis;
-            for (uint64_t d = 0; d < useful; d++) vis += (d ? "," : "") + to_string(d);
-            setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
-        }
-    }
+    // CUDA start-up overlaps the loading of the inputs.  (Showing the driver only the devices a small run can use -- CUDA_VISIBLE_DEVICES
+    // set before cuInit -- was tried and removed: on this pool's 8-GPU NVSwitch boxes cuInit took 5.9 s with one device visible
+    // against 1.0 s with all eight, profiles/r02_scale8_c3_g1.json.)
     future<int> devCount = async(launch::async, [] { return b200scan_device_count(); });
     MotifSet mc;
     mc.load(argv[argc - 2], true);
