@@ -4,7 +4,7 @@
 NVCC     ?= nvcc
 CXX      := /usr/bin/g++
 LIBDIR   := blamm_b200/lib
-NVFLAGS  := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+NVFLAGS  := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 186
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off
 CSRC     := $(wildcard blamm_b200/csrc/*.cu blamm_b200/csrc/*.cuh) include/b200scan.h
 HSRC     := blamm_b200/host/motifs.cpp blamm_b200/host/sequence.cpp
