@@ -13,6 +13,12 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>            // header-only NVTX 3: ranges show up in nsys / ncu timelines, cost nothing without a tool attached
+#define B200_NVTX 1
+#endif
+#endif
 #include "common.cuh"
 #include "filter_tc.cuh"
 #include "gather.cuh"
@@ -25,6 +31,17 @@ using namespace b200;
 namespace {
 
 thread_local std::string g_create_error;
+
+// NVTX range for the lifetime of the object: the host-side phases of the ABI (submit = upload + launches, collect = wait + hit
+// download, set_motifs = folding + tile planning) in a profiler's timeline (tracing)
+struct NvtxRange {
+#ifdef B200_NVTX
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char*) {}
+#endif
+};
 
 constexpr uint32_t kPadBytes = 16384;             // slack behind every device sequence buffer (window / span over-reads)
 constexpr size_t   kGatherSmemW = 64 * 1024;      // FP32 weights per gather column tile
@@ -969,6 +986,7 @@ int b200scan_set_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t 
     }
     if (ctx->hit_format == B200SCAN_HITS_8 && (uint32_t)n_cols > (1u << 24))
         return fail(ctx, B200SCAN_ELIMIT, "B200SCAN_HITS_8 records hold 24-bit column indices (%d columns)", n_cols);
+    NvtxRange nvtx("b200scan_set_motifs");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     return build_motifs(ctx, P, ldp, n_cols, col_len, thr);
@@ -977,6 +995,7 @@ int b200scan_set_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t 
 int b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64_t n_total, uint64_t n_payload,
                           const uint64_t* frag_starts, uint64_t n_frag, int lowercase_mode)
 {
+    NvtxRange nvtx("b200scan_submit_ascii");
     int rc = check_common(ctx, slot, n_total, n_payload, frag_starts, n_frag);
     if (rc) return rc;
     if (!block && n_total) return fail(ctx, B200SCAN_EINVAL, "block is NULL");
@@ -1020,6 +1039,7 @@ int b200scan_submit_ascii(b200scan_ctx* ctx, int slot, const char* block, uint64
 int b200scan_submit_packed(b200scan_ctx* ctx, int slot, const uint32_t* codes2, const uint32_t* zero_mask, uint64_t n_total,
                            uint64_t n_payload, const uint64_t* frag_starts, uint64_t n_frag)
 {
+    NvtxRange nvtx("b200scan_submit_packed");
     int rc = check_common(ctx, slot, n_total, n_payload, frag_starts, n_frag);
     if (rc) return rc;
     if (!codes2 && n_total) return fail(ctx, B200SCAN_EINVAL, "codes2 is NULL");
@@ -1145,6 +1165,7 @@ int b200scan_hist_read(b200scan_ctx* ctx, uint64_t* counts, uint64_t n_counts)
 static int collect_impl(b200scan_ctx* ctx, int slot, int want_bytes, const void** hits, uint64_t* n_hits, b200scan_timing* timing,
                         const uint32_t** bucket_start = nullptr, uint64_t* n_buckets = nullptr)
 {
+    NvtxRange nvtx("b200scan_collect");
     if (!ctx) return B200SCAN_EINVAL;
     if (slot < 0 || slot >= B200SCAN_NUM_SLOTS) return fail(ctx, B200SCAN_EINVAL, "slot %d out of range", slot);
     Slot& s = ctx->slot[slot];
