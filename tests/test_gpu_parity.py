@@ -794,3 +794,32 @@ def test_cli_splits_chunks_too_dense_for_the_device_buffers(tmp_path):
     # without the budget the same run takes the normal path and writes the same file
     r = subprocess.run([cli, "scan", "-rc", "-at", "-6", "-t", "4", "-o", "plain.txt", "motifs.jaspar", "sequences.mf"], cwd=work, capture_output=True, text=True)
     assert r.returncode == 0 and open(os.path.join(work, "plain.txt")).read().splitlines(True) == got
+
+
+@pytest.mark.parametrize("forced", [False, True])
+def test_rescorer_tiles_beyond_the_shared_memory_budget(forced, monkeypatch):
+    """The fused rescorer keeps a column tile's FP32 weights in shared memory; a tile that does not fit (256 columns of more than
+    ~38 positions) is scored from global memory by the same code.  Natural case: 260 columns of length 48..64; forced case: a budget
+    of 64 positions (B200SCAN_FUSE_MAXW) puts every tile of an ordinary set on that path.  Bit-exact against the oracle, with a
+    soft-masked stretch (the masked instance takes the same path)."""
+    if forced:
+        monkeypatch.setenv("B200SCAN_FUSE_MAXW", "64")
+        case = util.random_case(81, n_motifs=60, n_nt=400_000, len_range=(5, 30), lower=True)
+    else:
+        case = util.random_case(82, n_motifs=130, n_nt=200_000, len_range=(48, 64), lower=True)
+        assert len(case["col_len"]) == 260 and int(np.sort(case["col_len"])[-256:].sum()) > 9728
+        # (such long random motifs never reach the usual thresholds: a low absolute one gives 25,214 occurrences with lower case
+        #  scored like upper case, and millions where the masked stretch contributes zero -- the regrow path on top)
+        case["thr"] = np.full(len(case["thr"]), -20.0, dtype=np.float32)
+    s = capi.Scanner(0, max_block_nt=1 << 20, max_hits=1 << 20)
+    try:
+        s.set_engine(capi.ENGINE_TENSOR)
+        s.set_motifs(case["P"], case["col_len"], case["thr"])
+        for lower in (capi.LOWER_ZERO, capi.LOWER_FOLD):
+            hits, t = s.scan(case["chars"], case["frag_start"][1:], lower=lower)
+            assert t["engine_used"] == capi.ENGINE_TENSOR
+            want = _oracle_hits(case, lower_fold=(lower == capi.LOWER_FOLD))
+            assert len(want[0]) > 0
+            _assert_same(hits, *want)
+    finally:
+        s.close()
