@@ -89,3 +89,22 @@ def test_gloo_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+def test_chunk_ordered_concatenation_is_the_merge():
+    """What bench.py and the CLI rely on since the device returns every chunk's hits in (position, column) order: the merge in
+    reference order is the plain concatenation of the per-chunk lists in chunk order (positions + the chunk's start) -- no sort,
+    whatever rank scored which chunk."""
+    case = util.random_case(9, n_motifs=12, n_nt=90_000)
+    halo = int(case["col_len"].max()) - 1
+    pos, col, sc = O.scan_stream(bytes(case["chars"]), case["frag_start"], case["P"], case["col_len"], case["thr"])
+    for world, chunk in [(2, 9001), (8, 4096), (3, 90_000)]:
+        shards = shard.plan_shards(len(case["chars"]), world, halo, chunk)
+        per_rank = {r: dict(_scan_shards(case, shards, r)) for r in range(world)}
+        cat_pos, cat_col, cat_sc = [], [], []
+        for s in shards:                                              # chunk order, not rank order
+            h = per_rank[s.rank][s.index]
+            assert np.all(np.diff(h["pos"].astype(np.int64)) >= 0)    # (the oracle, like the device, lists a chunk in position order)
+            cat_pos.append(h["pos"] + np.uint64(s.start)); cat_col.append(h["col"]); cat_sc.append(h["score"])
+        assert np.array_equal(np.concatenate(cat_pos), pos) and np.array_equal(np.concatenate(cat_col), col)
+        assert np.array_equal(np.concatenate(cat_sc).view(np.uint32), sc.view(np.uint32))
