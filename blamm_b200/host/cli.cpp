@@ -335,13 +335,21 @@ public:
         t->fn = &fn; t->n = n;
         { lock_guard<mutex> l(m); q.push_back(t); }
         cv.notify_all();
-        for (size_t i; (i = t->next.fetch_add(1)) < n;) { fn(i); t->done.fetch_add(1); }
-        unique_lock<mutex> l(m);
-        cvDone.wait(l, [&] { return t->done.load() == n; });
-        for (auto it = q.begin(); it != q.end(); ++it) if (*it == t) { q.erase(it); break; }
+        for (size_t i; (i = t->next.fetch_add(1)) < n;) { run(*t, i); t->done.fetch_add(1); }
+        {
+            unique_lock<mutex> l(m);
+            cvDone.wait(l, [&] { return t->done.load() == n; });
+            for (auto it = q.begin(); it != q.end(); ++it) if (*it == t) { q.erase(it); break; }
+        }
+        if (t->err) rethrow_exception(t->err);            // an exception of any item reaches the caller, not std::terminate
     }
 private:
-    struct Task { const function<void(size_t)>* fn = nullptr; size_t n = 0; atomic<size_t> next{0}, done{0}; };
+    struct Task { const function<void(size_t)>* fn = nullptr; size_t n = 0; atomic<size_t> next{0}, done{0}; mutex em; exception_ptr err; };
+    static void run(Task& t, size_t i)
+    {
+        try { (*t.fn)(i); }
+        catch (...) { lock_guard<mutex> l(t.em); if (!t.err) t.err = current_exception(); }
+    }
     void loop()
     {
         for (;;) {
@@ -358,7 +366,7 @@ private:
                 if (!q.empty() && q.front() == t) q.pop_front();
                 continue;
             }
-            (*t->fn)(i);
+            run(*t, i);
             if (t->done.fetch_add(1) + 1 == t->n) { lock_guard<mutex> l(m); cvDone.notify_all(); }
         }
     }
@@ -779,6 +787,7 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
         pendingSplit.clear(); held.clear();
         return true;
     };
+    try {
     while (!sh.failed) {
         if (!pendingSplit.empty() && !resolveSplits()) break;
         unique_ptr<Job> job;
@@ -822,6 +831,9 @@ void deviceWorker(ScanShared& sh, int engine, bool foldLower, b200scan_ctx** ctx
     }
     while (nFlight > 0 && !sh.failed) if (!collectOldest()) break;
     if (!pendingSplit.empty() && !sh.failed) resolveSplits();
+    } catch (const exception& e) {                       // e.g. a record the .dict does not know (formatting runs on the pool: WorkPool rethrows here)
+        die(e.what());
+    }
 }
 
 // `blamm-b200 selftest-writer [hits] [threads]` (no GPU): the occurrence writer -- partition, radix sort, formatting, writer
