@@ -823,3 +823,20 @@ def test_rescorer_tiles_beyond_the_shared_memory_budget(forced, monkeypatch):
             _assert_same(hits, *want)
     finally:
         s.close()
+
+
+def test_cli_reports_a_stale_dictionary_instead_of_aborting(tmp_path):
+    """A FASTA file that changed after `dict` (one record more than the dictionary knows): the formatting threads meet a record
+    index without a name.  The run must end with an error message and exit code 1 (the reference's behaviour for every failure,
+    blstools.cpp:93-101), not with std::terminate from a pool thread."""
+    cli = os.path.join(lib_dir(), "blamm-b200")
+    work = str(tmp_path)
+    synth.make_jaspar_like(os.path.join(work, "motifs.jaspar"), 8, 5, uniform_len=(6, 9))
+    seq = synth.random_acgt(90_000, 21)
+    synth.write_fasta(os.path.join(work, "a.fa"), [("s1", seq[:45_000]), ("s2", seq[45_000:])])
+    open(os.path.join(work, "sequences.mf"), "w").write("g\ta.fa\n")
+    subprocess.run([cli, "dict", "sequences.mf"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+    synth.write_fasta(os.path.join(work, "a.fa"), [("s1", seq[:30_000]), ("s2", seq[30_000:60_000]), ("s3", seq[60_000:])])
+    r = subprocess.run([cli, "scan", "-rc", "-at", "2", "motifs.jaspar", "sequences.mf"], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 1, (r.returncode, r.stderr[-500:])
+    assert r.stderr.strip() != "" and "bye" not in r.stdout
