@@ -25,6 +25,7 @@
 #include <unordered_map>
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 using namespace std;
@@ -441,8 +442,23 @@ struct Text {
 struct ScanShared {
     vector<MotifText> mtext;
     int fd = -1;                                   // occurrence file (byte ranges handed out in chunk order)
-    // write through shared mappings (falls back to pwrite where the file cannot be mapped; BLAMM_B200_WRITER=pwrite forces that)
-    atomic<bool> useMmap{!(getenv("BLAMM_B200_WRITER") && string(getenv("BLAMM_B200_WRITER")) == "pwrite")};
+    // Write through shared mappings where the file lives in tmpfs, with pwrite elsewhere (BLAMM_B200_WRITER=mmap|pwrite forces one):
+    // measured on a 16-core B200 box (tools/micro/file_write.cpp, one new file, GB/s at 4 / 8 / 16 threads) -- tmpfs: mapping
+    // 5.3 / 8.1 / 6.7, pwrite 3.8 / 3.8 / 3.8 (the inode lock serialises buffered writes); ext4: mapping 4.2, pwrite 5.1 at 16.
+    // More than eight threads faulting pages of one file get in each other's way, so the copies of all chunks share eight slots.
+    atomic<bool> useMmap{true};
+    void chooseWriter()
+    {
+        const char* e = getenv("BLAMM_B200_WRITER");
+        if (e && string(e) == "pwrite") { useMmap = false; return; }
+        if (e && string(e) == "mmap") { useMmap = true; return; }
+        struct statfs st;
+        useMmap = fd >= 0 && fstatfs(fd, &st) == 0 && (unsigned long)st.f_type == 0x01021994ul;      // TMPFS_MAGIC
+    }
+    mutex cMutex; condition_variable cCv;
+    int copySlots = getenv("BLAMM_B200_COPY_THREADS") ? max(1, atoi(getenv("BLAMM_B200_COPY_THREADS"))) : 8;
+    void acquireCopySlot() { unique_lock<mutex> l(cMutex); cCv.wait(l, [&] { return copySlots > 0; }); copySlots--; }
+    void releaseCopySlot() { { lock_guard<mutex> l(cMutex); copySlots++; } cCv.notify_one(); }
     WorkPool* pool = nullptr;
     atomic<uint64_t> totMatches{0};
     // job queue (producer = FASTA reader, consumers = one thread per GPU)
@@ -567,7 +583,12 @@ void emitText(ScanShared& sh, const Job& job, vector<Text>& text, uint64_t n)
         if (m == MAP_FAILED) { mapped = false; sh.useMmap = false; } else base = static_cast<char*>(m);
     }
     sh.pool->parallel(pieces.size(), [&](size_t i) {
-        if (mapped) { memcpy(base + (pieces[i].at - mapAt), pieces[i].p, pieces[i].n); return; }
+        if (mapped) {
+            sh.acquireCopySlot();
+            memcpy(base + (pieces[i].at - mapAt), pieces[i].p, pieces[i].n);
+            sh.releaseCopySlot();
+            return;
+        }
         const char* p = pieces[i].p; size_t left = pieces[i].n; uint64_t o = pieces[i].at;
         while (left) {
             const ssize_t w = pwrite(sh.fd, p, left, (off_t)o);
@@ -857,6 +878,7 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
     auto fillShared = [&](ScanShared& sh, int fd) {
         for (const auto& m : ms.motifs) sh.mtext.push_back({m.name, (uint64_t)m.size(), m.revComp});
         sh.fd = fd; sh.pool = &workPool;
+        sh.chooseWriter();
     };
     Job job;
     job.group = group;
@@ -887,7 +909,7 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
                                seqPos, seqPos + (unsigned long long)m.size(), (double)h.score, m.revComp ? '-' : '+');
         want.append(line, (size_t)n);
     }
-    const string path = "/tmp/blamm_b200_selftest_" + to_string((long)getpid()) + ".txt";
+    const string path = string(getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp") + "/blamm_b200_selftest_" + to_string((long)getpid()) + ".txt";
     {
         const int fd = openOut(path);
         ScanShared sh;
@@ -1081,6 +1103,7 @@ int runScan(int argc, char** argv)
     ScanShared sh;
     for (const auto& m : mc.motifs) sh.mtext.push_back({m.name, (uint64_t)m.size(), m.revComp});
     sh.fd = outFd; sh.pool = &workPool;
+    sh.chooseWriter();
     sh.maxQueue = (size_t)nDev + 1;
     vector<thread> workers;
     for (int d = 0; d < nDev; d++)

@@ -301,9 +301,13 @@ def test_occurrence_writer_selftest(n_hits, threads):
     line formatting, in-order writer thread -- for 16-byte and 12-byte hit records, and for the ordered 8-byte records + bucket
     index the device hands over under B200SCAN_HITS_8 (no host sort), against a plain std::sort + snprintf restatement of
     the reference's line format (pwmscan.cpp:88-95), compiled into the same binary."""
-    r = subprocess.run([CLI, "selftest-writer", str(n_hits), str(threads)], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("identical") == 3 and "DIFFERENT" not in r.stdout
+    # in tmpfs the writer copies through shared mappings, elsewhere it uses pwrite: both, and both forced
+    for env in ({}, {"TMPDIR": "/dev/shm"}, {"BLAMM_B200_WRITER": "mmap"}, {"TMPDIR": "/dev/shm", "BLAMM_B200_WRITER": "pwrite"}):
+        if env.get("TMPDIR") and not os.path.isdir(env["TMPDIR"]):
+            continue
+        r = subprocess.run([CLI, "selftest-writer", str(n_hits), str(threads)], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("identical") == 3 and "DIFFERENT" not in r.stdout
 
 
 def test_fasta_rejects_headerless_input(tmp_path):
