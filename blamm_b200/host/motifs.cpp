@@ -5,6 +5,8 @@
 #include <charconv>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
+#include <iterator>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -166,61 +168,121 @@ void ScoreHistogram::load(const std::string& dir, const std::string& base)
     if (!in) throw std::runtime_error("Unexpected end-of-file reached");
 }
 
+// The two files of a histogram are assembled in memory and written with one call each (`hist` writes two files per motif and
+// group: 43,200 files for configs[2]).  Number formatting: `ostream << x` in its default state is printf("%g", x), and
+// std::to_chars(general, precision 6) is specified as exactly that conversion.  Contents as the reference's
+// ScoreHistogram::writeGNUPlotFile (motif.cpp:71-107): bin centres are double expressions, the bounds floats.
+namespace {
+void putG(std::string& s, double v)
+{
+    char b[48];
+    s.append(b, std::to_chars(b, b + sizeof b, v, std::chars_format::general, 6).ptr);
+}
+void putU(std::string& s, uint64_t v)
+{
+    char b[24];
+    s.append(b, std::to_chars(b, b + sizeof b, v).ptr);
+}
+void spill(const std::string& filename, const std::string& bytes)
+{
+    FILE* f = fopen(filename.c_str(), "wb");
+    const bool ok = f && fwrite(bytes.data(), 1, bytes.size(), f) == bytes.size();
+    if (f && fclose(f) != 0) throw std::runtime_error("Error: cannot write to file " + filename);
+    if (!ok) throw std::runtime_error("Error: cannot write to file " + filename);
+}
+}
+
 void ScoreHistogram::writeGNUPlot(const std::string& dir, const std::string& base, const std::string& label) const
 {
-    std::string filename = dir + base + ".dat";
-    std::ofstream out(filename);
-    if (!out) throw std::runtime_error("Error: cannot write to file " + filename);
-    out << counts.size() << "\t" << minScore << "\t" << maxScore << "\n";
-    for (size_t i = 0; i < counts.size(); i++) out << (0.5 + i) * width + minScore << "\t" << counts[i] << "\n";
-    out.close();
+    std::string dat;
+    dat.reserve(32 + 24 * counts.size());
+    putU(dat, counts.size()); dat += '\t'; putG(dat, minScore); dat += '\t'; putG(dat, maxScore); dat += '\n';
+    uint64_t tallest = 0;
+    for (size_t i = 0; i < counts.size(); i++) {
+        putG(dat, (0.5 + i) * width + minScore); dat += '\t'; putU(dat, counts[i]); dat += '\n';
+        tallest = std::max(tallest, counts[i]);
+    }
+    spill(dir + base + ".dat", dat);
 
-    size_t maxy = 0;
-    for (uint64_t c : counts) maxy = std::max<size_t>(maxy, c);
-    maxy *= 1.1;
-    filename = dir + base + ".gnu";
-    out.open(filename);
-    if (!out) throw std::runtime_error("Error: cannot write to file " + filename);
-    out << "set output \"" << base << ".ps\"\n"
-        << "set key autotitle columnhead\n"
-        << "set terminal postscript landscape\n"
-        << "set terminal postscript noenhanced\n"
-        << "set xrange [" << minScore << ":" << maxScore << "]\n"
-        << "set yrange [" << 0 << ":" << maxy << "]\n"
-        << "set xlabel 'PWM score'" << std::endl
-        << "set ylabel 'count'" << std::endl
-        << "plot \"" << base << ".dat\" using 1:2 title '" << label << "' with boxes\n";
+    // the plot script: y range = the tallest bin + 10 %, truncated (an integer scaled in double, as `size_t *= 1.1` does)
+    const size_t yTop = (size_t)((double)(size_t)tallest * 1.1);
+    std::string range;
+    putG(range, minScore); range += ':'; putG(range, maxScore);
+    std::string gnu = "set output \"" + base + ".ps\"\n"
+                      "set key autotitle columnhead\n"
+                      "set terminal postscript landscape\n"
+                      "set terminal postscript noenhanced\n"
+                      "set xrange [" + range + "]\n"
+                      "set yrange [0:";
+    putU(gnu, yTop);
+    gnu += "]\nset xlabel 'PWM score'\nset ylabel 'count'\nplot \"" + base + ".dat\" using 1:2 title '" + label + "' with boxes\n";
+    spill(dir + base + ".gnu", gnu);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // MotifSet
 // ---------------------------------------------------------------------------------------------------------
+// JASPAR files, parsed from one in-memory copy with a cursor (10,000 PWMs for configs[3]).  The grammar is what the reference's
+// stream extraction accepts (motif.cpp:377-407), quirks included:
+//   * a record starts at the next white-space-delimited token, wherever it is (blank lines between records are skipped); its
+//     first character is dropped whatever it is (normally '>'), the rest of that line is ignored;
+//   * the next FOUR lines are the A, C, G, T rows, blank or not: two tokens are skipped ("A", "["), then unsigned integers are
+//     taken until the first thing that is not one -- "12]" still yields 12, "[1" as second token swallows a count;
+//   * a header token that ends the file yields no record.
+// Rows shorter than the first one are padded with zeros (the reference reads past the end of the shorter row).
+static bool isBlank(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+static void parseCounts(const char* p, const char* end, std::vector<uint64_t>& out)
+{
+    for (int skip = 0; skip < 2; skip++) {
+        while (p < end && isBlank(*p)) p++;
+        while (p < end && !isBlank(*p)) p++;
+    }
+    for (;;) {
+        while (p < end && isBlank(*p)) p++;
+        bool negative = false;
+        if (p < end && (*p == '+' || *p == '-')) negative = *p++ == '-';
+        uint64_t v = 0;
+        const auto r = std::from_chars(p, end, v);
+        if (r.ec != std::errc()) return;                   // no digits, or a count beyond 64 bits
+        out.push_back(negative ? 0 - v : v);               // (stream extraction of an unsigned value negates modulo 2^64)
+        p = r.ptr;
+        if (p < end && !isBlank(*p)) return;               // "12]": the next extraction would start at the ']' and fail
+    }
+}
+
 static void parseJaspar(const std::string& filename, std::vector<Motif>& out)
 {
-    // ">NAME anything" then four rows "X [ c c c ... ]"; the first two tokens of a row are skipped and
-    // unsigned integers are read until the first token that is not one (reference motif.cpp:377-407).
-    std::ifstream in(filename);
-    if (!in) throw std::runtime_error("Could not open file: " + filename);
-    while (in.good()) {
-        std::string name, rest;
-        in >> name;
-        if (!name.empty()) name = name.substr(1);
-        std::getline(in, rest);
-        if (!in) break;
-        std::vector<uint64_t> row[4];
-        for (int r = 0; r < 4; r++) {
-            std::string line, skip;
-            std::getline(in, line);
-            std::istringstream ls(line);
-            ls >> skip >> skip;
-            size_t v;
-            while (ls >> v) row[r].push_back(v);
-        }
+    std::string text;
+    {
+        std::ifstream in(filename, std::ios::binary);
+        if (!in) throw std::runtime_error("Could not open file: " + filename);
+        text.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+    }
+    const char* p = text.data();
+    const char* const end = p + text.size();
+    auto lineEnd = [end](const char* q) { const void* nl = memchr(q, '\n', (size_t)(end - q)); return nl ? static_cast<const char*>(nl) : end; };
+    for (;;) {
+        while (p < end && isBlank(*p)) p++;
+        const char* tok = p;
+        while (p < end && !isBlank(*p)) p++;
+        if (p == end) break;                               // nothing left, or a header token that ends the file
         Motif m;
-        m.name = name;
-        for (size_t j = 0; j < row[0].size(); j++)
-            m.pfm.push_back({row[0][j], j < row[1].size() ? row[1][j] : 0, j < row[2].size() ? row[2][j] : 0,
-                             j < row[3].size() ? row[3][j] : 0});
+        m.name.assign(tok + 1, p);
+        p = lineEnd(p);
+        if (p < end) p++;
+        std::vector<uint64_t> row[4];
+        for (auto& r : row) {
+            const char* e = lineEnd(p);
+            parseCounts(p, e, r);
+            p = e < end ? e + 1 : end;
+        }
+        m.pfm.reserve(row[0].size());
+        for (size_t j = 0; j < row[0].size(); j++) {
+            std::array<uint64_t, 4> col{};
+            for (int b = 0; b < 4; b++) col[b] = j < row[b].size() ? row[b][j] : 0;
+            m.pfm.push_back(col);
+        }
         out.push_back(std::move(m));
     }
 }

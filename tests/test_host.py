@@ -376,6 +376,55 @@ def test_cli_dict_and_hist_match_live_reference_binary(tmp_path):
         assert outs["b200"][f] == data, f
 
 
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/blamm (the compiled reference) has not been built")
+def test_jaspar_parser_quirks_match_live_reference_binary(tmp_path):
+    """The JASPAR grammar is whatever the reference's stream extraction accepts (motif.cpp:377-407): blank lines between records,
+    text after the name, tabs, a bracket glued to the last count ("12]"), signed counts ("+7"), CRLF line ends, rows that are not
+    labelled A/C/G/T, a last line without a newline, and a lone header token at the very end of the file (no record).  Both
+    binaries run `hist` on such a file; names, lengths and every histogram file must agree byte for byte."""
+    text = (
+        "\n\n>MA0001.1 first motif, description ignored\n"
+        "A  [ 10  2  3 40 12 ]\n"
+        "C  [  5 30  3  1  2 ]\n"
+        "G  [  5  3 30  1  2 ]\n"
+        "T  [  5  2  3  1 12]\n"
+        "\n   \n"
+        ">MA0002.2\tTAB\tseparated\r\n"
+        "A\t[\t1\t+7\t9\t]\r\n"
+        "C\t[\t8\t1\t0\t]\r\n"
+        "G\t[\t0\t1\t0\t]\r\n"
+        "T\t[\t0\t0\t0\t]\r\n"
+        ">shortest\n"
+        "x y 3 1 1 1 9 1 1\n"
+        "x y 1 3 1 1 1 9 1\n"
+        "x y 1 1 3 1 1 1 9\n"
+        "x y 9 9 9 3 1 1 1 junk 5 5\n"
+        "Xlast_motif trailing\n"
+        "A [ 100 0 ]\nC [ 0 100 ]\nG [ 0 0 ]\nT [ 0 0 ]"
+        "\n>dangling")
+    open(tmp_path / "motifs.jaspar", "w", newline="").write(text)
+    seq = synth.random_acgt(20_000, 5)
+    synth.write_fasta(str(tmp_path / "a.fa"), [("r1", seq)])
+    open(tmp_path / "seq.mf", "w").write("grp\ta.fa\n")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    ob = os.path.join(ROOT, "oracle", "_ref", "openblas_dir.txt")
+    if os.path.exists(ob):
+        env["LD_LIBRARY_PATH"] = open(ob).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
+    outs = {}
+    for who, exe in (("ref", REF_BIN), ("b200", CLI)):
+        d = tmp_path / who
+        os.makedirs(d)
+        for f in ("motifs.jaspar", "a.fa", "seq.mf"):
+            shutil.copy(tmp_path / f, d / f)
+        for args in (["dict", "seq.mf"], ["hist", "motifs.jaspar", "seq.mf"]):
+            r = subprocess.run([exe] + args, cwd=d, env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr
+        assert "Loaded 4 motifs" in r.stdout and "Maximum motif size: 7" in r.stdout, r.stdout
+        outs[who] = {f: (d / f).read_bytes() for f in os.listdir(d) if f.startswith("hist_")}
+    assert sorted(outs["ref"]) == sorted("hist_grp_%s.%s" % (n, e) for n in ("MA0001.1", "MA0002.2", "shortest", "last_motif") for e in ("dat", "gnu"))
+    assert outs["ref"] == outs["b200"]
+
+
 def test_cli_error_behaviour(golden, tmp_path):
     work = tmp_path / "ex"
     shutil.copytree(os.path.join(golden, "example"), work)
