@@ -155,6 +155,189 @@ uint16_t half_round_up(double x)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Conservative folding of ONE motif column into tensor-core filter weights (host code; no device needed).
+// build_motifs calls these per column; b200scan_debug_fold exposes them to the CPU tests, which check the recall
+// guarantee  "in-order FP32 score >= threshold  =>  accumulator >= 0"  on exhaustive and boundary windows.
+// ---------------------------------------------------------------------------------------------------------
+// Conservative folding.  With x_j the FP32 weights picked by a window (exact in-order FP32 score s = sum x_j + e1,
+// |e1| <= (L-1) 2^-24 A, A = sum_j max|x_j|), the tensor accumulator is  acc = sum y_j + e2  with
+//     y_j = fp16_up(x_j - thr'/L) >= x_j - thr'/L,      thr' = thr - margin,
+// so  s >= thr  =>  acc >= margin - |e1| - |e2|, and the filter is exact-recall when margin >= |e1| + |e2|.
+//   FP32 accumulators: |e2| <= L 2^-18 (A'+1)  (generous for any FP32-ish accumulate, A' = sum_j max|y_j|).
+//   FP16 accumulators: D is rounded to FP16 after every MMA (4 positions).  For a window that is a true hit
+//     (final sum >= 0) the partial sum after step k lies in [-R_k, M_k] (R_k = largest possible remaining sum,
+//     M_k = largest possible prefix), so |D_k| <= B_k = max(M_k, R_k, 0).  Allowing a rounding of one FP16 ulp
+//     (2^-10 relative: covers round-to-nearest and truncation) on EVERY internal add of the 4 products and the
+//     old accumulator:  |e2| <= 2^-10 * 4 * sum_k (B_{k-1} + A_k),  A_k = sum of max|y_j| over the step.
+struct Folded { std::vector<uint16_t> y; double margin; bool always; uint16_t bias = 0;
+                std::vector<int8_t> q; int32_t qbias = 0; bool never = false; };      // INT8 operands (fold_i8)
+Folded fold_col(const float4* wc, uint32_t L, float thr, bool acc16, double margin16_scale)
+{
+    Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false;
+    double A = 0;
+    bool finite = std::isfinite(thr);
+    for (uint32_t j = 0; j < L; j++) {
+        const float4 v = wc[j];
+        const float a4[4] = {v.x, v.y, v.z, v.w};
+        double m = 0;
+        for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); }
+        A += m;
+    }
+    if (!finite) { f.always = true; return f; }
+    const double e1 = (L - 1) * std::ldexp(A, -24);
+    double margin = 1e-3 + e1 + L * std::ldexp(A + std::fabs((double)thr) + 1.0, -18);
+    for (int iter = 0; iter < 6; iter++) {
+        const double share = ((double)thr - margin) / L;
+        std::vector<double> ymax(L), yabs(L);
+        for (uint32_t j = 0; j < L; j++) {
+            const float4 v = wc[j];
+            const float a4[4] = {v.x, v.y, v.z, v.w};
+            double mx = -1e300, ma = 0;
+            for (uint32_t o = 0; o < 4; o++) {
+                const double y = (double)a4[o] - share;
+                if (std::fabs(y) > 30000.0) { f.always = true; return f; }
+                const uint16_t h = half_round_up(y);
+                f.y[4 * j + o] = h;
+                __half hh; std::memcpy(&hh, &h, 2);
+                const double yr = (double)__half2float(hh);
+                mx = std::max(mx, yr); ma = std::max(ma, std::fabs(yr));
+            }
+            ymax[j] = mx; yabs[j] = ma;
+        }
+        if (!acc16) { f.margin = margin; return f; }
+        // FP16 accumulation bound
+        const uint32_t nk = (L + 3) / 4;
+        std::vector<double> pre(nk + 1, 0.0), suf(nk + 1, 0.0);
+        for (uint32_t k = 1; k <= nk; k++) { pre[k] = pre[k - 1]; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) pre[k] += ymax[j]; }
+        for (uint32_t k = nk; k-- > 0;) { suf[k] = suf[k + 1]; for (uint32_t j = 4 * k; j < std::min(L, 4 * (k + 1)); j++) suf[k] += ymax[j]; }
+        double sum = 0, tot_abs = 0;
+        for (uint32_t k = 1; k <= nk; k++) {
+            double Ak = 0; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) Ak += yabs[j];
+            const double Bprev = (k == 1) ? 0.0 : std::max(std::max(pre[k - 1], suf[k - 1]), 0.0);
+            sum += Bprev + Ak; tot_abs += Ak;
+        }
+        if (tot_abs > 30000.0) { f.always = true; return f; }
+        const double need = 1e-3 + e1 + margin16_scale * std::ldexp(4.0 * sum, -10);
+        if (need <= margin) { f.margin = margin; return f; }
+        margin = need * 1.02;
+    }
+    f.margin = 1e9;           // did not converge: the caller falls back to FP32 accumulators
+    return f;
+}
+
+// Blocks with zero-contribution characters (lower case under the reference's BLAS-path semantics, sequence.cpp:312-319)
+// use a second image: the weights are NOT shifted by a threshold share (a masked position must add exactly 0); instead
+// one extra leading MMA step adds the bias  b = fp16_up(-(thr - margin))  to every window through a constant one-hot
+// operand.  acc = b + sum y_j >= score - thr + margin as before, for either sign of the threshold, and a fully masked
+// window gets acc = b < 0 instead of a spurious candidate.  FP16 accumulation: D_0 = b exactly; for a true hit the
+// partial sum after position step k lies in [-R_k, b + M_k] with M_k / R_k built from max(y, 0) (a masked position
+// contributes 0), so |D_k| <= max(R_k, |b| + M_k) and the same per-add ulp bound applies.
+Folded fold_col_z(const float4* wc, uint32_t L, float thr, bool acc16, double margin16_scale)
+{
+    Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false; f.bias = 0;
+    double A = 0;
+    bool finite = std::isfinite(thr);
+    std::vector<double> ymax(L), ymin(L), yabs(L);
+    for (uint32_t j = 0; j < L; j++) {
+        const float4 v = wc[j];
+        const float a4[4] = {v.x, v.y, v.z, v.w};
+        double m = 0, mx = 0, mn = 0, ma = 0;              // mx / mn start at 0: the masked contribution
+        for (uint32_t o = 0; o < 4; o++) {
+            if (!std::isfinite(a4[o])) { finite = false; continue; }
+            m = std::max(m, std::fabs((double)a4[o]));
+            if (std::fabs((double)a4[o]) > 30000.0) { finite = false; continue; }
+            const uint16_t h = half_round_up((double)a4[o]);
+            f.y[4 * j + o] = h;
+            __half hh; std::memcpy(&hh, &h, 2);
+            const double yr = (double)__half2float(hh);
+            mx = std::max(mx, yr); mn = std::min(mn, yr); ma = std::max(ma, std::fabs(yr));
+        }
+        A += m; ymax[j] = mx; ymin[j] = mn; yabs[j] = ma;
+    }
+    if (!finite || std::fabs((double)thr) > 30000.0) { f.always = true; return f; }
+    const double e1 = (L - 1) * std::ldexp(A, -24);
+    double margin = 1e-3 + e1 + L * std::ldexp(A + std::fabs((double)thr) + 1.0, -18);
+    const uint32_t nk = (L + 3) / 4;
+    // prefix maxima / minima and suffix maxima of the position sums at the step boundaries
+    std::vector<double> pre(nk + 1, 0.0), pmin(nk + 1, 0.0), suf(nk + 1, 0.0);
+    for (uint32_t k = 1; k <= nk; k++) {
+        pre[k] = pre[k - 1]; pmin[k] = pmin[k - 1];
+        for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) { pre[k] += ymax[j]; pmin[k] += ymin[j]; }
+    }
+    for (uint32_t k = nk; k-- > 0;) { suf[k] = suf[k + 1]; for (uint32_t j = 4 * k; j < std::min(L, 4 * (k + 1)); j++) suf[k] += ymax[j]; }
+    for (int iter = 0; iter < 6; iter++) {
+        f.bias = half_round_up(-((double)thr - margin));
+        f.margin = margin;
+        if (!acc16) return f;
+        __half hb; std::memcpy(&hb, &f.bias, 2);
+        const double b = (double)__half2float(hb);
+        double sum = 0;
+        for (uint32_t k = 1; k <= nk; k++) {
+            double Ak = 0; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) Ak += yabs[j];
+            // D_{k-1} lies in [max(-R, b + Pmin), b + Pmax] for a window that ends up >= 0
+            const double hi = b + pre[k - 1], lo = std::max(-suf[k - 1], b + pmin[k - 1]);
+            sum += std::max(std::fabs(hi), std::fabs(lo)) + Ak;
+        }
+        const double need = 1e-3 + e1 + margin16_scale * std::ldexp(4.0 * sum, -10);
+        if (need <= margin) return f;
+        margin = need * 1.02;
+    }
+    f.margin = 1e9;           // did not converge: FP32 accumulators for this tile
+    return f;
+}
+
+// INT8 operands (filter_tc_kernel<.., I8 = true>: eight positions per MMA, exact S32 accumulation).  With x_j the FP32
+// weights a window picks, S their real sum and s the reference's in-order FP32 sum (|s - S| <= e1), a hit s >= thr has
+// S >= thr' = thr - e1 - 1e-3.  The integer weights are  q_j[b] = max(-127, ceil(scale * (x_j[b] - share_j)))  with
+// sum_j share_j = thr':  acc = sum q_j >= scale * (S - thr') >= 0 -- rounding up and clamping up can only ADD candidates,
+// so no accumulation margin is needed at all; what it costs is an overshoot of < 1 / scale per position.
+//   share_j = best_j - c, c = slack / L, slack = sum_j best_j - thr'  (every position's best letter gets the same value c),
+//   scale = 127 / max(c, slack - c + 1/8):  a letter that loses more than the whole slack kills a window on its own; it may
+//   clamp at -127, everything milder is represented to 1 / scale.  |acc| <= 127 L < 2^15.
+// zmode (blocks with zero-contribution characters): unshifted weights q = ceil(scale * x), the bias step adds
+//   B = max(-4064, ceil(-scale * thr')) spread over the 32 K rows of one MMA; a masked position contributes exactly 0;
+//   slack is taken over max(best_j, 0).  Returns the worst-case overshoot L / scale (score units) as `margin`.
+Folded fold_col_i8(const float4* wc, uint32_t L, float thr, int zmode)
+{
+    Folded f; f.q.assign(4 * L, 0); f.margin = 0; f.always = false;
+    double A = 0, smax = 0, pmax = 0;
+    bool finite = std::isfinite(thr);
+    std::vector<double> best(L);
+    for (uint32_t j = 0; j < L; j++) {
+        const float4 v = wc[j];
+        const float a4[4] = {v.x, v.y, v.z, v.w};
+        double m = 0, b = -1e300;
+        for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); b = std::max(b, (double)a); }
+        A += m; best[j] = zmode ? std::max(b, 0.0) : b; smax += best[j]; pmax = std::max(pmax, b);
+    }
+    if (!finite || A > 1e6 || std::fabs((double)thr) > 1e6) { f.always = true; return f; }
+    const double thrp = (double)thr - (L - 1) * std::ldexp(A, -24) - 1e-3;
+    const double slack = smax - thrp;
+    if (slack < 0) { f.never = true; return f; }                   // no window can reach the threshold
+    const double c = slack / L;
+    const double scale = zmode ? 127.0 / std::max(std::max(pmax, 0.0) + 1e-9, slack + 0.125)
+                               : 127.0 / std::max(c + 1e-9, slack - c + 0.125);
+    if (!(scale > 1e-3) || L / scale > 64.0) { f.always = true; f.margin = 1e9; return f; }      // threshold far below the best score: INT8 cannot resolve it (auto mode then keeps FP16 operands)
+    for (uint32_t j = 0; j < L; j++) {
+        const float4 v = wc[j];
+        const float a4[4] = {v.x, v.y, v.z, v.w};
+        const double share = zmode ? 0.0 : best[j] - c;
+        for (uint32_t o = 0; o < 4; o++) {
+            const double q = std::ceil(scale * ((double)a4[o] - share));
+            f.q[4 * j + o] = (int8_t)std::min(127.0, std::max(-127.0, q));      // q <= 127 by the choice of scale (min: guards the last ulp)
+            if (q > 127.0) { f.always = true; f.margin = 1e9; return f; }
+        }
+    }
+    if (zmode) {
+        const double b = std::ceil(-scale * thrp);
+        if (b > 4064.0) { f.always = true; f.margin = 1e9; return f; }
+        f.qbias = (int32_t)std::max(-4064.0, b);
+    }
+    f.margin = L / scale;
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Tensor-core tiling: sorted columns are cut into tiles of <= 256 columns (N padded to 32) minimising
 //   sum over tiles of  max(MMA cycles, epilogue cycles)  per 128-window tile.  This replaces the reference's
 // greedy zero-area tiling of P (MotifContainer::generateMatrixTiles, motif.cpp:482-540) -- like there, the
@@ -216,184 +399,10 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     }
     ctx->gather_smem = kGatherSmemW + max_meta;
 
-    // ---- tensor-core tiles and the FP16 B image ----
-    // Conservative folding.  With x_j the FP32 weights picked by a window (exact in-order FP32 score s = sum x_j + e1,
-    // |e1| <= (L-1) 2^-24 A, A = sum_j max|x_j|), the tensor accumulator is  acc = sum y_j + e2  with
-    //     y_j = fp16_up(x_j - thr'/L) >= x_j - thr'/L,      thr' = thr - margin,
-    // so  s >= thr  =>  acc >= margin - |e1| - |e2|, and the filter is exact-recall when margin >= |e1| + |e2|.
-    //   FP32 accumulators: |e2| <= L 2^-18 (A'+1)  (generous for any FP32-ish accumulate, A' = sum_j max|y_j|).
-    //   FP16 accumulators: D is rounded to FP16 after every MMA (4 positions).  For a window that is a true hit
-    //     (final sum >= 0) the partial sum after step k lies in [-R_k, M_k] (R_k = largest possible remaining sum,
-    //     M_k = largest possible prefix), so |D_k| <= B_k = max(M_k, R_k, 0).  Allowing a rounding of one FP16 ulp
-    //     (2^-10 relative: covers round-to-nearest and truncation) on EVERY internal add of the 4 products and the
-    //     old accumulator:  |e2| <= 2^-10 * 4 * sum_k (B_{k-1} + A_k),  A_k = sum of max|y_j| over the step.
-    struct Folded { std::vector<uint16_t> y; double margin; bool always; uint16_t bias = 0;
-                    std::vector<int8_t> q; int32_t qbias = 0; bool never = false; };      // INT8 operands (fold_i8)
-    auto fold = [&](uint32_t sc, bool acc16) {
-        const uint32_t L = len[sc];
-        Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false;
-        double A = 0;
-        bool finite = std::isfinite(thr_s[sc]);
-        for (uint32_t j = 0; j < L; j++) {
-            const float4 v = w[woff[sc] + j];
-            const float a4[4] = {v.x, v.y, v.z, v.w};
-            double m = 0;
-            for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); }
-            A += m;
-        }
-        if (!finite) { f.always = true; return f; }
-        const double e1 = (L - 1) * std::ldexp(A, -24);
-        double margin = 1e-3 + e1 + L * std::ldexp(A + std::fabs((double)thr_s[sc]) + 1.0, -18);
-        for (int iter = 0; iter < 6; iter++) {
-            const double share = ((double)thr_s[sc] - margin) / L;
-            std::vector<double> ymax(L), yabs(L);
-            for (uint32_t j = 0; j < L; j++) {
-                const float4 v = w[woff[sc] + j];
-                const float a4[4] = {v.x, v.y, v.z, v.w};
-                double mx = -1e300, ma = 0;
-                for (uint32_t o = 0; o < 4; o++) {
-                    const double y = (double)a4[o] - share;
-                    if (std::fabs(y) > 30000.0) { f.always = true; return f; }
-                    const uint16_t h = half_round_up(y);
-                    f.y[4 * j + o] = h;
-                    __half hh; std::memcpy(&hh, &h, 2);
-                    const double yr = (double)__half2float(hh);
-                    mx = std::max(mx, yr); ma = std::max(ma, std::fabs(yr));
-                }
-                ymax[j] = mx; yabs[j] = ma;
-            }
-            if (!acc16) { f.margin = margin; return f; }
-            // FP16 accumulation bound
-            const uint32_t nk = (L + 3) / 4;
-            std::vector<double> pre(nk + 1, 0.0), suf(nk + 1, 0.0);
-            for (uint32_t k = 1; k <= nk; k++) { pre[k] = pre[k - 1]; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) pre[k] += ymax[j]; }
-            for (uint32_t k = nk; k-- > 0;) { suf[k] = suf[k + 1]; for (uint32_t j = 4 * k; j < std::min(L, 4 * (k + 1)); j++) suf[k] += ymax[j]; }
-            double sum = 0, tot_abs = 0;
-            for (uint32_t k = 1; k <= nk; k++) {
-                double Ak = 0; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) Ak += yabs[j];
-                const double Bprev = (k == 1) ? 0.0 : std::max(std::max(pre[k - 1], suf[k - 1]), 0.0);
-                sum += Bprev + Ak; tot_abs += Ak;
-            }
-            if (tot_abs > 30000.0) { f.always = true; return f; }
-            const double need = 1e-3 + e1 + ctx->margin16_scale * std::ldexp(4.0 * sum, -10);
-            if (need <= margin) { f.margin = margin; return f; }
-            margin = need * 1.02;
-        }
-        f.margin = 1e9;           // did not converge: the caller falls back to FP32 accumulators
-        return f;
-    };
-
-    // Blocks with zero-contribution characters (lower case under the reference's BLAS-path semantics, sequence.cpp:312-319)
-    // use a second image: the weights are NOT shifted by a threshold share (a masked position must add exactly 0); instead
-    // one extra leading MMA step adds the bias  b = fp16_up(-(thr - margin))  to every window through a constant one-hot
-    // operand.  acc = b + sum y_j >= score - thr + margin as before, for either sign of the threshold, and a fully masked
-    // window gets acc = b < 0 instead of a spurious candidate.  FP16 accumulation: D_0 = b exactly; for a true hit the
-    // partial sum after position step k lies in [-R_k, b + M_k] with M_k / R_k built from max(y, 0) (a masked position
-    // contributes 0), so |D_k| <= max(R_k, |b| + M_k) and the same per-add ulp bound applies.
-    auto fold_z = [&](uint32_t sc, bool acc16) {
-        const uint32_t L = len[sc];
-        Folded f; f.y.assign(4 * L, 0); f.margin = 0; f.always = false; f.bias = 0;
-        double A = 0;
-        bool finite = std::isfinite(thr_s[sc]);
-        std::vector<double> ymax(L), ymin(L), yabs(L);
-        for (uint32_t j = 0; j < L; j++) {
-            const float4 v = w[woff[sc] + j];
-            const float a4[4] = {v.x, v.y, v.z, v.w};
-            double m = 0, mx = 0, mn = 0, ma = 0;              // mx / mn start at 0: the masked contribution
-            for (uint32_t o = 0; o < 4; o++) {
-                if (!std::isfinite(a4[o])) { finite = false; continue; }
-                m = std::max(m, std::fabs((double)a4[o]));
-                if (std::fabs((double)a4[o]) > 30000.0) { finite = false; continue; }
-                const uint16_t h = half_round_up((double)a4[o]);
-                f.y[4 * j + o] = h;
-                __half hh; std::memcpy(&hh, &h, 2);
-                const double yr = (double)__half2float(hh);
-                mx = std::max(mx, yr); mn = std::min(mn, yr); ma = std::max(ma, std::fabs(yr));
-            }
-            A += m; ymax[j] = mx; ymin[j] = mn; yabs[j] = ma;
-        }
-        if (!finite || std::fabs((double)thr_s[sc]) > 30000.0) { f.always = true; return f; }
-        const double e1 = (L - 1) * std::ldexp(A, -24);
-        double margin = 1e-3 + e1 + L * std::ldexp(A + std::fabs((double)thr_s[sc]) + 1.0, -18);
-        const uint32_t nk = (L + 3) / 4;
-        // prefix maxima / minima and suffix maxima of the position sums at the step boundaries
-        std::vector<double> pre(nk + 1, 0.0), pmin(nk + 1, 0.0), suf(nk + 1, 0.0);
-        for (uint32_t k = 1; k <= nk; k++) {
-            pre[k] = pre[k - 1]; pmin[k] = pmin[k - 1];
-            for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) { pre[k] += ymax[j]; pmin[k] += ymin[j]; }
-        }
-        for (uint32_t k = nk; k-- > 0;) { suf[k] = suf[k + 1]; for (uint32_t j = 4 * k; j < std::min(L, 4 * (k + 1)); j++) suf[k] += ymax[j]; }
-        for (int iter = 0; iter < 6; iter++) {
-            f.bias = half_round_up(-((double)thr_s[sc] - margin));
-            f.margin = margin;
-            if (!acc16) return f;
-            __half hb; std::memcpy(&hb, &f.bias, 2);
-            const double b = (double)__half2float(hb);
-            double sum = 0;
-            for (uint32_t k = 1; k <= nk; k++) {
-                double Ak = 0; for (uint32_t j = 4 * (k - 1); j < std::min(L, 4 * k); j++) Ak += yabs[j];
-                // D_{k-1} lies in [max(-R, b + Pmin), b + Pmax] for a window that ends up >= 0
-                const double hi = b + pre[k - 1], lo = std::max(-suf[k - 1], b + pmin[k - 1]);
-                sum += std::max(std::fabs(hi), std::fabs(lo)) + Ak;
-            }
-            const double need = 1e-3 + e1 + ctx->margin16_scale * std::ldexp(4.0 * sum, -10);
-            if (need <= margin) return f;
-            margin = need * 1.02;
-        }
-        f.margin = 1e9;           // did not converge: FP32 accumulators for this tile
-        return f;
-    };
-
-    // INT8 operands (filter_tc_kernel<.., I8 = true>: eight positions per MMA, exact S32 accumulation).  With x_j the FP32
-    // weights a window picks, S their real sum and s the reference's in-order FP32 sum (|s - S| <= e1), a hit s >= thr has
-    // S >= thr' = thr - e1 - 1e-3.  The integer weights are  q_j[b] = max(-127, ceil(scale * (x_j[b] - share_j)))  with
-    // sum_j share_j = thr':  acc = sum q_j >= scale * (S - thr') >= 0 -- rounding up and clamping up can only ADD candidates,
-    // so no accumulation margin is needed at all; what it costs is an overshoot of < 1 / scale per position.
-    //   share_j = best_j - c, c = slack / L, slack = sum_j best_j - thr'  (every position's best letter gets the same value c),
-    //   scale = 127 / max(c, slack - c + 1/8):  a letter that loses more than the whole slack kills a window on its own; it may
-    //   clamp at -127, everything milder is represented to 1 / scale.  |acc| <= 127 L < 2^15.
-    // zmode (blocks with zero-contribution characters): unshifted weights q = ceil(scale * x), the bias step adds
-    //   B = max(-4064, ceil(-scale * thr')) spread over the 32 K rows of one MMA; a masked position contributes exactly 0;
-    //   slack is taken over max(best_j, 0).  Returns the worst-case overshoot L / scale (score units) as `margin`.
-    auto fold_i8 = [&](uint32_t sc, int zmode) {
-        const uint32_t L = len[sc];
-        Folded f; f.q.assign(4 * L, 0); f.margin = 0; f.always = false;
-        double A = 0, smax = 0, pmax = 0;
-        bool finite = std::isfinite(thr_s[sc]);
-        std::vector<double> best(L);
-        for (uint32_t j = 0; j < L; j++) {
-            const float4 v = w[woff[sc] + j];
-            const float a4[4] = {v.x, v.y, v.z, v.w};
-            double m = 0, b = -1e300;
-            for (float a : a4) { if (!std::isfinite(a)) finite = false; m = std::max(m, std::fabs((double)a)); b = std::max(b, (double)a); }
-            A += m; best[j] = zmode ? std::max(b, 0.0) : b; smax += best[j]; pmax = std::max(pmax, b);
-        }
-        if (!finite || A > 1e6 || std::fabs((double)thr_s[sc]) > 1e6) { f.always = true; return f; }
-        const double thrp = (double)thr_s[sc] - (L - 1) * std::ldexp(A, -24) - 1e-3;
-        const double slack = smax - thrp;
-        if (slack < 0) { f.never = true; return f; }                   // no window can reach the threshold
-        const double c = slack / L;
-        const double scale = zmode ? 127.0 / std::max(std::max(pmax, 0.0) + 1e-9, slack + 0.125)
-                                   : 127.0 / std::max(c + 1e-9, slack - c + 0.125);
-        if (!(scale > 1e-3) || L / scale > 64.0) { f.always = true; f.margin = 1e9; return f; }      // threshold far below the best score: INT8 cannot resolve it (auto mode then keeps FP16 operands)
-        for (uint32_t j = 0; j < L; j++) {
-            const float4 v = w[woff[sc] + j];
-            const float a4[4] = {v.x, v.y, v.z, v.w};
-            const double share = zmode ? 0.0 : best[j] - c;
-            for (uint32_t o = 0; o < 4; o++) {
-                const double q = std::ceil(scale * ((double)a4[o] - share));
-                f.q[4 * j + o] = (int8_t)std::min(127.0, std::max(-127.0, q));      // q <= 127 by the choice of scale (min: guards the last ulp)
-                if (q > 127.0) { f.always = true; f.margin = 1e9; return f; }
-            }
-        }
-        if (zmode) {
-            const double b = std::ceil(-scale * thrp);
-            if (b > 4064.0) { f.always = true; f.margin = 1e9; return f; }
-            f.qbias = (int32_t)std::max(-4064.0, b);
-        }
-        f.margin = L / scale;
-        return f;
-    };
+    // ---- tensor-core tiles and the FP16 B image ----  (the per-column folding rules: fold_col / fold_col_z / fold_col_i8 above)
+    auto fold    = [&](uint32_t sc, bool acc16) { return fold_col(&w[woff[sc]], len[sc], thr_s[sc], acc16, ctx->margin16_scale); };
+    auto fold_z  = [&](uint32_t sc, bool acc16) { return fold_col_z(&w[woff[sc]], len[sc], thr_s[sc], acc16, ctx->margin16_scale); };
+    auto fold_i8 = [&](uint32_t sc, int zmode) { return fold_col_i8(&w[woff[sc]], len[sc], thr_s[sc], zmode); };
 
     // Accumulator type PER TILE: FP16 accumulators (half the epilogue work) where every column of the tile keeps its margin
     // <= 2 score units, FP32 otherwise -- a few long or extreme motifs then cost their own tile, not the whole set.
@@ -1363,6 +1372,30 @@ int b200scan_debug_trace(b200scan_ctx* ctx, unsigned long long* out, int n)
     return B200SCAN_OK;
 }
 #endif
+
+// Diagnostic, no device needed (tests/test_fold.py): the filter weights build_motifs derives for ONE column.  w = 4 * L FP32 weights
+// (ACGT per position), kind = 8 (INT8 operands), 16 or 32 (FP16 operands with FP16 / FP32 accumulators), zmode = 1 for the image
+// used on blocks with zero-contribution characters.  weights[4 * L] receive the operand values as real numbers, *bias the bias
+// step's value (zmode), *margin the safety margin (INT8: the worst-case overshoot), *flags bit 0 "always a candidate", bit 1
+// "no window can reach the threshold".
+int b200scan_debug_fold(const float* w, int32_t L, float thr, int32_t kind, int32_t zmode, double margin16_scale,
+                        double* weights, double* bias, double* margin, int32_t* flags)
+{
+    if (!w || L < 1 || L > B200SCAN_MAX_MOTIF_LEN || (kind != 8 && kind != 16 && kind != 32) || !weights || !bias || !margin || !flags)
+        return B200SCAN_EINVAL;
+    std::vector<float4> wc((size_t)L);
+    for (int32_t j = 0; j < L; j++) wc[(size_t)j] = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    const Folded f = kind == 8 ? fold_col_i8(wc.data(), (uint32_t)L, thr, zmode)
+                   : zmode ? fold_col_z(wc.data(), (uint32_t)L, thr, kind == 16, margin16_scale)
+                           : fold_col(wc.data(), (uint32_t)L, thr, kind == 16, margin16_scale);
+    *flags = (f.always ? 1 : 0) | (f.never ? 2 : 0);
+    *margin = f.margin;
+    auto half = [](uint16_t h) { __half hh; std::memcpy(&hh, &h, 2); return (double)__half2float(hh); };
+    *bias = kind == 8 ? (double)f.qbias : (zmode ? half(f.bias) : 0.0);
+    for (int32_t i = 0; i < 4 * L; i++)
+        weights[i] = kind == 8 ? (f.q.size() == (size_t)(4 * L) ? (double)f.q[(size_t)i] : 0.0) : (f.y.size() == (size_t)(4 * L) ? half(f.y[(size_t)i]) : 0.0);
+    return B200SCAN_OK;
+}
 
 int b200scan_flush_l2(b200scan_ctx* ctx)
 {
