@@ -397,7 +397,27 @@ struct Job {
     shared_ptr<const GroupParams> group;
 };
 
-struct MotifText { string name; uint64_t size = 0; bool revComp = false; };
+// A column's share of an occurrence line (pwmscan.cpp:88-95):  <sequence> mid <pos> \t <pos + size> \t <score> tail
+struct MotifText {
+    string name; uint64_t size = 0; bool revComp = false;
+    string mid;                                    // "\tblamm\t<motif>\t"
+    char tail[8];                                  // "\t+\t.\t.\n" or "\t-\t.\t.\n" (7 characters) + one spare byte: one 8-byte store
+    MotifText(const string& n, uint64_t sz, bool rc) : name(n), size(sz), revComp(rc), mid("\tblamm\t" + n + "\t")
+    {
+        memcpy(tail, rc ? "\t-\t.\t.\n" : "\t+\t.\t.\n", 8);             // (the 8th byte is the literal's terminator; the next line overwrites it)
+    }
+};
+// One line at p (the caller's buffer has room for the worst case, formatRange / formatBuckets); returns the end of the line.
+inline char* formatLine(char* p, const string& seqName, const MotifText& m, uint64_t seqPos, float score)
+{
+    memcpy(p, seqName.data(), seqName.size()); p += seqName.size();
+    memcpy(p, m.mid.data(), m.mid.size()); p += m.mid.size();
+    p = to_chars(p, p + 24, (unsigned long long)seqPos).ptr; *p++ = '\t';
+    p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size)).ptr; *p++ = '\t';
+    p += formatScore(p, score);
+    memcpy(p, m.tail, 8);
+    return p + 7;
+}
 // Buffers for formatted text are recycled: a fresh multi-megabyte allocation is mapped and unmapped by malloc every time, and every
 // page of it faults (and is zeroed by the kernel) again -- as much memory traffic as the formatting itself.
 class TextPool {
@@ -524,22 +544,16 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, Tex
     // worst-case line: names + 2 positions of <= 20 digits + score (<= 16) + 5 tabs + strand + "\t.\t.\n"
     char* const base = text.alloc(hits.size() * (job.group->maxNameLen + 96) + 64);
     char* p = base;
+    const vector<string>& names = job.group->species->seqNames;
     size_t f = 0;
+    const string* sn = nullptr;                   // name of fragment f's record, looked up when the fragment changes
     for (const auto& h : hits) {
-        while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= h.pos) f++;
+        if (!sn || (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= h.pos)) {
+            while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= h.pos) f++;
+            sn = &names.at(job.frags[f].seqIdx);                                     // (.at: a record the .dict does not know ends the run with an error)
+        }
         const Fragment& fr = job.frags[f];
-        const uint64_t seqPos = fr.seqPos + (h.pos - fr.streamPos);
-        const MotifText& m = sh.mtext[h.col];
-        const string& sn = job.group->species->seqNames.at(fr.seqIdx);
-        memcpy(p, sn.data(), sn.size()); p += sn.size();
-        memcpy(p, "\tblamm\t", 7); p += 7;
-        memcpy(p, m.name.data(), m.name.size()); p += m.name.size();
-        *p++ = '\t';
-        p = to_chars(p, p + 24, (unsigned long long)seqPos).ptr; *p++ = '\t';
-        p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size)).ptr; *p++ = '\t';
-        p += formatScore(p, h.score);
-        *p++ = '\t'; *p++ = m.revComp ? '-' : '+';
-        memcpy(p, "\t.\t.\n", 5); p += 5;
+        p = formatLine(p, *sn, sh.mtext[h.col], fr.seqPos + (h.pos - fr.streamPos), h.score);
     }
     text.n = (size_t)(p - base);
 }
@@ -641,25 +655,19 @@ void formatBuckets(const ScanShared& sh, const Job& job, const b200scan_hit8* hi
     const uint64_t n = bucketStart[b1] - bucketStart[b0];
     char* const base = text.alloc(n * (job.group->maxNameLen + 96) + 64);
     char* p = base;
+    const vector<string>& names = job.group->species->seqNames;
     size_t f = 0;
+    const string* sn = nullptr;                   // name of fragment f's record, looked up when the fragment changes
     for (uint64_t b = b0; b < b1; b++) {
+        const uint64_t bucketPos = posOffset + (b << B200SCAN_BUCKET_SHIFT);
         for (uint32_t i = bucketStart[b]; i < bucketStart[b + 1]; i++) {
-            const uint64_t pos = posOffset + (b << B200SCAN_BUCKET_SHIFT) + (hits[i].key >> 24);
-            const uint32_t col = hits[i].key & 0xFFFFFFu;
-            while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= pos) f++;
+            const uint64_t pos = bucketPos + (hits[i].key >> 24);
+            if (!sn || (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= pos)) {
+                while (f + 1 < job.frags.size() && job.frags[f + 1].streamPos <= pos) f++;
+                sn = &names.at(job.frags[f].seqIdx);                                 // (.at: a record the .dict does not know ends the run with an error)
+            }
             const Fragment& fr = job.frags[f];
-            const uint64_t seqPos = fr.seqPos + (pos - fr.streamPos);
-            const MotifText& m = sh.mtext[col];
-            const string& sn = job.group->species->seqNames.at(fr.seqIdx);
-            memcpy(p, sn.data(), sn.size()); p += sn.size();
-            memcpy(p, "\tblamm\t", 7); p += 7;
-            memcpy(p, m.name.data(), m.name.size()); p += m.name.size();
-            *p++ = '\t';
-            p = to_chars(p, p + 24, (unsigned long long)seqPos).ptr; *p++ = '\t';
-            p = to_chars(p, p + 24, (unsigned long long)(seqPos + m.size)).ptr; *p++ = '\t';
-            p += formatScore(p, hits[i].score);
-            *p++ = '\t'; *p++ = m.revComp ? '-' : '+';
-            memcpy(p, "\t.\t.\n", 5); p += 5;
+            p = formatLine(p, *sn, sh.mtext[hits[i].key & 0xFFFFFFu], fr.seqPos + (pos - fr.streamPos), hits[i].score);
         }
     }
     text.n = (size_t)(p - base);
@@ -876,7 +884,7 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
     WorkPool workPool(threads);
     auto openOut = [](const string& path) { return open(path.c_str(), O_CREAT | O_TRUNC | O_RDWR, 0644); };
     auto fillShared = [&](ScanShared& sh, int fd) {
-        for (const auto& m : ms.motifs) sh.mtext.push_back({m.name, (uint64_t)m.size(), m.revComp});
+        for (const auto& m : ms.motifs) sh.mtext.emplace_back(m.name, (uint64_t)m.size(), m.revComp);
         sh.fd = fd; sh.pool = &workPool;
         sh.chooseWriter();
     };
@@ -1101,7 +1109,7 @@ int runScan(int argc, char** argv)
     // chunks in flight when it loads the next group's motifs.
     WorkPool workPool(numThreads);
     ScanShared sh;
-    for (const auto& m : mc.motifs) sh.mtext.push_back({m.name, (uint64_t)m.size(), m.revComp});
+    for (const auto& m : mc.motifs) sh.mtext.emplace_back(m.name, (uint64_t)m.size(), m.revComp);
     sh.fd = outFd; sh.pool = &workPool;
     sh.chooseWriter();
     sh.maxQueue = (size_t)nDev + 1;

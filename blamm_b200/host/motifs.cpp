@@ -10,6 +10,9 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace blamm {
 
@@ -407,6 +410,26 @@ void MotifSet::theoreticalHistogram(const Motif& m, const std::array<float, 4>& 
 // dropped.  The comparisons against the double constants 1e-4 .. 1e-1 are exact for float inputs (no float lies between
 // such a constant and the decimal it approximates).  Everything else (zero, exponent notation, non-finite) goes to
 // std::to_chars / snprintf.  tests/test_host.py checks the function against printf on random bit patterns, ties and edges.
+namespace {
+// "000" .. "999", four bytes apart: the six significant digits come out of two table reads
+struct Digits3 {
+    char d[1000][4];
+    Digits3() { for (int i = 0; i < 1000; i++) { d[i][0] = (char)('0' + i / 100); d[i][1] = (char)('0' + i / 10 % 10); d[i][2] = (char)('0' + i % 10); d[i][3] = 0; } }
+};
+const Digits3 kDigits3;
+
+// y in [1e5, 1e6], exact in double: round to nearest, ties to even (what printf does with the exact binary value).
+// x86-64: CVTSD2SI under the default MXCSR rounding mode; elsewhere nearbyint under the default rounding mode.
+inline uint32_t roundEven(double y)
+{
+#if defined(__SSE2__)
+    return (uint32_t)_mm_cvtsd_si32(_mm_set_sd(y));
+#else
+    return (uint32_t)std::nearbyint(y);
+#endif
+}
+}
+
 int formatScore(char* dst, float v)
 {
     static const double kPow10[10] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9};
@@ -414,24 +437,30 @@ int formatScore(char* dst, float v)
     if (a >= 1e-4 && a < 1e6) {
         int X = a >= 1e2 ? (a >= 1e4 ? (a >= 1e5 ? 5 : 4) : (a >= 1e3 ? 3 : 2))
                          : (a >= 1e0 ? (a >= 1e1 ? 1 : 0) : (a >= 1e-2 ? (a >= 1e-1 ? -1 : -2) : (a >= 1e-3 ? -3 : -4)));
-        uint32_t r = (uint32_t)std::nearbyint(a * kPow10[5 - X]);           // 100000 .. 1000000
+        uint32_t r = roundEven(a * kPow10[5 - X]);                          // 100000 .. 1000000
         if (r >= 1000000u) { r = 100000u; X++; }                            // 999999.5 -> 1.00000 x 10^(X+1)
         if (X <= 5) {
-            char dig[6];
-            for (int i = 5; i >= 0; i--) { dig[i] = (char)('0' + r % 10); r /= 10; }
+            const uint32_t hi = r / 1000u, lo = r - 1000u * hi;
+            char dig[16] = {};                                               // (16: the 8-byte copies below start at up to dig + 6)
+            std::memcpy(dig, kDigits3.d[hi], 4);
+            std::memcpy(dig + 3, kDigits3.d[lo], 4);
             int nd = 6;
             while (nd > 1 && dig[nd - 1] == '0') nd--;                      // significant digits left after dropping trailing zeros
             char* p = dst;
             if (std::signbit(v)) *p++ = '-';
             if (X >= 0) {
-                for (int i = 0; i <= X; i++) *p++ = dig[i];                 // (zeros inside the integer part are digits, not trailing zeros)
-                if (nd > X + 1) { *p++ = '.'; for (int i = X + 1; i < nd; i++) *p++ = dig[i]; }
-            } else {
-                *p++ = '0'; *p++ = '.';
-                for (int i = -1; i > X; i--) *p++ = '0';
-                for (int i = 0; i < nd; i++) *p++ = dig[i];
+                // all six digits, then the fraction moved one place right behind the point (the caller's buffer has room: a score
+                // takes at most 16 characters and every writer leaves 32); zeros inside the integer part are digits, not trailing zeros
+                std::memcpy(p, dig, 8);
+                if (nd <= X + 1) return (int)(p - dst) + X + 1;
+                p[X + 1] = '.';
+                std::memcpy(p + X + 2, dig + X + 1, 8);
+                return (int)(p - dst) + nd + 1;
             }
-            return (int)(p - dst);
+            *p++ = '0'; *p++ = '.';
+            for (int i = -1; i > X; i--) *p++ = '0';
+            std::memcpy(p, dig, 8);
+            return (int)(p - dst) + nd;
         }
     }
     if (!std::isfinite(v)) return snprintf(dst, 32, "%g", (double)v);
