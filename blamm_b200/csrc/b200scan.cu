@@ -418,8 +418,8 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
     double margin_sum = 0;
     // zmode 0: blocks without zero-contribution characters; zmode 1: with (bias step first, see fold_z)
     auto build_image = [&](int zmode, std::vector<TcTile>& tt, std::vector<uint8_t>& bimg, uint32_t& n16, uint32_t& n8) {
-        std::vector<Folded> folded(n_cols);
-        for (int32_t sc = 0; sc < n_cols; sc++) folded[sc] = zmode ? fold_z((uint32_t)sc, try16) : fold((uint32_t)sc, try16);
+        std::vector<Folded> folded(n_cols);                    // filled tile by tile: the FP16 folds (3/4 of the host time of a set_motifs when
+                                                               // computed for every column) only for tiles that do not end up on INT8 operands
         std::vector<uint32_t> tile_acc16(cuts.size(), 0);      // 1 FP16 accumulators, 0 FP32, 2 INT8 operands
         for (size_t ti = 0; ti < cuts.size(); ti++) {
             if (try8) {
@@ -435,6 +435,7 @@ int build_motifs(b200scan_ctx* ctx, const float* P, int32_t ldp, int32_t n_cols,
                     continue;
                 }
             }
+            for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++) folded[sc] = zmode ? fold_z(sc, try16) : fold(sc, try16);
             bool ok = try16;
             if (ok && ctx->acc_pref != 16)
                 for (uint32_t sc = cuts[ti].first; sc < cuts[ti].second; sc++)
