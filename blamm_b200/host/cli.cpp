@@ -206,18 +206,23 @@ int runHist(int argc, char** argv)
                 return b200scan_create(&ctxs[(size_t)d], d, chunk + halo + 64, 1024) == B200SCAN_OK ? string() : string(b200scan_last_error(nullptr));
             }));
         string err;
+        const double tCreate = now();
         for (auto& m : made) { const string e = m.get(); if (!e.empty() && err.empty()) err = e; }
+        gTimer.add("hist -e: CUDA start-up (contexts of all GPUs)", now() - tCreate);
         if (!err.empty()) { destroyAll(); throw runtime_error("CUDA error: " + err); }
     }
     for (const auto& sp : sc.species) {
+        double tPhase = now();                      // BLAMM_B200_TIMING=1: the phases of the module on stderr
         cout << "Generating histograms for species: " << sp.name;
         sp.printNuclProb(settings.pseudocount);
         mc.generateMatrix(sp.nuclCounts, settings.pseudocount);
         const auto bg = sp.nuclProb(settings.pseudocount);
         vector<ScoreHistogram> hists;
         for (const auto& m : mc.motifs) hists.emplace_back(m.minScore(), m.maxScore(), numBins);
+        gTimer.add("hist: matrix P per group", now() - tPhase); tPhase = now();
         if (!empirical) {
             forEachMotif(mc.motifs.size(), [&](size_t i) { MotifSet::theoreticalHistogram(mc.motifs[i], bg, numBins, maxLength, hists[i]); });
+            gTimer.add("hist: theoretical spectra", now() - tPhase); tPhase = now();
         } else {
             // reference: FastaBatch(filenames, maxLength) + histThread (hist.cpp:95-160)
             const auto len = mc.colLen();
@@ -227,10 +232,13 @@ int runHist(int argc, char** argv)
             mutex qm; condition_variable qcv; deque<unique_ptr<HistJob>> q; bool done = false; string failure;
             auto worker = [&](b200scan_ctx* ctx) {
                 auto fail = [&](const string& e) { lock_guard<mutex> l(qm); if (failure.empty()) failure = e; qcv.notify_all(); };
+                double t0 = now();
                 if (b200scan_set_motifs(ctx, mc.P().data(), mc.ldp(), (int32_t)len.size(), len.data(), thr.data()) != B200SCAN_OK ||
                     b200scan_hist_begin(ctx, mn.data(), mx.data(), (uint32_t)numBins) != B200SCAN_OK) { fail(b200scan_last_error(ctx)); return; }
+                gTimer.add("hist -e: set_motifs + hist_begin (summed over GPUs)", now() - t0);
                 for (;;) {
                     unique_ptr<HistJob> job;
+                    t0 = now();
                     {
                         unique_lock<mutex> l(qm);
                         qcv.wait(l, [&] { return !q.empty() || done || !failure.empty(); });
@@ -238,8 +246,10 @@ int runHist(int argc, char** argv)
                         job = std::move(q.front()); q.pop_front();
                         qcv.notify_all();
                     }
+                    gTimer.add("hist -e: workers wait for chunks (summed over GPUs)", now() - t0); t0 = now();
                     if (b200scan_hist_block_ascii(ctx, job->chars.get(), job->nTotal, job->nPayload, job->fragStarts.data(), job->fragStarts.size(),
                                                   B200SCAN_LOWER_ZERO) != B200SCAN_OK) { fail(b200scan_last_error(ctx)); return; }
+                    gTimer.add("hist -e: hist_block (previous block's kernels + staging, summed over GPUs)", now() - t0);
                 }
             };
             vector<thread> workers;
@@ -270,6 +280,7 @@ int runHist(int argc, char** argv)
                 destroyAll();
                 throw;
             }
+            gTimer.add("hist -e: read FASTA + deal chunks (reader, incl. waiting for queue room)", now() - tPhase); tPhase = now();
             { lock_guard<mutex> l(qm); done = true; }
             qcv.notify_all();
             for (auto& w : workers) w.join();
@@ -282,12 +293,15 @@ int runHist(int argc, char** argv)
             }
             for (size_t i = 0; i < hists.size(); i++)
                 for (size_t b = 0; b < numBins; b++) hists[i].counts[b] = total[i * numBins + b];
+            gTimer.add("hist -e: last kernels + counters of all GPUs", now() - tPhase); tPhase = now();
         }
         forEachMotif(hists.size(), [&](size_t i) {
             hists[i].writeGNUPlot(histdir, "hist_" + sp.name + "_" + mc.motifs[i].name, mc.motifs[i].name + " (" + sp.name + ")");
         });
+        gTimer.add("hist: write the histogram files", now() - tPhase);
     }
     destroyAll();
+    gTimer.report();
     return EXIT_SUCCESS;
 }
 
