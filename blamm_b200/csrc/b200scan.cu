@@ -118,6 +118,10 @@ struct b200scan_ctx {
     // empirical histograms
     uint32_t hist_bins = 0;  unsigned long long* d_hist = nullptr;  float *d_hmin = nullptr, *d_hwid = nullptr;
     GatherTile* d_htiles = nullptr;  std::vector<GatherTile> htiles;  size_t hist_smem = 0;
+    int hist_kernel = 3;          // 3: gather_hist2_kernel (position-row weights, lanes count different columns at a time); 2: the same with
+                                  // match-aggregated counts; 1 / 0: gather_hist_kernel with / without aggregated counts (env
+                                  // B200SCAN_HIST_KERNEL: comparison and independent check)
+    HistTile2* d_htiles2 = nullptr;  std::vector<HistTile2> htiles2;
     std::vector<uint32_t> h_len_sorted, h_woff_sorted, h_orig_sorted;      // host copies of the sorted column metadata
 };
 
@@ -902,6 +906,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     if (const char* e = getenv("B200SCAN_PAIR")) c->pair_mode = atoi(e) != 0;
     if (const char* e = getenv("B200SCAN_MARGIN16_SCALE")) c->margin16_scale = atof(e);
     if (const char* e = getenv("B200SCAN_I8_MAX_OVERSHOOT")) c->i8_max_overshoot = atof(e);
+    if (const char* e = getenv("B200SCAN_HIST_KERNEL")) c->hist_kernel = std::max(0, std::min(3, atoi(e)));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(filter_tc_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     CUB(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGatherSmemW + 16384)));
@@ -961,7 +966,7 @@ void b200scan_destroy(b200scan_ctx* c)
     dfree(c->d_bucket_cnt); dfree(c->d_bucket_cursor); dfree(c->d_coarse_start); dfree(c->d_sort_tmp);
     dfree(c->d_w); dfree(c->d_woff); dfree(c->d_len); dfree(c->d_orig); dfree(c->d_thr);
     dfree(c->d_gtiles); dfree(c->d_ttiles); dfree(c->d_bimg); dfree(c->d_ttiles_z); dfree(c->d_bimg_z);
-    dfree(c->d_hist); dfree(c->d_hmin); dfree(c->d_hwid); dfree(c->d_htiles);
+    dfree(c->d_hist); dfree(c->d_hmin); dfree(c->d_hwid); dfree(c->d_htiles); dfree(c->d_htiles2);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1111,7 +1116,24 @@ int b200scan_hist_begin(b200scan_ctx* ctx, const float* col_min, const float* co
         mn[sc] = col_min[c];
         wid[sc] = (col_max[c] - col_min[c]) / (float)num_bins;        // ScoreHistogram ctor, motif.h:66
     }
-    dfree(ctx->d_hist); dfree(ctx->d_hmin); dfree(ctx->d_hwid); dfree(ctx->d_htiles);
+    // the same for gather_hist2_kernel: position rows of the tile's longest column (+ the zero row) for every column, padded to
+    // groups of kHist2U columns; 100 KB per CTA so that two CTAs share an SM (a column whose table alone exceeds that gets a
+    // tile of its own within the large budget)
+    std::vector<HistTile2> ht2;
+    if (ctx->hist_kernel >= 2) {
+        const size_t budget2 = 100 * 1024;
+        for (uint32_t sc = 0; sc < n;) {
+            HistTile2 t{sc, 0, 0, 0};
+            while (sc < n && t.n_cols < 248 && hist2_smem_bytes(t.n_cols + 1, ctx->h_len_sorted[sc], num_bins) <= (t.n_cols ? budget2 : budget)) {
+                t.n_cols++; t.max_len = ctx->h_len_sorted[sc]; sc++;
+            }
+            if (t.n_cols == 0) return fail(ctx, B200SCAN_ELIMIT, "num_bins %u too large for the shared-memory histograms", num_bins);
+            t.n_pad = (t.n_cols + kHist2U - 1) / kHist2U * kHist2U;
+            max_smem = std::max(max_smem, hist2_smem_bytes(t.n_cols, t.max_len, num_bins));
+            ht2.push_back(t);
+        }
+    }
+    dfree(ctx->d_hist); dfree(ctx->d_hmin); dfree(ctx->d_hwid); dfree(ctx->d_htiles); dfree(ctx->d_htiles2);
     CU(cudaMalloc(&ctx->d_hist, (size_t)n * num_bins * 8));
     CU(cudaMemset(ctx->d_hist, 0, (size_t)n * num_bins * 8));
     CU(cudaMalloc(&ctx->d_hmin, 4 * n)); CU(cudaMalloc(&ctx->d_hwid, 4 * n));
@@ -1119,9 +1141,19 @@ int b200scan_hist_begin(b200scan_ctx* ctx, const float* col_min, const float* co
     CU(cudaMemcpy(ctx->d_hmin, mn.data(), 4 * n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_hwid, wid.data(), 4 * n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_htiles, ht.data(), sizeof(GatherTile) * ht.size(), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(gather_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    CU(cudaFuncSetAttribute(gather_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    ctx->htiles = ht; ctx->hist_smem = max_smem; ctx->hist_bins = num_bins;
+    if (!ht2.empty()) {
+        CU(cudaMalloc(&ctx->d_htiles2, sizeof(HistTile2) * ht2.size()));
+        CU(cudaMemcpy(ctx->d_htiles2, ht2.data(), sizeof(HistTile2) * ht2.size(), cudaMemcpyHostToDevice));
+    }
+    CU(cudaFuncSetAttribute(gather_hist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    CU(cudaFuncSetAttribute(gather_hist2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    ctx->htiles = ht; ctx->htiles2 = ht2; ctx->hist_smem = max_smem; ctx->hist_bins = num_bins;
     return B200SCAN_OK;
 }
 
@@ -1153,9 +1185,27 @@ int b200scan_hist_block_ascii(b200scan_ctx* ctx, const char* block, uint64_t n_t
                                                                       s.d_codes, s.d_zmask, reinterpret_cast<uint32_t*>(s.d_counters + 2));
     const MotifDev md = motif_dev(ctx);
     const BlockDev blk = block_dev(s);
-    const dim3 grid((unsigned)((n_payload + kHistSpan - 1) / kHistSpan), (unsigned)ctx->htiles.size());
-    gather_hist_kernel<false><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 0);
-    gather_hist_kernel<true><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 1);
+    // two instances per block: the one for blocks without zero-contribution characters and the masked one; each returns at once
+    // unless the block's has_zero flag (written by the pack kernel just before) asks for it
+    if (ctx->hist_kernel >= 2 && !ctx->htiles2.empty()) {
+        const dim3 grid((unsigned)((n_payload + kHistSpan - 1) / kHistSpan), (unsigned)ctx->htiles2.size());
+        if (ctx->hist_kernel == 3) {
+            gather_hist2_kernel<false, true><<<grid, kHist2Threads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles2, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 0);
+            gather_hist2_kernel<true, true><<<grid, kHist2Threads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles2, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 1);
+        } else {
+            gather_hist2_kernel<false, false><<<grid, kHist2Threads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles2, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 0);
+            gather_hist2_kernel<true, false><<<grid, kHist2Threads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles2, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 1);
+        }
+    } else {
+        const dim3 grid((unsigned)((n_payload + kHistSpan - 1) / kHistSpan), (unsigned)ctx->htiles.size());
+        if (ctx->hist_kernel == 1) {
+            gather_hist_kernel<false, true><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 0);
+            gather_hist_kernel<true, true><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 1);
+        } else {
+            gather_hist_kernel<false, false><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 0);
+            gather_hist_kernel<true, false><<<grid, kGatherThreads, ctx->hist_smem, ctx->stream>>>(md, blk, ctx->d_htiles, ctx->d_hmin, ctx->d_hwid, ctx->hist_bins, ctx->d_hist, 1);
+        }
+    }
     CU(cudaGetLastError());
     return B200SCAN_OK;
 }
