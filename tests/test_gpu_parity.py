@@ -840,3 +840,31 @@ def test_cli_reports_a_stale_dictionary_instead_of_aborting(tmp_path):
     r = subprocess.run([cli, "scan", "-rc", "-at", "2", "motifs.jaspar", "sequences.mf"], cwd=work, capture_output=True, text=True)
     assert r.returncode == 1, (r.returncode, r.stderr[-500:])
     assert r.stderr.strip() != "" and "bye" not in r.stdout
+
+
+@pytest.mark.parametrize("kernel", [3, 2, 1, 0])
+def test_histogram_kernels_agree_with_oracle(monkeypatch, kernel):
+    """Every histogram kernel of the library (B200SCAN_HIST_KERNEL, read by b200scan_create: 3 = position-row weights with the lanes
+    of a warp counting different columns, the default; 2 = the same with match-aggregated counts; 1 / 0 = the round-1 kernel with /
+    without aggregated counts) against the oracle, bin for bin: 150 columns of 5 to 64 positions (several shared-memory tiles, the
+    longest column the build supports), lower case under both rules, fragments, several blocks with a halo."""
+    monkeypatch.setenv("B200SCAN_HIST_KERNEL", str(kernel))
+    case = util.random_case(92, n_motifs=150, n_nt=120_000, len_range=(5, 64), lower=True)
+    P, col_len = case["P"], case["col_len"]
+    mm = [O.max_min_score(np.ascontiguousarray(P[c, :4 * int(col_len[c])])) for c in range(len(col_len))]
+    mx = np.array([a for a, b in mm], np.float32); mn = np.array([b for a, b in mm], np.float32)
+    bins = 250
+    halo = int(col_len.max()) - 1
+    s = capi.Scanner(0, max_block_nt=1 << 20, max_hits=1 << 16)
+    try:
+        s.set_motifs(P, col_len, np.zeros(len(col_len), np.float32))
+        for lower in (capi.LOWER_ZERO, capi.LOWER_FOLD):
+            want = O.empirical_hist(bytes(case["chars"]), case["frag_start"], P, col_len, mn, mx, bins, lower_fold=(lower == capi.LOWER_FOLD))
+            s.hist_begin(mn, mx, bins)
+            for sh in shard.plan_shards(len(case["chars"]), world=1, halo=halo, chunk=50_001):
+                s.hist_block(case["chars"][sh.start:sh.start + sh.n_total], shard.local_frag_starts(case["frag_start"], sh), sh.n_payload, lower=lower)
+            got = s.hist_read()
+            assert got.shape == want.shape and int(got.sum()) == int(want.sum()) > 0
+            assert np.array_equal(got, want)
+    finally:
+        s.close()
