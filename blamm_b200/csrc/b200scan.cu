@@ -1127,11 +1127,11 @@ int b200scan_hist_begin(b200scan_ctx* ctx, const float* col_min, const float* co
             while (sc < n && t.n_cols < 248 && hist2_smem_bytes(t.n_cols + 1, ctx->h_len_sorted[sc], num_bins) <= (t.n_cols ? budget2 : budget)) {
                 t.n_cols++; t.max_len = ctx->h_len_sorted[sc]; sc++;
             }
-            if (t.n_cols == 0) return fail(ctx, B200SCAN_ELIMIT, "num_bins %u too large for the shared-memory histograms", num_bins);
+            if (t.n_cols == 0) { ht2.clear(); break; }      // a table this large only fits the narrower tiles of gather_hist_kernel: that kernel runs instead
             t.n_pad = (t.n_cols + kHist2U - 1) / kHist2U * kHist2U;
-            max_smem = std::max(max_smem, hist2_smem_bytes(t.n_cols, t.max_len, num_bins));
             ht2.push_back(t);
         }
+        for (const HistTile2& t : ht2) max_smem = std::max(max_smem, hist2_smem_bytes(t.n_cols, t.max_len, num_bins));
     }
     dfree(ctx->d_hist); dfree(ctx->d_hmin); dfree(ctx->d_hwid); dfree(ctx->d_htiles); dfree(ctx->d_htiles2);
     CU(cudaMalloc(&ctx->d_hist, (size_t)n * num_bins * 8));
