@@ -972,6 +972,111 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
     return ok;
 }
 
+// `blamm-b200 selftest-order [chunks] [workers] [threads]` (no GPU): the stream-order merge of `scan -g N`.  `workers` threads play
+// the per-GPU workers: chunk k goes to worker k mod workers (or to whoever is free first), every worker formats and emits its
+// chunks after a random delay through the product's writeHits8 / emitText, so the chunks become ready in an order that has nothing
+// to do with the stream.  The file must hold the chunks in stream order -- byte for byte the text of a single worker doing them
+// one after the other -- whatever the number of workers (per-GPU hit lists merged on the host in reference order).
+bool orderSelfTest(size_t nChunks, size_t nWorkers, size_t threads)
+{
+    std::mt19937_64 rng(4711 + nChunks);
+    MotifSet ms;
+    const size_t nCols = 24;
+    for (size_t c = 0; c < nCols; c++) {
+        Motif m; m.name = "MB" + to_string(2000 + c / 2) + ".1"; m.pfm.resize(6 + c % 11); m.revComp = c & 1;
+        ms.motifs.push_back(m);
+    }
+    Species sp; sp.name = "syn";
+    sp.seqNames = {"chrA", "chrB"};
+    auto group = make_shared<GroupParams>();
+    group->species = &sp; group->maxNameLen = 4 + 8;
+    // the chunks: ordered 8-byte records + bucket index, as b200scan_collect8 returns them; chunk sizes differ (also empty ones)
+    struct Chunk { Job job; vector<b200scan_hit8> hits; vector<uint32_t> buckets; uint64_t nb = 0; };
+    vector<Chunk> chunks(nChunks);
+    uint64_t streamPos = 0;
+    for (size_t k = 0; k < nChunks; k++) {
+        Chunk& c = chunks[k];
+        c.job.group = group; c.job.seq = k;
+        c.job.nPayload = 20000 + (rng() % 7) * 9000; c.job.nTotal = c.job.nPayload + 20;
+        c.job.frags = {{0, k & 1, streamPos}};
+        streamPos += c.job.nPayload;
+        c.nb = (c.job.nPayload + (1u << B200SCAN_BUCKET_SHIFT) - 1) >> B200SCAN_BUCKET_SHIFT;
+        c.buckets.assign(c.nb + 1, 0);
+        const size_t want = (k % 5 == 3) ? 0 : 200 + (size_t)(rng() % 60000);
+        const uint64_t universe = c.job.nPayload * nCols, g = max<uint64_t>(1, universe / max<size_t>(1, want));
+        for (size_t i = 0; i < want && i * g < universe; i++) {
+            const uint64_t key = i * g + rng() % g;                  // ascending (position, column)
+            const uint64_t pos = key / nCols; const uint32_t col = (uint32_t)(key % nCols);
+            c.hits.push_back({(uint32_t)((pos & 255u) << 24) | col, (float)((double)(rng() % 2000001) / 1e5 - 10.0)});
+            c.buckets[(pos >> B200SCAN_BUCKET_SHIFT) + 1]++;
+        }
+        for (uint64_t b = 0; b < c.nb; b++) c.buckets[b + 1] += c.buckets[b];
+    }
+    WorkPool workPool(threads);
+    const string base = string(getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp") + "/blamm_b200_selftest_order_" + to_string((long)getpid());
+    auto run = [&](size_t workers, bool dynamicDeal, const string& path) -> bool {
+        const int fd = open(path.c_str(), O_CREAT | O_TRUNC | O_RDWR, 0644);
+        if (fd < 0) return false;
+        ScanShared sh;
+        for (const auto& m : ms.motifs) sh.mtext.emplace_back(m.name, (uint64_t)m.size(), m.revComp);
+        sh.fd = fd; sh.pool = &workPool;
+        sh.chooseWriter();
+        atomic<size_t> next{0};
+        vector<thread> th;
+        for (size_t w = 0; w < workers; w++) th.emplace_back([&, w] {
+            std::mt19937_64 r(99 + w);
+            // every worker emits ITS chunks in increasing stream order (deviceWorker does: a chunk is collected before the next one
+            // submitted behind it); between workers nothing is ordered
+            for (size_t k = dynamicDeal ? next.fetch_add(1) : w; k < nChunks; k = dynamicDeal ? next.fetch_add(1) : k + workers) {
+                if (workers > 1) std::this_thread::sleep_for(std::chrono::microseconds(r() % 3000));
+                const Chunk& c = chunks[k];
+                writeHits8(sh, c.job, c.hits.data(), c.hits.size(), c.buckets.data(), c.nb, threads);
+            }
+        });
+        for (auto& t : th) t.join();
+        close(fd);
+        uint64_t total = 0;
+        for (const auto& c : chunks) total += c.hits.size();
+        return !sh.failed && sh.totMatches == total && sh.nextOut == nChunks;
+    };
+    auto slurp = [](const string& path) { ifstream is(path, ios::binary); return string((istreambuf_iterator<char>(is)), istreambuf_iterator<char>()); };
+    bool ok = run(1, false, base + "_1.txt");
+    const string want = slurp(base + "_1.txt");
+    remove((base + "_1.txt").c_str());
+    {   // the single-worker file itself: one line per hit, stream positions never decreasing (chunk k's records start where chunk k-1's end)
+        uint64_t lines = 0, total = 0, last = 0;
+        for (const auto& c : chunks) total += c.hits.size();
+        for (size_t at = 0; at < want.size() && ok;) {
+            const size_t eol = want.find('\n', at);
+            if (eol == string::npos) { ok = false; break; }
+            size_t tab = at;
+            for (int f = 0; f < 3; f++) tab = want.find('\t', tab) + 1;      // <sequence> blamm <motif> <start> ...
+            const uint64_t start = strtoull(want.c_str() + tab, nullptr, 10);
+            if (start < last) ok = false;
+            last = start; lines++; at = eol + 1;
+        }
+        ok = ok && lines == total;
+        cout << "1 worker: " << lines << " lines of " << total << " hits, " << want.size() << " bytes, positions " << (ok ? "in stream order" : "OUT OF ORDER") << "\n";
+    }
+    for (int dynamicDeal = 0; dynamicDeal < 2 && ok; dynamicDeal++) {
+        const string path = base + "_n.txt";
+        const bool ran = run(nWorkers, dynamicDeal != 0, path);
+        const string got = slurp(path);
+        remove(path.c_str());
+        const bool same = ran && got == want;
+        cout << nWorkers << " workers, chunks " << (dynamicDeal ? "taken by whoever is free" : "dealt round robin") << ": " << got.size() << " bytes: "
+             << (same ? "identical" : "DIFFERENT") << "\n";
+        ok = ok && same;
+    }
+    return ok && !want.empty();
+}
+
+int runOrderSelfTest(int argc, char** argv)
+{
+    const size_t nChunks = argc > 2 ? (size_t)atoll(argv[2]) : 40, nWorkers = argc > 3 ? (size_t)atoll(argv[3]) : 8, threads = argc > 4 ? (size_t)atoll(argv[4]) : 4;
+    return orderSelfTest(max<size_t>(1, nChunks), max<size_t>(1, nWorkers), max<size_t>(1, threads)) ? EXIT_SUCCESS : EXIT_FAILURE;
+}
+
 int runWriterSelfTest(int argc, char** argv)
 {
     const size_t nHits = argc > 2 ? (size_t)atoll(argv[2]) : 300000, threads = argc > 3 ? (size_t)atoll(argv[3]) : 4;
@@ -1246,6 +1351,7 @@ int main(int argc, char** argv)
         if (cmd == "dict") { int rc = blamm::runDict(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
         if (cmd == "hist") { int rc = blamm::runHist(argc, argv); if (rc == EXIT_SUCCESS) cout << "Exiting... bye!" << endl; return rc; }
         if (cmd == "selftest-writer") return blamm::runWriterSelfTest(argc, argv);
+        if (cmd == "selftest-order") return blamm::runOrderSelfTest(argc, argv);
         if (cmd == "scan") {
             const double t0 = blamm::now();
             int rc = blamm::runScan(argc, argv);

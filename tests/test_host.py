@@ -310,6 +310,20 @@ def test_occurrence_writer_selftest(n_hits, threads):
         assert r.stdout.count("identical") == 3 and "DIFFERENT" not in r.stdout
 
 
+@pytest.mark.parametrize("chunks,workers,threads", [(40, 8, 4), (33, 2, 3), (1, 4, 1), (12, 12, 2)])
+def test_stream_order_merge_selftest(chunks, workers, threads):
+    """`blamm-b200 selftest-order` (no GPU): the host-side merge of `scan -g N`.  N threads stand in for the per-GPU workers and push
+    chunks of ordered 8-byte records through the product's formatter and emitter after random delays; the occurrence file must be
+    byte for byte what ONE worker writes -- every chunk in its place in the stream whichever worker finished first -- for chunks
+    dealt round robin and for chunks taken by whoever is free; in tmpfs (shared mappings) and on disk (pwrite)."""
+    for env in ({}, {"TMPDIR": "/dev/shm"}):
+        if env.get("TMPDIR") and not os.path.isdir(env["TMPDIR"]):
+            continue
+        r = subprocess.run([CLI, "selftest-order", str(chunks), str(workers), str(threads)], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("identical") == 2 and "DIFFERENT" not in r.stdout and "in stream order" in r.stdout
+
+
 def test_fasta_rejects_headerless_input(tmp_path):
     p = tmp_path / "bad.fa"
     p.write_text("ACGT\n>late\nACGT\n")
