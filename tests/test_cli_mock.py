@@ -1,0 +1,162 @@
+"""The blamm-b200 command line's HOST logic on the CPU suite (no GPU): `scan` runs against tests/mock/mock_b200scan.cpp, a
+test-only stand-in for libb200scan.so that answers the C ABI from the CPU oracle and can pretend to be several devices, finish
+out of order and refuse blocks as too dense.  What is under test is everything around the kernels: the reader and packer, one
+worker per device with three slots, group changes, chunks dealt to devices, halving of refused chunks, the formatter and the
+stream-order emission -- against the UNMODIFIED reference binary (oracle/_ref/blamm) where it is built, else the oracle's own
+`scan` restatement.  The CUDA path itself is the business of tests/test_gpu_parity.py; the product library has no CPU path
+(tests/test_host.py::test_create_fails_loudly_without_gpu) and nothing outside tests/ can load this stand-in."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from blamm_b200 import lib_dir, synth
+from oracle import oracle as O
+from tests import util
+
+ROOT = util.ROOT
+CLI = os.path.join(lib_dir(), "blamm-b200")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "blamm")
+MOCK_DIR = os.path.join(ROOT, "tests", "mock", "_build")
+
+
+@pytest.fixture(scope="module")
+def mock_env():
+    """Build the stand-in (g++, linked against oracle/liboracle.so) and return the environment that makes the CLI load it: the
+    CLI finds libb200scan.so through DT_RUNPATH=$ORIGIN, which LD_LIBRARY_PATH precedes."""
+    O.lib()                                                   # builds oracle/liboracle.so if it is missing
+    os.makedirs(MOCK_DIR, exist_ok=True)
+    so = os.path.join(MOCK_DIR, "libb200scan.so")
+    src = os.path.join(ROOT, "tests", "mock", "mock_b200scan.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", so, "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                               "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-lpthread"])
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = MOCK_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    env.pop("BLAMM_B200_HITS", None); env.pop("BLAMM_B200_ASCII", None); env.pop("BLAMM_B200_CHUNK", None)
+    return env
+
+
+def _scan(work, env, *flags, **extra):
+    e = dict(env, **{k: str(v) for k, v in extra.items()})
+    r = subprocess.run([CLI, "scan"] + list(flags) + ["motifs.jaspar", "seq.mf"], cwd=work, env=e, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    return open(os.path.join(work, "occurrences.txt"), "rb").read(), r.stdout
+
+
+def _make_inputs(work, seed, n_groups=3, n_motifs=30, max_len=14):
+    """several manifest groups with distinct backgrounds, several files per group, N runs, lower-case stretches, a record shorter
+    than a motif; motifs at most 14 long, where the reference's sgemm sums in position order"""
+    rng = np.random.default_rng(seed)
+    synth.make_jaspar_like(os.path.join(work, "motifs.jaspar"), n_motifs, seed, uniform_len=(5, max_len))
+    manifest = []
+    for g in range(n_groups):
+        gc = 0.36 + 0.07 * g
+        probs = ((1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2)
+        for f in range(1 + g % 2):
+            seq = synth.random_acgt(150_000 + 11_003 * g, seed * 10 + 3 * g + f, probs)
+            for _ in range(4):
+                a = int(rng.integers(0, len(seq) - 3000)); seq[a:a + int(rng.integers(1, 2000))] = ord("N")
+                b = int(rng.integers(0, len(seq) - 3000)); seq[b:b + int(rng.integers(1, 2500))] |= 0x20
+            recs = [("g%df%dchr1" % (g, f), seq[:70_000]), ("g%df%dtiny" % (g, f), seq[70_000:70_009]), ("g%df%dchr2 note" % (g, f), seq[70_009:])]
+            synth.write_fasta(os.path.join(work, "g%d_%d.fa" % (g, f)), recs)
+            manifest.append("grp%d\tg%d_%d.fa\n" % (g, g, f))
+    open(os.path.join(work, "seq.mf"), "w").write("".join(manifest))
+
+
+def _reference_lines(work, flags, mode):
+    """sorted occurrence lines of the reference for the inputs in `work` (its `dict` and `hist` outputs stay there for the CLI)"""
+    if os.path.exists(REF_BIN):
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+        ob = os.path.join(ROOT, "oracle", "_ref", "openblas_dir.txt")
+        if os.path.exists(ob):
+            env["LD_LIBRARY_PATH"] = open(ob).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
+        for args in (["dict", "seq.mf"], ["hist", "motifs.jaspar", "seq.mf"], ["scan", "-t", "2", "-o", "ref_occurrences.txt"] + flags + ["motifs.jaspar", "seq.mf"]):
+            r = subprocess.run([REF_BIN] + args, cwd=work, env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr
+        return sorted(open(os.path.join(work, "ref_occurrences.txt")).read().splitlines(True))
+    for args in (["dict", "seq.mf"], ["hist", "motifs.jaspar", "seq.mf"]):               # the CLI's own CPU modules (byte-identical to the reference's, tests/test_host.py)
+        subprocess.run([CLI] + args, cwd=work, check=True, stdout=subprocess.DEVNULL)
+    lines, _ = O.scan("motifs.jaspar", "seq.mf", mode[0], mode[1], mode[2], histdir=".", base_dir=str(work))
+    return sorted(lines)
+
+
+@pytest.mark.parametrize("seed,flags,mode", [(201, ["-rc", "-pt", "0.001"], ("pt", 0.001, True)), (202, ["-rc"], ("rt", 0.95, True)),
+                                             (203, ["-at", "7.5"], ("at", 7.5, False))])
+def test_cli_scan_on_mock_devices_matches_reference(tmp_path, mock_env, seed, flags, mode):
+    """Three groups (five files) through `blamm-b200 scan`: the occurrence set of the reference, and THE SAME FILE byte for byte
+    whether one device scores everything or five devices that finish out of order share chunks of 20,000 characters (stream-order
+    merge), with the unordered 12-byte records and the host sort, and with the character hand-over."""
+    work = str(tmp_path)
+    _make_inputs(work, seed)
+    want = _reference_lines(work, flags, mode)
+    assert len(want) > 200
+    one, out = _scan(work, mock_env, *flags, "-g", "1", MOCK_B200SCAN_DEVICES=1)
+    assert "Using 1 GPU devices" in out
+    assert sorted(one.decode().splitlines(True)) == want
+    many, out = _scan(work, mock_env, *flags, "-t", "3", MOCK_B200SCAN_DEVICES=5, MOCK_B200SCAN_DELAY_US=4000, BLAMM_B200_CHUNK=20000)
+    assert "Using 5 GPU devices" in out
+    assert sorted(many.decode().splitlines(True)) == want
+    # chunks in stream order, hits in (position, column) order inside: the file does not depend on the devices or on their timing
+    again, _ = _scan(work, mock_env, *flags, "-g", "2", MOCK_B200SCAN_DEVICES=5, MOCK_B200SCAN_DELAY_US=1500, BLAMM_B200_CHUNK=20000)
+    single, _ = _scan(work, mock_env, *flags, "-g", "1", MOCK_B200SCAN_DEVICES=5, BLAMM_B200_CHUNK=20000)
+    assert many == again == single
+    sorted12, _ = _scan(work, mock_env, *flags, MOCK_B200SCAN_DEVICES=3, MOCK_B200SCAN_DELAY_US=1500, BLAMM_B200_CHUNK=20000, BLAMM_B200_HITS=12)
+    assert sorted12 == many
+    chars, _ = _scan(work, mock_env, *flags, MOCK_B200SCAN_DEVICES=2, BLAMM_B200_CHUNK=20000, BLAMM_B200_ASCII=1)
+    assert chars == many
+
+
+def test_cli_halves_chunks_the_device_refuses(tmp_path, mock_env):
+    """A device that refuses every block with more than 300 hits (B200SCAN_ENOMEM at collect): the workers score such chunks in
+    halves, recursively, keep the chunks collected behind them in order, and the file is the one of an unconstrained run --
+    with several devices as well."""
+    work = str(tmp_path)
+    _make_inputs(work, 204, n_groups=2)
+    flags = ["-rc", "-pt", "0.002"]
+    want = _reference_lines(work, flags, ("pt", 0.002, True))
+    free, _ = _scan(work, mock_env, *flags, BLAMM_B200_CHUNK=30000)
+    assert sorted(free.decode().splitlines(True)) == want and len(want) > 2000
+    tight, _ = _scan(work, mock_env, *flags, BLAMM_B200_CHUNK=30000, MOCK_B200SCAN_HIT_BUDGET=300)
+    assert tight == free
+    tight3, _ = _scan(work, mock_env, *flags, BLAMM_B200_CHUNK=30000, MOCK_B200SCAN_HIT_BUDGET=300, MOCK_B200SCAN_DEVICES=3, MOCK_B200SCAN_DELAY_US=2000)
+    assert tight3 == free
+    # a budget no halving can meet ends the run with an error, not with a truncated file that looks complete
+    r = subprocess.run([CLI, "scan"] + flags + ["motifs.jaspar", "seq.mf"], cwd=work, capture_output=True, text=True,
+                       env=dict(mock_env, BLAMM_B200_CHUNK="30000", MOCK_B200SCAN_HIT_BUDGET="0"))
+    assert r.returncode == 1 and "too dense" in r.stderr
+
+
+def test_cli_simple_mode_on_mock_devices(tmp_path, mock_env):
+    """`-s`: lower case scored like upper case (the reference's naive path, motif.cpp:138-149), here with four devices."""
+    work = str(tmp_path)
+    _make_inputs(work, 205, n_groups=2)
+    if os.path.exists(REF_BIN):
+        want = _reference_lines(work, ["-s", "-rc", "-at", "8"], None)
+    else:
+        for args in (["dict", "seq.mf"],):
+            subprocess.run([CLI] + args, cwd=work, check=True, stdout=subprocess.DEVNULL)
+        lines, _ = O.scan("motifs.jaspar", "seq.mf", "at", 8.0, True, histdir=".", base_dir=work, lower_fold=True)
+        want = sorted(lines)
+    got, _ = _scan(work, mock_env, "-s", "-rc", "-at", "8", MOCK_B200SCAN_DEVICES=4, MOCK_B200SCAN_DELAY_US=1000, BLAMM_B200_CHUNK=25000)
+    assert len(want) > 100 and sorted(got.decode().splitlines(True)) == want
+    plain, _ = _scan(work, mock_env, "-rc", "-at", "8", MOCK_B200SCAN_DEVICES=4, BLAMM_B200_CHUNK=25000)
+    assert plain != got                                        # the lower-case stretches make the two rules differ
+
+
+def test_cli_on_the_example_with_mock_devices(golden, tmp_path, mock_env):
+    """The reference's own example (two groups) in the four threshold modes of the golden fixtures, with three devices: the golden
+    occurrence files (sorted text of the compiled reference) and its PWMthresholds.txt."""
+    work = tmp_path / "ex"
+    shutil.copytree(os.path.join(golden, "example"), work)
+    os.rename(work / "sequences.mf", work / "seq.mf")
+    os.rename(work / "sequences.mf.dict", work / "seq.mf.dict")
+    for mode_key, flags in (("pt_rc", ["-rc", "-pt", "0.0001"]), ("pt_fwd", ["-pt", "0.0001"]), ("rt_rc", ["-rc"]), ("at_rc", ["-rc", "-at", "9.5"])):
+        got, out = _scan(str(work), mock_env, *flags, MOCK_B200SCAN_DEVICES=3, MOCK_B200SCAN_DELAY_US=500, BLAMM_B200_CHUNK=30000)
+        lines = sorted(got.decode().splitlines(True))
+        assert lines == open(os.path.join(golden, "example", "occ_%s.txt" % mode_key)).read().splitlines(True)
+        assert ("Wrote %d matches" % len(lines)) in out
+        if mode_key == "pt_rc":
+            assert open(work / "PWMthresholds.txt").read() == open(os.path.join(golden, "example", "PWMthresholds_pt_rc.txt")).read()
