@@ -342,6 +342,7 @@ class WorkPool {
 public:
     explicit WorkPool(size_t threads) { for (size_t t = 0; t + 1 < threads; t++) workers.emplace_back([this] { loop(); }); }
     ~WorkPool() { { lock_guard<mutex> l(m); stop = true; } cv.notify_all(); for (auto& t : workers) t.join(); }
+    size_t size() const { return workers.size() + 1; }          // threads a parallel() call can occupy (the pool's + the caller)
     void parallel(size_t n, const function<void(size_t)>& fn)
     {
         if (n == 0) return;
@@ -479,7 +480,7 @@ struct ScanShared {
     // Write through shared mappings where the file lives in tmpfs, with pwrite elsewhere (BLAMM_B200_WRITER=mmap|pwrite forces one):
     // measured on a 16-core B200 box (tools/micro/file_write.cpp, one new file, GB/s at 4 / 8 / 16 threads) -- tmpfs: mapping
     // 5.3 / 8.1 / 6.7, pwrite 3.8 / 3.8 / 3.8 (the inode lock serialises buffered writes); ext4: mapping 4.2, pwrite 5.1 at 16.
-    // More than eight threads faulting pages of one file get in each other's way, so the copies of all chunks share eight slots.
+    // More than eight threads faulting pages of one file get in each other's way, so a chunk is copied on at most eight (copyToFile).
     atomic<bool> useMmap{true};
     void chooseWriter()
     {
@@ -489,11 +490,18 @@ struct ScanShared {
         struct statfs st;
         useMmap = fd >= 0 && fstatfs(fd, &st) == 0 && (unsigned long)st.f_type == 0x01021994ul;      // TMPFS_MAGIC
     }
-    mutex cMutex; condition_variable cCv;
-    int copySlots = getenv("BLAMM_B200_COPY_THREADS") ? max(1, atoi(getenv("BLAMM_B200_COPY_THREADS"))) : 8;
-    void acquireCopySlot() { unique_lock<mutex> l(cMutex); cCv.wait(l, [&] { return copySlots > 0; }); copySlots--; }
-    void releaseCopySlot() { { lock_guard<mutex> l(cMutex); copySlots++; } cCv.notify_one(); }
+    size_t copyThreads = getenv("BLAMM_B200_COPY_THREADS") ? (size_t)max(1, atoi(getenv("BLAMM_B200_COPY_THREADS"))) : 0;      // 0: 8 (mapping) / 16 (pwrite)
     WorkPool* pool = nullptr;
+    // The emitter: ONE thread puts the chunks' text into the file, chunk after chunk in the order the byte ranges were handed
+    // out, each chunk on the emitter's OWN copy threads -- so the device workers go on formatting the next chunk while the
+    // previous one is being written, no formatting thread ever waits for a turn to copy, and no copy waits behind formatting
+    // work in the shared pool's queue.  At most two chunks wait behind the one being written (their text is memory).
+    struct EmitJob { vector<Text> text; uint64_t at = 0, bytes = 0; };
+    mutex eMutex; condition_variable eCv; deque<EmitJob> eQueue; bool eStop = false, eBusy = false; thread emitter;
+    unique_ptr<WorkPool> copyPool;
+    void enqueueEmit(EmitJob&& j);             // cli.cpp: below emitText
+    void drainEmitter();                       // waits until everything queued is in the file, then ends the thread
+    ~ScanShared() { drainEmitter(); }
     atomic<uint64_t> totMatches{0};
     // job queue (producer = FASTA reader, consumers = one thread per GPU)
     mutex qMutex; condition_variable qCv;
@@ -512,6 +520,8 @@ struct ScanShared {
         qCv.notify_all();
         { lock_guard<mutex> l(oMutex); }
         oCv.notify_all();
+        { lock_guard<mutex> l(eMutex); }
+        eCv.notify_all();
     }
 };
 
@@ -572,61 +582,117 @@ void formatRange(const ScanShared& sh, const Job& job, std::vector<H>& hits, Tex
     text.n = (size_t)(p - base);
 }
 
-// formatted text of one chunk -> its place in the file: wait for the chunk's turn, take the byte range, write the pieces in parallel
+// The text of one chunk goes to its byte range of the file: pieces of at most 16 MiB, through a shared mapping of the range on
+// eight threads where the file lives in tmpfs (buffered write() calls on one file serialise on the inode lock -- measured: 16
+// threads of pwrite = one thread's 3.7 GB/s -- page faults of a mapping do not, but more than eight threads faulting pages of
+// one file get in each other's way), with pwrite on sixteen elsewhere (BLAMM_B200_COPY_THREADS).  Runs on the emitter thread.
+void copyToFile(ScanShared& sh, ScanShared::EmitJob& j)
+{
+    const double t0 = now();
+    bool mapped = sh.useMmap;
+    struct Piece { const char* p; size_t n; uint64_t at; };
+    vector<Piece> pieces;
+    {
+        uint64_t o = j.at;
+        for (const auto& t : j.text) {
+            for (size_t q = 0; q < t.size(); q += (16u << 20)) pieces.push_back({t.data() + q, min<size_t>(16u << 20, t.size() - q), o + q});
+            o += t.size();
+        }
+    }
+    atomic<bool> bad{false};
+    char* base = nullptr; uint64_t mapAt = 0; size_t mapLen = 0;
+    if (mapped) {
+        const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+        mapAt = j.at / page * page; mapLen = (size_t)(j.at + j.bytes - mapAt);
+        void* m = mmap(nullptr, mapLen, PROT_READ | PROT_WRITE, MAP_SHARED, sh.fd, (off_t)mapAt);
+        if (m == MAP_FAILED) { mapped = false; sh.useMmap = false; } else base = static_cast<char*>(m);
+    }
+    // strand i takes pieces i, i + S, ... on the emitter's own threads
+    const size_t S = min(pieces.size(), sh.copyPool->size());
+    sh.copyPool->parallel(S, [&](size_t strand) {
+        for (size_t i = strand; i < pieces.size(); i += S) {
+            if (mapped) { memcpy(base + (pieces[i].at - mapAt), pieces[i].p, pieces[i].n); continue; }
+            const char* p = pieces[i].p; size_t left = pieces[i].n; uint64_t o = pieces[i].at;
+            while (left) {
+                const ssize_t w = pwrite(sh.fd, p, left, (off_t)o);
+                if (w <= 0) { if (w < 0 && errno == EINTR) continue; bad = true; return; }
+                p += w; left -= (size_t)w; o += (uint64_t)w;
+            }
+        }
+    });
+    if (base) munmap(base, mapLen);
+    if (bad) sh.fail("Cannot write to the occurrence file");
+    gTimer.add("file write (emitter thread, overlaps the formatting)", now() - t0);
+}
+
+void ScanShared::enqueueEmit(EmitJob&& j)
+{
+    unique_lock<mutex> l(eMutex);
+    if (!emitter.joinable()) {
+        eStop = false;
+        copyPool.reset(new WorkPool(copyThreads ? copyThreads : (useMmap ? 8 : 16)));
+        emitter = thread([this] {
+            for (;;) {
+                EmitJob job;
+                {
+                    unique_lock<mutex> q(eMutex);
+                    eCv.wait(q, [&] { return eStop || !eQueue.empty(); });
+                    if (eQueue.empty()) return;
+                    job = std::move(eQueue.front()); eQueue.pop_front();
+                    eBusy = true;
+                }
+                eCv.notify_all();
+                try { if (!failed) copyToFile(*this, job); } catch (const exception& e) { fail(e.what()); }
+                job.text.clear();                                  // (the buffers go back to the pool before the next wait)
+                { lock_guard<mutex> q(eMutex); eBusy = false; }
+                eCv.notify_all();
+            }
+        });
+    }
+    eCv.wait(l, [&] { return eQueue.size() < 2 || failed; });
+    if (failed) return;
+    eQueue.push_back(std::move(j));
+    l.unlock();
+    eCv.notify_all();
+}
+
+void ScanShared::drainEmitter()
+{
+    {
+        unique_lock<mutex> l(eMutex);
+        if (!emitter.joinable()) return;
+        eCv.wait(l, [&] { return (eQueue.empty() && !eBusy) || failed; });
+        eStop = true;
+    }
+    eCv.notify_all();
+    emitter.join();
+}
+
+// formatted text of one chunk -> its place in the file: wait for the chunk's turn (all earlier chunks have taken their byte ranges),
+// take the next `bytes` of the file, and leave the copying to the emitter
 void emitText(ScanShared& sh, const Job& job, vector<Text>& text, uint64_t n)
 {
     double t0 = now();
-    uint64_t bytes = 0;
-    for (const auto& t : text) bytes += t.size();
-    uint64_t at;
-    bool mapped = sh.useMmap;
+    ScanShared::EmitJob j;
+    for (const auto& t : text) j.bytes += t.size();
     {
         unique_lock<mutex> lock(sh.oMutex);
         sh.oCv.wait(lock, [&] { return job.seq == sh.nextOut || sh.failed; });
         if (sh.failed) return;
-        at = sh.fileOffset;
-        sh.fileOffset += bytes;
+        j.at = sh.fileOffset;
+        sh.fileOffset += j.bytes;
         // (the file grows here, in chunk order, so that every chunk can map its own byte range)
-        if (mapped && bytes && ftruncate(sh.fd, (off_t)sh.fileOffset) != 0) mapped = sh.useMmap = false;
+        if (sh.useMmap && j.bytes && ftruncate(sh.fd, (off_t)sh.fileOffset) != 0) sh.useMmap = false;
         sh.nextOut++;
     }
     sh.oCv.notify_all();
     sh.totMatches += n;
     gTimer.add("wait for the chunk's turn in the file (wall)", now() - t0); t0 = now();
-    if (!bytes) return;
-    vector<uint64_t> off(text.size());
-    { uint64_t o = at; for (size_t i = 0; i < text.size(); i++) { off[i] = o; o += text[i].size(); } }
-    // pieces of at most 16 MiB.  Writes through a shared mapping of the chunk's byte range: buffered write() calls on one file
-    // serialise on the inode lock (measured: 16 threads of pwrite = one thread's 3.7 GB/s), page faults of a mapping do not.
-    struct Piece { const char* p; size_t n; uint64_t at; };
-    vector<Piece> pieces;
-    for (size_t i = 0; i < text.size(); i++)
-        for (size_t o = 0; o < text[i].size(); o += (16u << 20)) pieces.push_back({text[i].data() + o, min<size_t>(16u << 20, text[i].size() - o), off[i] + o});
-    atomic<bool> bad{false};
-    char* base = nullptr; uint64_t mapAt = 0; size_t mapLen = 0;
-    if (mapped) {
-        const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
-        mapAt = at / page * page; mapLen = (size_t)(at + bytes - mapAt);
-        void* m = mmap(nullptr, mapLen, PROT_READ | PROT_WRITE, MAP_SHARED, sh.fd, (off_t)mapAt);
-        if (m == MAP_FAILED) { mapped = false; sh.useMmap = false; } else base = static_cast<char*>(m);
-    }
-    sh.pool->parallel(pieces.size(), [&](size_t i) {
-        if (mapped) {
-            sh.acquireCopySlot();
-            memcpy(base + (pieces[i].at - mapAt), pieces[i].p, pieces[i].n);
-            sh.releaseCopySlot();
-            return;
-        }
-        const char* p = pieces[i].p; size_t left = pieces[i].n; uint64_t o = pieces[i].at;
-        while (left) {
-            const ssize_t w = pwrite(sh.fd, p, left, (off_t)o);
-            if (w <= 0) { if (w < 0 && errno == EINTR) continue; bad = true; return; }
-            p += w; left -= (size_t)w; o += (uint64_t)w;
-        }
-    });
-    if (base) munmap(base, mapLen);
-    if (bad) sh.fail("Cannot write to the occurrence file");
-    gTimer.add("file write (wall)", now() - t0);
+    if (!j.bytes) return;
+    j.text = std::move(text);
+    text.clear();
+    sh.enqueueEmit(std::move(j));
+    gTimer.add("wait for room behind the emitter (wall)", now() - t0);
 }
 
 template <class H>
@@ -937,6 +1003,7 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
         ScanShared sh;
         fillShared(sh, fd);
         writeHits(sh, job, hits.data(), hits.size(), threads);
+        sh.drainEmitter();
         close(fd);
         if (sh.totMatches != hits.size() || sh.failed) { cerr << label << ": match count differs\n"; return false; }
     }
@@ -960,6 +1027,7 @@ bool writerSelfTest(size_t nHits, size_t threads, const char* label)
             ScanShared sh;
             fillShared(sh, fd);
             writeHits8(sh, job, h8.data(), h8.size(), bs.data(), nb, threads);
+            sh.drainEmitter();
             close(fd);
         }
         ifstream is8(path, ios::binary);
@@ -1034,6 +1102,7 @@ bool orderSelfTest(size_t nChunks, size_t nWorkers, size_t threads)
             }
         });
         for (auto& t : th) t.join();
+        sh.drainEmitter();
         close(fd);
         uint64_t total = 0;
         for (const auto& c : chunks) total += c.hits.size();
@@ -1239,6 +1308,7 @@ int runScan(int argc, char** argv)
         { lock_guard<mutex> l(sh.qMutex); sh.done = true; }
         if (failed) sh.fail("input error"); else sh.qCv.notify_all();
         for (auto& w : workers) w.join();
+        sh.drainEmitter();                           // the last chunks' text is in the file
     };
     uint64_t nJobs = 0, groupId = 0;
     double tSetup = now();

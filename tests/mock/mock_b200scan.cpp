@@ -10,7 +10,8 @@
 //
 // Knobs (environment): MOCK_B200SCAN_DEVICES (device count, default 1), MOCK_B200SCAN_HIT_BUDGET (a block with more hits
 // makes collect return B200SCAN_ENOMEM, like a block too dense for the device buffers), MOCK_B200SCAN_DELAY_US (collect sleeps a
-// pseudo-random time below this bound, device dependent: the devices finish out of order).
+// pseudo-random time below this bound, device dependent: the devices finish out of order), MOCK_B200SCAN_SYNTH_HITS (hits per
+// window and column: no scoring, a pseudo-random ordered hit list of that density -- a benchmark of the CLI's host pipeline).
 #include "../../include/b200scan.h"
 
 #include <algorithm>
@@ -40,7 +41,7 @@ struct b200scan_ctx {
     int device = 0; std::string err; int fmt = B200SCAN_HITS_16;
     std::vector<float> P; int ldp = 0, n_cols = 0; std::vector<int32_t> len; std::vector<float> thr;
     Slot slot[B200SCAN_NUM_SLOTS];
-    uint64_t max_block = 0, budget = ~0ull; unsigned delay_us = 0; uint64_t rng = 1;
+    uint64_t max_block = 0, budget = ~0ull; unsigned delay_us = 0; uint64_t rng = 1; double synth_rate = 0;
 };
 
 namespace {
@@ -67,6 +68,31 @@ int scan_block(b200scan_ctx* c, int slot, const std::string& chars, uint64_t n_p
     }
     std::vector<uint64_t> pos(1 << 16); std::vector<uint32_t> col(1 << 16); std::vector<float> sc(1 << 16);
     uint64_t nh = 0;
+    if (c->synth_rate > 0 && c->fmt == B200SCAN_HITS_8) {
+        // host-pipeline benchmark mode (tools/host_pipeline_bench.sh): no scoring at all, a pseudo-random hit list of the given
+        // density per (window, column) in (position, column) order -- what the reader, formatter and writer have to keep up with.
+        // Written straight into the ordered 8-byte records: the stand-in should cost as little as a GPU does.
+        const double per_pos = c->synth_rate * c->n_cols;                  // expected hits per window position
+        const uint64_t nb = (n_payload + (1u << B200SCAN_BUCKET_SHIFT) - 1) >> B200SCAN_BUCKET_SHIFT;
+        s.h16.clear(); s.h12.clear(); s.h8.clear(); s.buckets.assign(nb + 1, 0);
+        s.h8.reserve((size_t)(per_pos * (double)n_payload * 1.05) + 1024);
+        uint64_t x = 0x9E3779B97F4A7C15ull ^ (chars.size() * 1315423911ull);
+        const double step = 1.0 / 1000.0 / per_pos;
+        double p = 0; uint64_t last = ~0ull;
+        for (;;) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            p += (double)(1 + (x >> 20) % 2000) * step;                      // mean gap 1 / per_pos
+            if (p >= (double)n_payload) break;
+            const uint64_t q = (uint64_t)p;
+            if (q == last) continue;                                          // one hit per position keeps the (position, column) order trivially
+            last = q;
+            s.h8.push_back({(uint32_t)((q & 255u) << 24) | (uint32_t)((x >> 3) % (uint64_t)c->n_cols), 5.0f + (float)(x % 100000) / 1e4f});
+            s.buckets[(q >> B200SCAN_BUCKET_SHIFT) + 1]++;
+        }
+        for (uint64_t b = 0; b < nb; b++) s.buckets[b + 1] += s.buckets[b];
+        s.in_flight = true; s.fmt = c->fmt; s.n_payload = n_payload; s.n_hits = s.h8.size(); s.too_dense = false;
+        return B200SCAN_OK;
+    } else
     for (int attempt = 0; attempt < 2; attempt++) {
         nh = oracle_scan_stream(chars.data(), chars.size(), n_payload, fs.data(), fs.size(), c->P.data(), c->ldp, c->n_cols, c->len.data(),
                                 c->thr.data(), lower_fold, pos.data(), col.data(), sc.data(), pos.size());
@@ -129,6 +155,7 @@ int b200scan_create(b200scan_ctx** out, int device, uint64_t max_block_nt, uint6
     c->device = device; c->max_block = max_block_nt; c->rng = 77 + (uint64_t)device;
     if (const char* e = getenv("MOCK_B200SCAN_HIT_BUDGET")) c->budget = strtoull(e, nullptr, 10);
     if (const char* e = getenv("MOCK_B200SCAN_DELAY_US")) c->delay_us = (unsigned)atoi(e);
+    if (const char* e = getenv("MOCK_B200SCAN_SYNTH_HITS")) c->synth_rate = atof(e);
     *out = c;
     return B200SCAN_OK;
 }
@@ -168,7 +195,7 @@ int b200scan_submit_packed(b200scan_ctx* c, int slot, const uint32_t* codes2, co
 {
     if (!c || (!codes2 && n_total)) return B200SCAN_EINVAL;
     std::string chars(n_total, 'A');
-    for (uint64_t i = 0; i < n_total; i++) {
+    for (uint64_t i = 0; i < n_total && c->synth_rate <= 0; i++) {
         const char up = "ACGT"[(codes2[i >> 4] >> (2 * (i & 15))) & 3u];
         const bool zero = zero_mask && ((zero_mask[i >> 5] >> (i & 31)) & 1u);
         chars[i] = zero ? (char)(up | 0x20) : up;             // a zero-contribution character = lower case under the BLAS-path rule
