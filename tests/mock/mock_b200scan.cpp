@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -33,6 +34,7 @@ struct Slot {
     bool in_flight = false; int fmt = B200SCAN_HITS_16; bool too_dense = false;
     std::vector<b200scan_hit> h16; std::vector<b200scan_hit12> h12; std::vector<b200scan_hit8> h8; std::vector<uint32_t> buckets;
     uint64_t n_payload = 0, n_hits = 0;
+    std::future<void> pending;                  // synthetic-hit mode: the list is made in the background, like a kernel on a device
 };
 thread_local std::string g_create_error;
 }
@@ -73,24 +75,28 @@ int scan_block(b200scan_ctx* c, int slot, const std::string& chars, uint64_t n_p
         // density per (window, column) in (position, column) order -- what the reader, formatter and writer have to keep up with.
         // Written straight into the ordered 8-byte records: the stand-in should cost as little as a GPU does.
         const double per_pos = c->synth_rate * c->n_cols;                  // expected hits per window position
-        const uint64_t nb = (n_payload + (1u << B200SCAN_BUCKET_SHIFT) - 1) >> B200SCAN_BUCKET_SHIFT;
-        s.h16.clear(); s.h12.clear(); s.h8.clear(); s.buckets.assign(nb + 1, 0);
-        s.h8.reserve((size_t)(per_pos * (double)n_payload * 1.05) + 1024);
-        uint64_t x = 0x9E3779B97F4A7C15ull ^ (chars.size() * 1315423911ull);
-        const double step = 1.0 / 1000.0 / per_pos;
-        double p = 0; uint64_t last = ~0ull;
-        for (;;) {
-            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
-            p += (double)(1 + (x >> 20) % 2000) * step;                      // mean gap 1 / per_pos
-            if (p >= (double)n_payload) break;
-            const uint64_t q = (uint64_t)p;
-            if (q == last) continue;                                          // one hit per position keeps the (position, column) order trivially
-            last = q;
-            s.h8.push_back({(uint32_t)((q & 255u) << 24) | (uint32_t)((x >> 3) % (uint64_t)c->n_cols), 5.0f + (float)(x % 100000) / 1e4f});
-            s.buckets[(q >> B200SCAN_BUCKET_SHIFT) + 1]++;
-        }
-        for (uint64_t b = 0; b < nb; b++) s.buckets[b + 1] += s.buckets[b];
-        s.in_flight = true; s.fmt = c->fmt; s.n_payload = n_payload; s.n_hits = s.h8.size(); s.too_dense = false;
+        const uint64_t n_total = chars.size(), n_cols = (uint64_t)c->n_cols;
+        s.in_flight = true; s.fmt = c->fmt; s.n_payload = n_payload; s.too_dense = false;
+        s.pending = std::async(std::launch::async, [&s, per_pos, n_total, n_payload, n_cols] {
+            const uint64_t nb = (n_payload + (1u << B200SCAN_BUCKET_SHIFT) - 1) >> B200SCAN_BUCKET_SHIFT;
+            s.h16.clear(); s.h12.clear(); s.h8.clear(); s.buckets.assign(nb + 1, 0);
+            s.h8.reserve((size_t)(per_pos * (double)n_payload * 1.05) + 1024);
+            uint64_t x = 0x9E3779B97F4A7C15ull ^ (n_total * 1315423911ull);
+            const double step = 1.0 / 1000.0 / per_pos;
+            double p = 0; uint64_t last = ~0ull;
+            for (;;) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                p += (double)(1 + (x >> 20) % 2000) * step;                  // mean gap 1 / per_pos
+                if (p >= (double)n_payload) break;
+                const uint64_t q = (uint64_t)p;
+                if (q == last) continue;                                      // one hit per position keeps the (position, column) order trivially
+                last = q;
+                s.h8.push_back({(uint32_t)((q & 255u) << 24) | (uint32_t)((x >> 3) % n_cols), 5.0f + (float)(x % 100000) / 1e4f});
+                s.buckets[(q >> B200SCAN_BUCKET_SHIFT) + 1]++;
+            }
+            for (uint64_t b = 0; b < nb; b++) s.buckets[b + 1] += s.buckets[b];
+            s.n_hits = s.h8.size();
+        });
         return B200SCAN_OK;
     } else
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -129,6 +135,7 @@ int collect_common(b200scan_ctx* c, int slot, int fmt, b200scan_timing* timing)
     if (!s.in_flight) return fail(c, B200SCAN_ESTATE, "slot %d has nothing to collect", slot);
     if (s.fmt != fmt) return fail(c, B200SCAN_ESTATE, "slot %d was submitted with %d-byte hit records", slot, s.fmt);
     s.in_flight = false;
+    if (s.pending.valid()) s.pending.get();
     if (c->delay_us) {
         c->rng = c->rng * 6364136223846793005ull + 1442695040888963407ull;
         std::this_thread::sleep_for(std::chrono::microseconds((c->rng >> 33) % c->delay_us));
