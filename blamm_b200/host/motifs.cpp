@@ -154,21 +154,39 @@ float ScoreHistogram::scoreCutoff(float pvalue) const
     return maxScore;
 }
 
+// Histogram file -> counts (reference: ScoreHistogram::loadHistogram, motif.cpp:109-132): "bins min max" and then one "centre
+// count" pair per bin, any white space between the numbers.  A `scan -pt` run loads one file per motif and group (21,600 for
+// configs[2]), so the file is read with one call and parsed with std::from_chars (correctly rounded, like the stream extraction of
+// the reference) instead of a stream.
 void ScoreHistogram::load(const std::string& dir, const std::string& base)
 {
     const std::string filename = dir + base + ".dat";
-    std::ifstream in(filename);
-    if (!in) throw std::runtime_error("Error: cannot read file " + filename + ". Did you run the hist module?");
-    size_t bins = 0;
-    in >> bins >> minScore >> maxScore;
+    std::string text;
+    {
+        FILE* f = fopen(filename.c_str(), "rb");
+        if (!f) throw std::runtime_error("Error: cannot read file " + filename + ". Did you run the hist module?");
+        char buf[1 << 16];
+        for (size_t n; (n = fread(buf, 1, sizeof buf, f)) > 0;) text.append(buf, n);
+        fclose(f);
+    }
+    const char* p = text.data();
+    const char* const end = p + text.size();
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; };
+    auto number = [&](auto& v) {
+        while (p < end && blank(*p)) p++;
+        if (p < end && *p == '+') p++;                              // (stream extraction accepts a leading plus sign)
+        const auto r = std::from_chars(p, end, v);
+        if (r.ec != std::errc()) throw std::runtime_error("Unexpected end-of-file reached");
+        p = r.ptr;
+    };
+    uint64_t bins = 0;
+    number(bins); number(minScore); number(maxScore);
     width = (maxScore - minScore) / (float)bins;
     counts.assign(bins, 0);
-    for (size_t i = 0; i < bins; i++) {
-        float centre; uint64_t v;
-        in >> centre >> v;
-        counts[i] = v;
+    for (uint64_t i = 0; i < bins; i++) {
+        float centre;
+        number(centre); number(counts[i]);
     }
-    if (!in) throw std::runtime_error("Unexpected end-of-file reached");
 }
 
 // The two files of a histogram are assembled in memory and written with one call each (`hist` writes two files per motif and
