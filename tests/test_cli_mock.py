@@ -160,3 +160,45 @@ def test_cli_on_the_example_with_mock_devices(golden, tmp_path, mock_env):
         assert ("Wrote %d matches" % len(lines)) in out
         if mode_key == "pt_rc":
             assert open(work / "PWMthresholds.txt").read() == open(os.path.join(golden, "example", "PWMthresholds_pt_rc.txt")).read()
+
+
+def test_cli_smallest_chunks_and_stats_account(tmp_path, mock_env):
+    """Chunks of 1,024 characters (the smallest the CLI accepts: hundreds of chunks per group, every halo and fragment rule at a
+    chunk border) on three devices: still the reference's occurrence set and the same file as one large chunk; `--stats` writes a
+    JSON account whose totals agree with the run."""
+    import json
+    work = str(tmp_path)
+    _make_inputs(work, 206, n_groups=2)
+    flags = ["-rc", "-pt", "0.001"]
+    want = _reference_lines(work, flags, ("pt", 0.001, True))
+    big, _ = _scan(work, mock_env, *flags)
+    tiny, out = _scan(work, mock_env, *flags, "--stats", "stats.json", MOCK_B200SCAN_DEVICES=3, MOCK_B200SCAN_DELAY_US=300, BLAMM_B200_CHUNK=1024)
+    assert sorted(big.decode().splitlines(True)) == want and tiny == big
+    st = json.load(open(os.path.join(work, "stats.json")))
+    assert st["matches"] == len(want) and st["columns"] == 60 and len(st["devices"]) == 3
+    assert sum(d["hits"] for d in st["devices"]) == len(want)
+    valid = sum(int(l.split("\t")[1]) for l in open(os.path.join(work, "seq.mf.dict")) if l.startswith("TOT_SEQ_LENGTH"))
+    assert sum(d["characters"] for d in st["devices"]) == valid and sum(d["chunks"] for d in st["devices"]) >= valid // 1024
+    assert ("Wrote %d matches" % len(want)) in out
+
+
+def test_cli_stale_dictionary_and_empty_group_on_mock(tmp_path, mock_env):
+    """A group whose FASTA file holds no valid character yields nothing and does not disturb its neighbours; a FASTA file that grew a
+    record after `dict` ends the run with an error and exit code 1 (the formatting threads meet a record without a name)."""
+    work = str(tmp_path)
+    synth.make_jaspar_like(os.path.join(work, "motifs.jaspar"), 8, 5, uniform_len=(6, 9))
+    seq = synth.random_acgt(90_000, 21)
+    synth.write_fasta(os.path.join(work, "a.fa"), [("s1", seq[:45_000]), ("s2", seq[45_000:])])
+    open(os.path.join(work, "n.fa"), "w").write(">only_gaps\n" + "N" * 300 + "\n")
+    synth.write_fasta(os.path.join(work, "b.fa"), [("t1", seq[10_000:50_000])])
+    open(os.path.join(work, "seq.mf"), "w").write("g1\ta.fa\ngap\tn.fa\ng2\tb.fa\n")
+    subprocess.run([CLI, "dict", "seq.mf"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+    got, out = _scan(work, mock_env, "-rc", "-at", "2", MOCK_B200SCAN_DEVICES=2, BLAMM_B200_CHUNK=7000)
+    lines, _ = O.scan("motifs.jaspar", "seq.mf", "at", 2.0, True, histdir=".", base_dir=work)
+    assert len(lines) > 100 and sorted(got.decode().splitlines(True)) == sorted(lines)
+    assert not any(l.startswith("only_gaps") for l in got.decode().splitlines())
+    synth.write_fasta(os.path.join(work, "a.fa"), [("s1", seq[:30_000]), ("s2", seq[30_000:60_000]), ("s3", seq[60_000:])])
+    r = subprocess.run([CLI, "scan", "-rc", "-at", "2", "motifs.jaspar", "seq.mf"], cwd=work, capture_output=True, text=True,
+                       env=dict(mock_env, MOCK_B200SCAN_DEVICES="2", BLAMM_B200_CHUNK="7000"))
+    assert r.returncode == 1, (r.returncode, r.stderr[-500:])
+    assert r.stderr.strip() != "" and "bye" not in r.stdout
