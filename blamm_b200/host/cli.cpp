@@ -260,7 +260,8 @@ int runHist(int argc, char** argv)
                 FastaStream::Chunk c;
                 // at least two chunks per GPU and group, so that every device works on every group (not below 4 Mi characters)
                 const uint64_t groupLen = std::min<uint64_t>(maxLength, sp.totSeqLen ? sp.totSeqLen : maxLength);
-                const uint64_t chunkSp = std::min<uint64_t>(chunk, std::max<uint64_t>(4ull << 20, groupLen / (2 * ctxs.size()) + 1));
+                uint64_t chunkSp = std::min<uint64_t>(chunk, std::max<uint64_t>(4ull << 20, groupLen / (2 * ctxs.size()) + 1));
+                if (const char* e = getenv("BLAMM_B200_CHUNK")) chunkSp = std::min<uint64_t>(chunk, std::max<uint64_t>(strtoull(e, nullptr, 10), 1024));
                 while (fs.next(chunkSp, halo, c)) {
                     unique_ptr<HistJob> job(new HistJob);
                     job->chars.reset(new char[c.nTotal]);

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- never built by `make`, never shipped, never loaded by the product.
 //
 // A stand-in for libb200scan.so on machines WITHOUT a GPU: the subset of include/b200scan.h that the blamm-b200 command line
-// drives, answered by the CPU oracle (oracle/oracle.c: oracle_scan_stream).  tests/test_cli_mock.py builds it into
+// drives, answered by the CPU oracle (oracle/oracle.c: oracle_scan_stream, oracle_empirical_hist).  tests/test_cli_mock.py builds it into
 // tests/mock/_build/libb200scan.so and puts that directory in front of the CLI's library search path, so that the CLI's HOST
 // logic -- reader and packer, one worker per "device", group changes, three slots in flight, chunks refused as too dense and
 // scored in halves, formatting, stream-order emission with several devices -- runs on the CPU suite against the reference
@@ -28,6 +28,8 @@
 extern "C" uint64_t oracle_scan_stream(const char* stream, uint64_t n, uint64_t n_payload, const uint64_t* frag_start, uint64_t n_frag,
                                        const float* P, int ldp, int n_cols, const int32_t* col_len, const float* thr, int lower_fold,
                                        uint64_t* hit_pos, uint32_t* hit_col, float* hit_score, uint64_t cap);
+extern "C" int oracle_empirical_hist(const char* stream, uint64_t n, const uint64_t* frag_start, uint64_t n_frag, const float* P, int ldp, int n_cols,
+                                     const int32_t* col_len, const float* mins, const float* maxs, int num_bins, int lower_fold, uint64_t* counts);
 
 namespace {
 struct Slot {
@@ -44,6 +46,7 @@ struct b200scan_ctx {
     std::vector<float> P; int ldp = 0, n_cols = 0; std::vector<int32_t> len; std::vector<float> thr;
     Slot slot[B200SCAN_NUM_SLOTS];
     uint64_t max_block = 0, budget = ~0ull; unsigned delay_us = 0; uint64_t rng = 1; double synth_rate = 0;
+    std::vector<float> hmin, hmax; uint32_t hbins = 0; std::vector<uint64_t> hist;
 };
 
 namespace {
@@ -234,9 +237,45 @@ int b200scan_collect8(b200scan_ctx* c, int slot, const b200scan_hit8** hits, uin
     return B200SCAN_OK;
 }
 
-// `hist -e` is not mocked: the histogram epilogue has no host logic worth a stand-in
-int b200scan_hist_begin(b200scan_ctx* c, const float*, const float*, uint32_t) { return fail(c, B200SCAN_ENODEVICE, "hist -e needs the real library (mock)"); }
-int b200scan_hist_block_ascii(b200scan_ctx* c, const char*, uint64_t, uint64_t, const uint64_t*, uint64_t, int) { return fail(c, B200SCAN_ENODEVICE, "hist -e needs the real library (mock)"); }
-int b200scan_hist_read(b200scan_ctx* c, uint64_t*, uint64_t) { return fail(c, B200SCAN_ENODEVICE, "hist -e needs the real library (mock)"); }
+// `hist -e`: every window that STARTS in the payload and lies inside one fragment, binned as the oracle bins it.  The oracle counts
+// every window of a stream, so a block's share is  counts(whole block) - counts(halo alone)  (a window starting in the halo that
+// fits the block fits the halo, and the fragment rule looks only forward).
+int b200scan_hist_begin(b200scan_ctx* c, const float* col_min, const float* col_max, uint32_t num_bins)
+{
+    if (!c || !col_min || !col_max || num_bins < 1) return B200SCAN_EINVAL;
+    if (c->n_cols == 0) return fail(c, B200SCAN_ESTATE, "no motifs loaded");
+    c->hmin.assign(col_min, col_min + c->n_cols); c->hmax.assign(col_max, col_max + c->n_cols);
+    c->hbins = num_bins; c->hist.assign((size_t)c->n_cols * num_bins, 0);
+    return B200SCAN_OK;
+}
+int b200scan_hist_block_ascii(b200scan_ctx* c, const char* block, uint64_t n_total, uint64_t n_payload, const uint64_t* frag_starts, uint64_t n_frag,
+                              int lowercase_mode)
+{
+    if (!c || (!block && n_total)) return B200SCAN_EINVAL;
+    if (!c->hbins) return fail(c, B200SCAN_ESTATE, "b200scan_hist_begin has not been called");
+    if (n_total > c->max_block || n_payload > n_total) return fail(c, B200SCAN_ELIMIT, "block larger than max_block_nt");
+    std::vector<uint64_t> fs(1, 0), fs_halo(1, 0);
+    for (uint64_t i = 0; i < n_frag; i++) {
+        fs.push_back(frag_starts[i]);
+        if (frag_starts[i] > n_payload) fs_halo.push_back(frag_starts[i] - n_payload);
+    }
+    std::vector<uint64_t> all((size_t)c->n_cols * c->hbins, 0), halo(all.size(), 0);
+    const int fold = lowercase_mode == B200SCAN_LOWER_FOLD;
+    if (oracle_empirical_hist(block, n_total, fs.data(), fs.size(), c->P.data(), c->ldp, c->n_cols, c->len.data(), c->hmin.data(), c->hmax.data(),
+                              (int)c->hbins, fold, all.data()) != 0) return fail(c, B200SCAN_ENOMEM, "oracle_empirical_hist failed");
+    if (n_total > n_payload &&
+        oracle_empirical_hist(block + n_payload, n_total - n_payload, fs_halo.data(), fs_halo.size(), c->P.data(), c->ldp, c->n_cols, c->len.data(),
+                              c->hmin.data(), c->hmax.data(), (int)c->hbins, fold, halo.data()) != 0) return fail(c, B200SCAN_ENOMEM, "oracle_empirical_hist failed");
+    for (size_t i = 0; i < all.size(); i++) c->hist[i] += all[i] - halo[i];
+    return B200SCAN_OK;
+}
+int b200scan_hist_read(b200scan_ctx* c, uint64_t* counts, uint64_t n_counts)
+{
+    if (!c || !counts) return B200SCAN_EINVAL;
+    if (!c->hbins) return fail(c, B200SCAN_ESTATE, "b200scan_hist_begin has not been called");
+    if (n_counts != c->hist.size()) return fail(c, B200SCAN_EINVAL, "hist_read: expected %llu counts", (unsigned long long)c->hist.size());
+    std::copy(c->hist.begin(), c->hist.end(), counts);
+    return B200SCAN_OK;
+}
 
 } // extern "C"

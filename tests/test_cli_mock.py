@@ -202,3 +202,32 @@ def test_cli_stale_dictionary_and_empty_group_on_mock(tmp_path, mock_env):
                        env=dict(mock_env, MOCK_B200SCAN_DEVICES="2", BLAMM_B200_CHUNK="7000"))
     assert r.returncode == 1, (r.returncode, r.stderr[-500:])
     assert r.stderr.strip() != "" and "bye" not in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/blamm (the compiled reference) has not been built")
+def test_cli_empirical_histograms_on_mock_devices_match_reference(tmp_path, mock_env):
+    """`hist -e -g N`: the chunks of a group are dealt to all devices, every device keeps its own bin counters and the host adds
+    them up (hist.cpp:95-160 runs histThread on -t host threads).  With four stand-in devices and chunks of 9,000 characters every
+    histogram file must equal the reference binary's `hist -e` byte for byte -- and the one-device, one-chunk run's."""
+    work = str(tmp_path)
+    _make_inputs(work, 207, n_groups=2, n_motifs=20)
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    ob = os.path.join(ROOT, "oracle", "_ref", "openblas_dir.txt")
+    if os.path.exists(ob):
+        env["LD_LIBRARY_PATH"] = open(ob).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
+    os.makedirs(os.path.join(work, "ref"))
+    for args in (["dict", "seq.mf"], ["hist", "-e", "-t", "3", "-H", "ref", "motifs.jaspar", "seq.mf"]):
+        r = subprocess.run([REF_BIN] + args, cwd=work, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    want = {f: open(os.path.join(work, "ref", f), "rb").read() for f in os.listdir(os.path.join(work, "ref"))}
+    assert len(want) == 2 * 2 * 20
+    for name, extra in (("one", {}), ("four", {"MOCK_B200SCAN_DEVICES": "4", "BLAMM_B200_CHUNK": "9000"}),
+                        ("two_of_four", {"MOCK_B200SCAN_DEVICES": "4", "BLAMM_B200_CHUNK": "20011"})):
+        os.makedirs(os.path.join(work, name))
+        flags = ["-g", "2"] if name == "two_of_four" else []
+        r = subprocess.run([CLI, "hist", "-e", "-H", name] + flags + ["motifs.jaspar", "seq.mf"], cwd=work, env=dict(mock_env, **extra), capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+        got = {f: open(os.path.join(work, name, f), "rb").read() for f in os.listdir(os.path.join(work, name))}
+        assert sorted(got) == sorted(want)
+        for f in want:
+            assert got[f] == want[f], (name, f)
