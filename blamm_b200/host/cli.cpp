@@ -508,10 +508,10 @@ struct ScanShared {
     mutex qMutex; condition_variable qCv;
     deque<unique_ptr<Job>> queue; bool done = false; size_t maxQueue = 2;
     // Output: the chunks land in the file in STREAM order whatever GPU scored them (Job::seq) -- the per-GPU hit lists are merged
-    // in the order of the input, so the file does not depend on -g.  There is no writer thread and no reorder buffer: when a
-    // chunk's text is ready its owner waits for its turn (all earlier chunks have taken their place), takes the next
-    // `bytes` of the file, and the pieces are written in parallel with pwrite (the reference formats outside and writes inside
-    // its output mutex, pwmscan.cpp:88-101).
+    // in the order of the input, so the file does not depend on -g.  There is no reorder buffer: when a chunk's text is ready
+    // its owner waits for its turn (all earlier chunks have taken their place), takes the next `bytes` of the file and leaves
+    // the text to the emitter, which writes the pieces in parallel (the reference formats outside and writes inside its output
+    // mutex, pwmscan.cpp:88-101).
     mutex oMutex; condition_variable oCv;
     uint64_t nextOut = 0, fileOffset = 0;
     string error; atomic<bool> failed{false};
@@ -527,9 +527,9 @@ struct ScanShared {
 };
 
 // hits of one block -> text lines (reference format: pwmscan.cpp:88-95), in (position, column) order.
-// The block is cut into position ranges; each formatting thread sorts and formats its range, the pieces are
-// handed to the writer thread in order.
-// H = b200scan_hit12: the CLI asks the context for 12-byte records (a quarter less PCIe and host-memory traffic per hit).
+// The block is cut into position ranges; each formatting thread sorts and formats its range, the pieces go to the file in order.
+// H = b200scan_hit12 under BLAMM_B200_HITS=12 (the round-1 hand-over: unordered records, host sort); the default hand-over is the
+// ordered 8-byte records of formatBuckets below.
 // (position, column) order by LSD radix sort: the hit list of a block comes back in no particular order, and a comparison sort
 // was half of the formatting time.  Digits of <= 12 bits over the column and then over the position relative to the smallest
 // one in the list (3 passes for 1800 columns and a 6 M position range); counting passes are stable.
