@@ -211,6 +211,7 @@ int runHist(int argc, char** argv)
         gTimer.add("hist -e: CUDA start-up (contexts of all GPUs)", now() - tCreate);
         if (!err.empty()) { destroyAll(); throw runtime_error("CUDA error: " + err); }
     }
+    future<void> pendingWrite;
     for (const auto& sp : sc.species) {
         double tPhase = now();                      // BLAMM_B200_TIMING=1: the phases of the module on stderr
         cout << "Generating histograms for species: " << sp.name;
@@ -296,10 +297,21 @@ int runHist(int argc, char** argv)
                 for (size_t b = 0; b < numBins; b++) hists[i].counts[b] = total[i * numBins + b];
             gTimer.add("hist -e: last kernels + counters of all GPUs", now() - tPhase); tPhase = now();
         }
-        forEachMotif(hists.size(), [&](size_t i) {
-            hists[i].writeGNUPlot(histdir, "hist_" + sp.name + "_" + mc.motifs[i].name, mc.motifs[i].name + " (" + sp.name + ")");
+        // the two files per motif are written in the background while the next group is read and scored
+        if (pendingWrite.valid()) pendingWrite.get();
+        gTimer.add("hist: wait for the previous group's files", now() - tPhase);
+        vector<string> names;
+        for (const auto& m : mc.motifs) names.push_back(m.name);
+        pendingWrite = async(launch::async, [&forEachMotif, &histdir, group = sp.name, names = std::move(names), hs = std::move(hists)] {
+            const double t0 = now();
+            forEachMotif(hs.size(), [&](size_t i) { hs[i].writeGNUPlot(histdir, "hist_" + group + "_" + names[i], names[i] + " (" + group + ")"); });
+            gTimer.add("hist: write the histogram files (background)", now() - t0);
         });
-        gTimer.add("hist: write the histogram files", now() - tPhase);
+    }
+    if (pendingWrite.valid()) {
+        const double t0 = now();
+        try { pendingWrite.get(); } catch (...) { destroyAll(); throw; }
+        gTimer.add("hist: wait for the last group's files", now() - t0);
     }
     destroyAll();
     gTimer.report();
