@@ -231,3 +231,76 @@ def test_cli_empirical_histograms_on_mock_devices_match_reference(tmp_path, mock
         assert sorted(got) == sorted(want)
         for f in want:
             assert got[f] == want[f], (name, f)
+
+
+def _odd_fasta(rng):
+    """records with odd headers (blanks, tabs, long names, descriptions), empty lines, lines of 0 to 3000 characters, lower case,
+    N and other IUPAC letters, LF or CRLF, with or without a final line end"""
+    out = []
+    for r in range(rng.randint(1, 4)):
+        out.append(">" + rng.choice(["s", "chr", "x y", "tab\tsep", "a" * rng.randint(1, 30)]) + str(r) + rng.choice(["", " desc"]))
+        for _ in range(rng.randint(0, 40)):
+            n = rng.choice([0, 1, 5, 60, 61, 200, rng.randint(1, 3000)])
+            alpha = rng.choice(["ACGT", "ACGT", "ACGTacgt", "ACGTN", "ACGTacgtNnRY"])
+            out.append("".join(rng.choice(alpha) for _ in range(n)))
+    eol = rng.choice(["\n", "\n", "\r\n"])
+    return eol.join(out) + (eol if rng.random() < 0.8 else "")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/blamm (the compiled reference) has not been built")
+def test_cli_fuzz_against_reference_binary(tmp_path, mock_env):
+    """Seeded fuzz of the whole command line against the UNMODIFIED reference: odd FASTA files x small random motif sets x the
+    threshold modes, with random device counts, chunk sizes, hand-overs and record formats on the stand-in library.  `dict` must be
+    byte-identical; `scan` must give the same occurrence text, or -- where the reference's sgemm sums in another order (it does for
+    some matrix shapes even with short motifs: a handful of scores then differ in the sixth digit) -- pass north_star's rule as
+    tools/parity_list.py implements it: identical sets, scores within 1e-4, exceptions only within 1e-4 of their threshold."""
+    import random
+    import sys
+    refenv = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    ob = os.path.join(ROOT, "oracle", "_ref", "openblas_dir.txt")
+    if os.path.exists(ob):
+        refenv["LD_LIBRARY_PATH"] = open(ob).read().strip() + ":" + refenv.get("LD_LIBRARY_PATH", "")
+    modes = [["-pt", "0.01"], ["-rt", "0.8"], ["-at", "3"], ["-rc", "-pt", "0.005"], ["-rc", "-at", "4.5"], ["-s", "-rc", "-at", "5"]]
+    identical = within_tolerance = 0
+    for it in range(14):
+        rng = random.Random(5000 + it)
+        w = tmp_path / ("it%d" % it)
+        os.makedirs(w / "b2")
+        synth.make_jaspar_like(str(w / "motifs.jaspar"), rng.randint(1, 12), 5000 + it, uniform_len=(5, 14))
+        manifest = []
+        for f in range(rng.randint(1, 3)):
+            open(w / ("f%d.fa" % f), "w", newline="").write(_odd_fasta(rng))
+            manifest.append("g%d\tf%d.fa\n" % (f % 2, f))
+        open(w / "seq.mf", "w").write("".join(manifest))
+        mode = rng.choice(modes)
+        ok = True
+        for args in (["dict", "seq.mf"], ["hist", "motifs.jaspar", "seq.mf"], ["scan", "-t", "2", "-o", "ref.txt"] + mode + ["motifs.jaspar", "seq.mf"]):
+            ok = ok and subprocess.run([REF_BIN] + args, cwd=w, env=refenv, capture_output=True, text=True).returncode == 0
+        # dict on its own copy of the inputs, with 1 to 5 parser threads
+        for f in os.listdir(w):
+            if f.endswith(".fa") or f == "seq.mf":
+                shutil.copy(w / f, w / "b2" / f)
+        r = subprocess.run([CLI, "dict", "seq.mf"], cwd=w / "b2", env=dict(os.environ, BLAMM_B200_INGEST_THREADS=str(rng.choice([1, 2, 5]))),
+                           capture_output=True, text=True)
+        if not ok:
+            continue                                      # (the reference refused the input)
+        assert r.returncode == 0 and (w / "b2" / "seq.mf.dict").read_bytes() == (w / "seq.mf.dict").read_bytes(), it
+        extra = {"MOCK_B200SCAN_DEVICES": rng.randint(1, 4), "BLAMM_B200_CHUNK": rng.choice([1024, 3000, 50000, 1 << 25]),
+                 "MOCK_B200SCAN_DELAY_US": rng.choice([0, 500])}
+        if rng.random() < 0.3:
+            extra["BLAMM_B200_HITS"] = 12
+        if rng.random() < 0.3:
+            extra["BLAMM_B200_ASCII"] = 1
+        got, _ = _scan(str(w), mock_env, "-o", "occurrences.txt", *mode, **extra)
+        if sorted(got.decode().splitlines(True)) == sorted(open(w / "ref.txt").read().splitlines(True)):
+            identical += 1
+            continue
+        m = [x for x in mode if x != "-s"]
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "parity_list.py"), "--ours", str(w / "occurrences.txt"), "--ref", str(w / "ref.txt"),
+               "--motifs", str(w / "motifs.jaspar"), "--manifest", str(w / "seq.mf"), "--histdir", str(w)]
+        if "-rc" in m:
+            cmd.append("--rc"); m.remove("-rc")
+        q = subprocess.run(cmd + ["--" + m[0][1:], m[1]], capture_output=True, text=True)
+        assert q.returncode == 0 and "PARITY OK" in q.stdout, (it, mode, q.stdout[-1500:])
+        within_tolerance += 1
+    assert identical >= 8 and identical + within_tolerance >= 12
