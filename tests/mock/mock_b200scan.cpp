@@ -11,10 +11,12 @@
 // Knobs (environment): MOCK_B200SCAN_DEVICES (device count, default 1), MOCK_B200SCAN_HIT_BUDGET (a block with more hits
 // makes collect return B200SCAN_ENOMEM, like a block too dense for the device buffers), MOCK_B200SCAN_DELAY_US (collect sleeps a
 // pseudo-random time below this bound, device dependent: the devices finish out of order), MOCK_B200SCAN_SYNTH_HITS (hits per
-// window and column: no scoring, a pseudo-random ordered hit list of that density -- a benchmark of the CLI's host pipeline).
+// window and column: no scoring, a pseudo-random ordered hit list of that density -- a benchmark of the CLI's host pipeline),
+// MOCK_B200SCAN_FAIL_SUBMIT / _COLLECT / _MOTIFS = n (fault injection: the process's n-th such call fails with B200SCAN_ECUDA).
 #include "../../include/b200scan.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -39,6 +41,14 @@ struct Slot {
     std::future<void> pending;                  // synthetic-hit mode: the list is made in the background, like a kernel on a device
 };
 thread_local std::string g_create_error;
+// fault injection: the n-th submit / collect / set_motifs of the process (counted over all devices, from 1) fails with B200SCAN_ECUDA
+std::atomic<long> g_submits{0}, g_collects{0}, g_motifs{0};
+bool inject(const char* var, std::atomic<long>& counter)
+{
+    const char* e = getenv(var);
+    const long n = ++counter;
+    return e && atol(e) == n;
+}
 }
 
 struct b200scan_ctx {
@@ -66,6 +76,7 @@ int scan_block(b200scan_ctx* c, int slot, const std::string& chars, uint64_t n_p
     if (n_payload > chars.size()) return fail(c, B200SCAN_EINVAL, "n_payload > n_total");
     Slot& s = c->slot[slot];
     if (s.in_flight) return fail(c, B200SCAN_ESTATE, "slot %d is in flight", slot);
+    if (inject("MOCK_B200SCAN_FAIL_SUBMIT", g_submits)) return fail(c, B200SCAN_ECUDA, "injected failure of a submit (mock)");
     std::vector<uint64_t> fs(1, 0);
     for (uint64_t i = 0; i < n_frag; i++) {
         if (frag[i] == 0 || frag[i] >= chars.size() || frag[i] <= fs.back()) return fail(c, B200SCAN_EINVAL, "fragment starts must ascend inside (0, n_total)");
@@ -139,6 +150,7 @@ int collect_common(b200scan_ctx* c, int slot, int fmt, b200scan_timing* timing)
     if (s.fmt != fmt) return fail(c, B200SCAN_ESTATE, "slot %d was submitted with %d-byte hit records", slot, s.fmt);
     s.in_flight = false;
     if (s.pending.valid()) s.pending.get();
+    if (inject("MOCK_B200SCAN_FAIL_COLLECT", g_collects)) return fail(c, B200SCAN_ECUDA, "injected failure of a collect (mock)");
     if (c->delay_us) {
         c->rng = c->rng * 6364136223846793005ull + 1442695040888963407ull;
         std::this_thread::sleep_for(std::chrono::microseconds((c->rng >> 33) % c->delay_us));
@@ -186,6 +198,7 @@ int b200scan_set_motifs(b200scan_ctx* c, const float* P, int32_t ldp, int32_t n_
 {
     if (!c || !P || !col_len || !thr || n_cols < 1) return B200SCAN_EINVAL;
     for (const Slot& s : c->slot) if (s.in_flight) return fail(c, B200SCAN_ESTATE, "set_motifs while a block is in flight");
+    if (inject("MOCK_B200SCAN_FAIL_MOTIFS", g_motifs)) return fail(c, B200SCAN_ECUDA, "injected failure of set_motifs (mock)");
     for (int32_t i = 0; i < n_cols; i++)
         if (col_len[i] < 1 || col_len[i] > B200SCAN_MAX_MOTIF_LEN || 4 * col_len[i] > ldp) return fail(c, B200SCAN_ELIMIT, "column %d: bad length", i);
     c->P.assign(P, P + (size_t)ldp * n_cols); c->ldp = ldp; c->n_cols = n_cols;

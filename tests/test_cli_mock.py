@@ -304,3 +304,24 @@ def test_cli_fuzz_against_reference_binary(tmp_path, mock_env):
         assert q.returncode == 0 and "PARITY OK" in q.stdout, (it, mode, q.stdout[-1500:])
         within_tolerance += 1
     assert identical >= 8 and identical + within_tolerance >= 12
+
+
+@pytest.mark.parametrize("devices", [1, 3])
+def test_cli_survives_injected_device_failures(tmp_path, mock_env, devices):
+    """Fault injection (the reference ignores every CUDA return code but cudaMalloc's): the n-th submit, collect
+    or set_motifs of the run fails with B200SCAN_ECUDA, early, in the middle of a group and near the end, with one and with three
+    devices and chunks in flight on all of them.  Every such run must END -- no worker, reader or emitter left waiting for a turn
+    that cannot come -- with exit code 1 and the library's error text, and must not claim success."""
+    work = str(tmp_path)
+    _make_inputs(work, 208, n_groups=2)
+    for args in (["dict", "seq.mf"], ["hist", "motifs.jaspar", "seq.mf"]):
+        subprocess.run([CLI] + args, cwd=work, check=True, stdout=subprocess.DEVNULL)
+    base = dict(mock_env, MOCK_B200SCAN_DEVICES=str(devices), BLAMM_B200_CHUNK="9000", MOCK_B200SCAN_DELAY_US="300")
+    ok = subprocess.run([CLI, "scan", "-rc", "-pt", "0.001", "motifs.jaspar", "seq.mf"], cwd=work, env=base, capture_output=True, text=True, timeout=120)
+    assert ok.returncode == 0 and "Wrote" in ok.stdout
+    for var, counts in (("MOCK_B200SCAN_FAIL_SUBMIT", (1, 2, 17, 40)), ("MOCK_B200SCAN_FAIL_COLLECT", (1, 3, 18, 41)), ("MOCK_B200SCAN_FAIL_MOTIFS", (1, devices + 1))):
+        for n in counts:
+            r = subprocess.run([CLI, "scan", "-rc", "-pt", "0.001", "motifs.jaspar", "seq.mf"], cwd=work, env=dict(base, **{var: str(n)}),
+                               capture_output=True, text=True, timeout=120)
+            assert r.returncode == 1, (var, n, r.returncode, r.stdout[-300:], r.stderr[-300:])
+            assert "injected failure" in r.stderr and "Wrote" not in r.stdout and "bye" not in r.stdout, (var, n, r.stderr[-300:])

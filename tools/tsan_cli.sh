@@ -29,6 +29,8 @@ run "scan, 4 devices"               env MOCK_B200SCAN_DEVICES=4 MOCK_B200SCAN_DE
 run "scan, 12-byte records"         env MOCK_B200SCAN_DEVICES=3 BLAMM_B200_HITS=12 BLAMM_B200_CHUNK=15000 $B scan -rc -pt 0.001 -t 4 motifs.jaspar seq.mf
 run "scan, refused chunks halved"   env MOCK_B200SCAN_DEVICES=3 MOCK_B200SCAN_DELAY_US=1000 BLAMM_B200_CHUNK=30000 MOCK_B200SCAN_HIT_BUDGET=2000 $B scan -rc -pt 0.002 -t 4 motifs.jaspar seq.mf
 run "scan, error path"              env MOCK_B200SCAN_DEVICES=3 BLAMM_B200_CHUNK=30000 MOCK_B200SCAN_HIT_BUDGET=0 $B scan -rc -pt 0.002 -t 4 motifs.jaspar seq.mf
+run "scan, injected collect failure" env MOCK_B200SCAN_DEVICES=3 MOCK_B200SCAN_DELAY_US=500 BLAMM_B200_CHUNK=9000 MOCK_B200SCAN_FAIL_COLLECT=7 $B scan -rc -pt 0.001 -t 4 motifs.jaspar seq.mf
+run "scan, injected submit failure"  env MOCK_B200SCAN_DEVICES=3 MOCK_B200SCAN_DELAY_US=500 BLAMM_B200_CHUNK=9000 MOCK_B200SCAN_FAIL_SUBMIT=9 $B scan -rc -pt 0.001 -t 4 motifs.jaspar seq.mf
 mkdir -p he
 run "hist -e, 3 devices"            env MOCK_B200SCAN_DEVICES=3 BLAMM_B200_CHUNK=9000 $B hist -e -H he -t 4 motifs.jaspar seq.mf
 run "selftest-order, 5 workers"     $B selftest-order 24 5 3
