@@ -12,7 +12,7 @@
 // makes collect return B200SCAN_ENOMEM, like a block too dense for the device buffers), MOCK_B200SCAN_DELAY_US (collect sleeps a
 // pseudo-random time below this bound, device dependent: the devices finish out of order), MOCK_B200SCAN_SYNTH_HITS (hits per
 // window and column: no scoring, a pseudo-random ordered hit list of that density -- a benchmark of the CLI's host pipeline),
-// MOCK_B200SCAN_FAIL_SUBMIT / _COLLECT / _MOTIFS = n (fault injection: the process's n-th such call fails with B200SCAN_ECUDA).
+// MOCK_B200SCAN_FAIL_SUBMIT / _COLLECT / _MOTIFS / _HIST = n (fault injection: the process's n-th such call fails with B200SCAN_ECUDA).
 #include "../../include/b200scan.h"
 
 #include <algorithm>
@@ -42,7 +42,7 @@ struct Slot {
 };
 thread_local std::string g_create_error;
 // fault injection: the n-th submit / collect / set_motifs of the process (counted over all devices, from 1) fails with B200SCAN_ECUDA
-std::atomic<long> g_submits{0}, g_collects{0}, g_motifs{0};
+std::atomic<long> g_submits{0}, g_collects{0}, g_motifs{0}, g_hist_blocks{0};
 bool inject(const char* var, std::atomic<long>& counter)
 {
     const char* e = getenv(var);
@@ -267,6 +267,7 @@ int b200scan_hist_block_ascii(b200scan_ctx* c, const char* block, uint64_t n_tot
     if (!c || (!block && n_total)) return B200SCAN_EINVAL;
     if (!c->hbins) return fail(c, B200SCAN_ESTATE, "b200scan_hist_begin has not been called");
     if (n_total > c->max_block || n_payload > n_total) return fail(c, B200SCAN_ELIMIT, "block larger than max_block_nt");
+    if (inject("MOCK_B200SCAN_FAIL_HIST", g_hist_blocks)) return fail(c, B200SCAN_ECUDA, "injected failure of a histogram block (mock)");
     std::vector<uint64_t> fs(1, 0), fs_halo(1, 0);
     for (uint64_t i = 0; i < n_frag; i++) {
         fs.push_back(frag_starts[i]);

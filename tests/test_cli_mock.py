@@ -325,3 +325,19 @@ def test_cli_survives_injected_device_failures(tmp_path, mock_env, devices):
                                capture_output=True, text=True, timeout=120)
             assert r.returncode == 1, (var, n, r.returncode, r.stdout[-300:], r.stderr[-300:])
             assert "injected failure" in r.stderr and "Wrote" not in r.stdout and "bye" not in r.stdout, (var, n, r.stderr[-300:])
+
+
+def test_cli_hist_e_survives_injected_device_failures(tmp_path, mock_env):
+    """The same for `hist -e`: a histogram block or a set_motifs that fails on one of three devices ends the run with exit code 1."""
+    work = str(tmp_path)
+    _make_inputs(work, 209, n_groups=2, n_motifs=12)
+    subprocess.run([CLI, "dict", "seq.mf"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+    os.makedirs(os.path.join(work, "he"))
+    base = dict(mock_env, MOCK_B200SCAN_DEVICES="3", BLAMM_B200_CHUNK="9000")
+    ok = subprocess.run([CLI, "hist", "-e", "-H", "he", "motifs.jaspar", "seq.mf"], cwd=work, env=base, capture_output=True, text=True, timeout=120)
+    assert ok.returncode == 0 and "bye" in ok.stdout
+    for var, counts in (("MOCK_B200SCAN_FAIL_HIST", (1, 5, 30)), ("MOCK_B200SCAN_FAIL_MOTIFS", (2, 4))):
+        for n in counts:
+            r = subprocess.run([CLI, "hist", "-e", "-H", "he", "motifs.jaspar", "seq.mf"], cwd=work, env=dict(base, **{var: str(n)}),
+                               capture_output=True, text=True, timeout=120)
+            assert r.returncode == 1 and "injected failure" in r.stderr and "bye" not in r.stdout, (var, n, r.returncode, r.stderr[-300:])
