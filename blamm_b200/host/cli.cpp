@@ -23,6 +23,7 @@
 #include <sstream>
 #include <thread>
 #include <unordered_map>
+#include <csignal>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/vfs.h>
@@ -502,6 +503,23 @@ struct ScanShared {
         if (e && string(e) == "mmap") { useMmap = true; return; }
         struct statfs st;
         useMmap = fd >= 0 && fstatfs(fd, &st) == 0 && (unsigned long)st.f_type == 0x01021994ul;      // TMPFS_MAGIC
+        installBusHandler();
+    }
+    // A store into the mapping of a tmpfs file that cannot get its page (the file system is full) raises SIGBUS: end the run
+    // with the message and the exit code a failed write() gives, not with a core dump.
+    static void installBusHandler()
+    {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            struct sigaction sa;
+            memset(&sa, 0, sizeof sa);
+            sa.sa_handler = [](int) {
+                static const char msg[] = "Cannot write to the occurrence file (no space left on the device?)\n";
+                if (write(2, msg, sizeof msg - 1) < 0) {}
+                _exit(EXIT_FAILURE);
+            };
+            sigaction(SIGBUS, &sa, nullptr);
+        });
     }
     size_t copyThreads = getenv("BLAMM_B200_COPY_THREADS") ? (size_t)max(1, atoi(getenv("BLAMM_B200_COPY_THREADS"))) : 0;      // 0: 8 (mapping) / 16 (pwrite)
     WorkPool* pool = nullptr;

@@ -529,3 +529,20 @@ def test_packer_sse2_and_avx2_paths_agree(tmp_path):
         subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, **env))
         res.append(np.load(f))
     assert len(res[0]) > 100000 and np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+
+
+def test_writer_reports_a_full_file_system(tmp_path):
+    """The occurrence file in a tmpfs that runs out of space: the mapped writer ends the run with a message and exit code 1 (a store
+    into such a mapping raises SIGBUS), the pwrite writer reports the failed write.  Needs the right to mount a 2 MB tmpfs."""
+    mnt = tmp_path / "tiny"
+    mnt.mkdir()
+    if subprocess.run(["mount", "-t", "tmpfs", "-o", "size=2m", "tmpfs", str(mnt)], capture_output=True).returncode != 0:
+        pytest.skip("cannot mount a tmpfs here")
+    try:
+        r = subprocess.run([CLI, "selftest-writer", "200000", "4"], capture_output=True, text=True, env=dict(os.environ, TMPDIR=str(mnt)), timeout=120)
+        assert r.returncode == 1 and "Cannot write to the occurrence file" in r.stderr
+        r = subprocess.run([CLI, "selftest-writer", "200000", "4"], capture_output=True, text=True,
+                           env=dict(os.environ, TMPDIR=str(mnt), BLAMM_B200_WRITER="pwrite"), timeout=120)
+        assert r.returncode == 1 and "identical" not in r.stdout
+    finally:
+        subprocess.run(["umount", str(mnt)], capture_output=True)
