@@ -514,7 +514,7 @@ struct ScanShared {
             struct sigaction sa;
             memset(&sa, 0, sizeof sa);
             sa.sa_handler = [](int) {
-                static const char msg[] = "Cannot write to the occurrence file (no space left on the device?)\n";
+                static const char msg[] = "Cannot write to the occurrence file (no space left on the device?), or a mapped input file shrank during the run\n";
                 if (write(2, msg, sizeof msg - 1) < 0) {}
                 _exit(EXIT_FAILURE);
             };
