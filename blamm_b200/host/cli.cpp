@@ -511,7 +511,8 @@ struct ScanShared {
     {
         static std::once_flag once;
         std::call_once(once, [] {
-            struct sigaction sa;
+            struct sigaction sa, old;
+            if (sigaction(SIGBUS, nullptr, &old) != 0 || old.sa_handler != SIG_DFL) return;      // somebody else's handler stays
             memset(&sa, 0, sizeof sa);
             sa.sa_handler = [](int) {
                 static const char msg[] = "Cannot write to the occurrence file (no space left on the device?), or a mapped input file shrank during the run\n";
