@@ -10,6 +10,8 @@
 #           oracle/_ref/blamm_cuda     the reference CLI with its own GPU path (`scan -c`: cuBLAS sgemm + kernel.cu's filterScore,
 #                                      pwmscan.cpp:297-437) compiled for sm_100 -- the "existing GPU implementation" bench.py times
 #                                      beside the B200-native path; only built where nvcc exists
+#           oracle/_ref/blamm_dropin   the reference CLI with INTEGRATION.md's three edits + integration/scanPWMB200.inc, linked against
+#                                      libb200scan.so: its `scan -c` runs the B200-native path (build_dropin.py; tests/test_reference_dropin.py)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${BLAMM_REFERENCE:-/root/reference}"
@@ -36,3 +38,5 @@ if command -v nvcc > /dev/null 2>&1; then
 fi
 echo "$OB" > "$OUT/openblas_dir.txt"
 echo "build_ref: built $OUT/blamm and $OUT/refdump"
+# the reference with INTEGRATION.md's binding applied (temporary copy of its sources, removed again): `scan -c` goes through libb200scan.so
+python3 "$HERE/build_dropin.py" "$REF" "$OUT" "$OB" "$OBLIB" || echo "build_ref: blamm_dropin not built"
