@@ -10,10 +10,9 @@ import os
 import shutil
 import subprocess
 
-import numpy as np
 import pytest
 
-from blamm_b200 import lib_dir, synth
+from blamm_b200 import lib_dir
 from tests import util
 
 ROOT = util.ROOT
